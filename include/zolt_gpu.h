@@ -1,0 +1,199 @@
+/* zolt_gpu.h -- C ABI of the B200-native prover hot path for Zolt (MatteoMer/zolt).
+ *
+ * The reference has NO FFI today; these entry points are what a `zig/zolt_gpu.zig`
+ * shim binds with @cImport so that the existing Zig call signatures stay intact.  Each function
+ * cites the reference interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - Every function returns an int32 status (ZOLT_OK == 0).  Nothing throws, nothing calls back.
+ *    Calls block until their outputs are valid unless the name ends in `_async`.
+ *  - There is NO CPU fallback: with no usable CUDA device zolt_gpu_init fails with
+ *    ZOLT_ERR_NOGPU and every other call needs a context.
+ *  - Field elements (zolt_fr / zolt_fq): uint64_t[4], little-endian limbs, Montgomery form
+ *    a*2^256 mod p, canonical (< p) -- bit-identical to `BN254Scalar.limbs` /
+ *    `MontgomeryField.limbs` (src/field/mod.zig:583-585, :124-130).
+ *  - G1 affine points: uint64_t xy[8] = x limbs then y limbs (Fq, Montgomery) plus a separate
+ *    uint8_t infinity flag.  Identity is x=0, y=0, infinity=1 (src/msm/mod.zig:24-30).
+ *    Zig's AffinePoint is not an extern struct, so the shim marshals once per SRS (SURVEY H-f).
+ *  - A handle must not be used from two host threads at once.  Host buffers are borrowed for the
+ *    duration of the call only.
+ */
+#ifndef ZOLT_GPU_H
+#define ZOLT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZOLT_OK 0
+#define ZOLT_ERR_CUDA 1  /* a CUDA runtime call or kernel failed (message on stderr) */
+#define ZOLT_ERR_ARG 2   /* invalid argument (null pointer, size not a power of two, ...) */
+#define ZOLT_ERR_STATE 3 /* call sequence violated (e.g. bind after the last round) */
+#define ZOLT_ERR_NOGPU 4 /* no CUDA device: there is no CPU path */
+
+typedef struct zolt_ctx zolt_ctx;     /* one device + one stream */
+typedef struct zolt_bases zolt_bases; /* device-resident G1 bases (an SRS) */
+typedef struct zolt_sc zolt_sc;       /* one sumcheck instance: k device-resident tables */
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* `stream` is a cudaStream_t to launch on (borrowed), or NULL to create a private one. */
+int zolt_gpu_init(int device, void* stream, zolt_ctx** out);
+int zolt_gpu_shutdown(zolt_ctx* ctx);
+int zolt_gpu_sync(zolt_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int zolt_gpu_launch_count(zolt_ctx* ctx, unsigned long long* out);
+const char* zolt_gpu_version(void);
+
+/* raw device buffers, so a host without CUDA bindings can keep tables resident */
+int zolt_dev_alloc(zolt_ctx* ctx, size_t bytes, void** dptr);
+int zolt_dev_free(zolt_ctx* ctx, void* dptr);
+int zolt_dev_upload(zolt_ctx* ctx, void* dptr, const void* hptr, size_t bytes);
+int zolt_dev_download(zolt_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
+
+/* ---- field vectors ---------------------------------------------------------------------------
+ * Element-wise ops on host vectors; replaces BatchOps.batchAdd/batchMul (src/field/mod.zig:1164-1280)
+ * and doubles as the parity hook for F1-F7 (montgomeryMul :735-779, add :782-798, sub :801-816,
+ * neg :944-947, inverse :955-983, fromMontgomery :642-645, toMontgomery :649-652). */
+enum { ZOLT_FIELD_FR = 0, ZOLT_FIELD_FQ = 1 };
+enum {
+  ZOLT_OP_MUL = 0,
+  ZOLT_OP_ADD = 1,
+  ZOLT_OP_SUB = 2,
+  ZOLT_OP_INV = 3,       /* b ignored; inverse(0) = 0 (batchInverse convention, :1243-1271) */
+  ZOLT_OP_FROM_MONT = 4, /* b ignored */
+  ZOLT_OP_TO_MONT = 5,   /* b ignored; a is any 256-bit integer (fromBytes semantics :625-639) */
+  ZOLT_OP_NEG = 6        /* b ignored */
+};
+int zolt_field_batch_op(zolt_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b,
+                        uint64_t* out, size_t n);
+
+/* ---- MSM -------------------------------------------------------------------------------------
+ * zolt_msm == msm.MSM(F, Fp).compute(bases[offset..offset+n], scalars)  (src/msm/mod.zig:355-372);
+ * callers: HyperKZG.commit (src/poly/commitment/mod.zig:249), Dory row commitments
+ * (src/poly/commitment/dory.zig:663, :1024).  Bases are uploaded once per SRS and stay resident
+ * (SetupParams.powers_of_tau_g1 is long-lived, commitment/mod.zig:122-140). */
+int zolt_msm_bases_upload(zolt_ctx* ctx, const uint64_t* xy /* n*8 */, const uint8_t* inf /* n or NULL */,
+                          size_t n, zolt_bases** out);
+int zolt_msm_bases_free(zolt_bases* bases);
+int zolt_msm_bases_len(const zolt_bases* bases, size_t* n);
+int zolt_msm_bases_download(const zolt_bases* bases, size_t offset, size_t n, uint64_t* xy, uint8_t* inf);
+
+int zolt_msm(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars /* n*4, host */,
+             size_t n, uint64_t out_xy[8], uint8_t* out_inf);
+/* same, scalars already on the device (e.g. a bound sumcheck table or a quotient in HyperKZG.open) */
+int zolt_msm_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const void* d_scalars, size_t n,
+                 uint64_t out_xy[8], uint8_t* out_inf);
+/* k MSMs over the same n bases: BatchMSM.compute (src/msm/mod.zig:551-563), the shape of
+ * DoryCommitmentScheme.computeRowCommitments (dory.zig:646-670) and HyperKZG.batchCommit
+ * (commitment/mod.zig:558-570). scalars = k*n*4, outputs k*8 / k. */
+int zolt_msm_batch(zolt_ctx* ctx, const zolt_bases* bases, const uint64_t* scalars, size_t k, size_t n,
+                   uint64_t* out_xy, uint8_t* out_inf);
+/* Multi-GPU: the un-normalised partial sum of this rank's point range as 16 u64 (extended Jacobian
+ * X, Y, ZZ, ZZZ in Fq Montgomery form; ZZ == 0 encodes the identity), left in device memory at d_out
+ * (128 bytes) so it can be all-gathered over NCCL; zolt_g1_sum_partials adds `count` such partials on
+ * the device and normalises.  Mirrors ParallelMSM.compute's chunk/combine split
+ * (src/msm/mod.zig:588-653). */
+int zolt_msm_partial_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const void* d_scalars,
+                         size_t n, void* d_out /* 16 u64 */);
+int zolt_g1_sum_partials(zolt_ctx* ctx, const void* d_partials /* count*16 u64 */, size_t count,
+                         uint64_t out_xy[8], uint8_t* out_inf);
+
+/* bases[i] = scalars[i] * G, G = (1,2): fixed-base generator used for SRS / workload generation.
+ * With scalars = tau^i this is HyperKZG.setup's powers_of_tau_g1 (commitment/mod.zig:174-213). */
+int zolt_g1_fixed_base_mul(zolt_ctx* ctx, const uint64_t* scalars /* n*4 Montgomery Fr */, size_t n,
+                           zolt_bases** out);
+/* HyperKZG.setup(max_degree): mock SRS with tau = 0x12345678 (commitment/mod.zig:189) built on device. */
+int zolt_hyperkzg_setup(zolt_ctx* ctx, size_t max_degree, zolt_bases** out);
+
+/* ---- dense multilinear tables ------------------------------------------------------------------
+ * Device-resident tables of 2^v Fr elements (32 B each, same layout as []F). */
+/* DensePolynomial.bindLow (src/poly/mod.zig:160-175): dst[i] = src[2i] + r*(src[2i+1]-src[2i]).
+ * dst may equal src (in place, like the reference) -- n is the CURRENT length, n/2 are written. */
+int zolt_poly_bind_low(zolt_ctx* ctx, void* d_dst, const void* d_src, size_t n, const uint64_t r[4]);
+/* DensePolynomial.bindFirst (src/poly/mod.zig:128-149): dst[i] = (1-r)*src[i] + r*src[i+n/2]. */
+int zolt_poly_bind_first(zolt_ctx* ctx, void* d_dst, const void* d_src, size_t n, const uint64_t r[4]);
+/* EqPolynomial.evals / evalsSliceWithScaling (src/poly/mod.zig:240-290): big-endian table
+ * eq(r, x), r[0] <-> MSB of the index; scale may be NULL (= one).  d_out holds 2^n_vars elements. */
+int zolt_eq_evals(zolt_ctx* ctx, const uint64_t* r /* n_vars*4 */, int n_vars, const uint64_t* scale,
+                  void* d_out);
+/* sum of all entries (initial sumcheck claim, src/subprotocols/mod.zig:306-309) */
+int zolt_poly_sum(zolt_ctx* ctx, const void* d_src, size_t n, uint64_t out[4]);
+
+/* ---- sumcheck prover inner loop ----------------------------------------------------------------
+ * One instance = k dense tables bound in lock-step.  The call pattern is the reference's:
+ *   round_evals -> (host transcript) -> bind -> round_evals -> ...
+ * (SumcheckInstance.computeRoundPolyFn / bindChallengeFn, src/zkvm/batched_sumcheck.zig:34-74;
+ *  prover.SumcheckInstance vtable, src/zkvm/prover.zig:30-69).
+ * zolt_sc_bind(r) launches ONE fused kernel that binds every table to r and accumulates the next
+ * round's evaluations in the same pass over HBM; the following zolt_sc_round_evals only reads the
+ * 128-byte result. */
+enum {
+  ZOLT_PAIR_ADJACENT = 0, /* LowToHigh: pairs (2i, 2i+1)   -- bindLow order */
+  ZOLT_PAIR_HALF = 1      /* HighToLow: pairs (i, i+n/2)   -- bindFirst order */
+};
+enum {
+  /* k=1. evals = [sum lo, sum hi].  Sumcheck.Prover.nextRound (src/subprotocols/mod.zig:69-109),
+   * JoltSpartanInterface.computeRoundPolynomial (src/zkvm/r1cs/jolt_r1cs.zig:413-454), stages 5/6
+   * (src/zkvm/prover.zig:905-946). */
+  ZOLT_SC_SUM = 0,
+  /* k=2. evals at X=0,1,2,3 of sum a(X)*b(X).  ValFinalProver (src/zkvm/ram/val_final.zig:150-184);
+   * the Eq*MLE shape of BASELINE config 2. */
+  ZOLT_SC_PROD2 = 1,
+  /* k=3. evals at X=0..3 of sum a*b*c.  ValEvaluationProver (src/zkvm/ram/val_evaluation.zig:554-604). */
+  ZOLT_SC_PROD3 = 2,
+  /* k=4 (eq, a, b, c). sum eq*a*(b-c).  OutputSumcheckProver (src/zkvm/ram/output_check.zig:375-433). */
+  ZOLT_SC_EQ_A_BMC = 3,
+  /* k=4 (eq, az, bz, cz). sum eq*(az*bz - cz): the Spartan-style shape of BASELINE config 3
+   * (elementwise form at src/zkvm/r1cs/jolt_r1cs.zig:352-360). */
+  ZOLT_SC_EQ_AB_MINUS_C = 4,
+  /* k=2 (left, right) + split-eq weights.  evals = [t0, t_inf]:
+   *   t0 = sum_g E_out[x_out] E_in[x_in] l_lo r_lo, t_inf = sum_g E_out E_in (l_hi-l_lo)(r_hi-r_lo)
+   * ProductVirtualRemainderProver (src/zkvm/spartan/product_remainder.zig:269-322),
+   * StreamingOuterProver.buildTPrimePoly (src/zkvm/spartan/streaming_outer.zig:411-457).
+   * The host finishes with GruenSplitEqPolynomial.computeCubicRoundPoly (src/poly/split_eq.zig:353). */
+  ZOLT_SC_GRUEN_AB = 5,
+  /* k=3 (az, bz, cz) + split-eq weights: t0 = sum w (az0 bz0 - cz0), t_inf = sum w daz dbz. */
+  ZOLT_SC_GRUEN_AB_MINUS_C = 6
+};
+
+/* tables: k host pointers (n*4 u64 each), n = 2^log_n.  n_extra further tables are bound in
+ * lock-step but do not enter the round polynomial (val_init in output_check.zig:454-476). */
+int zolt_sc_create(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
+                   const uint64_t* const* tables, zolt_sc** out);
+/* same, from device-resident tables (copied; the instance owns its buffers) */
+int zolt_sc_create_dev(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
+                       const void* const* d_tables, zolt_sc** out);
+/* Gruen combiners only: tau (n_tau*4, n_tau == log_n) -> builds the E_out / E_in prefix tables of
+ * GruenSplitEqPolynomial.initWithScaling on the device (src/poly/split_eq.zig:63-183). */
+int zolt_sc_set_split_eq(zolt_sc* sc, const uint64_t* tau, int n_tau);
+/* number of evaluations zolt_sc_round_evals writes (2 or 4) */
+int zolt_sc_num_evals(const zolt_sc* sc, int* out);
+int zolt_sc_round_evals(zolt_sc* sc, uint64_t* evals_out /* num_evals*4 */);
+int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]);
+/* current (bound) length of the tables and a copy of table t */
+int zolt_sc_len(const zolt_sc* sc, size_t* n);
+int zolt_sc_download(zolt_sc* sc, int table, uint64_t* dst /* len*4 */);
+/* device pointer of table t's current buffer (valid until the next bind) */
+int zolt_sc_table_dev(zolt_sc* sc, int table, const void** d_ptr);
+/* Multi-GPU: this rank's partial evaluations stay on the device at *d_ptr (num_evals*4 u64) so they
+ * can be all-gathered; zolt_fr_sum_rows folds `rows` gathered partials mod r on the device. */
+int zolt_sc_round_partials_dev(zolt_sc* sc, const void** d_ptr);
+int zolt_fr_sum_rows(zolt_ctx* ctx, const void* d_rows, size_t rows, size_t cols, uint64_t* out /* cols*4 */);
+int zolt_sc_free(zolt_sc* sc);
+
+/* ---- diagnostics ---------------------------------------------------------------------------------
+ * Integer-pipe micro-benchmarks (the MSM roofline denominator).  `kind`: 0 = IMAD (3-reg),
+ * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery products, 3 = Fq Montgomery products, 4 = IMAD immediate form.
+ * Returns ops per second (for kind 2/3: field products per second). */
+int zolt_bench_int_pipe(zolt_ctx* ctx, int kind, int iters, double* ops_per_s);
+/* device timing helpers on the context's stream (CUDA events) */
+int zolt_timer_start(zolt_ctx* ctx);
+int zolt_timer_stop_ms(zolt_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZOLT_GPU_H */

@@ -1,0 +1,146 @@
+"""ORACLE (test infrastructure only).  Big-integer restatement of the per-round loops of Zolt's
+sumcheck provers.  Tables are lists of STANDARD integers mod r.
+
+Each `round_*` function restates one reference computeRoundPolynomial loop; `bind_tables` restates
+the matching bind loops.  Reference anchors (relative to /root/reference):
+  S1  Sumcheck.Prover.nextRound / receiveChallenge   src/subprotocols/mod.zig:69-122 (half split)
+  S2  JoltSpartanInterface round / bind              src/zkvm/r1cs/jolt_r1cs.zig:413-489 (adjacent)
+  S3b ValFinalProver                                 src/zkvm/ram/val_final.zig:150-206
+  S4  ValEvaluationProver                            src/zkvm/ram/val_evaluation.zig:554-640
+  S4b OutputSumcheckProver                           src/zkvm/ram/output_check.zig:375-479
+  S5b ProductVirtualRemainderProver (Gruen)          src/zkvm/spartan/product_remainder.zig:269-378
+  elementwise eq*(Az*Bz - Cz)                        src/zkvm/r1cs/jolt_r1cs.zig:352-360
+"""
+from __future__ import annotations
+
+from .bn254 import FR_MOD as P
+from .poly import GruenSplitEq, bind_first, bind_low
+
+ADJACENT, HALF = 0, 1
+
+
+def _pairs(table: list[int], pairing: int):
+    n = len(table)
+    h = n // 2
+    if pairing == ADJACENT:
+        return [(table[2 * i], table[2 * i + 1]) for i in range(h)]
+    return [(table[i], table[i + h]) for i in range(h)]
+
+
+def bind_tables(tables: list[list[int]], r: int, pairing: int) -> list[list[int]]:
+    f = bind_low if pairing == ADJACENT else bind_first
+    return [f(t, r) for t in tables]
+
+
+def round_sum(tables, pairing):
+    """[sum lo, sum hi]: S1 g0/g1 (subprotocols/mod.zig:84-93), S2 p0/p1 (jolt_r1cs.zig:436-439)."""
+    lo = hi = 0
+    for a, b in _pairs(tables[0], pairing):
+        lo += a
+        hi += b
+    return [lo % P, hi % P]
+
+
+def round_prod2(tables, pairing):
+    """ValFinalProver (val_final.zig:164-184): evals at X=0..3 of sum a(X) b(X), f(X) = X f1 - (X-1) f0."""
+    e = [0, 0, 0, 0]
+    for (a0, a1), (b0, b1) in zip(_pairs(tables[0], pairing), _pairs(tables[1], pairing)):
+        for x in range(4):
+            e[x] += (x * a1 - (x - 1) * a0) * (x * b1 - (x - 1) * b0)
+    return [v % P for v in e]
+
+
+def round_prod3(tables, pairing):
+    """ValEvaluationProver (val_evaluation.zig:567-601)."""
+    e = [0, 0, 0, 0]
+    pa, pb, pc = (_pairs(t, pairing) for t in tables[:3])
+    for (a0, a1), (b0, b1), (c0, c1) in zip(pa, pb, pc):
+        for x in range(4):
+            e[x] += (x * a1 - (x - 1) * a0) * (x * b1 - (x - 1) * b0) % P * (x * c1 - (x - 1) * c0)
+    return [v % P for v in e]
+
+
+def round_eq_a_bmc(tables, pairing):
+    """OutputSumcheckProver (output_check.zig:385-433): sum eq(X) io(X) (vf(X) - vio(X))."""
+    e = [0, 0, 0, 0]
+    pe, pa, pb, pc = (_pairs(t, pairing) for t in tables[:4])
+    for (e0, e1), (a0, a1), (b0, b1), (c0, c1) in zip(pe, pa, pb, pc):
+        v0, v1 = b0 - c0, b1 - c1
+        for x in range(4):
+            e[x] += (e0 + x * (e1 - e0)) * (a0 + x * (a1 - a0)) % P * (v0 + x * (v1 - v0))
+    return [v % P for v in e]
+
+
+def round_eq_ab_minus_c(tables, pairing):
+    """Spartan-style sum eq(X) (az(X) bz(X) - cz(X)) (BASELINE config 3; elementwise form at
+    jolt_r1cs.zig:352-360)."""
+    e = [0, 0, 0, 0]
+    pe, pa, pb, pc = (_pairs(t, pairing) for t in tables[:4])
+    for (e0, e1), (a0, a1), (b0, b1), (c0, c1) in zip(pe, pa, pb, pc):
+        for x in range(4):
+            ex = e0 + x * (e1 - e0)
+            ax = a0 + x * (a1 - a0)
+            bx = b0 + x * (b1 - b0)
+            cx = c0 + x * (c1 - c0)
+            e[x] += ex * ((ax * bx - cx) % P)
+    return [v % P for v in e]
+
+
+def round_gruen_ab(tables, split_eq: GruenSplitEq, with_c: bool = False):
+    """product_remainder.zig:283-322: nested x_out / x_in loops, inner sums weighted by E_in, outer by
+    E_out.  Returns [t0, t_inf]."""
+    left, right = tables[0], tables[1]
+    cz = tables[2] if with_c else None
+    E_out, E_in, _ = split_eq.window_tables()
+    bits = (len(E_in).bit_length() - 1) if len(E_in) > 1 else 0
+    groups = len(left) // 2
+    t0 = tinf = 0
+    for xo, eo in enumerate(E_out):
+        i0 = ii = 0
+        for xi, ei in enumerate(E_in):
+            g = (xo << bits) | xi
+            if g < groups:
+                l0, l1 = left[2 * g], left[2 * g + 1]
+                r0, r1 = right[2 * g], right[2 * g + 1]
+                p0 = l0 * r0
+                if cz is not None:
+                    p0 -= cz[2 * g]
+                i0 += p0 % P * ei
+                ii += (l1 - l0) * (r1 - r0) % P * ei
+        t0 += i0 % P * eo
+        tinf += ii % P * eo
+    return [t0 % P, tinf % P]
+
+
+ROUND_FNS = {
+    "sum": round_sum,
+    "prod2": round_prod2,
+    "prod3": round_prod3,
+    "eq_a_bmc": round_eq_a_bmc,
+    "eq_ab_minus_c": round_eq_ab_minus_c,
+}
+
+
+def run_dense(kind: str, tables, pairing: int, challenges, n_extra: int = 0):
+    """Alternate round-eval / bind over all variables with the given challenges.
+    Returns (list of per-round evals, list of per-round bound tables [after each bind])."""
+    tabs = [list(t) for t in tables]
+    fn = ROUND_FNS[kind]
+    evals, bound = [], []
+    for r in challenges:
+        evals.append(fn(tabs, pairing))
+        tabs = bind_tables(tabs, r, pairing)
+        bound.append([list(t) for t in tabs])
+    return evals, bound
+
+
+def run_gruen(tables, tau, challenges, with_c: bool = False):
+    tabs = [list(t) for t in tables]
+    sq = GruenSplitEq(tau)
+    evals, bound = [], []
+    for r in challenges:
+        evals.append(round_gruen_ab(tabs, sq, with_c))
+        tabs = bind_tables(tabs, r, ADJACENT)
+        sq.bind(r)
+        bound.append([list(t) for t in tabs])
+    return evals, bound

@@ -1,0 +1,117 @@
+"""GPU parity: sumcheck round evaluations and bound tables, every round, vs the oracle.
+Bit-exact (integer work).  Shapes follow the reference provers listed in oracle/sumcheck.py."""
+import numpy as np
+import pytest
+
+import zolt_b200 as Z
+from oracle import poly as OP
+from oracle import sumcheck as OS
+from tests.util import P, fr_arr, fr_ints, rand_fr
+
+pytestmark = pytest.mark.gpu
+
+COMBINERS = [
+    ("sum", Z.SC_SUM, 1),
+    ("prod2", Z.SC_PROD2, 2),
+    ("prod3", Z.SC_PROD3, 3),
+    ("eq_a_bmc", Z.SC_EQ_A_BMC, 4),
+    ("eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4),
+]
+
+
+def _run_and_compare(ctx, kind, comb, k, pairing, log_n, seed, n_extra=0):
+    n = 1 << log_n
+    tables = [rand_fr(seed * 100 + t, n) for t in range(k + n_extra)]
+    challenges = rand_fr(seed * 100 + 99, log_n)
+    exp_evals, exp_bound = OS.run_dense(kind, tables, pairing, challenges)
+    inst = Z.SumcheckInstance(ctx, comb, pairing, [fr_arr(t) for t in tables[:k]], [fr_arr(t) for t in tables[k:]])
+    try:
+        for rnd, r in enumerate(challenges):
+            got = fr_ints(inst.compute_round_poly())
+            # oracle evaluates only the k combiner tables; extras are bound but not evaluated
+            assert got == exp_evals[rnd], f"round {rnd} evals differ ({kind}, pairing {pairing}, n=2^{log_n})"
+            inst.bind_challenge(fr_arr([r]))
+            assert len(inst) == n >> (rnd + 1)
+            for t in range(k + n_extra):
+                assert fr_ints(inst.table(t)) == exp_bound[rnd][t], f"round {rnd} table {t} differs"
+    finally:
+        inst.free()
+
+
+@pytest.mark.parametrize("kind,comb,k", COMBINERS)
+@pytest.mark.parametrize("pairing", [Z.PAIR_ADJACENT, Z.PAIR_HALF])
+@pytest.mark.parametrize("log_n", [1, 2, 3, 7, 11])
+def test_dense_rounds_and_tables(ctx, kind, comb, k, pairing, log_n):
+    _run_and_compare(ctx, kind, comb, k, pairing, log_n, seed=log_n + 17 * comb + pairing)
+
+
+def test_extra_tables_are_bound_in_lockstep(ctx):
+    # OutputSumcheckProver binds val_init too (output_check.zig:454-476)
+    _run_and_compare(ctx, "eq_a_bmc", Z.SC_EQ_A_BMC, 4, Z.PAIR_ADJACENT, 9, seed=5, n_extra=1)
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 8, 11])
+@pytest.mark.parametrize("with_c", [False, True])
+def test_gruen_rounds(ctx, log_n, with_c):
+    n = 1 << log_n
+    k = 3 if with_c else 2
+    tables = [rand_fr(900 + log_n * 10 + t, n) for t in range(k)]
+    tau = rand_fr(777 + log_n, log_n)
+    challenges = rand_fr(778 + log_n, log_n)
+    exp_evals, exp_bound = OS.run_gruen(tables, tau, challenges, with_c)
+    comb = Z.SC_GRUEN_AB_MINUS_C if with_c else Z.SC_GRUEN_AB
+    inst = Z.SumcheckInstance(ctx, comb, Z.PAIR_ADJACENT, [fr_arr(t) for t in tables], tau=fr_arr(tau))
+    try:
+        for rnd, r in enumerate(challenges):
+            assert fr_ints(inst.compute_round_poly()) == exp_evals[rnd], f"round {rnd}"
+            inst.bind_challenge(fr_arr([r]))
+            for t in range(k):
+                assert fr_ints(inst.table(t)) == exp_bound[rnd][t]
+    finally:
+        inst.free()
+
+
+def test_reference_unit_vectors(ctx):
+    # bindLow numeric examples (src/poly/mod.zig:816-888)
+    p = Z.DensePolynomial(ctx, fr_arr([1, 2, 3, 4]))
+    p.bind_low(fr_arr([3]))
+    assert fr_ints(p.evaluations()) == [4, 6]
+    p.free()
+    p = Z.DensePolynomial(ctx, fr_arr([10, 20, 30, 40, 50, 60, 70, 80]))
+    p.bind_low(fr_arr([5]))
+    assert fr_ints(p.evaluations()) == [60, 80, 100, 120]
+    p.free()
+    # half-split sumcheck rounds on [1,2,3,4] (src/subprotocols/mod.zig:379-436): g(0)=3, g(1)=7, r=2 -> [5,6]
+    inst = Z.SumcheckInstance(ctx, Z.SC_SUM, Z.PAIR_HALF, [fr_arr([1, 2, 3, 4])])
+    assert fr_ints(inst.compute_round_poly()) == [3, 7]
+    inst.bind_challenge(fr_arr([2]))
+    assert fr_ints(inst.table(0)) == [5, 6]
+    inst.free()
+    # total 36 over 8 values (src/subprotocols/mod.zig:441-461)
+    p = Z.DensePolynomial(ctx, fr_arr([1, 2, 3, 4, 5, 6, 7, 8]))
+    assert fr_ints(p.sum()) == [36]
+    p.bind_first(fr_arr([2]))  # (1-2)*lo + 2*hi
+    assert fr_ints(p.evaluations()) == [(2 * (5 + i) - (1 + i)) % P for i in range(4)]
+    p.free()
+
+
+@pytest.mark.parametrize("n_vars", [0, 1, 2, 5, 12])
+def test_eq_evals(ctx, n_vars):
+    r = rand_fr(4242 + n_vars, n_vars)
+    got = fr_ints(Z.EqPolynomial.evals(ctx, fr_arr(r) if n_vars else np.empty((0, 4), dtype=np.uint64)))
+    assert got == OP.eq_evals(r)
+    assert sum(got) % P == 1  # partition of unity (src/poly/mod.zig:689-753)
+    scale = rand_fr(1, 1)
+    got = fr_ints(Z.EqPolynomial.evals(ctx, fr_arr(r) if n_vars else np.empty((0, 4), dtype=np.uint64), fr_arr(scale)))
+    assert got == OP.eq_evals(r, scale[0])
+
+
+def test_call_sequence_errors(ctx):
+    inst = Z.SumcheckInstance(ctx, Z.SC_SUM, Z.PAIR_ADJACENT, [fr_arr([1, 2])])
+    inst.compute_round_poly()
+    inst.bind_challenge(fr_arr([9]))
+    with pytest.raises(Z.ZoltGpuError):
+        inst.bind_challenge(fr_arr([9]))  # all variables bound (ZOLT_ERR_STATE)
+    with pytest.raises(Z.ZoltGpuError):
+        inst.compute_round_poly()
+    inst.free()

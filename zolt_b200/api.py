@@ -1,0 +1,347 @@
+"""Python mirror of the reference call sites, over the C ABI.
+
+Names follow the reference (paths relative to /root/reference):
+    MSM.compute                 src/msm/mod.zig:355-372
+    HyperKZG.setup / commit     src/poly/commitment/mod.zig:174-213, :239-255
+    DensePolynomial.bindLow/... src/poly/mod.zig:128-175
+    EqPolynomial.evals          src/poly/mod.zig:240-290
+    SumcheckInstance            src/zkvm/batched_sumcheck.zig:34-74 (computeRoundPoly / bindChallenge)
+
+Data crosses this layer as numpy uint64 arrays in the reference's own layout: field elements are
+rows of 4 little-endian limbs in Montgomery form, points are rows of 8 limbs (x then y) plus a
+uint8 infinity flag.  Nothing here computes on the host: every method is one or two C-ABI calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def _as_u64(a, cols: int) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=np.uint64)
+    if arr.ndim == 1 and arr.size == cols:
+        arr = arr.reshape(1, cols)
+    if arr.ndim != 2 or arr.shape[1] != cols:
+        raise ValueError(f"expected an (n, {cols}) uint64 array, got shape {arr.shape}")
+    return arr
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device + one stream (zolt_gpu_init).  Raises if there is no GPU: no CPU path exists."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = _lib.load_library()
+        h = C.c_void_p()
+        check(self.lib.zolt_gpu_init(device, C.c_void_p(stream) if stream else None, C.byref(h)), "zolt_gpu_init")
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.zolt_gpu_shutdown(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def sync(self):
+        check(self.lib.zolt_gpu_sync(self.handle), "zolt_gpu_sync")
+
+    @property
+    def launch_count(self) -> int:
+        out = C.c_ulonglong()
+        check(self.lib.zolt_gpu_launch_count(self.handle, C.byref(out)), "zolt_gpu_launch_count")
+        return out.value
+
+    def timer_start(self):
+        check(self.lib.zolt_timer_start(self.handle), "zolt_timer_start")
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float()
+        check(self.lib.zolt_timer_stop_ms(self.handle, C.byref(ms)), "zolt_timer_stop_ms")
+        return ms.value
+
+    def bench_int_pipe(self, kind: int, iters: int = 2000) -> float:
+        out = C.c_double()
+        check(self.lib.zolt_bench_int_pipe(self.handle, kind, iters, C.byref(out)), "zolt_bench_int_pipe")
+        return out.value
+
+    # BatchOps (src/field/mod.zig:1164-1280) / parity hook for the field layer
+    def field_op(self, field: int, op: int, a, b=None) -> np.ndarray:
+        a = _as_u64(a, 4)
+        bb = _as_u64(b, 4) if b is not None else None
+        if bb is not None and bb.shape != a.shape:
+            raise ValueError("operand shapes differ")
+        out = np.empty_like(a)
+        check(
+            self.lib.zolt_field_batch_op(self.handle, field, op, _ptr(a), _ptr(bb), _ptr(out), a.shape[0]),
+            "zolt_field_batch_op",
+        )
+        return out
+
+    def fr_sum_rows(self, d_rows: int, rows: int, cols: int) -> np.ndarray:
+        out = np.empty((cols, 4), dtype=np.uint64)
+        check(self.lib.zolt_fr_sum_rows(self.handle, C.c_void_p(d_rows), rows, cols, _ptr(out)), "zolt_fr_sum_rows")
+        return out
+
+
+class DeviceBuffer:
+    """Raw device allocation (zolt_dev_alloc)."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx = ctx
+        self.nbytes = nbytes
+        p = C.c_void_p()
+        check(ctx.lib.zolt_dev_alloc(ctx.handle, nbytes, C.byref(p)), "zolt_dev_alloc")
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, ctx: Context, arr: np.ndarray) -> "DeviceBuffer":
+        arr = np.ascontiguousarray(arr)
+        buf = cls(ctx, arr.nbytes)
+        buf.upload(arr)
+        return buf
+
+    def upload(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        check(self.ctx.lib.zolt_dev_upload(self.ctx.handle, C.c_void_p(self.ptr), _ptr(arr), arr.nbytes), "zolt_dev_upload")
+
+    def download(self, shape, dtype=np.uint64) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        check(self.ctx.lib.zolt_dev_download(self.ctx.handle, _ptr(out), C.c_void_p(self.ptr), out.nbytes), "zolt_dev_download")
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.zolt_dev_free(self.ctx.handle, C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class Bases:
+    """Device-resident G1 bases (SetupParams.powers_of_tau_g1, commitment/mod.zig:122-140)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.handle = handle
+
+    @classmethod
+    def upload(cls, ctx: Context, xy, inf=None) -> "Bases":
+        xy = _as_u64(xy, 8)
+        infa = None if inf is None else np.ascontiguousarray(inf, dtype=np.uint8)
+        h = C.c_void_p()
+        check(ctx.lib.zolt_msm_bases_upload(ctx.handle, _ptr(xy), _ptr(infa), xy.shape[0], C.byref(h)), "zolt_msm_bases_upload")
+        return cls(ctx, h)
+
+    @classmethod
+    def fixed_base_mul(cls, ctx: Context, scalars) -> "Bases":
+        """bases[i] = scalars[i] * G with G = (1, 2)."""
+        s = _as_u64(scalars, 4)
+        h = C.c_void_p()
+        check(ctx.lib.zolt_g1_fixed_base_mul(ctx.handle, _ptr(s), s.shape[0], C.byref(h)), "zolt_g1_fixed_base_mul")
+        return cls(ctx, h)
+
+    def __len__(self) -> int:
+        n = C.c_size_t()
+        check(self.ctx.lib.zolt_msm_bases_len(self.handle, C.byref(n)), "zolt_msm_bases_len")
+        return n.value
+
+    def download(self, offset: int = 0, n: int | None = None):
+        n = len(self) - offset if n is None else n
+        xy = np.empty((n, 8), dtype=np.uint64)
+        inf = np.empty(n, dtype=np.uint8)
+        check(self.ctx.lib.zolt_msm_bases_download(self.handle, offset, n, _ptr(xy), _ptr(inf)), "zolt_msm_bases_download")
+        return xy, inf
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.zolt_msm_bases_free(self.handle)
+            self.handle = None
+
+
+class MSM:
+    """msm.MSM(F, Fp) (src/msm/mod.zig:345-542)."""
+
+    @staticmethod
+    def compute(bases: Bases, scalars, offset: int = 0):
+        """Sum_i scalars[i] * bases[offset + i] -> (xy (8,) uint64, infinity flag)."""
+        s = _as_u64(scalars, 4) if len(scalars) else np.empty((0, 4), dtype=np.uint64)
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_uint8()
+        ctx = bases.ctx
+        check(ctx.lib.zolt_msm(ctx.handle, bases.handle, offset, _ptr(s), s.shape[0], _ptr(out), C.byref(inf)), "zolt_msm")
+        return out, int(inf.value)
+
+    @staticmethod
+    def compute_dev(bases: Bases, d_scalars: int, n: int, offset: int = 0):
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_uint8()
+        ctx = bases.ctx
+        check(ctx.lib.zolt_msm_dev(ctx.handle, bases.handle, offset, C.c_void_p(d_scalars), n, _ptr(out), C.byref(inf)), "zolt_msm_dev")
+        return out, int(inf.value)
+
+    @staticmethod
+    def compute_batch(bases: Bases, scalars, k: int, n: int):
+        """BatchMSM.compute (src/msm/mod.zig:551-563): k scalar vectors over the same n bases."""
+        s = _as_u64(np.asarray(scalars).reshape(k * n, 4), 4)
+        out = np.zeros((k, 8), dtype=np.uint64)
+        inf = np.zeros(k, dtype=np.uint8)
+        ctx = bases.ctx
+        check(ctx.lib.zolt_msm_batch(ctx.handle, bases.handle, _ptr(s), k, n, _ptr(out), _ptr(inf)), "zolt_msm_batch")
+        return out, inf
+
+    @staticmethod
+    def partial_dev(bases: Bases, d_scalars: int, n: int, d_out: int, offset: int = 0):
+        ctx = bases.ctx
+        check(ctx.lib.zolt_msm_partial_dev(ctx.handle, bases.handle, offset, C.c_void_p(d_scalars), n, C.c_void_p(d_out)), "zolt_msm_partial_dev")
+
+    @staticmethod
+    def sum_partials(ctx: Context, d_partials: int, count: int):
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_uint8()
+        check(ctx.lib.zolt_g1_sum_partials(ctx.handle, C.c_void_p(d_partials), count, _ptr(out), C.byref(inf)), "zolt_g1_sum_partials")
+        return out, int(inf.value)
+
+
+class HyperKZG:
+    """HyperKZG(F) commit path (src/poly/commitment/mod.zig:108-255)."""
+
+    @staticmethod
+    def setup(ctx: Context, max_degree: int) -> Bases:
+        h = C.c_void_p()
+        check(ctx.lib.zolt_hyperkzg_setup(ctx.handle, max_degree, C.byref(h)), "zolt_hyperkzg_setup")
+        return Bases(ctx, h)
+
+    @staticmethod
+    def commit(params: Bases, evals):
+        """n = min(len(evals), len(powers)); MSM over the first n (commitment/mod.zig:241-249)."""
+        e = _as_u64(evals, 4) if len(evals) else np.empty((0, 4), dtype=np.uint64)
+        n = min(e.shape[0], len(params))
+        return MSM.compute(params, e[:n])
+
+
+class DensePolynomial:
+    """DensePolynomial(F) with its evaluation table resident on the device (src/poly/mod.zig:23-182)."""
+
+    def __init__(self, ctx: Context, evaluations):
+        ev = _as_u64(evaluations, 4)
+        n = ev.shape[0]
+        if n == 0 or n & (n - 1):
+            raise ValueError("length must be a power of two")  # std.debug.assert in init (:37)
+        self.ctx = ctx
+        self.n = n
+        self.buf = DeviceBuffer.from_host(ctx, ev)
+
+    @property
+    def num_vars(self) -> int:
+        return self.n.bit_length() - 1
+
+    def bind_low(self, r):
+        """bindLow (:160-175), in place."""
+        r = _as_u64(r, 4)
+        check(self.ctx.lib.zolt_poly_bind_low(self.ctx.handle, C.c_void_p(self.buf.ptr), C.c_void_p(self.buf.ptr), self.n, _ptr(r)), "zolt_poly_bind_low")
+        self.n //= 2
+
+    def bind_first(self, r):
+        """bindFirst (:128-149); the reference returns a new polynomial, here the table is reused."""
+        r = _as_u64(r, 4)
+        check(self.ctx.lib.zolt_poly_bind_first(self.ctx.handle, C.c_void_p(self.buf.ptr), C.c_void_p(self.buf.ptr), self.n, _ptr(r)), "zolt_poly_bind_first")
+        self.n //= 2
+
+    def sum(self) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        check(self.ctx.lib.zolt_poly_sum(self.ctx.handle, C.c_void_p(self.buf.ptr), self.n, _ptr(out)), "zolt_poly_sum")
+        return out
+
+    def evaluations(self) -> np.ndarray:
+        full = self.buf.download((self.buf.nbytes // 32, 4))
+        return full[: self.n]
+
+    def free(self):
+        self.buf.free()
+
+
+class EqPolynomial:
+    """EqPolynomial(F).evals (src/poly/mod.zig:240-290): big-endian eq table built on the device."""
+
+    @staticmethod
+    def evals(ctx: Context, r, scale=None) -> np.ndarray:
+        r = _as_u64(r, 4) if len(r) else np.empty((0, 4), dtype=np.uint64)
+        n_vars = r.shape[0]
+        buf = DeviceBuffer(ctx, 32 << n_vars)
+        sc = _as_u64(scale, 4) if scale is not None else None
+        check(ctx.lib.zolt_eq_evals(ctx.handle, _ptr(r), n_vars, _ptr(sc), C.c_void_p(buf.ptr)), "zolt_eq_evals")
+        out = buf.download((1 << n_vars, 4))
+        buf.free()
+        return out
+
+
+class SumcheckInstance:
+    """k dense tables bound in lock-step on the device.
+
+    compute_round_poly() / bind_challenge(r) are SumcheckInstance.computeRoundPolyFn /
+    bindChallengeFn (src/zkvm/batched_sumcheck.zig:34-74): strictly alternating, evaluations at
+    X = 0..3 (or [sum lo, sum hi] for SC_SUM, [t0, t_inf] for the Gruen combiners).
+    """
+
+    def __init__(self, ctx: Context, combiner: int, pairing: int, tables, extra_tables=(), tau=None):
+        tabs = [_as_u64(t, 4) for t in list(tables) + list(extra_tables)]
+        n = tabs[0].shape[0]
+        if n == 0 or n & (n - 1) or any(t.shape[0] != n for t in tabs):
+            raise ValueError("tables must share a power-of-two length")
+        self.ctx = ctx
+        self._keep = tabs
+        arr = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+        h = C.c_void_p()
+        check(
+            ctx.lib.zolt_sc_create(ctx.handle, combiner, pairing, n.bit_length() - 1, len(tables), len(extra_tables), arr, C.byref(h)),
+            "zolt_sc_create",
+        )
+        self.handle = h
+        self._keep = None
+        ne = C.c_int()
+        check(ctx.lib.zolt_sc_num_evals(h, C.byref(ne)), "zolt_sc_num_evals")
+        self.num_evals = ne.value
+        self.num_tables = len(tabs)
+        if tau is not None:
+            t = _as_u64(tau, 4)
+            check(ctx.lib.zolt_sc_set_split_eq(h, _ptr(t), t.shape[0]), "zolt_sc_set_split_eq")
+
+    def compute_round_poly(self) -> np.ndarray:
+        out = np.empty((self.num_evals, 4), dtype=np.uint64)
+        check(self.ctx.lib.zolt_sc_round_evals(self.handle, _ptr(out)), "zolt_sc_round_evals")
+        return out
+
+    def bind_challenge(self, r):
+        r = _as_u64(r, 4)
+        check(self.ctx.lib.zolt_sc_bind(self.handle, _ptr(r)), "zolt_sc_bind")
+
+    def __len__(self) -> int:
+        n = C.c_size_t()
+        check(self.ctx.lib.zolt_sc_len(self.handle, C.byref(n)), "zolt_sc_len")
+        return n.value
+
+    def table(self, t: int) -> np.ndarray:
+        out = np.empty((len(self), 4), dtype=np.uint64)
+        check(self.ctx.lib.zolt_sc_download(self.handle, t, _ptr(out)), "zolt_sc_download")
+        return out
+
+    def partials_dev(self) -> int:
+        p = C.c_void_p()
+        check(self.ctx.lib.zolt_sc_round_partials_dev(self.handle, C.byref(p)), "zolt_sc_round_partials_dev")
+        return p.value
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.zolt_sc_free(self.handle)
+            self.handle = None

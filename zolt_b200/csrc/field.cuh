@@ -1,0 +1,344 @@
+// BN254 Fr / Fq arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form, canonical outputs.
+//
+// Replaces (reference, /root/reference): MontgomeryField / BN254Scalar in
+// src/field/mod.zig:124-556, :583-1052 -- same representation on the wire
+// ([4]u64 little-endian limbs == 8 x u32 little-endian limbs, Montgomery form a*2^256 mod p,
+// always < p) so tables and points cross the C ABI without conversion.
+//
+// Multiplication is an interleaved (CIOS) Montgomery product on mad.lo.cc / madc.hi.cc carry
+// chains.  Products of even and odd limbs of the multiplicand accumulate in two separate
+// registers sets ("E" aligned at 2^0 and "O" aligned at 2^32) so that every lo/hi pair is one
+// uninterrupted carry chain; ptxas fuses each pair into a single IMAD.WIDE.U32(.X) -- 128 wide
+// multiplies + 8 IMAD per product (checked with cuobjdump).
+//
+// The primitive layer below has two back-ends with identical instruction sequences:
+//   * device  (__CUDA_ARCH__): one PTX instruction per primitive, carry in the hardware CC flag;
+//   * host    : exact emulation of the PTX carry semantics (thread-local CC bit).  The host
+//     back-end exists ONLY so tests/ can validate the algorithms on a machine without a GPU
+//     (tests/host_shim); no product entry point ever runs field math on the host.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define ZOLT_HD __host__ __device__ __forceinline__
+#define ZOLT_D __device__ __forceinline__
+#else
+#define ZOLT_HD inline
+#define ZOLT_D inline
+#endif
+
+namespace zolt {
+
+// ---------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+namespace ptx {
+ZOLT_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZOLT_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZOLT_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZOLT_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZOLT_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZOLT_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZOLT_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZOLT_D uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZOLT_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZOLT_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZOLT_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZOLT_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZOLT_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+}  // namespace ptx
+#else
+namespace ptx {
+// Host emulation of the PTX integer carry flag (PTX ISA "Extended-Precision Integer Arithmetic").
+inline uint32_t& cc() { static thread_local uint32_t flag = 0; return flag; }
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; cc() = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + cc(); cc() = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a + b + cc()); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b; cc() = (uint32_t)((s >> 32) & 1); return (uint32_t)s; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b - cc(); cc() = (uint32_t)((s >> 32) & 1); return (uint32_t)s; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a - b - cc()); }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_lo(a, b), c); }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_lo(a, b), c); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc(mul_hi(a, b), c); }
+}  // namespace ptx
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// field parameters (reference src/field/mod.zig:16-41 Fr, :51-75 Fq; 64-bit limbs split in two)
+// ---------------------------------------------------------------------------------------------
+// Constants are exposed through constexpr accessors with function-local tables: static constexpr
+// array members are not addressable from device code, while a local constexpr table indexed by an
+// unrolled loop counter folds to immediates.
+#define ZOLT_FIELD_TABLE(name, ...)                            \
+  static constexpr ZOLT_HD uint32_t name(int i) {              \
+    constexpr uint32_t t[8] = {__VA_ARGS__};                   \
+    return t[i];                                               \
+  }
+
+struct FrParams {
+  // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+  ZOLT_FIELD_TABLE(mod, 0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u,
+                   0xe131a029u, 0x30644e72u)
+  // R = 2^256 mod r  (== BN254Scalar.one())
+  ZOLT_FIELD_TABLE(one, 0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu,
+                   0x9a07df2fu, 0x0e0a77c1u)
+  // R^2 mod r
+  ZOLT_FIELD_TABLE(r2, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du,
+                   0x7f4e44a5u, 0x0216d0b1u)
+  static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32 (low word of 0xc2e1f593efffffff)
+};
+
+struct FqParams {
+  // q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+  ZOLT_FIELD_TABLE(mod, 0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u,
+                   0xe131a029u, 0x30644e72u)
+  ZOLT_FIELD_TABLE(one, 0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu,
+                   0x9a07df2fu, 0x0e0a77c1u)
+  ZOLT_FIELD_TABLE(r2, 0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu,
+                   0xcab8351fu, 0x06d89f71u)
+  static constexpr uint32_t INV = 0xe4866389u;  // -q^-1 mod 2^32 (low word of 0x87d20782e4866389)
+};
+
+// ---------------------------------------------------------------------------------------------
+// field element
+// ---------------------------------------------------------------------------------------------
+template <class P>
+struct alignas(16) Fp {
+  uint32_t v[8];
+
+  static ZOLT_HD Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+  }
+  static ZOLT_HD Fp one() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+    return r;
+  }
+  static ZOLT_HD Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::r2(i);
+    return r;
+  }
+  ZOLT_HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i];
+    return o == 0;
+  }
+  ZOLT_HD bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  ZOLT_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = a - MOD if a >= MOD else a   (a < 2*MOD)
+template <class P>
+ZOLT_HD void fp_reduce_once(uint32_t* a) {
+  uint32_t s[8];
+  s[0] = ptx::sub_cc(a[0], P::mod(0));
+#pragma unroll
+  for (int i = 1; i < 8; i++) s[i] = ptx::subc_cc(a[i], P::mod(i));
+  uint32_t borrow = ptx::subc(0u, 0u);  // 0xffffffff if a < MOD
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = borrow ? a[i] : s[i];
+}
+
+// canonical a + b  (reference add, src/field/mod.zig:782-798)
+template <class P>
+ZOLT_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+  r.v[7] = ptx::addc(a.v[7], b.v[7]);  // a,b < 2^254: no carry out of limb 7
+  fp_reduce_once<P>(r.v);
+  return r;
+}
+
+// canonical a - b  (reference sub, src/field/mod.zig:801-816)
+template <class P>
+ZOLT_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = ptx::subc(0u, 0u);  // all-ones when a < b
+  r.v[0] = ptx::add_cc(r.v[0], P::mod(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(r.v[i], P::mod(i) & borrow);
+  r.v[7] = ptx::addc(r.v[7], P::mod(7) & borrow);
+  return r;
+}
+
+template <class P>
+ZOLT_HD Fp<P> fp_neg(const Fp<P>& a) {
+  return fp_sub<P>(Fp<P>::zero(), a);
+}
+
+template <class P>
+ZOLT_HD Fp<P> fp_dbl(const Fp<P>& a) {
+  return fp_add<P>(a, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery product, interleaved reduction, even/odd accumulators.
+//
+// Invariant between rows: T = E + 2^32 * O, with E in e[0..8] (9 limbs) and O in o[0..7].
+// For a < 2^255 (any b): O < 2^256 (its chain never carries out) and E < 2^288.
+// After a row's reduction e[0] == 0 and the division by 2^32 is done by exchanging roles:
+//   E' = O + e[1]            (carry of the single limb add feeds the O' chain)
+//   O' = e[2..8] + a_odd*b_i
+// ---------------------------------------------------------------------------------------------
+template <class P>
+ZOLT_HD void mont_row_reduce(uint32_t* e, uint32_t* o) {
+  const uint32_t m = ptx::mul_lo(e[0], P::INV);
+  e[0] = ptx::mad_lo_cc(P::mod(0), m, e[0]);
+  e[1] = ptx::madc_hi_cc(P::mod(0), m, e[1]);
+  e[2] = ptx::madc_lo_cc(P::mod(2), m, e[2]);
+  e[3] = ptx::madc_hi_cc(P::mod(2), m, e[3]);
+  e[4] = ptx::madc_lo_cc(P::mod(4), m, e[4]);
+  e[5] = ptx::madc_hi_cc(P::mod(4), m, e[5]);
+  e[6] = ptx::madc_lo_cc(P::mod(6), m, e[6]);
+  e[7] = ptx::madc_hi_cc(P::mod(6), m, e[7]);
+  e[8] = ptx::addc(e[8], 0u);
+  o[0] = ptx::mad_lo_cc(P::mod(1), m, o[0]);
+  o[1] = ptx::madc_hi_cc(P::mod(1), m, o[1]);
+  o[2] = ptx::madc_lo_cc(P::mod(3), m, o[2]);
+  o[3] = ptx::madc_hi_cc(P::mod(3), m, o[3]);
+  o[4] = ptx::madc_lo_cc(P::mod(5), m, o[4]);
+  o[5] = ptx::madc_hi_cc(P::mod(5), m, o[5]);
+  o[6] = ptx::madc_lo_cc(P::mod(7), m, o[6]);
+  o[7] = ptx::madc_hi(P::mod(7), m, o[7]);
+}
+
+// First row: T = a * b0.
+template <class P>
+ZOLT_HD void mont_row_first(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    o[2 * t] = ptx::mul_lo(a[2 * t + 1], bi);
+    o[2 * t + 1] = ptx::mul_hi(a[2 * t + 1], bi);
+    e[2 * t] = ptx::mul_lo(a[2 * t], bi);
+    e[2 * t + 1] = ptx::mul_hi(a[2 * t], bi);
+  }
+  e[8] = 0;
+  mont_row_reduce<P>(e, o);
+}
+
+// Later rows.  `e` is the accumulator that was O in the previous row (8 live limbs, e[8] is
+// scratch), `o` is the previous row's E (9 live limbs, o[0] == 0).
+template <class P>
+ZOLT_HD void mont_row_next(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
+  e[0] = ptx::add_cc(e[0], o[1]);
+  o[0] = ptx::madc_lo_cc(a[1], bi, o[2]);
+  o[1] = ptx::madc_hi_cc(a[1], bi, o[3]);
+  o[2] = ptx::madc_lo_cc(a[3], bi, o[4]);
+  o[3] = ptx::madc_hi_cc(a[3], bi, o[5]);
+  o[4] = ptx::madc_lo_cc(a[5], bi, o[6]);
+  o[5] = ptx::madc_hi_cc(a[5], bi, o[7]);
+  o[6] = ptx::madc_lo_cc(a[7], bi, o[8]);
+  o[7] = ptx::madc_hi(a[7], bi, 0u);
+  e[0] = ptx::mad_lo_cc(a[0], bi, e[0]);
+  e[1] = ptx::madc_hi_cc(a[0], bi, e[1]);
+  e[2] = ptx::madc_lo_cc(a[2], bi, e[2]);
+  e[3] = ptx::madc_hi_cc(a[2], bi, e[3]);
+  e[4] = ptx::madc_lo_cc(a[4], bi, e[4]);
+  e[5] = ptx::madc_hi_cc(a[4], bi, e[5]);
+  e[6] = ptx::madc_lo_cc(a[6], bi, e[6]);
+  e[7] = ptx::madc_hi_cc(a[6], bi, e[7]);
+  e[8] = ptx::addc(0u, 0u);
+  mont_row_reduce<P>(e, o);
+}
+
+// r = a * b * 2^-256 mod p.  Requires a < 2^255 (b arbitrary 256-bit).  Output in [0, 2p) when
+// a*b < p * 2^256; fp_mul below makes it canonical.
+template <class P>
+ZOLT_HD void mont_mul_raw(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t x[9], y[9];
+  mont_row_first<P>(x, y, a, b[0]);
+  mont_row_next<P>(y, x, a, b[1]);
+  mont_row_next<P>(x, y, a, b[2]);
+  mont_row_next<P>(y, x, a, b[3]);
+  mont_row_next<P>(x, y, a, b[4]);
+  mont_row_next<P>(y, x, a, b[5]);
+  mont_row_next<P>(x, y, a, b[6]);
+  mont_row_next<P>(y, x, a, b[7]);
+  // last row had E = y (y[0] == 0), O = x:  result = O + (E >> 32)
+  r[0] = ptx::add_cc(x[0], y[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r[i] = ptx::addc_cc(x[i], y[i + 1]);
+  r[7] = ptx::addc(x[7], y[8]);
+}
+
+// canonical Montgomery product (reference montgomeryMul, src/field/mod.zig:269-308, :735-779)
+template <class P>
+ZOLT_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  mont_mul_raw<P>(r.v, a.v, b.v);
+  fp_reduce_once<P>(r.v);
+  return r;
+}
+
+template <class P>
+ZOLT_HD Fp<P> fp_sqr(const Fp<P>& a) {
+  return fp_mul<P>(a, a);
+}
+
+// Montgomery -> standard integer limbs (reference fromMontgomery, src/field/mod.zig:642-645)
+template <class P>
+ZOLT_HD Fp<P> fp_from_mont(const Fp<P>& a) {
+  Fp<P> one_raw = Fp<P>::zero();
+  one_raw.v[0] = 1;
+  return fp_mul<P>(a, one_raw);
+}
+
+// standard integer limbs (any 256-bit value) -> Montgomery (reference fromBytes/toMontgomery,
+// src/field/mod.zig:625-652).  R2 < p is the row-scanned operand so the bound a < 2^255 holds.
+template <class P>
+ZOLT_HD Fp<P> fp_to_mont(const Fp<P>& raw) {
+  return fp_mul<P>(Fp<P>::r2(), raw);
+}
+
+// small unsigned constant -> Montgomery form
+template <class P>
+ZOLT_HD Fp<P> fp_from_u32(uint32_t k) {
+  Fp<P> raw = Fp<P>::zero();
+  raw.v[0] = k;
+  return fp_to_mont<P>(raw);
+}
+
+// a^(p-2) (reference inverse, src/field/mod.zig:955-983 / :500-518); 0 -> 0.
+template <class P>
+ZOLT_HD Fp<P> fp_inv(const Fp<P>& a) {
+  // exponent p-2, MSB first square-and-multiply
+  uint32_t e[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+  e[0] -= 2u;  // MOD[0] >= 2 for both fields, no borrow
+  Fp<P> acc = Fp<P>::one();
+  for (int i = 7; i >= 0; i--) {
+    for (int bit = 31; bit >= 0; bit--) {
+      acc = fp_sqr<P>(acc);
+      if ((e[i] >> bit) & 1u) acc = fp_mul<P>(acc, a);
+    }
+  }
+  return acc;
+}
+
+using Fr = Fp<FrParams>;
+using Fq = Fp<FqParams>;
+
+}  // namespace zolt

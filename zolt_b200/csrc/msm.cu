@@ -1,0 +1,811 @@
+// BN254 G1 multi-scalar multiplication for sm_100a.
+//
+// Replaces (reference, /root/reference): MSM(F,G).compute / pippengerMSM (src/msm/mod.zig:355-438),
+// BatchMSM (:545-565), ParallelMSM's chunk/combine split (:588-653), and behind them
+// HyperKZG.commit (src/poly/commitment/mod.zig:239-255), HyperKZG.setup (:174-213) and the Dory
+// row commitments (src/poly/commitment/dory.zig:646-670).
+//
+// Pipeline (k MSMs over the same n bases share every stage; key = (batch, window, bucket)):
+//   1. digits   : Montgomery -> canonical scalar, signed c-bit digits, per-bucket histogram
+//   2. scan     : exclusive scan of the histogram -> bucket offsets
+//   3. scatter  : counting sort of (point index, sign) by key
+//   4. accumulate (level 0): each thread folds a fixed-length slice of the SORTED list with mixed
+//      additions; groups interior to a slice are complete buckets, the first/last group of a slice
+//      may continue in a neighbour and go to an "edge" list
+//   5. accumulate (levels 1..): the edge list (still sorted by key) is folded the same way with
+//      full additions until one thread sees everything.  Work per thread is bounded by the slice
+//      length whatever the digit distribution (all-equal scalars included).
+//   6. bucket reduction: chunked running sums per window, tree over chunks, Horner over windows
+//   7. normalisation to canonical affine
+// Bucket contents are group elements, so the order in which equal-key points are folded does not
+// change the canonical affine result.
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "curve.cuh"
+
+using namespace zolt;
+
+struct zolt_bases {
+  zolt_ctx* ctx = nullptr;
+  size_t n = 0;
+  AffineG1* d_xy = nullptr;
+  uint8_t* d_inf = nullptr;  // nullptr: no point at infinity in the set
+};
+
+namespace {
+
+constexpr uint32_t kInvalidKey = 0xffffffffu;
+constexpr int kSlice0 = 128;  // level-0 slice length (mixed additions per thread)
+constexpr int kSliceE = 8;    // edge-level slice length (full additions per thread)
+constexpr int kChunk = 32;    // buckets per thread in the running-sum reduction
+
+struct MsmGeom {
+  int c;         // window bits
+  int windows;   // ceil(255 / c)
+  uint32_t B;    // buckets per window = 2^(c-1)
+};
+
+// Window size by problem size (per MSM of the batch).  Cost model: windows * n mixed additions +
+// windows * B * ~3 addition-equivalents of reduction.
+MsmGeom choose_geom(size_t n) {
+  int c;
+  if (n < (size_t(1) << 8)) c = 5;
+  else if (n < (size_t(1) << 10)) c = 7;
+  else if (n < (size_t(1) << 12)) c = 8;
+  else if (n < (size_t(1) << 14)) c = 10;
+  else if (n < (size_t(1) << 16)) c = 11;
+  else if (n < (size_t(1) << 18)) c = 13;
+  else if (n < (size_t(1) << 20)) c = 14;
+  else if (n < (size_t(1) << 22)) c = 15;
+  else c = 16;
+  MsmGeom g;
+  g.c = c;
+  g.windows = (255 + c - 1) / c;
+  g.B = 1u << (c - 1);
+  return g;
+}
+
+__device__ __forceinline__ Fq ld_fq(const Fq* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  Fq r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_fq(Fq* p, const Fq& x) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ AffineG1 ld_affine(const AffineG1* p) {
+  AffineG1 r;
+  r.x = ld_fq(&p->x);
+  r.y = ld_fq(&p->y);
+  return r;
+}
+__device__ __forceinline__ XYZZ ld_xyzz(const XYZZ* p) {
+  XYZZ r;
+  r.x = ld_fq(&p->x);
+  r.y = ld_fq(&p->y);
+  r.zz = ld_fq(&p->zz);
+  r.zzz = ld_fq(&p->zzz);
+  return r;
+}
+// coherent (L2) load for data produced earlier in the same kernel by other threads
+__device__ __forceinline__ XYZZ ld_xyzz_cg(const XYZZ* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  XYZZ r;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint4 t = __ldcg(q + i);
+    w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+  }
+  return r;
+}
+__device__ __forceinline__ void st_xyzz(XYZZ* p, const XYZZ& v) {
+  st_fq(&p->x, v.x);
+  st_fq(&p->y, v.y);
+  st_fq(&p->zz, v.zz);
+  st_fq(&p->zzz, v.zzz);
+}
+
+// ---- 1. digits + histogram ---------------------------------------------------------------------------
+// digits[(batch*W + w)*n + i] = |d| | sign << 31 (0: nothing to add).  Signed recoding: d in
+// (-2^(c-1), 2^(c-1)], a carry moves to the next window; windows*c >= 255 leaves room for the
+// carry of a 254-bit scalar.  getWindow's per-call fromMontgomery (src/msm/mod.zig:441-442) becomes
+// one conversion per scalar.
+__global__ void __launch_bounds__(256)
+msm_digits_kernel(const Fr* __restrict__ scalars, const uint8_t* __restrict__ inf, size_t n, size_t k,
+                  MsmGeom g, uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
+  const size_t total = n * k;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t batch = t / n, i = t - batch * n;
+    Fr s = fp_from_mont<FrParams>(scalars[t]);
+    const bool skip = (inf != nullptr && inf[i] != 0);  // identity bases are skipped (msm/mod.zig:407)
+    uint32_t carry = 0;
+    const uint32_t mask = (1u << g.c) - 1u;
+    for (int w = 0; w < g.windows; w++) {
+      const int pos = w * g.c;
+      const int word = pos >> 5, sh = pos & 31;
+      uint64_t two = (uint64_t)s.v[word < 8 ? word : 7];
+      if (word >= 8) two = 0;
+      if (word + 1 < 8) two |= (uint64_t)s.v[word + 1] << 32;
+      uint32_t d = ((uint32_t)(two >> sh) & mask) + carry;
+      uint32_t neg = 0;
+      if (d > g.B) {
+        d = (1u << g.c) - d;
+        neg = 1;
+        carry = 1;
+      } else {
+        carry = 0;
+      }
+      if (skip) d = 0;
+      const size_t row = batch * g.windows + w;
+      digits[row * n + i] = d ? (d | (neg << 31)) : 0u;
+      if (d) atomicAdd(&counts[row * g.B + (d - 1)], 1u);
+    }
+  }
+}
+
+// ---- 2. exclusive scan (u32), three passes ---------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;  // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem, uint32_t* total) {
+  // smem: kScanThreads entries
+  const int tid = threadIdx.x;
+  smem[tid] = v;
+  __syncthreads();
+  for (int off = 1; off < kScanThreads; off <<= 1) {
+    uint32_t x = tid >= off ? smem[tid - off] : 0;
+    __syncthreads();
+    smem[tid] += x;
+    __syncthreads();
+  }
+  uint32_t incl = smem[tid];
+  if (total) *total = smem[kScanThreads - 1];
+  __syncthreads();
+  return incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* in, size_t n, uint32_t* tile_sums) {
+  __shared__ uint32_t smem[kScanThreads];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; j++)
+    if (base + j < n) s += in[base + j];
+  uint32_t total;
+  block_exclusive_scan(s, smem, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of tile sums in place; writes the grand total to tile_sums[num_tiles]
+__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(uint32_t* tile_sums, size_t num_tiles) {
+  __shared__ uint32_t smem[kScanThreads];
+  __shared__ uint32_t running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  for (size_t base = 0; base < num_tiles; base += kScanThreads) {
+    const size_t i = base + threadIdx.x;
+    uint32_t v = i < num_tiles ? tile_sums[i] : 0;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(v, smem, &total);
+    if (i < num_tiles) tile_sums[i] = running + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) running += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_sums[num_tiles] = running;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const uint32_t* in, size_t n, const uint32_t* tile_offsets, uint32_t* out /* n+1 */) {
+  __shared__ uint32_t smem[kScanThreads];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; j++) {
+    v[j] = (base + j < n) ? in[base + j] : 0;
+    s += v[j];
+  }
+  uint32_t ex = block_exclusive_scan(s, smem, nullptr) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kScanItems; j++) {
+    if (base + j < n) out[base + j] = ex;
+    ex += v[j];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = tile_offsets[gridDim.x];
+}
+
+// ---- 3. scatter ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, MsmGeom g,
+                   const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                   uint32_t* __restrict__ sorted) {
+  const size_t total = n * rows;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t d = digits[t];
+    if (!d) continue;
+    const size_t row = t / n, i = t - row * n;
+    const size_t key = row * g.B + ((d & 0x7fffffffu) - 1);
+    const uint32_t pos = offsets[key] + atomicAdd(&cursor[key], 1u);
+    sorted[pos] = (uint32_t)i | (d & 0x80000000u);
+  }
+}
+
+// ---- 4. accumulate, level 0 ---------------------------------------------------------------------------
+// Thread t folds sorted[t*S, (t+1)*S).  Keys are implicit: entry p belongs to the bucket k with
+// offsets[k] <= p < offsets[k+1].
+__global__ void __launch_bounds__(128)
+msm_accum_points_kernel(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets, uint32_t num_keys,
+                        const AffineG1* __restrict__ bases, XYZZ* __restrict__ buckets,
+                        uint32_t* __restrict__ edge_keys, XYZZ* __restrict__ edge_pts, size_t num_slices) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= num_slices) return;
+  const uint32_t total = offsets[num_keys];
+  const uint64_t p0 = (uint64_t)t * kSlice0;
+  uint32_t ek0 = kInvalidKey, ek1 = kInvalidKey;
+  if (p0 < total) {
+    const uint32_t p1 = (uint32_t)min((uint64_t)total, p0 + kSlice0);
+    // largest k with offsets[k] <= p0 (skips empty buckets automatically)
+    uint32_t lo = 0, hi = num_keys;  // invariant: offsets[lo] <= p0 < offsets[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (offsets[mid] <= (uint32_t)p0) lo = mid; else hi = mid;
+    }
+    uint32_t key = lo;
+    uint32_t pos = (uint32_t)p0;
+    bool first = true;
+    while (pos < p1) {
+      const uint32_t bucket_end = offsets[key + 1];
+      const uint32_t end = bucket_end < p1 ? bucket_end : p1;
+      XYZZ acc = XYZZ::identity();
+      for (; pos < end; pos++) {
+        const uint32_t e = sorted[pos];
+        AffineG1 pt = ld_affine(bases + (e & 0x7fffffffu));
+        if (e >> 31) pt.y = fp_neg<FqParams>(pt.y);
+        xyzz_madd(acc, pt);
+      }
+      const bool last = (pos >= p1);
+      if (first) {
+        edge_keys[2 * t] = key;  // may continue in the previous slice
+        st_xyzz(&edge_pts[2 * t], acc);
+        ek0 = key;
+      } else if (last) {
+        edge_keys[2 * t + 1] = key;  // may continue in the next slice
+        st_xyzz(&edge_pts[2 * t + 1], acc);
+        ek1 = key;
+      } else {
+        st_xyzz(&buckets[key], acc);  // bucket lies strictly inside this slice: complete
+      }
+      first = false;
+      if (last) break;
+      key++;
+      while (offsets[key + 1] == pos) key++;  // skip empty buckets
+    }
+  }
+  if (ek0 == kInvalidKey) edge_keys[2 * t] = kInvalidKey;
+  if (ek1 == kInvalidKey) edge_keys[2 * t + 1] = kInvalidKey;
+}
+
+// ---- 5. accumulate, edge levels --------------------------------------------------------------------------
+// in: L entries (key, point), keys non-decreasing over the valid entries.  Thread t folds entries
+// [t*S, (t+1)*S).  With `final` set (single thread sees all entries) every group is complete.
+__global__ void __launch_bounds__(128)
+msm_accum_edges_kernel(const uint32_t* __restrict__ in_keys, const XYZZ* __restrict__ in_pts, size_t L,
+                       XYZZ* __restrict__ buckets, uint32_t* __restrict__ out_keys, XYZZ* __restrict__ out_pts,
+                       size_t num_slices, int final_level) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= num_slices) return;
+  const size_t p0 = t * kSliceE;
+  const size_t p1 = min(L, p0 + (final_level ? L : (size_t)kSliceE));
+  uint32_t ek0 = kInvalidKey, ek1 = kInvalidKey;
+  size_t pos = p0;
+  bool first = true;
+  while (pos < p1) {
+    uint32_t key = in_keys[pos];
+    if (key == kInvalidKey) { pos++; continue; }
+    XYZZ acc = ld_xyzz(&in_pts[pos]);
+    pos++;
+    while (pos < p1) {
+      const uint32_t k2 = in_keys[pos];
+      if (k2 == kInvalidKey) { pos++; continue; }
+      if (k2 != key) break;
+      XYZZ b = ld_xyzz(&in_pts[pos]);
+      xyzz_add(acc, b);
+      pos++;
+    }
+    const bool last = (pos >= p1);
+    if (final_level) {
+      st_xyzz(&buckets[key], acc);
+    } else if (first) {
+      out_keys[2 * t] = key;
+      st_xyzz(&out_pts[2 * t], acc);
+      ek0 = key;
+    } else if (last) {
+      out_keys[2 * t + 1] = key;
+      st_xyzz(&out_pts[2 * t + 1], acc);
+      ek1 = key;
+    } else {
+      st_xyzz(&buckets[key], acc);
+    }
+    first = false;
+  }
+  if (!final_level) {
+    if (ek0 == kInvalidKey) out_keys[2 * t] = kInvalidKey;
+    if (ek1 == kInvalidKey) out_keys[2 * t + 1] = kInvalidKey;
+  }
+}
+
+// ---- 6. bucket reduction ----------------------------------------------------------------------------------
+// window sum = sum_{b=0}^{B-1} (b+1) * bucket[b]  (reference running-sum loop, src/msm/mod.zig:423-432).
+// Thread (row, ch) covers buckets [ch*Lc, (ch+1)*Lc): T = sum (b-b_lo+1)*bucket[b], S = sum bucket[b],
+// contribution T + b_lo*S.
+__global__ void __launch_bounds__(128)
+msm_chunk_sums_kernel(const XYZZ* __restrict__ buckets, uint32_t B, uint32_t Lc, uint32_t chunks_per_row,
+                      size_t rows, XYZZ* __restrict__ chunk_out) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= rows * chunks_per_row) return;
+  const size_t row = t / chunks_per_row;
+  const uint32_t ch = (uint32_t)(t - row * chunks_per_row);
+  const uint32_t b_lo = ch * Lc;
+  const uint32_t b_hi = min(B, b_lo + Lc);
+  const XYZZ* bk = buckets + row * B;
+  XYZZ running = XYZZ::identity(), tsum = XYZZ::identity();
+  for (uint32_t b = b_hi; b-- > b_lo;) {
+    XYZZ v = ld_xyzz(&bk[b]);
+    xyzz_add(running, v);
+    xyzz_add(tsum, running);
+  }
+  if (b_lo) {
+    XYZZ scaled = xyzz_mul_small(running, b_lo);
+    xyzz_add(tsum, scaled);
+  }
+  st_xyzz(&chunk_out[t], tsum);
+}
+
+// One block per row (batch, window): tree over the row's chunk sums, in place in global memory.
+__global__ void __launch_bounds__(256) msm_row_tree_kernel(XYZZ* chunk_sums, uint32_t chunks_per_row, XYZZ* row_out) {
+  XYZZ* p = chunk_sums + (size_t)blockIdx.x * chunks_per_row;
+  uint32_t active = chunks_per_row;
+  while (active > 1) {
+    const uint32_t half = (active + 1) >> 1;
+    for (uint32_t i = threadIdx.x; i + half < active; i += blockDim.x) {
+      XYZZ a = ld_xyzz_cg(&p[i]);
+      XYZZ b = ld_xyzz_cg(&p[i + half]);
+      xyzz_add(a, b);
+      st_xyzz(&p[i], a);
+    }
+    __syncthreads();
+    active = half;
+  }
+  if (threadIdx.x == 0) st_xyzz(&row_out[blockIdx.x], ld_xyzz_cg(&p[0]));
+}
+
+// result[batch] = sum_w 2^(c*w) * row[batch*W + w]  (Horner from the top window down, the reference's
+// "double c times then add", src/msm/mod.zig:393-398,434).
+__global__ void msm_horner_kernel(const XYZZ* __restrict__ rows, int windows, int c, size_t k, XYZZ* __restrict__ out) {
+  const size_t batch = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (batch >= k) return;
+  XYZZ acc = XYZZ::identity();
+  for (int w = windows - 1; w >= 0; w--) {
+    for (int j = 0; j < c; j++) acc = xyzz_dbl(acc);
+    XYZZ r = ld_xyzz(&rows[batch * windows + w]);
+    xyzz_add(acc, r);
+  }
+  st_xyzz(&out[batch], acc);
+}
+
+// ---- 7. normalisation ---------------------------------------------------------------------------------------
+__global__ void msm_to_affine_kernel(const XYZZ* __restrict__ in, size_t k, AffineG1* __restrict__ out_xy,
+                                     uint8_t* __restrict__ out_inf) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  AffineG1 a;
+  const bool finite = xyzz_to_affine(ld_xyzz(&in[i]), a);
+  st_fq(&out_xy[i].x, a.x);
+  st_fq(&out_xy[i].y, a.y);
+  out_inf[i] = finite ? 0 : 1;
+}
+
+__global__ void g1_sum_partials_kernel(const XYZZ* __restrict__ parts, size_t count, XYZZ* __restrict__ out) {
+  XYZZ acc = XYZZ::identity();
+  for (size_t i = 0; i < count; i++) {
+    XYZZ p = ld_xyzz(&parts[i]);
+    xyzz_add(acc, p);
+  }
+  st_xyzz(out, acc);
+}
+
+// ---- fixed-base multiplication by G = (1, 2) ---------------------------------------------------------------------
+// table[w*255 + (d-1)] = d * 2^(8w) * G, affine, for w < 32, d in 1..255.
+__global__ void __launch_bounds__(128) g1_fixed_table_kernel(AffineG1* __restrict__ table) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 32 * 255) return;
+  const int w = t / 255, d = t % 255 + 1;
+  AffineG1 gen;
+  gen.x = Fq::one();
+  gen.y = fp_add<FqParams>(Fq::one(), Fq::one());
+  XYZZ p = xyzz_from_affine(gen);
+  for (int j = 0; j < 8 * w; j++) p = xyzz_dbl(p);
+  XYZZ r = xyzz_mul_small(p, (uint32_t)d);
+  AffineG1 a;
+  xyzz_to_affine(r, a);
+  st_fq(&table[t].x, a.x);
+  st_fq(&table[t].y, a.y);
+}
+
+__global__ void __launch_bounds__(128)
+g1_fixed_base_kernel(const Fr* __restrict__ scalars, size_t n, const AffineG1* __restrict__ table,
+                     AffineG1* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr s = fp_from_mont<FrParams>(scalars[i]);
+    XYZZ acc = XYZZ::identity();
+#pragma unroll 1
+    for (int w = 0; w < 32; w++) {
+      const uint32_t d = (s.v[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+      if (d) xyzz_madd(acc, ld_affine(&table[w * 255 + (d - 1)]));
+    }
+    AffineG1 a;
+    const bool finite = xyzz_to_affine(acc, a);
+    st_fq(&out_xy[i].x, a.x);
+    st_fq(&out_xy[i].y, a.y);
+    out_inf[i] = finite ? 0 : 1;
+  }
+}
+
+// scalars[i] = tau^i (Montgomery), tau = 0x12345678 (src/poly/commitment/mod.zig:189-199)
+__global__ void __launch_bounds__(256) tau_powers_kernel(Fr* __restrict__ out, size_t n, uint32_t tau) {
+  const Fr t = fp_from_u32<FrParams>(tau);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr acc = Fr::one();
+    Fr base = t;
+    size_t e = i;
+    while (e) {
+      if (e & 1) acc = fp_mul<FrParams>(acc, base);
+      base = fp_mul<FrParams>(base, base);
+      e >>= 1;
+    }
+    out[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+struct Arena {  // one cudaMalloc per MSM call, carved with 256-byte alignment
+  char* base = nullptr;
+  size_t size = 0, used = 0;
+  template <class T>
+  T* take(size_t count) {
+    used = (used + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + used);
+    used += count * sizeof(T);
+    return p;
+  }
+};
+
+size_t edge_levels_total(size_t L0) {  // total entries over all edge levels after level 0
+  size_t total = 0, L = L0;
+  while (L > (size_t)kSliceE) {
+    size_t slices = (L + kSliceE - 1) / kSliceE;
+    L = 2 * slices;
+    total += L;
+  }
+  return total;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// Core: k MSMs of n points over bases[offset..offset+n), scalars on the device (k*n Fr, Montgomery).
+// Leaves k XYZZ results at d_out.
+int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_scalars, size_t k, size_t n,
+             XYZZ* d_out) {
+  cudaStream_t st = ctx->stream;
+  if (n == 0 || k == 0) {
+    if (k) ZOLT_CUDA_TRY(cudaMemsetAsync(d_out, 0, k * sizeof(XYZZ), st));  // identity (ZZ == 0)
+    return ZOLT_OK;
+  }
+  const MsmGeom g = choose_geom(n);
+  const size_t rows = k * (size_t)g.windows;
+  const size_t num_keys = rows * g.B;
+  const size_t max_entries = rows * n;
+  if (num_keys >= 0xfffffff0ull || max_entries >= 0xfffffff0ull || n >= 0x7fffffffull) return ZOLT_ERR_ARG;
+
+  const size_t slices0 = (max_entries + kSlice0 - 1) / kSlice0;
+  const size_t L0 = 2 * slices0;
+  const size_t edge_total = L0 + edge_levels_total(L0);
+  const uint32_t Lc = kChunk;
+  const uint32_t chunks_per_row = (g.B + Lc - 1) / Lc;
+  const size_t num_tiles = (num_keys + kScanTile - 1) / kScanTile;
+
+  size_t bytes = 0;
+  bytes += align256(max_entries * 4) * 2;                     // digits, sorted
+  bytes += align256(num_keys * 4) + align256((num_keys + 1) * 4);  // counts/cursor, offsets
+  bytes += align256((num_tiles + 1) * 4);
+  bytes += align256(num_keys * sizeof(XYZZ));                 // buckets
+  bytes += align256(edge_total * 4) + align256(edge_total * sizeof(XYZZ));
+  bytes += align256(rows * chunks_per_row * sizeof(XYZZ)) + align256(rows * sizeof(XYZZ));
+  bytes += 4096;
+  Arena ar;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&ar.base, bytes));
+  ar.size = bytes;
+  uint32_t* digits = ar.take<uint32_t>(max_entries);
+  uint32_t* sorted = ar.take<uint32_t>(max_entries);
+  uint32_t* counts = ar.take<uint32_t>(num_keys);
+  uint32_t* offsets = ar.take<uint32_t>(num_keys + 1);
+  uint32_t* tiles = ar.take<uint32_t>(num_tiles + 1);
+  XYZZ* buckets = ar.take<XYZZ>(num_keys);
+  uint32_t* edge_keys = ar.take<uint32_t>(edge_total);
+  XYZZ* edge_pts = ar.take<XYZZ>(edge_total);
+  XYZZ* chunk_sums = ar.take<XYZZ>(rows * chunks_per_row);
+  XYZZ* row_sums = ar.take<XYZZ>(rows);
+
+  int status = ZOLT_OK;
+  auto fail = [&](cudaError_t e, const char* what) {
+    fprintf(stderr, "[zolt_gpu] msm: %s -> %s\n", what, cudaGetErrorString(e));
+    status = ZOLT_ERR_CUDA;
+  };
+#define MSM_CHECK(expr)                              \
+  do {                                               \
+    cudaError_t _e = (expr);                         \
+    if (_e != cudaSuccess) { fail(_e, #expr); goto done; } \
+  } while (0)
+
+  {
+    const AffineG1* d_pts = bases->d_xy + offset;
+    const uint8_t* d_inf = bases->d_inf ? bases->d_inf + offset : nullptr;
+    const unsigned sm = (unsigned)ctx->num_sms;
+
+    MSM_CHECK(cudaMemsetAsync(counts, 0, num_keys * 4, st));
+    MSM_CHECK(cudaMemsetAsync(buckets, 0, num_keys * sizeof(XYZZ), st));  // identity everywhere
+    {
+      size_t blocks = (k * n + 255) / 256;
+      if (blocks > (size_t)sm * 16) blocks = (size_t)sm * 16;
+      msm_digits_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_scalars, d_inf, n, k, g, digits, counts);
+      ctx->launches++;
+    }
+    scan_tile_sums_kernel<<<(unsigned)num_tiles, kScanThreads, 0, st>>>(counts, num_keys, tiles);
+    scan_tile_offsets_kernel<<<1, kScanThreads, 0, st>>>(tiles, num_tiles);
+    scan_apply_kernel<<<(unsigned)num_tiles, kScanThreads, 0, st>>>(counts, num_keys, tiles, offsets);
+    ctx->launches += 3;
+    MSM_CHECK(cudaMemsetAsync(counts, 0, num_keys * 4, st));  // reused as the scatter cursor
+    {
+      size_t blocks = (max_entries + 255) / 256;
+      if (blocks > (size_t)sm * 16) blocks = (size_t)sm * 16;
+      msm_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(digits, n, rows, g, offsets, counts, sorted);
+      ctx->launches++;
+    }
+    // level 0
+    msm_accum_points_kernel<<<(unsigned)((slices0 + 127) / 128), 128, 0, st>>>(
+        sorted, offsets, (uint32_t)num_keys, d_pts, buckets, edge_keys, edge_pts, slices0);
+    ctx->launches++;
+    // edge levels
+    {
+      size_t L = L0, in_off = 0;
+      for (;;) {
+        const bool final_level = (L <= (size_t)kSliceE);
+        const size_t slices = final_level ? 1 : (L + kSliceE - 1) / kSliceE;
+        const size_t out_off = in_off + L;
+        msm_accum_edges_kernel<<<(unsigned)((slices + 127) / 128), 128, 0, st>>>(
+            edge_keys + in_off, edge_pts + in_off, L, buckets, edge_keys + out_off, edge_pts + out_off, slices,
+            final_level ? 1 : 0);
+        ctx->launches++;
+        if (final_level) break;
+        in_off = out_off;
+        L = 2 * slices;
+      }
+    }
+    // bucket reduction
+    {
+      const size_t threads = rows * chunks_per_row;
+      msm_chunk_sums_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(buckets, g.B, Lc, chunks_per_row, rows,
+                                                                             chunk_sums);
+      unsigned tb = ((chunks_per_row + 1) / 2 + 31) / 32 * 32;
+      if (tb > 256) tb = 256;
+      msm_row_tree_kernel<<<(unsigned)rows, tb, 0, st>>>(chunk_sums, chunks_per_row, row_sums);
+      msm_horner_kernel<<<(unsigned)((k + 31) / 32), 32, 0, st>>>(row_sums, g.windows, g.c, k, d_out);
+      ctx->launches += 3;
+    }
+    MSM_CHECK(cudaGetLastError());
+    MSM_CHECK(cudaStreamSynchronize(st));  // the arena is freed below
+  }
+done:
+#undef MSM_CHECK
+  cudaFree(ar.base);
+  return status;
+}
+
+int finish_affine(zolt_ctx* ctx, const XYZZ* d_xyzz, size_t k, uint64_t* out_xy, uint8_t* out_inf) {
+  AffineG1* d_xy = nullptr;
+  uint8_t* d_inf = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_xy, k * sizeof(AffineG1)));
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_inf, k));
+  msm_to_affine_kernel<<<(unsigned)((k + 31) / 32), 32, 0, ctx->stream>>>(d_xyzz, k, d_xy, d_inf);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(out_xy, d_xy, k * sizeof(AffineG1), cudaMemcpyDeviceToHost, ctx->stream));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(out_inf, d_inf, k, cudaMemcpyDeviceToHost, ctx->stream));
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_xy);
+  cudaFree(d_inf);
+  return ZOLT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int zolt_msm_bases_upload(zolt_ctx* ctx, const uint64_t* xy, const uint8_t* inf, size_t n, zolt_bases** out) {
+  if (!ctx || !out || (n && !xy)) return ZOLT_ERR_ARG;
+  *out = nullptr;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  zolt_bases* b = new (std::nothrow) zolt_bases();
+  if (!b) return ZOLT_ERR_ARG;
+  b->ctx = ctx;
+  b->n = n;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&b->d_xy, (n ? n : 1) * sizeof(AffineG1)));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(b->d_xy, xy, n * sizeof(AffineG1), cudaMemcpyHostToDevice, ctx->stream));
+  bool any_inf = false;
+  if (inf)
+    for (size_t i = 0; i < n; i++)
+      if (inf[i]) { any_inf = true; break; }
+  if (any_inf) {
+    ZOLT_CUDA_TRY(cudaMalloc((void**)&b->d_inf, n));
+    ZOLT_CUDA_TRY(cudaMemcpyAsync(b->d_inf, inf, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *out = b;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_msm_bases_free(zolt_bases* b) {
+  if (!b) return ZOLT_ERR_ARG;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  if (b->d_xy) cudaFree(b->d_xy);
+  if (b->d_inf) cudaFree(b->d_inf);
+  delete b;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_msm_bases_len(const zolt_bases* b, size_t* n) {
+  if (!b || !n) return ZOLT_ERR_ARG;
+  *n = b->n;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_msm_bases_download(const zolt_bases* b, size_t offset, size_t n, uint64_t* xy, uint8_t* inf) {
+  if (!b || !xy || offset + n > b->n) return ZOLT_ERR_ARG;
+  zolt_ctx* ctx = b->ctx;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(xy, b->d_xy + offset, n * sizeof(AffineG1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (inf) {
+    if (b->d_inf) ZOLT_CUDA_TRY(cudaMemcpyAsync(inf, b->d_inf + offset, n, cudaMemcpyDeviceToHost, ctx->stream));
+    else memset(inf, 0, n);
+  }
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_msm_partial_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const void* d_scalars,
+                                    size_t n, void* d_out) {
+  if (!ctx || !bases || !d_out || (n && !d_scalars) || offset + n > bases->n) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  return msm_core(ctx, bases, offset, (const Fr*)d_scalars, 1, n, (XYZZ*)d_out);
+}
+
+extern "C" int zolt_g1_sum_partials(zolt_ctx* ctx, const void* d_partials, size_t count, uint64_t out_xy[8],
+                                    uint8_t* out_inf) {
+  if (!ctx || !d_partials || !out_xy || !out_inf) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  XYZZ* d_sum = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_sum, sizeof(XYZZ)));
+  g1_sum_partials_kernel<<<1, 1, 0, ctx->stream>>>((const XYZZ*)d_partials, count, d_sum);
+  ctx->launches++;
+  int s = finish_affine(ctx, d_sum, 1, out_xy, out_inf);
+  cudaFree(d_sum);
+  return s;
+}
+
+extern "C" int zolt_msm_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const void* d_scalars, size_t n,
+                            uint64_t out_xy[8], uint8_t* out_inf) {
+  if (!ctx || !bases || !out_xy || !out_inf || (n && !d_scalars) || offset + n > bases->n) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_res, sizeof(XYZZ)));
+  int s = msm_core(ctx, bases, offset, (const Fr*)d_scalars, 1, n, d_res);
+  if (s == ZOLT_OK) s = finish_affine(ctx, d_res, 1, out_xy, out_inf);
+  cudaFree(d_res);
+  return s;
+}
+
+extern "C" int zolt_msm(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n,
+                        uint64_t out_xy[8], uint8_t* out_inf) {
+  if (!ctx || !bases || !out_xy || !out_inf || (n && !scalars) || offset + n > bases->n) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Fr* d_s = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_s, (n ? n : 1) * sizeof(Fr)));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  int s = zolt_msm_dev(ctx, bases, offset, d_s, n, out_xy, out_inf);
+  cudaFree(d_s);
+  return s;
+}
+
+extern "C" int zolt_msm_batch(zolt_ctx* ctx, const zolt_bases* bases, const uint64_t* scalars, size_t k, size_t n,
+                              uint64_t* out_xy, uint8_t* out_inf) {
+  if (!ctx || !bases || !out_xy || !out_inf || (n && k && !scalars) || n > bases->n) return ZOLT_ERR_ARG;
+  if (k == 0) return ZOLT_OK;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Fr* d_s = nullptr;
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_s, (n * k ? n * k : 1) * sizeof(Fr)));
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_res, k * sizeof(XYZZ)));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * k * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  int s = msm_core(ctx, bases, 0, d_s, k, n, d_res);
+  if (s == ZOLT_OK) s = finish_affine(ctx, d_res, k, out_xy, out_inf);
+  cudaFree(d_s);
+  cudaFree(d_res);
+  return s;
+}
+
+static int fixed_base_dev(zolt_ctx* ctx, const Fr* d_scalars, size_t n, zolt_bases** out) {
+  zolt_bases* b = new (std::nothrow) zolt_bases();
+  if (!b) return ZOLT_ERR_ARG;
+  b->ctx = ctx;
+  b->n = n;
+  AffineG1* d_table = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&b->d_xy, (n ? n : 1) * sizeof(AffineG1)));
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&b->d_inf, n ? n : 1));
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_table, 32 * 255 * sizeof(AffineG1)));
+  g1_fixed_table_kernel<<<(32 * 255 + 127) / 128, 128, 0, ctx->stream>>>(d_table);
+  ctx->launches++;
+  if (n) {
+    size_t blocks = (n + 127) / 128;
+    if (blocks > (size_t)ctx->num_sms * 16) blocks = (size_t)ctx->num_sms * 16;
+    g1_fixed_base_kernel<<<(unsigned)blocks, 128, 0, ctx->stream>>>(d_scalars, n, d_table, b->d_xy, b->d_inf);
+    ctx->launches++;
+  }
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_table);
+  *out = b;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_g1_fixed_base_mul(zolt_ctx* ctx, const uint64_t* scalars, size_t n, zolt_bases** out) {
+  if (!ctx || !out || (n && !scalars)) return ZOLT_ERR_ARG;
+  *out = nullptr;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Fr* d_s = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_s, (n ? n : 1) * sizeof(Fr)));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  int s = fixed_base_dev(ctx, d_s, n, out);
+  cudaFree(d_s);
+  return s;
+}
+
+extern "C" int zolt_hyperkzg_setup(zolt_ctx* ctx, size_t max_degree, zolt_bases** out) {
+  if (!ctx || !out) return ZOLT_ERR_ARG;
+  *out = nullptr;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Fr* d_s = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_s, (max_degree ? max_degree : 1) * sizeof(Fr)));
+  if (max_degree) {
+    size_t blocks = (max_degree + 255) / 256;
+    if (blocks > (size_t)ctx->num_sms * 16) blocks = (size_t)ctx->num_sms * 16;
+    tau_powers_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_s, max_degree, 0x12345678u);
+    ctx->launches++;
+  }
+  int s = fixed_base_dev(ctx, d_s, max_degree, out);
+  cudaFree(d_s);
+  return s;
+}
