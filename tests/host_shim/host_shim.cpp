@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE: compiles the device headers' host (PTX-emulation) back-end so the
 // algorithms in zolt_b200/csrc/*.cuh can be validated against the oracle without a GPU.
 // Never linked into the product library.
-#include "../../zolt_b200/csrc/field.cuh"
+#include "../../zolt_b200/csrc/curve.cuh"
 #include <cstddef>
 #include <cstring>
 using namespace zolt;
@@ -29,4 +29,49 @@ static void binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, s
 extern "C" void shim_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
   if (field == 0) binop<FrParams>(op, a, b, out, n);
   else binop<FqParams>(op, a, b, out, n);
+}
+
+static AffineG1 load_affine(const uint64_t* xy) {
+  AffineG1 p;
+  memcpy(p.x.v, xy, 32);
+  memcpy(p.y.v, xy + 4, 32);
+  return p;
+}
+
+// Fold a list of affine points with the XYZZ formulas.  mode 0: sequential mixed additions;
+// mode 1: pairwise tree of full additions; mode 2: sum, then doubled `dbl` times; mode 3: sum
+// multiplied by the small constant `dbl` (xyzz_mul_small).  Output: canonical affine + flag.
+extern "C" void shim_g1_fold(int mode, const uint64_t* xy, const uint8_t* neg, size_t n, uint32_t dbl, uint64_t* out_xy,
+                             uint8_t* out_inf) {
+  XYZZ acc = XYZZ::identity();
+  if (mode == 1) {
+    XYZZ* tmp = new XYZZ[n ? n : 1];
+    for (size_t i = 0; i < n; i++) {
+      AffineG1 p = load_affine(xy + 8 * i);
+      if (neg && neg[i]) p = affine_neg(p);
+      tmp[i] = XYZZ::identity();
+      xyzz_madd(tmp[i], p);
+    }
+    for (size_t m = n; m > 1;) {
+      size_t half = (m + 1) / 2;
+      for (size_t i = 0; i + half < m; i++) xyzz_add(tmp[i], tmp[i + half]);
+      m = half;
+    }
+    if (n) acc = tmp[0];
+    delete[] tmp;
+  } else {
+    for (size_t i = 0; i < n; i++) {
+      AffineG1 p = load_affine(xy + 8 * i);
+      if (neg && neg[i]) p = affine_neg(p);
+      xyzz_madd(acc, p);
+    }
+    if (mode == 2)
+      for (uint32_t j = 0; j < dbl; j++) acc = xyzz_dbl(acc);
+    if (mode == 3) acc = xyzz_mul_small(acc, dbl);
+  }
+  AffineG1 a;
+  bool finite = xyzz_to_affine(acc, a);
+  memcpy(out_xy, a.x.v, 32);
+  memcpy(out_xy + 4, a.y.v, 32);
+  *out_inf = finite ? 0 : 1;
 }

@@ -1,0 +1,74 @@
+"""CPU tier: the DEVICE headers (zolt_b200/csrc/field.cuh, curve.cuh) compiled with their host
+back-end -- an exact emulation of the PTX carry-flag semantics -- against the big-integer oracle.
+This validates the algorithms (carry chains, even/odd accumulators, XYZZ special cases) on a box
+without a GPU; the -m gpu tier checks the same functions as real PTX."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as B
+from tests.util import rand_fr
+
+
+def _run(shim, field, op, a, b):
+    out = np.zeros_like(a)
+    shim.shim_field_op(field, op, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(len(a)))
+    return out
+
+
+@pytest.mark.parametrize("field,mod", [(0, B.FR_MOD), (1, B.FQ_MOD)])
+def test_field_algorithms(host_shim, field, mod):
+    rng = np.random.default_rng(1)
+    n = 20000
+    av = [v % mod for v in B.random_fr(rng, n)]
+    bv = [v % mod for v in B.random_fr(rng, n)]
+    av[:6], bv[:6] = [0, 1, mod - 1, mod - 1, 0, mod - 2], [0, mod - 1, mod - 1, 1, 5, mod - 1]
+    a, b = B.ints_to_raw_array(av), B.ints_to_raw_array(bv)
+    rinv = pow(1 << 256, -1, mod)
+    assert B.raw_array_to_ints(_run(host_shim, field, 0, a, b)) == [x * y * rinv % mod for x, y in zip(av, bv)]
+    assert B.raw_array_to_ints(_run(host_shim, field, 1, a, b)) == [(x + y) % mod for x, y in zip(av, bv)]
+    assert B.raw_array_to_ints(_run(host_shim, field, 2, a, b)) == [(x - y) % mod for x, y in zip(av, bv)]
+    assert B.raw_array_to_ints(_run(host_shim, field, 6, a, b)) == [(-x) % mod for x in av]
+    assert B.raw_array_to_ints(_run(host_shim, field, 4, a, b)) == [x * rinv % mod for x in av]
+    raw = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    raw[0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert B.raw_array_to_ints(_run(host_shim, field, 5, raw, raw)) == [(x << 256) % mod for x in B.raw_array_to_ints(raw)]
+    R = (1 << 256) % mod
+    got = B.raw_array_to_ints(_run(host_shim, field, 3, a[:100], b[:100]))
+    assert got == [0 if x == 0 else pow(x * rinv % mod, -1, mod) * R % mod for x in av[:100]]
+
+
+def _fold(shim, mode, pts, neg=None, dbl=0):
+    xy, _ = B.points_to_arrays(pts)
+    out = np.zeros(8, dtype=np.uint64)
+    oinf = C.c_uint8()
+    negp = None if neg is None else np.asarray(neg, dtype=np.uint8).ctypes.data_as(C.c_void_p)
+    shim.shim_g1_fold(mode, xy.ctypes.data_as(C.c_void_p), negp, C.c_size_t(len(pts)), C.c_uint32(dbl),
+                      out.ctypes.data_as(C.c_void_p), C.byref(oinf))
+    return B.arrays_to_points(out.reshape(1, 8), [oinf.value])[0]
+
+
+def test_curve_formulas(host_shim):
+    logs = rand_fr(11, 24)
+    pts = [B.g1_mul(B.G1_GEN, k) for k in logs]
+    total = B.g1_mul(B.G1_GEN, sum(logs))
+    assert _fold(host_shim, 0, pts) == total          # mixed additions
+    assert _fold(host_shim, 1, pts) == total          # full additions (tree)
+    assert _fold(host_shim, 2, pts, dbl=5) == B.g1_mul(total, 32)
+    assert _fold(host_shim, 3, pts, dbl=1000) == B.g1_mul(total, 1000)
+    assert _fold(host_shim, 3, pts, dbl=0) is None
+    neg = [i % 2 for i in range(24)]
+    exp = B.g1_mul(B.G1_GEN, sum(-k if s else k for k, s in zip(logs, neg)))
+    assert _fold(host_shim, 0, pts, neg) == exp
+
+
+def test_curve_special_cases(host_shim):
+    p = B.g1_mul(B.G1_GEN, 77)
+    assert _fold(host_shim, 0, []) is None
+    assert _fold(host_shim, 0, [p, p]) == B.g1_mul(B.G1_GEN, 154)            # P + P -> doubling (mixed)
+    assert _fold(host_shim, 1, [p, p, p, p]) == B.g1_mul(B.G1_GEN, 308)      # P + P -> doubling (full)
+    assert _fold(host_shim, 0, [p, p], neg=[0, 1]) is None                   # P + (-P) -> identity
+    assert _fold(host_shim, 1, [p, p], neg=[0, 1]) is None
+    assert _fold(host_shim, 0, [p, p, p], neg=[0, 1, 0]) == p               # identity + P
+    assert _fold(host_shim, 1, [p, p, p, p], neg=[0, 1, 1, 0]) is None      # identity + identity

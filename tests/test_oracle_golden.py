@@ -1,0 +1,166 @@
+"""CPU tier: pin the oracle against the reference's own golden vectors.
+
+  * logs/zolt.log claim-update KATs (committed as tests/golden/zolt_log_kats.json by make_golden.py)
+  * the exact values asserted by the reference's unit tests (file:line cited per test)
+  * the Montgomery constants of src/field/mod.zig:16-75
+"""
+import json
+from pathlib import Path
+
+from oracle import bn254 as B
+from oracle import poly as OP
+from oracle import sumcheck as OS
+from oracle import transcript as OT
+
+P = B.FR_MOD
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def test_log_claim_update_kats():
+    kats = json.loads((GOLD / "zolt_log_kats.json").read_text())["kats"]
+    assert len(kats) >= 20
+    le = lambda b: int.from_bytes(bytes(b), "little")  # noqa: E731
+    for k in kats:
+        got = OP.compressed_claim_update(le(k["current_claim"]), le(k["c0"]), le(k["c2"]), le(k["c3"]), le(k["challenge"]))
+        assert got == le(k["next_claim"]), (k["stage"], k["round"])
+        assert B.fr_to_bytes(got) == bytes(k["next_claim"])  # toBytes = canonical LE (field/mod.zig:685-695)
+
+
+def test_montgomery_constants_match_reference_source():
+    # src/field/mod.zig:24-41 (Fr) and :59-75 (Fq)
+    assert B.int_to_limbs(B.FR_R) == [0xAC96341C4FFFFFFB, 0x36FC76959F60CD29, 0x666EA36F7879462E, 0x0E0A77C19A07DF2F]
+    assert B.int_to_limbs(B.FR_R2) == [0x1BB8E645AE216DA7, 0x53FE3AB1E35C59E3, 0x8C49833D53BB8085, 0x0216D0B17F4E44A5]
+    assert B.FR_INV64 == 0xC2E1F593EFFFFFFF
+    assert B.int_to_limbs(B.FQ_R) == [0xD35D438DC58F0D9D, 0x0A78EB28F5C70B3D, 0x666EA36F7879462C, 0x0E0A77C19A07DF2F]
+    assert B.int_to_limbs(B.FQ_R2) == [0xF32CFC5B538AFA89, 0xB5E71911D44501FB, 0x47AB1EFF0A417FF6, 0x06D89F71CAB8351F]
+    assert B.FQ_INV64 == 0x87D20782E4866389
+
+
+def test_bind_low_unit_vectors():
+    # src/poly/mod.zig:816-888
+    assert OP.bind_low([1, 2, 3, 4], 3) == [4, 6]
+    assert OP.bind_low([10, 20, 30, 40, 50, 60, 70, 80], 5) == [60, 80, 100, 120]
+
+
+def test_half_split_sumcheck_unit_vectors():
+    # src/subprotocols/mod.zig:379-436: g(0)=3, g(1)=7, after r=2 -> [5,6]; :441-461 total 36
+    assert OS.round_sum([[1, 2, 3, 4]], OS.HALF) == [3, 7]
+    assert OP.bind_first([1, 2, 3, 4], 2) == [5, 6]
+    assert sum(range(1, 9)) == 36 and sum(OS.round_sum([list(range(1, 9))], OS.HALF)) == 36
+
+
+def test_interpolation_unit_vectors():
+    # src/poly/mod.zig:755-795: 1 + 2X + 3X^2 + 4X^3 from [1, 10, 49, 142]; compressed [1, 3, 4]
+    assert OP.interpolate_degree3([1, 10, 49, 142]) == [1, 2, 3, 4]
+    assert OP.evals_to_compressed([1, 10, 49, 142]) == [1, 3, 4]
+    # cubic evaluation (src/zkvm/batched_sumcheck.zig:475-494)
+    for x in (0, 1, 2, 3, 5, 12345):
+        assert OP.evaluate_cubic_at_point([1, 10, 49, 142], x) == (1 + 2 * x + 3 * x * x + 4 * x**3) % P
+
+
+def test_eq_partition_of_unity_and_big_endian():
+    # src/poly/mod.zig:689-753
+    r = [3, 5, 7]
+    ev = OP.eq_evals(r)
+    assert sum(ev) % P == 1
+    for idx in range(8):
+        bits = [(idx >> (2 - j)) & 1 for j in range(3)]  # r[0] <-> MSB
+        assert ev[idx] == OP.eq_mle(r, bits)
+
+
+def test_split_eq_tables_unit_vectors():
+    # src/poly/split_eq.zig:575-676: tau=[2,3,5] -> m=1, E_out over tau[0], E_in over tau[1]; eq(3,5)=23 (:554-573)
+    sq = OP.GruenSplitEq([2, 3, 5])
+    assert sq.E_out_vec == [[1], [(1 - 2) % P, 2]]
+    assert sq.E_in_vec == [[1], [(1 - 3) % P, 3]]
+    sq4 = OP.GruenSplitEq([3, 5, 7, 11])
+    assert len(sq4.E_out_vec) == 3 and len(sq4.E_in_vec) == 2
+    one = OP.GruenSplitEq([3])
+    one.bind(5)
+    assert one.current_scalar == (3 * 5 + (1 - 3) * (1 - 5)) % P == 23
+
+
+def test_gruen_cubic_is_consistent_with_dense_eq():
+    # s(X) from computeCubicRoundPoly must equal the dense sum eq(tau,x) l(x) r(x) round polynomial
+    import numpy as np
+
+    rng = np.random.default_rng(5)
+    n_vars = 5
+    tau = B.random_fr(rng, n_vars)
+    left, right = B.random_fr(rng, 1 << n_vars), B.random_fr(rng, 1 << n_vars)
+    eq = OP.eq_evals(tau)
+    sq = OP.GruenSplitEq(tau)
+    claim = sum(e * a * b for e, a, b in zip(eq, left, right)) % P
+    tabs = [left, right]
+    dense = [eq, left, right]
+    for _ in range(n_vars):
+        t0, tinf = OS.round_gruen_ab(tabs, sq)
+        s = sq.cubic_round_poly(t0, tinf, claim)
+        assert s == OS.round_prod3(dense, OS.ADJACENT)
+        assert (s[0] + s[1]) % P == claim
+        r = B.random_fr(rng, 1)[0]
+        claim = OP.evaluate_cubic_at_point(s, r)
+        tabs = OS.bind_tables(tabs, r, OS.ADJACENT)
+        dense = OS.bind_tables(dense, r, OS.ADJACENT)
+        sq.bind(r)
+
+
+def test_field_small_integer_identities():
+    # src/field/mod.zig:1101-1140, :1452-1494: 3*7=21, 2^3=8, inner product 70, Horner 49
+    m = lambda v: B.fr_to_mont(v)  # noqa: E731
+    assert B.fr_from_mont(B.mont_mul(m(3), m(7), P)) == 21
+    assert B.fr_from_mont(B.mont_mul(B.mont_mul(m(2), m(2), P), m(2), P)) == 8
+    assert sum(a * b for a, b in zip([1, 2, 3, 4], [5, 6, 7, 8])) % P == 70
+    assert OP.unipoly_evaluate([1, 2, 3, 4], 2) == 49
+
+
+def test_window_digits_and_sizes():
+    # src/msm/mod.zig:827-851
+    assert [B.optimal_window_size(n) for n in (1, 7, 8, 31, 32, 127, 128, 511, 512, 2047, 2048, 8191, 8192, 32767, 32768, 1 << 24)] == [
+        1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8]
+    s = 0b11001010
+    assert [B.get_window(s, w, 2) for w in range(4)] == [0b10, 0b10, 0b00, 0b11]
+    assert B.get_window(s, 0, 4) == 0b1010 and B.get_window(s, 1, 4) == 0b1100
+
+
+def test_msm_literal_pippenger_equals_closed_form():
+    # bench.zig workloads (src/bench.zig:243-287) -- scalars 7i+13, bases (i+1)G
+    for n in (16, 64, 256):
+        bases, acc = [], None
+        for i in range(n):
+            acc = B.g1_add(acc, B.G1_GEN)
+            bases.append(acc)
+        scalars = [7 * i + 13 for i in range(n)]
+        assert B.msm(bases, scalars) == B.msm_closed_form(range(1, n + 1), scalars)
+    assert B.msm([], []) is None
+
+
+def test_commit_kat():
+    # SURVEY 8c.3 derived KAT for the mock SRS (tau = 0x12345678, commitment/mod.zig:189)
+    pt = B.hyperkzg_commit(B.hyperkzg_setup(4), [1, 2, 3, 4])
+    assert pt == (
+        0x07AEB450B7B66FDF44A37824224849B29C1ED87D705324299A17C8FB790F75CE,
+        0x166808E4F5E0101BE322704903A3156ABBE3AD2C7A8992563F704CE020B05D14,
+    )
+    assert B.int_to_limbs(B.fq_to_mont(pt[0])) == [0x34686E9C2DC1A390, 0x6E093777DB13CF10, 0xAE87848108CE376F, 0x23A755E5AA7A0FD3]
+    assert B.g1_is_on_curve(pt) and B.hyperkzg_setup(2)[1] == B.g1_mul(B.G1_GEN, B.HYPERKZG_TAU)
+
+
+def test_transcript_is_deterministic_and_sensitive():
+    # src/integration_tests.zig:80-118 (determinism); byte contract of src/transcripts/mod.zig:87-131
+    a, b = OT.Transcript(b"Jolt"), OT.Transcript(b"Jolt")
+    a.append_scalar(b"x", 5)
+    b.append_scalar(b"x", 5)
+    ca, cb = a.challenge_scalar(b"c"), b.challenge_scalar(b"c")
+    assert ca == cb and 0 <= ca < P
+    c = OT.Transcript(b"Jolt")
+    c.append_scalar(b"x", 6)
+    assert c.challenge_scalar(b"c") != ca
+    # absorbing exactly the rate triggers one permutation and resets the position
+    t = OT.Transcript(b"")
+    t.append_bytes(bytes(136))
+    assert t.position == 0 and any(t.state)
+    # keccak-f[1600] on the zero state: first lane of the well-known test vector
+    st = bytearray(200)
+    OT.keccak_f(st)
+    assert int.from_bytes(st[:8], "little") == 0xF1258F7940E1DDE7
