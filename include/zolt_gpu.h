@@ -189,6 +189,13 @@ int zolt_sc_free(zolt_sc* sc);
  * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery products, 3 = Fq Montgomery products, 4 = IMAD immediate form.
  * Returns ops per second (for kind 2/3: field products per second). */
 int zolt_bench_int_pipe(zolt_ctx* ctx, int kind, int iters, double* ops_per_s);
+/* Per-kernel device timings (CUDA events on the context's stream, the stream the kernels are launched
+ * on).  zolt_prof_enable(ctx, 1) clears the log and starts recording one (tag, ms) entry per phase of
+ * every subsequent MSM / sumcheck call (up to 96 entries); zolt_prof_read synchronises and copies them.
+ * Tags: 1 digits, 2 scan, 3 scatter, 4 bucket accumulation (level 0), 5 edge levels, 6 bucket
+ * reduction, 7 normalisation; 16 sumcheck round-0 evaluation, 17 fused bind+evaluate round. */
+int zolt_prof_enable(zolt_ctx* ctx, int on);
+int zolt_prof_read(zolt_ctx* ctx, int* tags, float* ms, int max_entries, int* n_entries);
 /* device timing helpers on the context's stream (CUDA events) */
 int zolt_timer_start(zolt_ctx* ctx);
 int zolt_timer_stop_ms(zolt_ctx* ctx, float* ms);

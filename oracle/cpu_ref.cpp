@@ -634,7 +634,7 @@ void ref_sc_prove(int kind, int pairing, uint64_t* const* tables, int k, size_t 
   for (int rnd = 0; rnd < rounds; rnd++) {
     uint64_t ev[16];
     ref_sc_round(kind, pairing, tables, n, ev);
-    const int ne = kind == 0 ? 2 : 4;
+    const int ne = kind == 0 ? 2 : (kind == 1 ? 3 : 4);  // degree + 1 evaluations are absorbed
     for (int j = 0; j < ne; j++) {
       char label[32];
       int ln = snprintf(label, sizeof label, "round_poly_%d", j);

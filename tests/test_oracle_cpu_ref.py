@@ -103,7 +103,7 @@ def test_transcript_and_full_prove():
     for rnd in range(log_n):
         e = OS.round_prod2(tabs, 0)
         assert fr_ints(evals[rnd]) == e
-        for j, v in enumerate(e):
+        for j, v in enumerate(e[:3]):  # degree + 1 evaluations
             tr.append_scalar(b"round_poly_%d" % j, v)
         r = tr.challenge_scalar(b"round")
         assert fr_ints(chal[rnd]) == [r]

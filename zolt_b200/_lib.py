@@ -73,6 +73,8 @@ SIGNATURES = {
     "zolt_fr_sum_rows": [_vp, _vp, _sz, _sz, _vp],
     "zolt_sc_free": [_vp],
     "zolt_bench_int_pipe": [_vp, _i, _i, C.POINTER(C.c_double)],
+    "zolt_prof_enable": [_vp, _i],
+    "zolt_prof_read": [_vp, C.POINTER(_i), C.POINTER(C.c_float), _i, C.POINTER(_i)],
     "zolt_timer_start": [_vp],
     "zolt_timer_stop_ms": [_vp, C.POINTER(C.c_float)],
 }

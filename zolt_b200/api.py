@@ -72,6 +72,17 @@ class Context:
         check(self.lib.zolt_timer_stop_ms(self.handle, C.byref(ms)), "zolt_timer_stop_ms")
         return ms.value
 
+    def prof_enable(self, on: bool = True):
+        check(self.lib.zolt_prof_enable(self.handle, int(on)), "zolt_prof_enable")
+
+    def prof_read(self):
+        """-> list of (tag, ms) recorded since the last read (see include/zolt_gpu.h for tags)."""
+        tags = (C.c_int * 96)()
+        ms = (C.c_float * 96)()
+        n = C.c_int()
+        check(self.lib.zolt_prof_read(self.handle, tags, ms, 96, C.byref(n)), "zolt_prof_read")
+        return [(tags[i], ms[i]) for i in range(n.value)]
+
     def bench_int_pipe(self, kind: int, iters: int = 2000) -> float:
         out = C.c_double()
         check(self.lib.zolt_bench_int_pipe(self.handle, kind, iters, C.byref(out)), "zolt_bench_int_pipe")

@@ -55,6 +55,10 @@ extern "C" int zolt_gpu_shutdown(zolt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->h_mailbox) cudaFreeHost(ctx->h_mailbox);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->ws_in) cudaFree(ctx->ws_in);
+  for (int i = 0; i < 2 * zolt_ctx::kMaxProf; i++)
+    if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ZOLT_OK;
@@ -100,6 +104,27 @@ extern "C" int zolt_dev_download(zolt_ctx* ctx, void* hptr, const void* dptr, si
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   ZOLT_CUDA_TRY(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_prof_enable(zolt_ctx* ctx, int on) {
+  if (!ctx) return ZOLT_ERR_ARG;
+  ctx->prof_on = on != 0;
+  ctx->prof_used = 0;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_prof_read(zolt_ctx* ctx, int* tags, float* ms, int max_entries, int* n_entries) {
+  if (!ctx || !tags || !ms || !n_entries) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  int n = ctx->prof_used < max_entries ? ctx->prof_used : max_entries;
+  for (int i = 0; i < n; i++) {
+    tags[i] = ctx->prof_tag[i];
+    ZOLT_CUDA_TRY(cudaEventElapsedTime(&ms[i], ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+  }
+  *n_entries = n;
+  ctx->prof_used = 0;
   return ZOLT_OK;
 }
 

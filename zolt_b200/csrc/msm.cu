@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(256) tau_powers_kernel(Fr* __restrict__ out, s
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-struct Arena {  // one cudaMalloc per MSM call, carved with 256-byte alignment
+struct Arena {  // carves the context's workspace with 256-byte alignment
   char* base = nullptr;
   size_t size = 0, used = 0;
   template <class T>
@@ -534,8 +534,18 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   bytes += align256(edge_total * 4) + align256(edge_total * sizeof(XYZZ));
   bytes += align256(rows * chunks_per_row * sizeof(XYZZ)) + align256(rows * sizeof(XYZZ));
   bytes += 4096;
+  if (ctx->ws_bytes < bytes) {
+    if (ctx->ws) {
+      ZOLT_CUDA_TRY(cudaStreamSynchronize(st));
+      ZOLT_CUDA_TRY(cudaFree(ctx->ws));
+      ctx->ws = nullptr;
+      ctx->ws_bytes = 0;
+    }
+    ZOLT_CUDA_TRY(cudaMalloc(&ctx->ws, bytes));
+    ctx->ws_bytes = bytes;
+  }
   Arena ar;
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&ar.base, bytes));
+  ar.base = static_cast<char*>(ctx->ws);
   ar.size = bytes;
   uint32_t* digits = ar.take<uint32_t>(max_entries);
   uint32_t* sorted = ar.take<uint32_t>(max_entries);
@@ -569,25 +579,34 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
     {
       size_t blocks = (k * n + 255) / 256;
       if (blocks > (size_t)sm * 16) blocks = (size_t)sm * 16;
+      const int ps = prof_begin(ctx, PROF_MSM_DIGITS);
       msm_digits_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_scalars, d_inf, n, k, g, digits, counts);
+      prof_end(ctx, ps);
       ctx->launches++;
     }
+    int ps = prof_begin(ctx, PROF_MSM_SCAN);
     scan_tile_sums_kernel<<<(unsigned)num_tiles, kScanThreads, 0, st>>>(counts, num_keys, tiles);
     scan_tile_offsets_kernel<<<1, kScanThreads, 0, st>>>(tiles, num_tiles);
     scan_apply_kernel<<<(unsigned)num_tiles, kScanThreads, 0, st>>>(counts, num_keys, tiles, offsets);
+    prof_end(ctx, ps);
     ctx->launches += 3;
     MSM_CHECK(cudaMemsetAsync(counts, 0, num_keys * 4, st));  // reused as the scatter cursor
     {
       size_t blocks = (max_entries + 255) / 256;
       if (blocks > (size_t)sm * 16) blocks = (size_t)sm * 16;
+      ps = prof_begin(ctx, PROF_MSM_SCATTER);
       msm_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(digits, n, rows, g, offsets, counts, sorted);
+      prof_end(ctx, ps);
       ctx->launches++;
     }
     // level 0
+    ps = prof_begin(ctx, PROF_MSM_ACCUM0);
     msm_accum_points_kernel<<<(unsigned)((slices0 + 127) / 128), 128, 0, st>>>(
         sorted, offsets, (uint32_t)num_keys, d_pts, buckets, edge_keys, edge_pts, slices0);
+    prof_end(ctx, ps);
     ctx->launches++;
     // edge levels
+    ps = prof_begin(ctx, PROF_MSM_EDGES);
     {
       size_t L = L0, in_off = 0;
       for (;;) {
@@ -603,7 +622,9 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
         L = 2 * slices;
       }
     }
+    prof_end(ctx, ps);
     // bucket reduction
+    ps = prof_begin(ctx, PROF_MSM_REDUCE);
     {
       const size_t threads = rows * chunks_per_row;
       msm_chunk_sums_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(buckets, g.B, Lc, chunks_per_row, rows,
@@ -614,13 +635,27 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
       msm_horner_kernel<<<(unsigned)((k + 31) / 32), 32, 0, st>>>(row_sums, g.windows, g.c, k, d_out);
       ctx->launches += 3;
     }
+    prof_end(ctx, ps);
     MSM_CHECK(cudaGetLastError());
-    MSM_CHECK(cudaStreamSynchronize(st));  // the arena is freed below
   }
 done:
 #undef MSM_CHECK
-  cudaFree(ar.base);
   return status;
+}
+
+int staging_for(zolt_ctx* ctx, size_t bytes, Fr** out) {
+  if (ctx->ws_in_bytes < bytes) {
+    if (ctx->ws_in) {
+      ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      ZOLT_CUDA_TRY(cudaFree(ctx->ws_in));
+      ctx->ws_in = nullptr;
+      ctx->ws_in_bytes = 0;
+    }
+    ZOLT_CUDA_TRY(cudaMalloc(&ctx->ws_in, bytes ? bytes : 32));
+    ctx->ws_in_bytes = bytes ? bytes : 32;
+  }
+  *out = static_cast<Fr*>(ctx->ws_in);
+  return ZOLT_OK;
 }
 
 int finish_affine(zolt_ctx* ctx, const XYZZ* d_xyzz, size_t k, uint64_t* out_xy, uint8_t* out_inf) {
@@ -628,7 +663,9 @@ int finish_affine(zolt_ctx* ctx, const XYZZ* d_xyzz, size_t k, uint64_t* out_xy,
   uint8_t* d_inf = nullptr;
   ZOLT_CUDA_TRY(cudaMalloc((void**)&d_xy, k * sizeof(AffineG1)));
   ZOLT_CUDA_TRY(cudaMalloc((void**)&d_inf, k));
+  const int ps = prof_begin(ctx, PROF_MSM_AFFINE);
   msm_to_affine_kernel<<<(unsigned)((k + 31) / 32), 32, 0, ctx->stream>>>(d_xyzz, k, d_xy, d_inf);
+  prof_end(ctx, ps);
   ctx->launches++;
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaMemcpyAsync(out_xy, d_xy, k * sizeof(AffineG1), cudaMemcpyDeviceToHost, ctx->stream));
@@ -733,11 +770,9 @@ extern "C" int zolt_msm(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, c
   if (!ctx || !bases || !out_xy || !out_inf || (n && !scalars) || offset + n > bases->n) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   Fr* d_s = nullptr;
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_s, (n ? n : 1) * sizeof(Fr)));
+  ZOLT_TRY(staging_for(ctx, n * sizeof(Fr), &d_s));
   ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  int s = zolt_msm_dev(ctx, bases, offset, d_s, n, out_xy, out_inf);
-  cudaFree(d_s);
-  return s;
+  return zolt_msm_dev(ctx, bases, offset, d_s, n, out_xy, out_inf);
 }
 
 extern "C" int zolt_msm_batch(zolt_ctx* ctx, const zolt_bases* bases, const uint64_t* scalars, size_t k, size_t n,
@@ -747,12 +782,11 @@ extern "C" int zolt_msm_batch(zolt_ctx* ctx, const zolt_bases* bases, const uint
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   Fr* d_s = nullptr;
   XYZZ* d_res = nullptr;
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_s, (n * k ? n * k : 1) * sizeof(Fr)));
+  ZOLT_TRY(staging_for(ctx, n * k * sizeof(Fr), &d_s));
   ZOLT_CUDA_TRY(cudaMalloc((void**)&d_res, k * sizeof(XYZZ)));
   ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * k * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
   int s = msm_core(ctx, bases, 0, d_s, k, n, d_res);
   if (s == ZOLT_OK) s = finish_affine(ctx, d_res, k, out_xy, out_inf);
-  cudaFree(d_s);
   cudaFree(d_res);
   return s;
 }

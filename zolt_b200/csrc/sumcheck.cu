@@ -439,12 +439,14 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   const size_t n_cur = fused ? sc->n / 2 : sc->n;
   const unsigned grid = grid_for(sc->ctx, n_cur / 2, 4);
   SplitEqDev sq = split_eq_for(sc, n_cur);
+  const int ps = prof_begin(sc->ctx, fused ? PROF_SC_FUSED : PROF_SC_EVAL);
   if (fused)
     sc_round_kernel<COMB, PAIR, true><<<grid, kScThreads, 0, sc->ctx->stream>>>(
         t, sc->n_extra, sc->n, r, sq, sc->d_partials, sc->d_ticket, sc->d_evals, sc->h_evals_dev);
   else
     sc_round_kernel<COMB, PAIR, false><<<grid, kScThreads, 0, sc->ctx->stream>>>(
         t, sc->n_extra, sc->n, r, sq, sc->d_partials, sc->d_ticket, sc->d_evals, sc->h_evals_dev);
+  prof_end(sc->ctx, ps);
   sc->ctx->launches++;
 }
 

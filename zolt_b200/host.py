@@ -1,0 +1,120 @@
+"""ctypes binding of the C++ host mirror (zolt_b200/host/*.hpp -> lib/libzolt_host.so).
+
+The host mirror is what sits above the C ABI on the CPU side: the Keccak transcript, the O(1) field
+glue (UniPoly, Gruen cubic, claim updates) and the per-round loop of the stage provers
+(reference src/zkvm/prover.zig:405-428).  The O(N) work is always the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .api import Context, _as_u64, _ptr
+
+_host = None
+
+
+def load_host() -> C.CDLL:
+    global _host
+    if _host is None:
+        _lib.load_library()  # libzolt_host.so links against libzolt_gpu.so
+        if not _lib.HOST_LIB_PATH.exists():
+            raise FileNotFoundError(f"{_lib.HOST_LIB_PATH} not found: run `python -m zolt_b200.build`")
+        _host = C.CDLL(str(_lib.HOST_LIB_PATH))
+        _host.zolt_host_transcript_new.restype = C.c_void_p
+        _host.zolt_host_transcript_new.argtypes = [C.c_char_p, C.c_size_t]
+        _host.zolt_host_transcript_free.argtypes = [C.c_void_p]
+        _host.zolt_host_transcript_append_bytes.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        _host.zolt_host_transcript_append_scalar.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
+        _host.zolt_host_transcript_challenge_scalar.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
+        _host.zolt_host_fr_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        _host.zolt_host_evals_to_compressed.argtypes = [C.c_void_p, C.c_void_p]
+        _host.zolt_host_cubic_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _host.zolt_host_sumcheck_prove.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                                   C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _host.zolt_host_sumcheck_prove_gruen.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                                         C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p]
+        _host.zolt_host_hyperkzg_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    return _host
+
+
+class Transcript:
+    """Keccak Transcript(F) (reference src/transcripts/mod.zig:49-221), host side."""
+
+    def __init__(self, domain: bytes):
+        self.h = load_host().zolt_host_transcript_new(domain, len(domain))
+
+    def append_bytes(self, data: bytes):
+        load_host().zolt_host_transcript_append_bytes(self.h, data, len(data))
+
+    def append_scalar(self, label: bytes, scalar):
+        s = _as_u64(scalar, 4)
+        load_host().zolt_host_transcript_append_scalar(self.h, label, len(label), _ptr(s))
+
+    def challenge_scalar(self, label: bytes) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        load_host().zolt_host_transcript_challenge_scalar(self.h, label, len(label), _ptr(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) and _host is not None:
+            _host.zolt_host_transcript_free(self.h)
+            self.h = None
+
+
+def fr_op(op: int, a, b=None) -> np.ndarray:
+    a = _as_u64(a, 4)
+    bb = _as_u64(b, 4) if b is not None else None
+    out = np.zeros_like(a)
+    load_host().zolt_host_fr_op(op, _ptr(a), _ptr(bb), _ptr(out), a.shape[0])
+    return out
+
+
+def evals_to_compressed(evals) -> np.ndarray:
+    e = _as_u64(evals, 4)
+    out = np.zeros((3, 4), dtype=np.uint64)
+    load_host().zolt_host_evals_to_compressed(_ptr(e), _ptr(out))
+    return out
+
+
+def cubic_eval(evals, x) -> np.ndarray:
+    e, xx = _as_u64(evals, 4), _as_u64(x, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    load_host().zolt_host_cubic_eval(_ptr(e), _ptr(xx), _ptr(out))
+    return out
+
+
+def sumcheck_prove(ctx: Context, combiner: int, pairing: int, tables, n_extra: int = 0, domain: bytes = b"bench",
+                   label: bytes = b"round"):
+    """Whole dense sumcheck from HOST tables: upload, then per round GPU evals -> Keccak -> GPU fused
+    bind+evals.  Returns (evals (rounds,4,4), challenges (rounds,4), final table values (k,4))."""
+    tabs = [_as_u64(t, 4) for t in tables]
+    n = tabs[0].shape[0]
+    log_n = n.bit_length() - 1
+    arr = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+    evals = np.zeros((log_n, 4, 4), dtype=np.uint64)
+    chal = np.zeros((log_n, 4), dtype=np.uint64)
+    final = np.zeros((len(tabs), 4), dtype=np.uint64)
+    st = load_host().zolt_host_sumcheck_prove(ctx.handle, combiner, pairing, log_n, len(tabs), n_extra, arr, domain, len(domain),
+                                              label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
+    _lib.check(st, "zolt_host_sumcheck_prove")
+    return evals, chal, final
+
+
+def sumcheck_prove_gruen(ctx: Context, tables, tau, claim, with_c: bool = False, domain: bytes = b"bench",
+                         label: bytes = b"round"):
+    tabs = [_as_u64(t, 4) for t in tables]
+    n = tabs[0].shape[0]
+    log_n = n.bit_length() - 1
+    arr = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+    t, cl = _as_u64(tau, 4), _as_u64(claim, 4)
+    evals = np.zeros((log_n, 4, 4), dtype=np.uint64)
+    chal = np.zeros((log_n, 4), dtype=np.uint64)
+    final_claim = np.zeros(4, dtype=np.uint64)
+    st = load_host().zolt_host_sumcheck_prove_gruen(ctx.handle, int(with_c), log_n, len(tabs), arr, _ptr(t), _ptr(cl), domain,
+                                                    len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final_claim))
+    _lib.check(st, "zolt_host_sumcheck_prove_gruen")
+    return evals, chal, final_claim

@@ -1,0 +1,100 @@
+// C exports of the C++ host mirror (zolt_host.hpp) so the Python harness (tests/, bench.py) can drive
+// the same host code a Zig/C++ caller would: the Keccak transcript round loop around the GPU kernels.
+#include "zolt_host.hpp"
+
+using namespace zolt::host;
+
+extern "C" {
+
+// ---- transcript ------------------------------------------------------------------------------------
+void* zolt_host_transcript_new(const char* domain, size_t n) { return new Transcript(std::string_view(domain, n)); }
+void zolt_host_transcript_free(void* t) { delete static_cast<Transcript*>(t); }
+void zolt_host_transcript_append_bytes(void* t, const void* data, size_t n) { static_cast<Transcript*>(t)->appendBytes(data, n); }
+void zolt_host_transcript_append_scalar(void* t, const char* label, size_t ln, const uint64_t* scalar) {
+  static_cast<Transcript*>(t)->appendScalar(std::string_view(label, ln), Fr::fromRaw(scalar));
+}
+void zolt_host_transcript_challenge_scalar(void* t, const char* label, size_t ln, uint64_t* out) {
+  static_cast<Transcript*>(t)->challengeScalar(std::string_view(label, ln)).store(out);
+}
+
+// ---- host field glue (parity hook for fr_host.hpp) -----------------------------------------------------
+// op: 0 mul, 1 add, 2 sub, 3 inverse, 4 fromBytes (a = raw 256-bit LE), 5 toBytes, 6 neg
+void zolt_host_fr_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fr x = Fr::fromRaw(a + 4 * i), y = b ? Fr::fromRaw(b + 4 * i) : Fr::zero(), r;
+    switch (op) {
+      case 0: r = x.mul(y); break;
+      case 1: r = x.add(y); break;
+      case 2: r = x.sub(y); break;
+      case 3: r = x.isZero() ? x : x.inverse(); break;
+      case 4: r = Fr::fromBytes(reinterpret_cast<const uint8_t*>(a + 4 * i)); break;
+      case 5: x.toBytes(reinterpret_cast<uint8_t*>(out + 4 * i)); continue;
+      default: r = x.neg(); break;
+    }
+    r.store(out + 4 * i);
+  }
+}
+void zolt_host_evals_to_compressed(const uint64_t* evals, uint64_t* out3) {
+  auto c = UniPoly::evalsToCompressed({Fr::fromRaw(evals), Fr::fromRaw(evals + 4), Fr::fromRaw(evals + 8), Fr::fromRaw(evals + 12)});
+  for (int i = 0; i < 3; i++) c[i].store(out3 + 4 * i);
+}
+void zolt_host_cubic_eval(const uint64_t* evals, const uint64_t* x, uint64_t* out) {
+  evaluateCubicAtPoint({Fr::fromRaw(evals), Fr::fromRaw(evals + 4), Fr::fromRaw(evals + 8), Fr::fromRaw(evals + 12)}, Fr::fromRaw(x)).store(out);
+}
+
+// ---- round loops ------------------------------------------------------------------------------------------
+static void store_proof(const SumcheckProof& proof, uint64_t* evals_out, uint64_t* challenges_out) {
+  for (size_t r = 0; r < proof.round_polys.size(); r++) {
+    for (int j = 0; j < 4; j++) proof.round_polys[r][j].store(evals_out + 16 * r + 4 * j);
+    proof.challenges[r].store(challenges_out + 4 * r);
+  }
+}
+
+// Dense sumcheck over host tables with the Keccak transcript: upload, then per round
+// {GPU evals -> absorb -> squeeze -> fused GPU bind+evals}.  final_out: n_tables elements.
+int zolt_host_sumcheck_prove(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
+                             const uint64_t* const* tables, const char* domain, size_t dn, const char* label, size_t ln,
+                             uint64_t* evals_out, uint64_t* challenges_out, uint64_t* final_out) {
+  Context c(ctx);
+  std::vector<const uint64_t*> tabs(tables, tables + n_tables);
+  DenseSumcheckProver prover(c, combiner, pairing, tabs, log_n, n_extra);
+  Transcript tr(std::string_view(domain, dn));
+  SumcheckProof proof = proveSumcheck(prover, tr, std::string_view(label, ln));
+  store_proof(proof, evals_out, challenges_out);
+  if (final_out)
+    for (int t = 0; t < n_tables; t++) prover.table(t)[0].store(final_out + 4 * t);
+  return ZOLT_OK;
+}
+
+// Gruen split-eq degree-3 sumcheck (ProductVirtualRemainderProver shape); claim = initial claim.
+int zolt_host_sumcheck_prove_gruen(zolt_ctx* ctx, int with_c, int log_n, int n_tables, const uint64_t* const* tables,
+                                   const uint64_t* tau, const uint64_t* claim, const char* domain, size_t dn,
+                                   const char* label, size_t ln, uint64_t* evals_out, uint64_t* challenges_out,
+                                   uint64_t* final_claim_out) {
+  Context c(ctx);
+  std::vector<const uint64_t*> tabs(tables, tables + n_tables);
+  std::vector<Fr> tv(log_n);
+  for (int i = 0; i < log_n; i++) tv[i] = Fr::fromRaw(tau + 4 * i);
+  GruenProductProver prover(c, tabs, log_n, tv, Fr::fromRaw(claim), with_c != 0);
+  Transcript tr(std::string_view(domain, dn));
+  SumcheckProof proof = proveSumcheck(prover, tr, std::string_view(label, ln));
+  store_proof(proof, evals_out, challenges_out);
+  if (final_claim_out) prover.current_claim.store(final_claim_out);
+  return ZOLT_OK;
+}
+
+// HyperKZG.commit through the mirror (params = device bases handle)
+int zolt_host_hyperkzg_commit(zolt_ctx* ctx, zolt_bases* params, const uint64_t* evals, size_t n, uint64_t* out_xy,
+                              uint8_t* out_inf) {
+  size_t len = 0;
+  must(zolt_msm_bases_len(params, &len), "zolt_msm_bases_len");
+  const size_t m = n < len ? n : len;
+  if (m == 0) {
+    std::memset(out_xy, 0, 64);
+    *out_inf = 1;
+    return ZOLT_OK;
+  }
+  return zolt_msm(ctx, params, 0, evals, m, out_xy, out_inf);
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// C++ host mirror of the reference's interfaces for the hot path, above the C ABI (include/zolt_gpu.h).
+//
+// The reference is Zig; no Zig toolchain exists in this image, so the host side that a
+// `zig/zolt_gpu.zig` shim would provide is written in C++ with the reference's names, argument
+// meaning and error behaviour (INTEGRATION.md shows the Zig binding).  Paths are relative to
+// /root/reference:
+//   AffinePoint / MSM.compute            src/msm/mod.zig:15-140, :355-372   (infallible: panics on error)
+//   HyperKZG.setup / commit / batchCommit src/poly/commitment/mod.zig:174-255, :558-570
+//   DensePolynomial bindLow / bindFirst  src/poly/mod.zig:128-175
+//   EqPolynomial.evals                   src/poly/mod.zig:240-290
+//   UniPoly interpolateDegree3 / ...     src/poly/mod.zig:608-685
+//   GruenSplitEqPolynomial               src/poly/split_eq.zig:63-434 (scalar state + cubic on host,
+//                                        E tables and the O(N) sums on the device)
+//   SumcheckInstance                     src/zkvm/batched_sumcheck.zig:34-74
+//   stage round loop with transcript     src/zkvm/prover.zig:405-428
+// Everything O(N) is a CUDA kernel; the host keeps only O(1)-per-round field glue and Keccak.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/zolt_gpu.h"
+#include "fr_host.hpp"
+#include "transcript.hpp"
+
+namespace zolt::host {
+
+// MSM.compute / HyperKZG.commit have no error channel in the reference (no error union): a failing
+// device call is a panic, exactly what the Zig shim does with @panic.
+[[noreturn]] inline void panic(const char* what, int status) {
+  std::fprintf(stderr, "zolt_gpu panic: %s failed with status %d (no CPU fallback)\n", what, status);
+  std::abort();
+}
+inline void must(int status, const char* what) {
+  if (status != ZOLT_OK) panic(what, status);
+}
+
+class Context {
+ public:
+  explicit Context(int device = 0, void* stream = nullptr) { must(zolt_gpu_init(device, stream, &ctx_), "zolt_gpu_init"); }
+  explicit Context(zolt_ctx* borrowed) : ctx_(borrowed), owned_(false) {}
+  ~Context() {
+    if (owned_) zolt_gpu_shutdown(ctx_);
+  }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  zolt_ctx* raw() const { return ctx_; }
+
+ private:
+  zolt_ctx* ctx_ = nullptr;
+  bool owned_ = true;
+};
+
+// AffinePoint(Fq): x, y in Montgomery form + infinity flag; identity = (0, 0, true) (msm/mod.zig:24-30)
+struct AffinePoint {
+  uint64_t x[4] = {0, 0, 0, 0};
+  uint64_t y[4] = {0, 0, 0, 0};
+  bool infinity = true;
+  static AffinePoint identity() { return AffinePoint{}; }
+  bool eql(const AffinePoint& o) const {
+    if (infinity || o.infinity) return infinity == o.infinity;
+    return std::memcmp(x, o.x, 32) == 0 && std::memcmp(y, o.y, 32) == 0;
+  }
+};
+
+// Device-resident bases: SetupParams.powers_of_tau_g1 uploaded once (commitment/mod.zig:122-140).
+class DeviceBases {
+ public:
+  DeviceBases(Context& ctx, const std::vector<AffinePoint>& pts) : ctx_(ctx) {
+    std::vector<uint64_t> xy(pts.size() * 8);
+    std::vector<uint8_t> inf(pts.size());
+    for (size_t i = 0; i < pts.size(); i++) {
+      std::memcpy(&xy[8 * i], pts[i].x, 32);
+      std::memcpy(&xy[8 * i + 4], pts[i].y, 32);
+      inf[i] = pts[i].infinity ? 1 : 0;
+    }
+    must(zolt_msm_bases_upload(ctx.raw(), xy.data(), inf.data(), pts.size(), &h_), "zolt_msm_bases_upload");
+  }
+  DeviceBases(Context& ctx, zolt_bases* h) : ctx_(ctx), h_(h) {}
+  ~DeviceBases() { zolt_msm_bases_free(h_); }
+  DeviceBases(const DeviceBases&) = delete;
+  size_t len() const {
+    size_t n = 0;
+    must(zolt_msm_bases_len(h_, &n), "zolt_msm_bases_len");
+    return n;
+  }
+  zolt_bases* raw() const { return h_; }
+  Context& ctx() const { return ctx_; }
+
+ private:
+  Context& ctx_;
+  zolt_bases* h_ = nullptr;
+};
+
+// msm.MSM(F, Fp)
+struct MSM {
+  // compute(bases, scalars): sum_i scalars[i] * bases[i]; lengths must match (assert, msm/mod.zig:359)
+  static AffinePoint compute(const DeviceBases& bases, const std::vector<Fr>& scalars, size_t offset = 0) {
+    AffinePoint out;
+    uint64_t xy[8];
+    uint8_t inf = 0;
+    must(zolt_msm(bases.ctx().raw(), bases.raw(), offset, reinterpret_cast<const uint64_t*>(scalars.data()),
+                  scalars.size(), xy, &inf),
+         "zolt_msm");
+    std::memcpy(out.x, xy, 32);
+    std::memcpy(out.y, xy + 4, 32);
+    out.infinity = inf != 0;
+    return out;
+  }
+};
+
+// HyperKZG(F): commit path only (open/verify are outside this tier)
+struct HyperKZG {
+  struct SetupParams {
+    std::unique_ptr<DeviceBases> powers_of_tau_g1;
+  };
+  // setup(max_degree): mock SRS tau = 0x12345678, powers[i] = tau^i * G, generated on the device
+  static SetupParams setup(Context& ctx, size_t max_degree) {
+    zolt_bases* h = nullptr;
+    must(zolt_hyperkzg_setup(ctx.raw(), max_degree, &h), "zolt_hyperkzg_setup");
+    SetupParams p;
+    p.powers_of_tau_g1 = std::make_unique<DeviceBases>(ctx, h);
+    return p;
+  }
+  // commit(params, evals): n = min(len(evals), len(powers)); empty -> identity (commitment/mod.zig:239-255)
+  static AffinePoint commit(const SetupParams& params, const std::vector<Fr>& evals) {
+    const size_t n = std::min(evals.size(), params.powers_of_tau_g1->len());
+    if (n == 0) return AffinePoint::identity();
+    std::vector<Fr> head(evals.begin(), evals.begin() + n);
+    return MSM::compute(*params.powers_of_tau_g1, head);
+  }
+  static std::vector<AffinePoint> batchCommit(const SetupParams& params, const std::vector<std::vector<Fr>>& polys) {
+    std::vector<AffinePoint> out;
+    for (const auto& p : polys) out.push_back(commit(params, p));
+    return out;
+  }
+};
+
+// UniPoly(F) helpers used around the round loop (src/poly/mod.zig:608-685)
+struct UniPoly {
+  static Fr evaluate(const std::vector<Fr>& coeffs, const Fr& x) {
+    Fr acc = Fr::zero();
+    for (size_t i = coeffs.size(); i-- > 0;) acc = acc.mul(x).add(coeffs[i]);
+    return acc;
+  }
+  static std::array<Fr, 4> interpolateDegree3(const std::array<Fr, 4>& e) {
+    const Fr inv6 = Fr::fromU64(6).inverse(), inv2 = Fr::fromU64(2).inverse();
+    auto k = [](uint64_t v) { return Fr::fromU64(v); };
+    Fr c1 = Fr::zero().sub(k(11).mul(e[0])).add(k(18).mul(e[1])).sub(k(9).mul(e[2])).add(k(2).mul(e[3])).mul(inv6);
+    Fr c2 = k(2).mul(e[0]).sub(k(5).mul(e[1])).add(k(4).mul(e[2])).sub(e[3]).mul(inv2);
+    Fr c3 = Fr::zero().sub(e[0]).add(k(3).mul(e[1])).sub(k(3).mul(e[2])).add(e[3]).mul(inv6);
+    return {e[0], c1, c2, c3};
+  }
+  static std::array<Fr, 3> evalsToCompressed(const std::array<Fr, 4>& e) {
+    auto c = interpolateDegree3(e);
+    return {c[0], c[2], c[3]};
+  }
+};
+
+// evaluateCubicAtPointGeneric (src/zkvm/batched_sumcheck.zig:437-457)
+inline Fr evaluateCubicAtPoint(const std::array<Fr, 4>& e, const Fr& x) {
+  const Fr one = Fr::one(), two = Fr::fromU64(2), three = Fr::fromU64(3), six = Fr::fromU64(6);
+  const Fr x1 = x.sub(one), x2 = x.sub(two), x3 = x.sub(three);
+  const Fr L0 = x1.mul(x2).mul(x3).mul(six.neg().inverse());
+  const Fr L1 = x.mul(x2).mul(x3).mul(two.inverse());
+  const Fr L2 = x.mul(x1).mul(x3).mul(two.neg().inverse());
+  const Fr L3 = x.mul(x1).mul(x2).mul(six.inverse());
+  return e[0].mul(L0).add(e[1].mul(L1)).add(e[2].mul(L2)).add(e[3].mul(L3));
+}
+
+// DensePolynomial(F) with the evaluation table on the device
+class DensePolynomial {
+ public:
+  DensePolynomial(Context& ctx, const std::vector<Fr>& evaluations) : ctx_(ctx), len_(evaluations.size()) {
+    if (len_ == 0 || (len_ & (len_ - 1))) panic("DensePolynomial.init: length must be a power of two", ZOLT_ERR_ARG);
+    must(zolt_dev_alloc(ctx.raw(), len_ * 32, &d_), "zolt_dev_alloc");
+    must(zolt_dev_upload(ctx.raw(), d_, evaluations.data(), len_ * 32), "zolt_dev_upload");
+  }
+  ~DensePolynomial() { zolt_dev_free(ctx_.raw(), d_); }
+  DensePolynomial(const DensePolynomial&) = delete;
+  size_t boundLen() const { return len_; }
+  size_t numVars() const {
+    size_t v = 0;
+    while ((size_t(1) << v) < len_) v++;
+    return v;
+  }
+  void bindLow(const Fr& r) {  // in place, src/poly/mod.zig:160-175
+    must(zolt_poly_bind_low(ctx_.raw(), d_, d_, len_, r.limbs.data()), "zolt_poly_bind_low");
+    len_ /= 2;
+  }
+  void bindFirst(const Fr& r) {  // src/poly/mod.zig:128-149 (the table is reused instead of reallocated)
+    must(zolt_poly_bind_first(ctx_.raw(), d_, d_, len_, r.limbs.data()), "zolt_poly_bind_first");
+    len_ /= 2;
+  }
+  Fr sum() const {
+    Fr out;
+    must(zolt_poly_sum(ctx_.raw(), d_, len_, out.limbs.data()), "zolt_poly_sum");
+    return out;
+  }
+  std::vector<Fr> evaluations() const {
+    std::vector<Fr> out(len_);
+    must(zolt_dev_download(ctx_.raw(), out.data(), d_, len_ * 32), "zolt_dev_download");
+    return out;
+  }
+  const void* devicePtr() const { return d_; }
+
+ private:
+  Context& ctx_;
+  size_t len_;
+  void* d_ = nullptr;
+};
+
+struct EqPolynomial {
+  // evals(): big-endian table eq(r, .) (src/poly/mod.zig:240-290), computed on the device
+  static std::vector<Fr> evals(Context& ctx, const std::vector<Fr>& r, const Fr* scale = nullptr) {
+    const size_t n = size_t(1) << r.size();
+    void* d = nullptr;
+    must(zolt_dev_alloc(ctx.raw(), n * 32, &d), "zolt_dev_alloc");
+    must(zolt_eq_evals(ctx.raw(), reinterpret_cast<const uint64_t*>(r.data()), (int)r.size(),
+                       scale ? scale->limbs.data() : nullptr, d),
+         "zolt_eq_evals");
+    std::vector<Fr> out(n);
+    must(zolt_dev_download(ctx.raw(), out.data(), d, n * 32), "zolt_dev_download");
+    zolt_dev_free(ctx.raw(), d);
+    return out;
+  }
+};
+
+// Host part of GruenSplitEqPolynomial: the running scalar, the bound-variable counter and the cubic
+// assembly (src/poly/split_eq.zig:213-248, :353-434).  The prefix tables live on the device.
+class GruenSplitEqPolynomial {
+ public:
+  explicit GruenSplitEqPolynomial(std::vector<Fr> tau, const Fr* scaling = nullptr)
+      : tau_(std::move(tau)), current_index(tau_.size()), current_scalar(scaling ? *scaling : Fr::one()) {}
+  void bind(const Fr& r) {
+    if (current_index == 0) return;
+    const Fr& t = tau_[current_index - 1];
+    const Fr eq = t.mul(r).add(Fr::one().sub(t).mul(Fr::one().sub(r)));
+    current_scalar = current_scalar.mul(eq);
+    current_index--;
+  }
+  std::array<Fr, 4> computeCubicRoundPoly(const Fr& q_constant, const Fr& q_quadratic_coeff, const Fr& previous_claim) const {
+    if (current_index == 0) return {previous_claim, Fr::zero(), Fr::zero(), Fr::zero()};
+    const Fr& t = tau_[current_index - 1];
+    const Fr eq0 = current_scalar.mul(Fr::one().sub(t)), eq1 = current_scalar.mul(t);
+    const Fr slope = eq1.sub(eq0);
+    const Fr l2 = eq0.add(slope.mul(Fr::fromU64(2))), l3 = eq0.add(slope.mul(Fr::fromU64(3)));
+    const Fr q1 = eq1.isZero() ? Fr::zero() : previous_claim.sub(eq0.mul(q_constant)).mul(eq1.inverse());
+    const Fr e2 = q_quadratic_coeff.add(q_quadratic_coeff);
+    const Fr q2 = q1.add(q1).sub(q_constant).add(e2);
+    const Fr q3 = q2.add(q1).sub(q_constant).add(e2).add(e2);
+    return {eq0.mul(q_constant), eq1.mul(q1), l2.mul(q2), l3.mul(q3)};
+  }
+  const std::vector<Fr>& tau() const { return tau_; }
+  size_t current_index;
+  Fr current_scalar;
+
+ private:
+  std::vector<Fr> tau_;
+};
+
+// SumcheckInstance (src/zkvm/batched_sumcheck.zig:34-74): evaluations at X = 0,1,2,3, strictly
+// alternating computeRoundPoly -> bindChallenge.
+class SumcheckInstance {
+ public:
+  virtual ~SumcheckInstance() = default;
+  virtual size_t numRounds() const = 0;
+  virtual size_t degree() const = 0;
+  virtual std::array<Fr, 4> computeRoundPoly(size_t round) = 0;
+  virtual void bindChallenge(const Fr& challenge) = 0;
+};
+
+// k dense tables combined by one of the ZOLT_SC_* combiners; covers ValEvaluationProver,
+// ValFinalProver, OutputSumcheckProver, JoltSpartanInterface and the config-3 Spartan shape.
+class DenseSumcheckProver : public SumcheckInstance {
+ public:
+  DenseSumcheckProver(Context& ctx, int combiner, int pairing, const std::vector<const uint64_t*>& tables, int log_n,
+                      int n_extra = 0)
+      : log_n_(log_n), combiner_(combiner) {
+    must(zolt_sc_create(ctx.raw(), combiner, pairing, log_n, (int)tables.size() - n_extra, n_extra, tables.data(), &sc_),
+         "zolt_sc_create");
+    must(zolt_sc_num_evals(sc_, &ne_), "zolt_sc_num_evals");
+  }
+  ~DenseSumcheckProver() override { zolt_sc_free(sc_); }
+  size_t numRounds() const override { return (size_t)log_n_; }
+  size_t degree() const override {
+    return combiner_ == ZOLT_SC_SUM ? 1 : (combiner_ == ZOLT_SC_PROD2 ? 2 : 3);
+  }
+  std::array<Fr, 4> computeRoundPoly(size_t) override {
+    std::array<Fr, 4> e{};
+    uint64_t buf[16] = {0};
+    must(zolt_sc_round_evals(sc_, buf), "zolt_sc_round_evals");
+    for (int i = 0; i < ne_; i++) e[i] = Fr::fromRaw(buf + 4 * i);
+    if (combiner_ == ZOLT_SC_SUM) {
+      // linear round polynomial: p(2) = 2 p(1) - p(0), p(3) = 3 p(1) - 2 p(0) (jolt_r1cs.zig:441-444)
+      const Fr d = e[1].sub(e[0]);
+      e[2] = e[1].add(d);
+      e[3] = e[2].add(d);
+    }
+    return e;
+  }
+  void bindChallenge(const Fr& r) override { must(zolt_sc_bind(sc_, r.limbs.data()), "zolt_sc_bind"); }
+  std::vector<Fr> table(int t) {
+    size_t n = 0;
+    must(zolt_sc_len(sc_, &n), "zolt_sc_len");
+    std::vector<Fr> out(n);
+    must(zolt_sc_download(sc_, t, reinterpret_cast<uint64_t*>(out.data())), "zolt_sc_download");
+    return out;
+  }
+  zolt_sc* raw() const { return sc_; }
+
+ private:
+  zolt_sc* sc_ = nullptr;
+  int log_n_, combiner_, ne_ = 0;
+};
+
+// ProductVirtualRemainderProver / StreamingOuterProver linear phase
+// (src/zkvm/spartan/product_remainder.zig:269-378): Gruen split-eq degree 3.
+class GruenProductProver : public SumcheckInstance {
+ public:
+  GruenProductProver(Context& ctx, const std::vector<const uint64_t*>& tables, int log_n, const std::vector<Fr>& tau,
+                     const Fr& initial_claim, bool with_c = false)
+      : log_n_(log_n), split_eq_(tau), current_claim(initial_claim) {
+    must(zolt_sc_create(ctx.raw(), with_c ? ZOLT_SC_GRUEN_AB_MINUS_C : ZOLT_SC_GRUEN_AB, ZOLT_PAIR_ADJACENT, log_n,
+                        (int)tables.size(), 0, tables.data(), &sc_),
+         "zolt_sc_create");
+    must(zolt_sc_set_split_eq(sc_, reinterpret_cast<const uint64_t*>(tau.data()), (int)tau.size()), "zolt_sc_set_split_eq");
+  }
+  ~GruenProductProver() override { zolt_sc_free(sc_); }
+  size_t numRounds() const override { return (size_t)log_n_; }
+  size_t degree() const override { return 3; }
+  std::array<Fr, 4> computeRoundPoly(size_t) override {
+    uint64_t buf[8];
+    must(zolt_sc_round_evals(sc_, buf), "zolt_sc_round_evals");
+    last_ = split_eq_.computeCubicRoundPoly(Fr::fromRaw(buf), Fr::fromRaw(buf + 4), current_claim);
+    return last_;
+  }
+  void bindChallenge(const Fr& r) override {
+    current_claim = evaluateCubicAtPoint(last_, r);  // updateClaim (product_remainder.zig:381-384)
+    must(zolt_sc_bind(sc_, r.limbs.data()), "zolt_sc_bind");
+    split_eq_.bind(r);
+  }
+  zolt_sc* raw() const { return sc_; }
+  Fr current_claim;
+
+ private:
+  zolt_sc* sc_ = nullptr;
+  int log_n_;
+  GruenSplitEqPolynomial split_eq_;
+  std::array<Fr, 4> last_{};
+};
+
+struct SumcheckProof {
+  std::vector<std::array<Fr, 4>> round_polys;  // evaluations at 0..3
+  std::vector<Fr> challenges;
+};
+
+// The stage loop of MultiStageProver (src/zkvm/prover.zig:405-428): per round absorb the first
+// degree+1 evaluations as "round_poly_j", squeeze `challenge_label`, bind.
+inline SumcheckProof proveSumcheck(SumcheckInstance& inst, Transcript& transcript, std::string_view challenge_label) {
+  SumcheckProof proof;
+  const size_t n_absorb = inst.degree() + 1;
+  for (size_t round = 0; round < inst.numRounds(); round++) {
+    const auto evals = inst.computeRoundPoly(round);
+    for (size_t j = 0; j < n_absorb; j++) {
+      char label[24];
+      const int ln = std::snprintf(label, sizeof label, "round_poly_%zu", j);
+      transcript.appendScalar(std::string_view(label, (size_t)ln), evals[j]);
+    }
+    const Fr r = transcript.challengeScalar(challenge_label);
+    inst.bindChallenge(r);
+    proof.round_polys.push_back(evals);
+    proof.challenges.push_back(r);
+  }
+  return proof;
+}
+
+}  // namespace zolt::host
