@@ -231,6 +231,8 @@ struct EqPolynomial {
 // Host part of GruenSplitEqPolynomial: the running scalar, the bound-variable counter and the cubic
 // assembly (src/poly/split_eq.zig:213-248, :353-434).  The prefix tables live on the device.
 class GruenSplitEqPolynomial {
+  std::vector<Fr> tau_;  // declared first: current_index is initialised from it
+
  public:
   explicit GruenSplitEqPolynomial(std::vector<Fr> tau, const Fr* scaling = nullptr)
       : tau_(std::move(tau)), current_index(tau_.size()), current_scalar(scaling ? *scaling : Fr::one()) {}
@@ -256,9 +258,6 @@ class GruenSplitEqPolynomial {
   const std::vector<Fr>& tau() const { return tau_; }
   size_t current_index;
   Fr current_scalar;
-
- private:
-  std::vector<Fr> tau_;
 };
 
 // SumcheckInstance (src/zkvm/batched_sumcheck.zig:34-74): evaluations at X = 0,1,2,3, strictly
