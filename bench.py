@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: "BN254 MSM ms @2^24 pts (1/2/4/8 B200); sumcheck Fr elems/s & HBM GB/s".
+
+One step = one pass of the hot path over one batch of synthetic input:
+    (a) one BN254 G1 MSM of 2^24 points (the HyperKZG commit of a 2^24-entry MLE, BASELINE config 4)
+    (b) one degree-3 Spartan-style sumcheck  sum eq*(Az*Bz - Cz)  over 2^24 entries with the host Keccak
+        transcript in the loop (BASELINE config 3)
+`value` is the MSM time in ms with inputs resident in HBM (the metric's first component, lower is
+better); the sumcheck numbers ride in the "sumcheck" object of the same JSON line.  `e2e` is the same
+MSM through the reference-facing C-ABI call with HOST (pinned) buffers, copies inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Multi-GPU (strong scaling, total work fixed): the MSM shards by point range and all-gathers one 128-byte
+partial per rank; the sumcheck shards the hypercube in contiguous blocks and all-gathers 128 bytes of
+partial evaluations per round.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "bn254_g1_msm_ms_at_2^24_points"
+IMAD_PER_POINT = 42240  # SURVEY 8d convention: 16 windows x 10 modmul x 264 int32 multiply-adds
+TAGS = {1: "digits", 2: "scan", 3: "scatter", 4: "accum0", 5: "edges", 6: "reduce", 7: "affine", 16: "sc_eval", 17: "sc_fused"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------
+def rand_mont(rng: np.random.Generator, n: int, out: np.ndarray | None = None) -> np.ndarray:
+    """n canonical field elements as Montgomery limbs: uniform below 2^252 < r (synthetic data)."""
+    a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    if out is not None:
+        out[:] = a
+        return out
+    return a
+
+
+def pinned_u64(n_rows: int, cols: int = 4) -> np.ndarray:
+    import torch
+
+    t = torch.empty((n_rows, cols), dtype=torch.int64, pin_memory=True)
+    return t.numpy().view(np.uint64)  # the numpy view keeps the pinned tensor alive
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(key: str):
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(key)
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithms (C++ restatement, oracle/cpu_ref.cpp) on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_msm_sample(log_sample: int, threads: int, seed: int = 7):
+    """Time MSM.compute / ParallelMSM.compute (reference src/msm/mod.zig:355-438, :588-653) on 2^log_sample
+    points (bases generated by the same CPU code, untimed)."""
+    from oracle import cpu_ref as R  # the one place bench.py may execute oracle/: the CPU baseline
+
+    rng = np.random.default_rng(seed)
+    n = 1 << log_sample
+    xy, inf = R.g1_multiples(n)  # bases (i+1)*G as in src/bench.zig:251-262; scalars uniform
+    scalars = rand_mont(rng, n)
+    t0 = time.perf_counter()
+    R.msm(xy, inf, scalars, threads=threads)
+    return (time.perf_counter() - t0) * 1e3
+
+
+def cpu_sumcheck_sample(log_sample: int, seed: int = 9):
+    from oracle import cpu_ref as R
+
+    rng = np.random.default_rng(seed)
+    tabs = [rand_mont(rng, 1 << log_sample) for _ in range(4)]
+    t0 = time.perf_counter()
+    R.sc_prove("eq_ab_minus_c", 0, tabs)
+    return (time.perf_counter() - t0) * 1e3
+
+
+def pick_cpu_sample(threads: int, budget_s: float = 12.0, lo: int = 14, hi: int = 20) -> tuple[int, float]:
+    """Largest 2^s whose MSM fits the time budget, probing upward (the algorithm is linear in n)."""
+    s = lo
+    ms = cpu_msm_sample(s, threads)
+    while s < hi and ms * 2.2 / 1e3 < budget_s:
+        s += 1
+        ms = cpu_msm_sample(s, threads)
+    return s, ms
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the reference is a single-process CPU program; other ranks exit 0 without work
+    cores = os.cpu_count() or 1
+    threads = min(8, cores)  # detectOptimalThreads caps at 8 (src/msm/mod.zig:673-678)
+    log_n = args.log_n
+    s, _ = pick_cpu_sample(threads, budget_s=max(4.0, 40.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_msm_sample(s, threads)
+    t0 = time.perf_counter()
+    times = [cpu_msm_sample(s, threads) for _ in range(args.steps)]
+    wall = (time.perf_counter() - t0) * 1e3
+    scale = float(1 << (log_n - s))
+    value = statistics.mean(times) * scale
+    sc_log = min(args.sc_log_n, 20)
+    sc_ms = cpu_sumcheck_sample(sc_log)
+    sc_scale = float(1 << (args.sc_log_n - sc_log))
+    sample = (f"MSM: 2^{s} points timed with ParallelMSM.compute semantics on {threads} threads, linearly extrapolated x{scale:.0f} to 2^{log_n}; "
+              f"sumcheck: 2^{sc_log} entries single-threaded (the reference has no threaded sumcheck), extrapolated x{sc_scale:.0f}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall / max(1, args.steps), "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
+        "config": {"workload": f"BN254 G1 MSM 2^{log_n} points + degree-3 sumcheck eq*(Az*Bz-Cz) 2^{args.sc_log_n} entries (BASELINE configs 4 and 3)",
+                   "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "ms", "cores": threads, "kind": "port", "sample": sample,
+                         "sumcheck_ms_extrapolated": sc_ms * sc_scale, "host_cores_available": cores},
+        "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sumcheck": {"ms": sc_ms * sc_scale, "fr_elems_per_s": 4 * (1 << args.sc_log_n) / (sc_ms * sc_scale * 1e-3)},
+        "gpu_launches": 0,
+        "note": "reference cannot be compiled here (no zig toolchain): timed arm is the C++ restatement of its CPU algorithms (oracle/cpu_ref.cpp)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import zolt_b200 as Z
+    from zolt_b200 import host as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    ctx = Z.Context(local_rank, stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    log_n, sc_log_n = args.log_n, args.sc_log_n
+    shift = (world - 1).bit_length()
+    if (1 << shift) != world:
+        raise SystemExit("world size must be a power of two")
+    n_local = 1 << (log_n - shift)
+    sc_local_log = sc_log_n - shift
+    K_TABLES = 4
+    rng = np.random.default_rng(0x5A170000 + rank)
+
+    # ---- setup (untimed): bases k_i*G generated on the device, host inputs in pinned memory -------------
+    bases = Z.Bases.fixed_base_mul(ctx, rand_mont(rng, n_local))
+    h_scalars = rand_mont(rng, n_local, pinned_u64(n_local))
+    d_scalars = Z.DeviceBuffer.from_host(ctx, h_scalars)
+    h_tabs = [rand_mont(rng, 1 << sc_local_log, pinned_u64(1 << sc_local_log)) for _ in range(K_TABLES)]
+    d_tabs = [Z.DeviceBuffer.from_host(ctx, t) for t in h_tabs]
+    d_tab_ptrs = [b.ptr for b in d_tabs]
+    part = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    gathered = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
+    ev_part = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    ev_gath = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
+
+    def msm_resident():
+        if world == 1:
+            return Z.MSM.compute_dev(bases, d_scalars.ptr, n_local)
+        with torch.cuda.stream(stream):
+            Z.MSM.partial_dev(bases, d_scalars.ptr, n_local, part.data_ptr())
+            dist.all_gather_into_tensor(gathered, part)
+            return Z.MSM.sum_partials(ctx, gathered.data_ptr(), world)
+
+    def sumcheck_resident():
+        if world == 1:
+            return H.sumcheck_prove_dev(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, d_tab_ptrs, sc_local_log)
+        from zolt_b200 import dist as ZD
+
+        return ZD.sharded_sumcheck_gpu(ctx, stream, Z.SC_EQ_AB_MINUS_C, d_tab_ptrs, sc_local_log, world, ev_part, ev_gath)
+
+    def msm_e2e():
+        if world == 1:
+            return Z.MSM.compute(bases, h_scalars)
+        with torch.cuda.stream(stream):
+            d_scalars.upload(h_scalars)
+            Z.MSM.partial_dev(bases, d_scalars.ptr, n_local, part.data_ptr())
+            dist.all_gather_into_tensor(gathered, part)
+            return Z.MSM.sum_partials(ctx, gathered.data_ptr(), world)
+
+    def sumcheck_e2e():
+        if world == 1:
+            return H.sumcheck_prove(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, h_tabs)
+        for b, t in zip(d_tabs, h_tabs):
+            b.upload(t)
+        return sumcheck_resident()
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    # ---- warm-up -----------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 1)):
+        r_msm = msm_resident()
+        sumcheck_resident()
+    if args.warmup:
+        msm_e2e()
+        sumcheck_e2e()
+    int_peak = ctx.bench_int_pipe(0, 4000) if rank == 0 else 0.0  # IMAD/s, measured live (untimed region)
+
+    # ---- timed loop 1: inputs resident in HBM --------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ctx.prof_enable(True)
+    msm_ms, sc_ms, phase_log = [], [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a = ev()
+        r_msm = msm_resident()
+        b = ev()
+        sumcheck_resident()
+        c = ev()
+        c.synchronize()
+        msm_ms.append(a.elapsed_time(b))
+        sc_ms.append(b.elapsed_time(c))
+        phase_log.append(ctx.prof_read())
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ctx.prof_enable(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed loop 2: end to end through the C ABI with host buffers -------------------------------------------
+    barrier()
+    e2e_msm, e2e_sc = [], []
+    for _ in range(args.steps):
+        a = ev()
+        msm_e2e()
+        b = ev()
+        sumcheck_e2e()
+        c = ev()
+        c.synchronize()
+        e2e_msm.append(a.elapsed_time(b))
+        e2e_sc.append(b.elapsed_time(c))
+    barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    v_msm = max_over_ranks(statistics.mean(msm_ms))
+    v_sc = max_over_ranks(statistics.mean(sc_ms))
+    v_wall = max_over_ranks(wall_ms)
+    v_e2e_msm = max_over_ranks(statistics.mean(e2e_msm))
+    v_e2e_sc = max_over_ranks(statistics.mean(e2e_sc))
+
+    if rank == 0:
+        # per-kernel device times (CUDA events inside the library, on the launching stream)
+        acc = {}
+        for log in phase_log:
+            for tag, ms in log:
+                acc.setdefault(TAGS.get(tag, str(tag)), []).append(ms)
+        steps = max(1, len(phase_log))
+        phase_ms = {k: sum(v) / steps for k, v in acc.items()}
+        accum_ms = phase_ms.get("accum0", float("nan"))
+        sc_kernel_ms = phase_ms.get("sc_eval", 0.0) + phase_ms.get("sc_fused", 0.0)
+        hbm_peak, peak_src = measured_peaks()
+        achieved_imad = IMAD_PER_POINT * n_local / (accum_ms * 1e-3) / 1e12
+        sc_bytes = 128 * K_TABLES * (1 << sc_local_log)
+        sc_gbs = sc_bytes / (sc_kernel_ms * 1e-3) / 1e9 if sc_kernel_ms else float("nan")
+        n_sc = 1 << sc_log_n
+        line = {
+            "metric": METRIC, "value": v_msm, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": v_wall / args.steps, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
+            "config": {
+                "workload": f"BN254 G1 MSM 2^{log_n} points (HyperKZG commit shape) + degree-3 sumcheck eq*(Az*Bz-Cz) over 2^{sc_log_n} entries with host Keccak transcript (BASELINE configs 4 and 3)",
+                "sharding": "MSM by point range, sumcheck by contiguous hypercube blocks" if world > 1 else "single GPU",
+                "l2": "inputs (1.5 GiB MSM, 2 GiB sumcheck) exceed the 126 MB L2; no flush needed",
+                "window_bits": 16 if n_local >= (1 << 22) else None,
+            },
+            "roofline": {
+                "kernel": "msm_accum_points_kernel (bucket accumulation, mixed additions)", "bound": "int32",
+                "achieved": achieved_imad, "peak": int_peak / 1e12, "unit": "TIMAD/s", "frac": achieved_imad / (int_peak / 1e12) if int_peak else None,
+                "peak_source": "IMAD micro-benchmark run live in this process (zolt_bench_int_pipe kind 0)",
+                "work_per_launch": f"{IMAD_PER_POINT} IMAD/point x {n_local} points (SURVEY 8d convention)",
+                "kernel_ms": accum_ms, "traffic": ncu_traffic("msm_accum_points_kernel"),
+            },
+            "roofline_sumcheck": {
+                "kernel": "sc_round_kernel (round-0 eval + fused bind/eval rounds, all launches of one sumcheck)", "bound": "hbm",
+                "achieved": sc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sc_gbs / hbm_peak, "peak_source": peak_src,
+                "frac_of_8000_spec": sc_gbs / 8000.0, "bytes_per_sumcheck": sc_bytes, "kernel_ms": sc_kernel_ms,
+                "traffic": ncu_traffic("sc_round_kernel"),
+            },
+            "sumcheck": {
+                "ms": v_sc, "kernel_ms": sc_kernel_ms, "fr_elems_per_s": K_TABLES * n_sc / (v_sc * 1e-3), "hbm_gbs_wall": 128 * K_TABLES * n_sc / (v_sc * 1e-3) / 1e9,
+                "e2e_ms": v_e2e_sc, "e2e_fr_elems_per_s": K_TABLES * n_sc / (v_e2e_sc * 1e-3),
+            },
+            "msm_phases_ms": {k: round(v, 4) for k, v in phase_ms.items() if not k.startswith("sc_")},
+            "e2e": {"value": v_e2e_msm, "unit": "ms", "h2d_bytes_per_step": int(n_local * 32 + K_TABLES * (1 << sc_local_log) * 32),
+                    "d2h_bytes_per_step": int(65 + sc_log_n * (128 + 32) + K_TABLES * 32), "sumcheck_ms": v_e2e_sc},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "result_check": {"msm_infinity_flag": int(r_msm[1]), "msm_x_limb0": int(r_msm[0][0])},
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            threads = min(8, cores)
+            s, ms = pick_cpu_sample(threads, budget_s=10.0)
+            scale = float(1 << (log_n - s))
+            sc_s = min(sc_log_n, 20)
+            sc_cpu = cpu_sumcheck_sample(sc_s)
+            line["cpu_baseline"] = {
+                "value": ms * scale, "unit": "ms", "cores": threads, "kind": "port",
+                "sample": f"MSM 2^{s} points on {threads} threads (ParallelMSM.compute semantics, src/msm/mod.zig:588-653), {ms:.0f} ms, linear x{scale:.0f} to 2^{log_n}; reference cannot be built here (no zig)",
+                "sumcheck_ms": sc_cpu * (1 << (sc_log_n - sc_s)), "sumcheck_sample": f"2^{sc_s} entries single-threaded, {sc_cpu:.0f} ms, linear x{1 << (sc_log_n - sc_s)}",
+                "host_cores_available": cores,
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=24, help="MSM size (log2 points)")
+    ap.add_argument("--sc-log-n", type=int, default=24, help="sumcheck table size (log2 entries)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

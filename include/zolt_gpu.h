@@ -52,6 +52,8 @@ int zolt_dev_alloc(zolt_ctx* ctx, size_t bytes, void** dptr);
 int zolt_dev_free(zolt_ctx* ctx, void* dptr);
 int zolt_dev_upload(zolt_ctx* ctx, void* dptr, const void* hptr, size_t bytes);
 int zolt_dev_download(zolt_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
+/* device-to-device copy, asynchronous on the context's stream */
+int zolt_dev_copy(zolt_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
 
 /* ---- field vectors ---------------------------------------------------------------------------
  * Element-wise ops on host vectors; replaces BatchOps.batchAdd/batchMul (src/field/mod.zig:1164-1280)
@@ -163,7 +165,8 @@ enum {
  * lock-step but do not enter the round polynomial (val_init in output_check.zig:454-476). */
 int zolt_sc_create(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
                    const uint64_t* const* tables, zolt_sc** out);
-/* same, from device-resident tables (copied; the instance owns its buffers) */
+/* same, from device-resident tables: BORROWED read-only (never written, no copy); they must stay valid
+ * until the first zolt_sc_bind has completed (or the instance is freed before that). */
 int zolt_sc_create_dev(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
                        const void* const* d_tables, zolt_sc** out);
 /* Gruen combiners only: tau (n_tau*4, n_tau == log_n) -> builds the E_out / E_in prefix tables of

@@ -460,6 +460,31 @@ void ref_g1_fixed_mul(const uint64_t* scalars, size_t n, int threads, uint64_t* 
   for (auto& x : th) x.join();
 }
 
+// bases[i] = (i+1) * G (the bench.zig base set, src/bench.zig:251-262) by repeated mixed addition and
+// one batch inversion -- a fast way to get many distinct valid bases for the timed CPU baseline.
+void ref_g1_multiples(size_t n, uint64_t* out_xy, uint8_t* out_inf) {
+  Affine gen{Fq::one(), Fq::one().add(Fq::one()), false};
+  std::vector<Jac> pts(n);
+  Jac acc = Jac::identity();
+  for (size_t i = 0; i < n; i++) {
+    acc = acc.add_affine(gen);
+    pts[i] = acc;
+  }
+  std::vector<Fq> prefix(n);
+  Fq run = Fq::one();
+  for (size_t i = 0; i < n; i++) {
+    prefix[i] = run;
+    run = run.mul(pts[i].z);
+  }
+  Fq inv = run.inverse();
+  for (size_t i = n; i-- > 0;) {
+    Fq zi = inv.mul(prefix[i]);
+    inv = inv.mul(pts[i].z);
+    Fq zi2 = zi.sqr();
+    store_point(Affine{pts[i].x.mul(zi2), pts[i].y.mul(zi2.mul(zi)), false}, out_xy + 8 * i, out_inf + i);
+  }
+}
+
 // DensePolynomial.bindLow in place (src/poly/mod.zig:160-175): n = current length
 void ref_bind_low(uint64_t* table, size_t n, const uint64_t* r) {
   Fr* t = reinterpret_cast<Fr*>(table);

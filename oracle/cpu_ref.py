@@ -64,6 +64,14 @@ def g1_fixed_mul(scalars, threads: int = 1):
     return xy, inf
 
 
+def g1_multiples(n: int):
+    """bases[i] = (i+1) * G."""
+    xy = np.zeros((n, 8), dtype=np.uint64)
+    inf = np.zeros(n, dtype=np.uint8)
+    lib().ref_g1_multiples(C.c_size_t(n), _p(xy), _p(inf))
+    return xy, inf
+
+
 def bind_low(table, r) -> np.ndarray:
     t = _u64(table, 4).copy()
     rr = _u64(r, 4)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "zolt_dev_free": [_vp, _vp],
     "zolt_dev_upload": [_vp, _vp, _vp, _sz],
     "zolt_dev_download": [_vp, _vp, _vp, _sz],
+    "zolt_dev_copy": [_vp, _vp, _vp, _sz],
     "zolt_field_batch_op": [_vp, _i, _i, _vp, _vp, _vp, _sz],
     "zolt_msm_bases_upload": [_vp, _vp, _vp, _sz, C.POINTER(_vp)],
     "zolt_msm_bases_free": [_vp],

@@ -328,6 +328,26 @@ class SumcheckInstance:
             t = _as_u64(tau, 4)
             check(ctx.lib.zolt_sc_set_split_eq(h, _ptr(t), t.shape[0]), "zolt_sc_set_split_eq")
 
+    @classmethod
+    def from_device(cls, ctx: Context, combiner: int, pairing: int, d_tables, log_n: int, n_extra: int = 0, tau=None):
+        """zolt_sc_create_dev: tables are device pointers, borrowed read-only until the first bind."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        arr = (C.c_void_p * len(d_tables))(*d_tables)
+        h = C.c_void_p()
+        check(ctx.lib.zolt_sc_create_dev(ctx.handle, combiner, pairing, log_n, len(d_tables) - n_extra, n_extra, arr, C.byref(h)),
+              "zolt_sc_create_dev")
+        self.handle = h
+        self._keep = None
+        ne = C.c_int()
+        check(ctx.lib.zolt_sc_num_evals(h, C.byref(ne)), "zolt_sc_num_evals")
+        self.num_evals = ne.value
+        self.num_tables = len(d_tables)
+        if tau is not None:
+            t = _as_u64(tau, 4)
+            check(ctx.lib.zolt_sc_set_split_eq(h, _ptr(t), t.shape[0]), "zolt_sc_set_split_eq")
+        return self
+
     def compute_round_poly(self) -> np.ndarray:
         out = np.empty((self.num_evals, 4), dtype=np.uint64)
         check(self.ctx.lib.zolt_sc_round_evals(self.handle, _ptr(out)), "zolt_sc_round_evals")

@@ -107,6 +107,13 @@ extern "C" int zolt_dev_download(zolt_ctx* ctx, void* hptr, const void* dptr, si
   return ZOLT_OK;
 }
 
+extern "C" int zolt_dev_copy(zolt_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+  if (!ctx || (bytes && (!d_dst || !d_src))) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return ZOLT_OK;
+}
+
 extern "C" int zolt_prof_enable(zolt_ctx* ctx, int on) {
   if (!ctx) return ZOLT_ERR_ARG;
   ctx->prof_on = on != 0;

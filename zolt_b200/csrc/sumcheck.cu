@@ -377,8 +377,12 @@ struct zolt_sc {
   zolt_ctx* ctx = nullptr;
   int combiner = 0, pairing = 0, log_n0 = 0, k = 0, n_extra = 0, ne = 0;
   size_t n = 0;  // current table length
+  // Round 0/1 read the input tables (owned uploads or borrowed device pointers, never written);
+  // later rounds ping-pong between buf[0] (n0/2 entries) and buf[1] (n0/4 entries).
+  const Fr* tab_in[kMaxTables] = {};
+  bool owns_in = false;
   Fr* buf[2][kMaxTables] = {};
-  int cur = 0;
+  int cur = -1;  // -1: current tables are tab_in; 0/1: buf[cur]
   bool evals_valid = false;
   Fr* d_partials = nullptr;
   unsigned* d_ticket = nullptr;
@@ -433,8 +437,8 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   ScPtrs t{};
   const int total = sc->k + sc->n_extra;
   for (int i = 0; i < total; i++) {
-    t.src[i] = sc->buf[sc->cur][i];
-    t.dst[i] = sc->buf[sc->cur ^ 1][i];
+    t.src[i] = sc->cur < 0 ? sc->tab_in[i] : sc->buf[sc->cur][i];
+    t.dst[i] = sc->buf[sc->cur < 0 ? 0 : (sc->cur ^ 1)][i];
   }
   const size_t n_cur = fused ? sc->n / 2 : sc->n;
   const unsigned grid = grid_for(sc->ctx, n_cur / 2, 4);
@@ -489,8 +493,8 @@ int sc_alloc(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, 
   sc->n = size_t(1) << log_n;
   const size_t n = sc->n;
   for (int i = 0; i < k + n_extra; i++) {
-    ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->buf[0][i], n * sizeof(Fr)));
-    ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->buf[1][i], (n / 2 ? n / 2 : 1) * sizeof(Fr)));
+    ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->buf[0][i], (n / 2 ? n / 2 : 1) * sizeof(Fr)));
+    ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->buf[1][i], (n / 4 ? n / 4 : 1) * sizeof(Fr)));
   }
   sc->max_grid = (unsigned)ctx->num_sms * 4;
   ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->d_partials, (size_t)sc->max_grid * 4 * sizeof(Fr)));
@@ -510,11 +514,15 @@ extern "C" int zolt_sc_create(zolt_ctx* ctx, int combiner, int pairing, int log_
   if (!tables) return ZOLT_ERR_ARG;
   zolt_sc* sc = nullptr;
   ZOLT_TRY(sc_alloc(ctx, combiner, pairing, log_n, n_tables, n_extra, &sc));
+  sc->owns_in = true;
   for (int i = 0; i < n_tables + n_extra; i++) {
     if (!tables[i]) { zolt_sc_free(sc); return ZOLT_ERR_ARG; }
-    ZOLT_CUDA_TRY(cudaMemcpyAsync(sc->buf[0][i], tables[i], sc->n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    Fr* d = nullptr;
+    ZOLT_CUDA_TRY(cudaMalloc((void**)&d, sc->n * sizeof(Fr)));
+    sc->tab_in[i] = d;
+    ZOLT_CUDA_TRY(cudaMemcpyAsync(d, tables[i], sc->n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
   }
-  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host buffers are only borrowed for the call
   *out = sc;
   return ZOLT_OK;
 }
@@ -524,9 +532,10 @@ extern "C" int zolt_sc_create_dev(zolt_ctx* ctx, int combiner, int pairing, int 
   if (!d_tables) return ZOLT_ERR_ARG;
   zolt_sc* sc = nullptr;
   ZOLT_TRY(sc_alloc(ctx, combiner, pairing, log_n, n_tables, n_extra, &sc));
+  sc->owns_in = false;
   for (int i = 0; i < n_tables + n_extra; i++) {
     if (!d_tables[i]) { zolt_sc_free(sc); return ZOLT_ERR_ARG; }
-    ZOLT_CUDA_TRY(cudaMemcpyAsync(sc->buf[0][i], d_tables[i], sc->n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    sc->tab_in[i] = static_cast<const Fr*>(d_tables[i]);  // borrowed, read-only
   }
   *out = sc;
   return ZOLT_OK;
@@ -598,16 +607,18 @@ extern "C" int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]) {
   } else {
     // last variable: bind only, nothing left to evaluate
     for (int i = 0; i < sc->k + sc->n_extra; i++) {
+      const Fr* src = sc->cur < 0 ? sc->tab_in[i] : sc->buf[sc->cur][i];
+      Fr* dst = sc->buf[sc->cur < 0 ? 0 : (sc->cur ^ 1)][i];
       if (sc->pairing == ZOLT_PAIR_ADJACENT)
-        bind_kernel<ZOLT_PAIR_ADJACENT><<<1, kScThreads, 0, ctx->stream>>>(sc->buf[sc->cur ^ 1][i], sc->buf[sc->cur][i], sc->n, r);
+        bind_kernel<ZOLT_PAIR_ADJACENT><<<1, kScThreads, 0, ctx->stream>>>(dst, src, sc->n, r);
       else
-        bind_kernel<ZOLT_PAIR_HALF><<<1, kScThreads, 0, ctx->stream>>>(sc->buf[sc->cur ^ 1][i], sc->buf[sc->cur][i], sc->n, r);
+        bind_kernel<ZOLT_PAIR_HALF><<<1, kScThreads, 0, ctx->stream>>>(dst, src, sc->n, r);
       ctx->launches++;
     }
     sc->evals_valid = false;
   }
   ZOLT_CUDA_TRY(cudaGetLastError());
-  sc->cur ^= 1;
+  sc->cur = sc->cur < 0 ? 0 : (sc->cur ^ 1);
   sc->n /= 2;
   return ZOLT_OK;
 }
@@ -621,14 +632,15 @@ extern "C" int zolt_sc_len(const zolt_sc* sc, size_t* n) {
 extern "C" int zolt_sc_download(zolt_sc* sc, int table, uint64_t* dst) {
   if (!sc || !dst || table < 0 || table >= sc->k + sc->n_extra) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(sc->ctx->device));
-  ZOLT_CUDA_TRY(cudaMemcpyAsync(dst, sc->buf[sc->cur][table], sc->n * sizeof(Fr), cudaMemcpyDeviceToHost, sc->ctx->stream));
+  const Fr* src = sc->cur < 0 ? sc->tab_in[table] : sc->buf[sc->cur][table];
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(dst, src, sc->n * sizeof(Fr), cudaMemcpyDeviceToHost, sc->ctx->stream));
   ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
   return ZOLT_OK;
 }
 
 extern "C" int zolt_sc_table_dev(zolt_sc* sc, int table, const void** d_ptr) {
   if (!sc || !d_ptr || table < 0 || table >= sc->k + sc->n_extra) return ZOLT_ERR_ARG;
-  *d_ptr = sc->buf[sc->cur][table];
+  *d_ptr = sc->cur < 0 ? sc->tab_in[table] : sc->buf[sc->cur][table];
   return ZOLT_OK;
 }
 
@@ -637,6 +649,7 @@ extern "C" int zolt_sc_free(zolt_sc* sc) {
   cudaSetDevice(sc->ctx->device);
   cudaStreamSynchronize(sc->ctx->stream);
   for (int i = 0; i < kMaxTables; i++) {
+    if (sc->owns_in && sc->tab_in[i]) cudaFree(const_cast<Fr*>(sc->tab_in[i]));
     if (sc->buf[0][i]) cudaFree(sc->buf[0][i]);
     if (sc->buf[1][i]) cudaFree(sc->buf[1][i]);
   }

@@ -34,6 +34,7 @@ def load_host() -> C.CDLL:
         _host.zolt_host_cubic_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_sumcheck_prove.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                                    C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _host.zolt_host_sumcheck_prove_dev.argtypes = _host.zolt_host_sumcheck_prove.argtypes
         _host.zolt_host_sumcheck_prove_gruen.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
                                                          C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p,
                                                          C.c_void_p, C.c_void_p]
@@ -101,6 +102,19 @@ def sumcheck_prove(ctx: Context, combiner: int, pairing: int, tables, n_extra: i
     st = load_host().zolt_host_sumcheck_prove(ctx.handle, combiner, pairing, log_n, len(tabs), n_extra, arr, domain, len(domain),
                                               label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
     _lib.check(st, "zolt_host_sumcheck_prove")
+    return evals, chal, final
+
+
+def sumcheck_prove_dev(ctx: Context, combiner: int, pairing: int, d_tables, log_n: int, n_extra: int = 0,
+                       domain: bytes = b"bench", label: bytes = b"round"):
+    """Same as sumcheck_prove for tables already resident on the device (list of device pointers)."""
+    arr = (C.c_void_p * len(d_tables))(*d_tables)
+    evals = np.zeros((log_n, 4, 4), dtype=np.uint64)
+    chal = np.zeros((log_n, 4), dtype=np.uint64)
+    final = np.zeros((len(d_tables), 4), dtype=np.uint64)
+    st = load_host().zolt_host_sumcheck_prove_dev(ctx.handle, combiner, pairing, log_n, len(d_tables), n_extra, arr, domain,
+                                                  len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
+    _lib.check(st, "zolt_host_sumcheck_prove_dev")
     return evals, chal, final
 
 

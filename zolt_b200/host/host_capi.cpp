@@ -66,6 +66,21 @@ int zolt_host_sumcheck_prove(zolt_ctx* ctx, int combiner, int pairing, int log_n
   return ZOLT_OK;
 }
 
+// Same round loop over tables that are already resident on the device.
+int zolt_host_sumcheck_prove_dev(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
+                                 const void* const* d_tables, const char* domain, size_t dn, const char* label, size_t ln,
+                                 uint64_t* evals_out, uint64_t* challenges_out, uint64_t* final_out) {
+  Context c(ctx);
+  std::vector<const void*> tabs(d_tables, d_tables + n_tables);
+  DenseSumcheckProver prover(c, DenseSumcheckProver::DeviceTables{}, combiner, pairing, tabs, log_n, n_extra);
+  Transcript tr(std::string_view(domain, dn));
+  SumcheckProof proof = proveSumcheck(prover, tr, std::string_view(label, ln));
+  store_proof(proof, evals_out, challenges_out);
+  if (final_out)
+    for (int t = 0; t < n_tables; t++) prover.table(t)[0].store(final_out + 4 * t);
+  return ZOLT_OK;
+}
+
 // Gruen split-eq degree-3 sumcheck (ProductVirtualRemainderProver shape); claim = initial claim.
 int zolt_host_sumcheck_prove_gruen(zolt_ctx* ctx, int with_c, int log_n, int n_tables, const uint64_t* const* tables,
                                    const uint64_t* tau, const uint64_t* claim, const char* domain, size_t dn,

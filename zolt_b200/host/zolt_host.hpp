@@ -282,6 +282,15 @@ class DenseSumcheckProver : public SumcheckInstance {
          "zolt_sc_create");
     must(zolt_sc_num_evals(sc_, &ne_), "zolt_sc_num_evals");
   }
+  // tables already resident on the device (borrowed read-only by the instance)
+  struct DeviceTables {};
+  DenseSumcheckProver(Context& ctx, DeviceTables, int combiner, int pairing, const std::vector<const void*>& d_tables,
+                      int log_n, int n_extra = 0)
+      : log_n_(log_n), combiner_(combiner) {
+    must(zolt_sc_create_dev(ctx.raw(), combiner, pairing, log_n, (int)d_tables.size() - n_extra, n_extra, d_tables.data(), &sc_),
+         "zolt_sc_create_dev");
+    must(zolt_sc_num_evals(sc_, &ne_), "zolt_sc_num_evals");
+  }
   ~DenseSumcheckProver() override { zolt_sc_free(sc_); }
   size_t numRounds() const override { return (size_t)log_n_; }
   size_t degree() const override {
