@@ -40,7 +40,7 @@ static AffineG1 load_affine(const uint64_t* xy) {
 
 // Fold a list of affine points with the XYZZ formulas.  mode 0: sequential mixed additions;
 // mode 1: pairwise tree of full additions; mode 2: sum, then doubled `dbl` times; mode 3: sum
-// multiplied by the small constant `dbl` (xyzz_mul_small).  Output: canonical affine + flag.
+// multiplied by the small constant `dbl` (xyzz_mul_small); mode 4: sequential xyzz_madd_uniform.  Output: canonical affine + flag.
 extern "C" void shim_g1_fold(int mode, const uint64_t* xy, const uint8_t* neg, size_t n, uint32_t dbl, uint64_t* out_xy,
                              uint8_t* out_inf) {
   XYZZ acc = XYZZ::identity();
@@ -63,7 +63,8 @@ extern "C" void shim_g1_fold(int mode, const uint64_t* xy, const uint8_t* neg, s
     for (size_t i = 0; i < n; i++) {
       AffineG1 p = load_affine(xy + 8 * i);
       if (neg && neg[i]) p = affine_neg(p);
-      xyzz_madd(acc, p);
+      if (mode == 4) xyzz_madd_uniform(acc, p);
+      else xyzz_madd(acc, p);
     }
     if (mode == 2)
       for (uint32_t j = 0; j < dbl; j++) acc = xyzz_dbl(acc);

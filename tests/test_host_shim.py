@@ -54,6 +54,7 @@ def test_curve_formulas(host_shim):
     pts = [B.g1_mul(B.G1_GEN, k) for k in logs]
     total = B.g1_mul(B.G1_GEN, sum(logs))
     assert _fold(host_shim, 0, pts) == total          # mixed additions
+    assert _fold(host_shim, 4, pts) == total          # warp-uniform mixed additions
     assert _fold(host_shim, 1, pts) == total          # full additions (tree)
     assert _fold(host_shim, 2, pts, dbl=5) == B.g1_mul(total, 32)
     assert _fold(host_shim, 3, pts, dbl=1000) == B.g1_mul(total, 1000)
@@ -71,4 +72,8 @@ def test_curve_special_cases(host_shim):
     assert _fold(host_shim, 0, [p, p], neg=[0, 1]) is None                   # P + (-P) -> identity
     assert _fold(host_shim, 1, [p, p], neg=[0, 1]) is None
     assert _fold(host_shim, 0, [p, p, p], neg=[0, 1, 0]) == p               # identity + P
+    assert _fold(host_shim, 4, [p, p]) == B.g1_mul(B.G1_GEN, 154)
+    assert _fold(host_shim, 4, [p, p], neg=[0, 1]) is None
+    assert _fold(host_shim, 4, [p, p, p], neg=[0, 1, 0]) == p
+    assert _fold(host_shim, 4, [p, p, p, p]) == B.g1_mul(B.G1_GEN, 308)
     assert _fold(host_shim, 1, [p, p, p, p], neg=[0, 1, 1, 0]) is None      # identity + identity

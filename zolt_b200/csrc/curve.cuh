@@ -102,6 +102,39 @@ ZOLT_HD void xyzz_madd(XYZZ& acc, const AffineG1& q) {
   acc.zzz = fq_mul(acc.zzz, ppp);
 }
 
+// acc += (x2, y2) with warp-uniform control flow: every lane runs the ten field products of the
+// general case; identity accumulators are fixed up by a select afterwards, so lanes of a warp that
+// sit at different positions of their buckets stay converged.  Only the (rare) P == +-Q cases branch.
+ZOLT_HD void xyzz_madd_uniform(XYZZ& acc, const AffineG1& q) {
+  const bool ident = acc.is_identity();
+  Fq u2 = fq_mul(q.x, acc.zz);
+  Fq s2 = fq_mul(q.y, acc.zzz);
+  Fq p = fq_sub(u2, acc.x);
+  Fq r = fq_sub(s2, acc.y);
+  Fq pp = fq_sqr(p);
+  Fq ppp = fq_mul(p, pp);
+  Fq qq = fq_mul(acc.x, pp);
+  Fq x3 = fq_sub(fq_sub(fq_sqr(r), ppp), fq_add(qq, qq));
+  Fq y3 = fq_sub(fq_mul(r, fq_sub(qq, x3)), fq_mul(acc.y, ppp));
+  Fq zz3 = fq_mul(acc.zz, pp);
+  Fq zzz3 = fq_mul(acc.zzz, ppp);
+  if (!ident && p.is_zero()) {  // same x: P + P or P + (-P)
+    XYZZ d = r.is_zero() ? xyzz_dbl_affine(q) : XYZZ::identity();
+    x3 = d.x;
+    y3 = d.y;
+    zz3 = d.zz;
+    zzz3 = d.zzz;
+  }
+  const Fq one = Fq::one();
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    acc.x.v[i] = ident ? q.x.v[i] : x3.v[i];
+    acc.y.v[i] = ident ? q.y.v[i] : y3.v[i];
+    acc.zz.v[i] = ident ? one.v[i] : zz3.v[i];
+    acc.zzz.v[i] = ident ? one.v[i] : zzz3.v[i];
+  }
+}
+
 // acc += b   (add-2008-s)
 ZOLT_HD void xyzz_add(XYZZ& acc, const XYZZ& b) {
   if (b.is_identity()) return;

@@ -261,34 +261,47 @@ msm_accum_points_kernel(const uint32_t* __restrict__ sorted, const uint32_t* __r
       if (offsets[mid] <= (uint32_t)p0) lo = mid; else hi = mid;
     }
     uint32_t key = lo;
-    uint32_t pos = (uint32_t)p0;
+    uint32_t boundary = offsets[key + 1];  // first position that belongs to a later bucket
     bool first = true;
-    while (pos < p1) {
-      const uint32_t bucket_end = offsets[key + 1];
-      const uint32_t end = bucket_end < p1 ? bucket_end : p1;
-      XYZZ acc = XYZZ::identity();
-      for (; pos < end; pos++) {
-        const uint32_t e = sorted[pos];
-        AffineG1 pt = ld_affine(bases + (e & 0x7fffffffu));
-        if (e >> 31) pt.y = fp_neg<FqParams>(pt.y);
-        xyzz_madd(acc, pt);
+    XYZZ acc = XYZZ::identity();
+    // One flat loop over the slice: every lane performs exactly one mixed addition per iteration, so
+    // the warp stays converged although its lanes cross bucket boundaries at different positions.
+    // The point of iteration i+1 is fetched while iteration i computes.
+    uint32_t e = sorted[(uint32_t)p0];
+    AffineG1 pt = ld_affine(bases + (e & 0x7fffffffu));
+    for (uint32_t pos = (uint32_t)p0; pos < p1; pos++) {
+      const uint32_t e_cur = e;
+      AffineG1 cur = pt;
+      if (pos + 1 < p1) {
+        e = sorted[pos + 1];
+        pt = ld_affine(bases + (e & 0x7fffffffu));
       }
-      const bool last = (pos >= p1);
-      if (first) {
-        edge_keys[2 * t] = key;  // may continue in the previous slice
-        st_xyzz(&edge_pts[2 * t], acc);
-        ek0 = key;
-      } else if (last) {
-        edge_keys[2 * t + 1] = key;  // may continue in the next slice
-        st_xyzz(&edge_pts[2 * t + 1], acc);
-        ek1 = key;
-      } else {
-        st_xyzz(&buckets[key], acc);  // bucket lies strictly inside this slice: complete
+      if (pos == boundary) {  // bucket `key` ended at pos: publish it and move on
+        if (first) {
+          edge_keys[2 * t] = key;  // may continue in the previous slice
+          st_xyzz(&edge_pts[2 * t], acc);
+          ek0 = key;
+          first = false;
+        } else {
+          st_xyzz(&buckets[key], acc);  // strictly inside this slice: complete
+        }
+        acc = XYZZ::identity();
+        key++;
+        while (offsets[key + 1] == pos) key++;  // skip empty buckets
+        boundary = offsets[key + 1];
       }
-      first = false;
-      if (last) break;
-      key++;
-      while (offsets[key + 1] == pos) key++;  // skip empty buckets
+      if (e_cur >> 31) cur.y = fp_neg<FqParams>(cur.y);
+      xyzz_madd_uniform(acc, cur);
+    }
+    // the bucket open at the end of the slice may continue in the next slice
+    if (first) {
+      edge_keys[2 * t] = key;
+      st_xyzz(&edge_pts[2 * t], acc);
+      ek0 = key;
+    } else {
+      edge_keys[2 * t + 1] = key;
+      st_xyzz(&edge_pts[2 * t + 1], acc);
+      ek1 = key;
     }
   }
   if (ek0 == kInvalidKey) edge_keys[2 * t] = kInvalidKey;
