@@ -1,0 +1,77 @@
+"""GPU parity, 2 ranks over NCCL (skipped unless >= 2 GPUs are visible): the sharded MSM and sharded
+sumcheck of zolt_b200/dist.py must reproduce the single-process results bit for bit."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ZOLT_ROOT"])
+import zolt_b200 as Z
+from zolt_b200 import dist as ZD
+from oracle import bn254 as B, cpu_ref as R
+from tests.util import P, fr_arr, fr_ints, rand_fr
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+stream = torch.cuda.Stream()
+ctx = Z.Context(rank, stream.cuda_stream)
+
+# --- MSM sharded by point range -------------------------------------------------------------------
+n = 1 << 13
+logs, scalars = rand_fr(11, n), rand_fr(12, n)
+lo, hi = ZD.shard_range(n, rank, world)
+bases = Z.Bases.fixed_base_mul(ctx, fr_arr(logs[lo:hi]))
+d_s = Z.DeviceBuffer.from_host(ctx, fr_arr(scalars[lo:hi]))
+part = torch.zeros(128, dtype=torch.uint8, device="cuda")
+gathered = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
+with torch.cuda.stream(stream):
+    Z.MSM.partial_dev(bases, d_s.ptr, hi - lo, part.data_ptr())
+    dist.all_gather_into_tensor(gathered, part)
+    xy, inf = Z.MSM.sum_partials(ctx, gathered.data_ptr(), world)
+got = B.arrays_to_points(xy.reshape(1, 8), [inf])[0]
+assert got == B.msm_closed_form(logs, scalars), "sharded MSM differs"
+
+# --- sumcheck sharded by contiguous hypercube blocks ---------------------------------------------------
+log_n, k = 12, 4
+full = [fr_arr(rand_fr(100 + t, 1 << log_n)) for t in range(k)]
+lo, hi = ZD.shard_range(1 << log_n, rank, world)
+d_tabs = [Z.DeviceBuffer.from_host(ctx, t[lo:hi]) for t in full]
+ev_part = torch.zeros(128, dtype=torch.uint8, device="cuda")
+ev_gath = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
+evals, chal, final = ZD.sharded_sumcheck_gpu(ctx, stream, Z.SC_EQ_AB_MINUS_C, [b.ptr for b in d_tabs],
+                                             log_n - ZD.log2_exact(world), world, ev_part, ev_gath)
+r_evals, r_chal, r_final = R.sc_prove("eq_ab_minus_c", 0, full)
+assert (chal == r_chal).all(), "challenges differ"
+assert (evals == r_evals).all(), "round evaluations differ"
+assert all((final[t] == r_final[t][0]).all() for t in range(k)), "final values differ"
+dist.barrier()
+if rank == 0:
+    print("MULTI_GPU_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_nccl_parity(tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, ZOLT_ROOT=str(ROOT))
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+         "--master-port", "29533", str(script)],
+        capture_output=True, text=True, env=env, timeout=600,
+    )
+    assert res.returncode == 0 and "MULTI_GPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]

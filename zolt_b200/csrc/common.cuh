@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
+#include <vector>
 
 #include "../../include/zolt_gpu.h"
 
@@ -45,6 +47,11 @@ struct zolt_ctx {
   size_t ws_bytes = 0;
   void* ws_in = nullptr;  // staging for host scalars (zolt_msm / zolt_msm_batch)
   size_t ws_in_bytes = 0;
+  // recycled device buffers (sumcheck ping-pong tables, small scratch): cudaMalloc/cudaFree per
+  // instance would cost more than the rounds themselves
+  std::vector<std::pair<void*, size_t>> pool_free;
+  size_t pool_bytes = 0;
+  std::vector<void*> pinned_free;  // recycled 256-byte mapped pinned mailboxes (one per live instance)
   // counters for the bench's "gpu_launches" claim
   unsigned long long launches = 0;
   // phase profiling (CUDA events on `stream`): begin/end pairs tagged by the caller
@@ -68,6 +75,47 @@ enum ProfTag {
   PROF_SC_EVAL = 16,     // round-0 evaluation kernel
   PROF_SC_FUSED = 17     // fused bind + next-round evaluation kernel
 };
+// Stream-ordered reuse: buffers are only handed out again to work queued on the same stream.
+inline cudaError_t pool_alloc(zolt_ctx* ctx, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 32;
+  int best = -1;
+  for (int i = 0; i < (int)ctx->pool_free.size(); i++) {
+    const size_t cap = ctx->pool_free[i].second;
+    if (cap >= bytes && cap <= 2 * bytes + 4096 && (best < 0 || cap < ctx->pool_free[best].second)) best = i;
+  }
+  if (best >= 0) {
+    *out = ctx->pool_free[best].first;
+    ctx->pool_free.erase(ctx->pool_free.begin() + best);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaSuccess) ctx->pool_bytes += bytes;
+  return e;
+}
+inline size_t pool_capacity_of(size_t bytes) { return bytes == 0 ? 32 : bytes; }
+inline void pool_release(zolt_ctx* ctx, void* p, size_t bytes) {
+  if (p) ctx->pool_free.emplace_back(p, pool_capacity_of(bytes));
+}
+inline void pool_destroy(zolt_ctx* ctx) {
+  for (auto& b : ctx->pool_free) cudaFree(b.first);
+  ctx->pool_free.clear();
+  for (void* p : ctx->pinned_free) cudaFreeHost(p);
+  ctx->pinned_free.clear();
+}
+inline cudaError_t pinned_mailbox_alloc(zolt_ctx* ctx, void** host, void** dev) {
+  if (!ctx->pinned_free.empty()) {
+    *host = ctx->pinned_free.back();
+    ctx->pinned_free.pop_back();
+  } else {
+    cudaError_t e = cudaHostAlloc(host, 256, cudaHostAllocMapped);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaHostGetDevicePointer(dev, *host, 0);
+}
+inline void pinned_mailbox_release(zolt_ctx* ctx, void* host) {
+  if (host) ctx->pinned_free.push_back(host);
+}
+
 inline int prof_begin(zolt_ctx* ctx, int tag) {
   if (!ctx->prof_on || ctx->prof_used >= zolt_ctx::kMaxProf) return -1;
   const int slot = ctx->prof_used++;

@@ -57,6 +57,7 @@ extern "C" int zolt_gpu_shutdown(zolt_ctx* ctx) {
   if (ctx->h_mailbox) cudaFreeHost(ctx->h_mailbox);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws_in) cudaFree(ctx->ws_in);
+  pool_destroy(ctx);
   for (int i = 0; i < 2 * zolt_ctx::kMaxProf; i++)
     if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);

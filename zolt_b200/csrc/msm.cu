@@ -674,8 +674,8 @@ int staging_for(zolt_ctx* ctx, size_t bytes, Fr** out) {
 int finish_affine(zolt_ctx* ctx, const XYZZ* d_xyzz, size_t k, uint64_t* out_xy, uint8_t* out_inf) {
   AffineG1* d_xy = nullptr;
   uint8_t* d_inf = nullptr;
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_xy, k * sizeof(AffineG1)));
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_inf, k));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, k * sizeof(AffineG1), (void**)&d_xy));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, k, (void**)&d_inf));
   const int ps = prof_begin(ctx, PROF_MSM_AFFINE);
   msm_to_affine_kernel<<<(unsigned)((k + 31) / 32), 32, 0, ctx->stream>>>(d_xyzz, k, d_xy, d_inf);
   prof_end(ctx, ps);
@@ -684,8 +684,8 @@ int finish_affine(zolt_ctx* ctx, const XYZZ* d_xyzz, size_t k, uint64_t* out_xy,
   ZOLT_CUDA_TRY(cudaMemcpyAsync(out_xy, d_xy, k * sizeof(AffineG1), cudaMemcpyDeviceToHost, ctx->stream));
   ZOLT_CUDA_TRY(cudaMemcpyAsync(out_inf, d_inf, k, cudaMemcpyDeviceToHost, ctx->stream));
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_xy);
-  cudaFree(d_inf);
+  pool_release(ctx, d_xy, k * sizeof(AffineG1));
+  pool_release(ctx, d_inf, k);
   return ZOLT_OK;
 }
 
@@ -758,11 +758,11 @@ extern "C" int zolt_g1_sum_partials(zolt_ctx* ctx, const void* d_partials, size_
   if (!ctx || !d_partials || !out_xy || !out_inf) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   XYZZ* d_sum = nullptr;
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_sum, sizeof(XYZZ)));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, sizeof(XYZZ), (void**)&d_sum));
   g1_sum_partials_kernel<<<1, 1, 0, ctx->stream>>>((const XYZZ*)d_partials, count, d_sum);
   ctx->launches++;
   int s = finish_affine(ctx, d_sum, 1, out_xy, out_inf);
-  cudaFree(d_sum);
+  pool_release(ctx, d_sum, sizeof(XYZZ));
   return s;
 }
 
@@ -771,10 +771,10 @@ extern "C" int zolt_msm_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offse
   if (!ctx || !bases || !out_xy || !out_inf || (n && !d_scalars) || offset + n > bases->n) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   XYZZ* d_res = nullptr;
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_res, sizeof(XYZZ)));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, sizeof(XYZZ), (void**)&d_res));
   int s = msm_core(ctx, bases, offset, (const Fr*)d_scalars, 1, n, d_res);
   if (s == ZOLT_OK) s = finish_affine(ctx, d_res, 1, out_xy, out_inf);
-  cudaFree(d_res);
+  pool_release(ctx, d_res, sizeof(XYZZ));
   return s;
 }
 

@@ -382,6 +382,7 @@ struct zolt_sc {
   const Fr* tab_in[kMaxTables] = {};
   bool owns_in = false;
   Fr* buf[2][kMaxTables] = {};
+  size_t buf_bytes[2] = {0, 0}, in_bytes = 0;
   int cur = -1;  // -1: current tables are tab_in; 0/1: buf[cur]
   bool evals_valid = false;
   Fr* d_partials = nullptr;
@@ -492,17 +493,19 @@ int sc_alloc(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, 
   sc->ne = combiner_ne(combiner);
   sc->n = size_t(1) << log_n;
   const size_t n = sc->n;
+  sc->buf_bytes[0] = (n / 2 ? n / 2 : 1) * sizeof(Fr);
+  sc->buf_bytes[1] = (n / 4 ? n / 4 : 1) * sizeof(Fr);
+  sc->in_bytes = n * sizeof(Fr);
   for (int i = 0; i < k + n_extra; i++) {
-    ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->buf[0][i], (n / 2 ? n / 2 : 1) * sizeof(Fr)));
-    ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->buf[1][i], (n / 4 ? n / 4 : 1) * sizeof(Fr)));
+    ZOLT_CUDA_TRY(pool_alloc(ctx, sc->buf_bytes[0], (void**)&sc->buf[0][i]));
+    ZOLT_CUDA_TRY(pool_alloc(ctx, sc->buf_bytes[1], (void**)&sc->buf[1][i]));
   }
   sc->max_grid = (unsigned)ctx->num_sms * 4;
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->d_partials, (size_t)sc->max_grid * 4 * sizeof(Fr)));
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->d_ticket, sizeof(unsigned)));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, (size_t)sc->max_grid * 4 * sizeof(Fr), (void**)&sc->d_partials));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 256, (void**)&sc->d_ticket));
   ZOLT_CUDA_TRY(cudaMemsetAsync(sc->d_ticket, 0, sizeof(unsigned), ctx->stream));
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&sc->d_evals, 4 * sizeof(Fr)));
-  ZOLT_CUDA_TRY(cudaHostAlloc((void**)&sc->h_evals, 4 * sizeof(Fr), cudaHostAllocMapped));
-  ZOLT_CUDA_TRY(cudaHostGetDevicePointer((void**)&sc->h_evals_dev, sc->h_evals, 0));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(Fr), (void**)&sc->d_evals));
+  ZOLT_CUDA_TRY(pinned_mailbox_alloc(ctx, (void**)&sc->h_evals, (void**)&sc->h_evals_dev));
   *out = sc;
   return ZOLT_OK;
 }
@@ -518,7 +521,7 @@ extern "C" int zolt_sc_create(zolt_ctx* ctx, int combiner, int pairing, int log_
   for (int i = 0; i < n_tables + n_extra; i++) {
     if (!tables[i]) { zolt_sc_free(sc); return ZOLT_ERR_ARG; }
     Fr* d = nullptr;
-    ZOLT_CUDA_TRY(cudaMalloc((void**)&d, sc->n * sizeof(Fr)));
+    ZOLT_CUDA_TRY(pool_alloc(ctx, sc->in_bytes, (void**)&d));
     sc->tab_in[i] = d;
     ZOLT_CUDA_TRY(cudaMemcpyAsync(d, tables[i], sc->n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
   }
@@ -648,15 +651,16 @@ extern "C" int zolt_sc_free(zolt_sc* sc) {
   if (!sc) return ZOLT_ERR_ARG;
   cudaSetDevice(sc->ctx->device);
   cudaStreamSynchronize(sc->ctx->stream);
+  zolt_ctx* ctx = sc->ctx;
   for (int i = 0; i < kMaxTables; i++) {
-    if (sc->owns_in && sc->tab_in[i]) cudaFree(const_cast<Fr*>(sc->tab_in[i]));
-    if (sc->buf[0][i]) cudaFree(sc->buf[0][i]);
-    if (sc->buf[1][i]) cudaFree(sc->buf[1][i]);
+    if (sc->owns_in && sc->tab_in[i]) pool_release(ctx, const_cast<Fr*>(sc->tab_in[i]), sc->in_bytes);
+    if (sc->buf[0][i]) pool_release(ctx, sc->buf[0][i], sc->buf_bytes[0]);
+    if (sc->buf[1][i]) pool_release(ctx, sc->buf[1][i], sc->buf_bytes[1]);
   }
-  if (sc->d_partials) cudaFree(sc->d_partials);
-  if (sc->d_ticket) cudaFree(sc->d_ticket);
-  if (sc->d_evals) cudaFree(sc->d_evals);
-  if (sc->h_evals) cudaFreeHost(sc->h_evals);
+  if (sc->d_partials) pool_release(ctx, sc->d_partials, (size_t)sc->max_grid * 4 * sizeof(Fr));
+  if (sc->d_ticket) pool_release(ctx, sc->d_ticket, 256);
+  if (sc->d_evals) pool_release(ctx, sc->d_evals, 4 * sizeof(Fr));
+  pinned_mailbox_release(ctx, sc->h_evals);
   if (sc->d_e_out) cudaFree(sc->d_e_out);
   if (sc->d_e_in) cudaFree(sc->d_e_in);
   if (sc->d_tau) cudaFree(sc->d_tau);
@@ -675,16 +679,16 @@ struct Scratch {
 };
 // per-context scratch for zolt_poly_sum / zolt_fr_sum_rows, allocated on demand and freed per call
 int scratch_alloc(zolt_ctx* ctx, Scratch* s) {
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&s->partials, (size_t)ctx->num_sms * 4 * 4 * sizeof(Fr)));
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&s->ticket, sizeof(unsigned)));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, (size_t)ctx->num_sms * 4 * 4 * sizeof(Fr), (void**)&s->partials));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 256, (void**)&s->ticket));
   ZOLT_CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), ctx->stream));
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&s->d_out, 16 * sizeof(Fr)));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 16 * sizeof(Fr), (void**)&s->d_out));
   return ZOLT_OK;
 }
-void scratch_free(Scratch* s) {
-  cudaFree(s->partials);
-  cudaFree(s->ticket);
-  cudaFree(s->d_out);
+void scratch_free(zolt_ctx* ctx, Scratch* s) {
+  pool_release(ctx, s->partials, (size_t)ctx->num_sms * 4 * 4 * sizeof(Fr));
+  pool_release(ctx, s->ticket, 256);
+  pool_release(ctx, s->d_out, 16 * sizeof(Fr));
 }
 }  // namespace
 
@@ -751,7 +755,7 @@ extern "C" int zolt_poly_sum(zolt_ctx* ctx, const void* d_src, size_t n, uint64_
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(out, ctx->h_mailbox, 32);
-  scratch_free(&s);
+  scratch_free(ctx, &s);
   return ZOLT_OK;
 }
 
@@ -765,6 +769,6 @@ extern "C" int zolt_fr_sum_rows(zolt_ctx* ctx, const void* d_rows, size_t rows, 
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(out, ctx->h_mailbox, cols * 32);
-  scratch_free(&s);
+  scratch_free(ctx, &s);
   return ZOLT_OK;
 }
