@@ -181,17 +181,35 @@ int zolt_sc_len(const zolt_sc* sc, size_t* n);
 int zolt_sc_download(zolt_sc* sc, int table, uint64_t* dst /* len*4 */);
 /* device pointer of table t's current buffer (valid until the next bind) */
 int zolt_sc_table_dev(zolt_sc* sc, int table, const void** d_ptr);
-/* Multi-GPU: this rank's partial evaluations stay on the device at *d_ptr (num_evals*4 u64) so they
- * can be all-gathered; zolt_fr_sum_rows folds `rows` gathered partials mod r on the device. */
+/* Optional: the instance's input claim (SumcheckInstance.input_claim, src/zkvm/batched_sumcheck.zig:34-74).
+ * Every round after the first derives p(1) from the sumcheck identity p(0) + p(1) = claim (claim =
+ * previous round polynomial at the challenge, tracked on the device); with the input claim set the first
+ * round does too.  Must be called before the first zolt_sc_round_evals.  The evaluations are the same
+ * canonical field elements either way. */
+int zolt_sc_set_claim(zolt_sc* sc, const uint64_t claim[4]);
+/* Multi-GPU (hypercube shards, one instance per rank).  After zolt_sc_set_sharded(sc, 1) a round is:
+ *   zolt_sc_round_partials_dev -> this rank's 4 raw partial sums, left on the device (16 u64) for the
+ *                                 all-gather;
+ *   zolt_sc_finish_partials    -> folds the `rows` gathered partials mod r on the device, completes the
+ *                                 round polynomial (p(1) from the claim, p(3) from the third difference)
+ *                                 and returns the evaluations; every rank calls it with the same rows;
+ *   zolt_sc_bind               -> as usual. */
+int zolt_sc_set_sharded(zolt_sc* sc, int on);
 int zolt_sc_round_partials_dev(zolt_sc* sc, const void** d_ptr);
+int zolt_sc_finish_partials(zolt_sc* sc, const void* d_rows /* rows*16 u64 */, size_t rows,
+                            uint64_t* evals_out /* num_evals*4 */);
 int zolt_fr_sum_rows(zolt_ctx* ctx, const void* d_rows, size_t rows, size_t cols, uint64_t* out /* cols*4 */);
 int zolt_sc_free(zolt_sc* sc);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------
  * Integer-pipe micro-benchmarks (the MSM roofline denominator).  `kind`: 0 = IMAD (3-reg),
- * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery products, 3 = Fq Montgomery products, 4 = IMAD immediate form.
+ * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery products, 3 = Fq Montgomery products, 4 = IMAD immediate form,
+ * 5 = FP64 FMA, 6 = FP64 FMA interleaved 1:1 with IMAD (ops/s counts the FP64 FMAs only).
  * Returns ops per second (for kind 2/3: field products per second). */
 int zolt_bench_int_pipe(zolt_ctx* ctx, int kind, int iters, double* ops_per_s);
+/* same with an explicit launch shape (threads per block, resident blocks per SM): occupancy sweeps */
+int zolt_bench_int_pipe_cfg(zolt_ctx* ctx, int kind, int iters, int threads, int blocks_per_sm,
+                            double* ops_per_s);
 /* Per-kernel device timings (CUDA events on the context's stream, the stream the kernels are launched
  * on).  zolt_prof_enable(ctx, 1) clears the log and starts recording one (tag, ms) entry per phase of
  * every subsequent MSM / sumcheck call (up to 96 entries); zolt_prof_read synchronises and copies them.

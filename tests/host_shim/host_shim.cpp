@@ -76,3 +76,22 @@ extern "C" void shim_g1_fold(int mode, const uint64_t* xy, const uint8_t* neg, s
   memcpy(out_xy + 4, a.y.v, 32);
   *out_inf = finite ? 0 : 1;
 }
+
+// Delayed reduction (field.cuh wide_*): out = sum_i a_i * b_i * 2^-256 mod p through one 512-bit
+// accumulator that is normalised after every term, exactly like the sumcheck kernels use it.
+template <class P>
+static void wide_dot(const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
+  uint32_t acc[16];
+  wide_zero(acc);
+  for (size_t i = 0; i < n; i++) {
+    wide_mul_add(acc, a + 8 * i, b + 8 * i);
+    wide_normalize<P>(acc);
+  }
+  Fp<P> r = wide_reduce<P>(acc);
+  memcpy(out, r.v, 32);
+}
+
+extern "C" void shim_wide_dot(int field, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
+  if (field == 0) wide_dot<FrParams>(a, b, n, out);
+  else wide_dot<FqParams>(a, b, n, out);
+}

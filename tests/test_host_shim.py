@@ -77,3 +77,26 @@ def test_curve_special_cases(host_shim):
     assert _fold(host_shim, 4, [p, p, p], neg=[0, 1, 0]) == p
     assert _fold(host_shim, 4, [p, p, p, p]) == B.g1_mul(B.G1_GEN, 308)
     assert _fold(host_shim, 1, [p, p, p, p], neg=[0, 1, 1, 0]) is None      # identity + identity
+
+
+@pytest.mark.parametrize("field,mod", [(0, B.FR_MOD), (1, B.FQ_MOD)])
+def test_wide_accumulator(host_shim, field, mod):
+    """Delayed reduction: the sum of n unreduced 512-bit products, reduced once, equals the sum of the
+    individually reduced Montgomery products.  Includes the extreme operands (p-1 and lazy values up to
+    4p-1) that drive the accumulator to its 2^511 normalisation threshold."""
+    rng = np.random.default_rng(5)
+    rinv = pow(1 << 256, -1, mod)
+    for n, kind in [(1, "rand"), (7, "rand"), (300, "rand"), (300, "max"), (64, "lazy")]:
+        if kind == "rand":
+            av = [v % mod for v in B.random_fr(rng, n)]
+            bv = [v % mod for v in B.random_fr(rng, n)]
+        elif kind == "max":
+            av, bv = [mod - 1] * n, [mod - 1 - i for i in range(n)]
+        else:
+            av, bv = [mod - 1 - i for i in range(n)], [4 * mod - 1 - i for i in range(n)]
+        a, b = B.ints_to_raw_array(av), B.ints_to_raw_array(bv)
+        out = np.zeros(4, dtype=np.uint64)
+        host_shim.shim_wide_dot(field, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_size_t(n),
+                                out.ctypes.data_as(C.c_void_p))
+        want = sum(x * y for x, y in zip(av, bv)) * rinv % mod
+        assert B.raw_array_to_ints(out.reshape(1, 4)) == [want], (n, kind)

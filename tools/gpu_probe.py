@@ -22,9 +22,9 @@ def rand_mont(rng, n):
 def main():
     out = {}
     ctx = Z.Context(0)
-    names = {0: "imad_reg", 4: "imad_imm", 1: "imad_wide", 2: "fr_mul", 3: "fq_mul"}
+    names = {0: "imad_reg", 4: "imad_imm", 1: "imad_wide", 2: "fr_mul", 3: "fq_mul", 5: "dfma", 6: "dfma_with_imad"}
     for kind, name in names.items():
-        out[name + "_per_s"] = ctx.bench_int_pipe(kind, 4000 if kind in (0, 1, 4) else 400)
+        out[name + "_per_s"] = ctx.bench_int_pipe(kind, 4000 if kind in (0, 1, 4, 5, 6) else 400)
         print(name, f"{out[name + '_per_s']:.4g}", flush=True)
     rng = np.random.default_rng(1)
     for log_n in [int(x) for x in os.environ.get("PROBE_MSM", "16,20,22,24").split(",") if x]:

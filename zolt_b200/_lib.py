@@ -70,10 +70,14 @@ SIGNATURES = {
     "zolt_sc_len": [_vp, C.POINTER(_sz)],
     "zolt_sc_download": [_vp, _i, _vp],
     "zolt_sc_table_dev": [_vp, _i, C.POINTER(_vp)],
+    "zolt_sc_set_claim": [_vp, _vp],
+    "zolt_sc_set_sharded": [_vp, _i],
     "zolt_sc_round_partials_dev": [_vp, C.POINTER(_vp)],
+    "zolt_sc_finish_partials": [_vp, _vp, _sz, _vp],
     "zolt_fr_sum_rows": [_vp, _vp, _sz, _sz, _vp],
     "zolt_sc_free": [_vp],
     "zolt_bench_int_pipe": [_vp, _i, _i, C.POINTER(C.c_double)],
+    "zolt_bench_int_pipe_cfg": [_vp, _i, _i, _i, _i, C.POINTER(C.c_double)],
     "zolt_prof_enable": [_vp, _i],
     "zolt_prof_read": [_vp, C.POINTER(_i), C.POINTER(C.c_float), _i, C.POINTER(_i)],
     "zolt_timer_start": [_vp],

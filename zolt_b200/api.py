@@ -88,6 +88,11 @@ class Context:
         check(self.lib.zolt_bench_int_pipe(self.handle, kind, iters, C.byref(out)), "zolt_bench_int_pipe")
         return out.value
 
+    def bench_int_pipe_cfg(self, kind: int, iters: int, threads: int, blocks_per_sm: int) -> float:
+        out = C.c_double()
+        check(self.lib.zolt_bench_int_pipe_cfg(self.handle, kind, iters, threads, blocks_per_sm, C.byref(out)), "zolt_bench_int_pipe_cfg")
+        return out.value
+
     # BatchOps (src/field/mod.zig:1164-1280) / parity hook for the field layer
     def field_op(self, field: int, op: int, a, b=None) -> np.ndarray:
         a = _as_u64(a, 4)
@@ -367,10 +372,24 @@ class SumcheckInstance:
         check(self.ctx.lib.zolt_sc_download(self.handle, t, _ptr(out)), "zolt_sc_download")
         return out
 
+    def set_claim(self, claim):
+        """SumcheckInstance.input_claim: lets the first round derive p(1) = claim - p(0) too."""
+        c = _as_u64(claim, 4)
+        check(self.ctx.lib.zolt_sc_set_claim(self.handle, _ptr(c)), "zolt_sc_set_claim")
+
+    def set_sharded(self, on: bool = True):
+        check(self.ctx.lib.zolt_sc_set_sharded(self.handle, int(on)), "zolt_sc_set_sharded")
+
     def partials_dev(self) -> int:
+        """Device pointer of this rank's 4 raw partial sums (128 bytes) for the all-gather."""
         p = C.c_void_p()
         check(self.ctx.lib.zolt_sc_round_partials_dev(self.handle, C.byref(p)), "zolt_sc_round_partials_dev")
         return p.value
+
+    def finish_partials(self, d_rows: int, rows: int) -> np.ndarray:
+        out = np.empty((self.num_evals, 4), dtype=np.uint64)
+        check(self.ctx.lib.zolt_sc_finish_partials(self.handle, C.c_void_p(d_rows), rows, _ptr(out)), "zolt_sc_finish_partials")
+        return out
 
     def free(self):
         if self.handle:

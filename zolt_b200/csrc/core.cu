@@ -261,6 +261,28 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(uint32_t* out, int iters,
 #pragma unroll
     for (int j = 0; j < 8; j++) s ^= x[j];
     out[tid] = (uint32_t)s ^ (uint32_t)(s >> 32);
+  } else if (KIND == 5 || KIND == 6) {
+    // KIND 5: FP64 fused multiply-adds alone; KIND 6: the same DFMA stream interleaved 1:1 with IMADs,
+    // to see whether the FP64 and the integer multiply pipes issue concurrently.
+    double d[8], dm = 1.0000001 + (double)(seed & 3), dc = (double)tid;
+    uint32_t x[8], m = seed | 1u, c = tid;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { d[j] = (double)(tid + j); x[j] = tid + j; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[j]) : "d"(dm), "d"(dc));
+          if (KIND == 6) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(m), "r"(c));
+        }
+      }
+    }
+    double s = 0;
+    uint32_t sx = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s += d[j]; sx ^= x[j]; }
+    out[tid] = (uint32_t)__double2ll_rn(s) ^ sx;
   } else {
     // field products: 2 independent chains
     using P = typename std::conditional<KIND == 2, FrParams, FqParams>::type;
@@ -287,11 +309,17 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(uint32_t* out, int iters,
   }
 }
 
+extern "C" int zolt_bench_int_pipe_cfg(zolt_ctx* ctx, int kind, int iters, int threads, int blocks_per_sm, double* ops_per_s);
 extern "C" int zolt_bench_int_pipe(zolt_ctx* ctx, int kind, int iters, double* ops_per_s) {
-  if (!ctx || !ops_per_s || kind < 0 || kind > 4 || iters <= 0) return ZOLT_ERR_ARG;
+  return zolt_bench_int_pipe_cfg(ctx, kind, iters, 256, 8, ops_per_s);
+}
+
+extern "C" int zolt_bench_int_pipe_cfg(zolt_ctx* ctx, int kind, int iters, int threads, int blocks_per_sm,
+                                       double* ops_per_s) {
+  if (!ctx || !ops_per_s || kind < 0 || kind > 6 || iters <= 0) return ZOLT_ERR_ARG;
+  if (threads < 32 || threads > 256 || (threads & 31) || blocks_per_sm < 1 || blocks_per_sm > 16) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
-  const int threads = 256;
-  const int blocks = ctx->num_sms * 8;
+  const int blocks = ctx->num_sms * blocks_per_sm;
   uint32_t* d_out = nullptr;
   ZOLT_CUDA_TRY(cudaMalloc(&d_out, (size_t)threads * blocks * sizeof(uint32_t)));
   cudaEvent_t e0, e1;
@@ -305,7 +333,9 @@ extern "C" int zolt_bench_int_pipe(zolt_ctx* ctx, int kind, int iters, double* o
       case 1: int_pipe_kernel<1><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u); break;
       case 2: int_pipe_kernel<2><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u); break;
       case 3: int_pipe_kernel<3><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u); break;
-      default: int_pipe_kernel<4><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u); break;
+      case 4: int_pipe_kernel<4><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u); break;
+      case 5: int_pipe_kernel<5><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u); break;
+      default: int_pipe_kernel<6><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u); break;
     }
     ctx->launches++;
     ZOLT_CUDA_TRY(cudaEventRecord(e1, ctx->stream));

@@ -90,6 +90,14 @@ struct FrParams {
   // R^2 mod r
   ZOLT_FIELD_TABLE(r2, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du,
                    0x7f4e44a5u, 0x0216d0b1u)
+  // 2r (subtracted from the top half of a 512-bit accumulator by wide_normalize)
+  ZOLT_FIELD_TABLE(mod2, 0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u, 0x0302b0bau, 0x70a08b6du,
+                   0xc2634053u, 0x60c89ce5u)
+  // 1/2 and 1/6 in Montgomery form (Newton interpolation of the previous round polynomial)
+  ZOLT_FIELD_TABLE(inv2, 0x1ffffffeu, 0x783c14d8u, 0x0c8d1eddu, 0xaf982f6fu, 0xfcfd4f45u, 0x8f5f7492u,
+                   0x3d9cbfacu, 0x1f37631au)
+  ZOLT_FIELD_TABLE(inv6, 0x0aaaaaaau, 0x7d695c48u, 0xaed9b4f4u, 0x3a880fcfu, 0xa9a9c517u, 0xda7526dbu,
+                   0x69deea8eu, 0x0a67cbb3u)
   static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32 (low word of 0xc2e1f593efffffff)
 };
 
@@ -101,6 +109,12 @@ struct FqParams {
                    0x9a07df2fu, 0x0e0a77c1u)
   ZOLT_FIELD_TABLE(r2, 0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu,
                    0xcab8351fu, 0x06d89f71u)
+  ZOLT_FIELD_TABLE(mod2, 0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du,
+                   0xc2634053u, 0x60c89ce5u)
+  ZOLT_FIELD_TABLE(inv2, 0x4f060572u, 0x87bee7d2u, 0x2f1c6ae5u, 0xd0fd2addu, 0xfcfd4f44u, 0x8f5f7492u,
+                   0x3d9cbfacu, 0x1f37631au)
+  ZOLT_FIELD_TABLE(inv6, 0x1a575726u, 0xd7ea4d46u, 0x0fb423a1u, 0xf054639fu, 0xa9a9c516u, 0xda7526dbu,
+                   0x69deea8eu, 0x0a67cbb3u)
   static constexpr uint32_t INV = 0xe4866389u;  // -q^-1 mod 2^32 (low word of 0x87d20782e4866389)
 };
 
@@ -336,6 +350,140 @@ ZOLT_HD Fp<P> fp_inv(const Fp<P>& a) {
     }
   }
   return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Delayed reduction: sums of products kept as unreduced 512-bit integers.
+//
+// A sum  S = sum_i a_i * b_i  of Montgomery-form products needs ONE Montgomery reduction at the end
+// instead of one per term: each term then costs the 64 wide multiplies of the plain product instead
+// of the 128 + 8 of a Montgomery product.  The result  S * 2^-256 mod p  is the same canonical field
+// element as the sum of the individually reduced products, so outputs stay bit-identical to the
+// reference's per-term montgomeryMul + add (src/field/mod.zig:735-798).
+//
+// Invariant of an accumulator acc[16]: acc < 2^511.  Every term is < 2^509.3 (operands < p and
+// < 4p), so acc + term < 2^512 never carries out; wide_normalize then subtracts (2p) * 2^256
+// (a multiple of p, 0.378 * 2^512) while bit 511 is set, which restores the invariant.
+// ---------------------------------------------------------------------------------------------
+// acc[s .. s+7] += (m0, m1, m2, m3) * bi laid out as four (lo, hi) pairs; the carry out goes to
+// acc[s+8], which at that point only ever holds earlier carries (see wide_mul_add).
+template <int S>
+ZOLT_HD void wide_chain(uint32_t* acc, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t bi) {
+  acc[S + 0] = ptx::mad_lo_cc(m0, bi, acc[S + 0]);
+  acc[S + 1] = ptx::madc_hi_cc(m0, bi, acc[S + 1]);
+  acc[S + 2] = ptx::madc_lo_cc(m1, bi, acc[S + 2]);
+  acc[S + 3] = ptx::madc_hi_cc(m1, bi, acc[S + 3]);
+  acc[S + 4] = ptx::madc_lo_cc(m2, bi, acc[S + 4]);
+  acc[S + 5] = ptx::madc_hi_cc(m2, bi, acc[S + 5]);
+  acc[S + 6] = ptx::madc_lo_cc(m3, bi, acc[S + 6]);
+  if constexpr (S + 8 < 16) {
+    acc[S + 7] = ptx::madc_hi_cc(m3, bi, acc[S + 7]);
+    acc[S + 8] = ptx::addc(acc[S + 8], 0u);
+  } else {
+    acc[S + 7] = ptx::madc_hi(m3, bi, acc[S + 7]);
+  }
+}
+
+// prod[0..15] = a * b  (plain 256 x 256 -> 512-bit product, no reduction).
+// The product is formed in two 16-limb temporaries: E collects the partial products a_j*b_i with
+// i+j even (their low words sit on even limbs), O those with i+j odd, shifted down one limb, so that
+// every (lo, hi) pair is one carry chain that ptxas turns into IMAD.WIDE.  Rows are visited in order,
+// so the limb a chain carries into has so far only received carries and cannot ripple.
+ZOLT_HD void wide_mul(uint32_t* e, const uint32_t* a, const uint32_t* b) {
+  uint32_t o[16];
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    e[2 * t] = ptx::mul_lo(a[2 * t], b[0]);
+    e[2 * t + 1] = ptx::mul_hi(a[2 * t], b[0]);
+    o[2 * t] = ptx::mul_lo(a[2 * t + 1], b[0]);
+    o[2 * t + 1] = ptx::mul_hi(a[2 * t + 1], b[0]);
+  }
+#pragma unroll
+  for (int k = 8; k < 16; k++) e[k] = o[k] = 0;
+  // odd rows i: E takes a1,a3,a5,a7 at limb i+1, O takes a0,a2,a4,a6 at limb i-1
+  // even rows i: E takes a0,a2,a4,a6 at limb i,  O takes a1,a3,a5,a7 at limb i
+  wide_chain<2>(e, a[1], a[3], a[5], a[7], b[1]);
+  wide_chain<0>(o, a[0], a[2], a[4], a[6], b[1]);
+  wide_chain<2>(e, a[0], a[2], a[4], a[6], b[2]);
+  wide_chain<2>(o, a[1], a[3], a[5], a[7], b[2]);
+  wide_chain<4>(e, a[1], a[3], a[5], a[7], b[3]);
+  wide_chain<2>(o, a[0], a[2], a[4], a[6], b[3]);
+  wide_chain<4>(e, a[0], a[2], a[4], a[6], b[4]);
+  wide_chain<4>(o, a[1], a[3], a[5], a[7], b[4]);
+  wide_chain<6>(e, a[1], a[3], a[5], a[7], b[5]);
+  wide_chain<4>(o, a[0], a[2], a[4], a[6], b[5]);
+  wide_chain<6>(e, a[0], a[2], a[4], a[6], b[6]);
+  wide_chain<6>(o, a[1], a[3], a[5], a[7], b[6]);
+  wide_chain<8>(e, a[1], a[3], a[5], a[7], b[7]);
+  wide_chain<6>(o, a[0], a[2], a[4], a[6], b[7]);
+  // prod = E + (O << 32)
+  e[1] = ptx::add_cc(e[1], o[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) e[k] = ptx::addc_cc(e[k], o[k - 1]);
+  e[15] = ptx::addc(e[15], o[14]);
+}
+
+// acc += prod (no carry out: see the invariant above)
+ZOLT_HD void wide_add(uint32_t* acc, const uint32_t* prod) {
+  acc[0] = ptx::add_cc(acc[0], prod[0]);
+#pragma unroll
+  for (int k = 1; k < 15; k++) acc[k] = ptx::addc_cc(acc[k], prod[k]);
+  acc[15] = ptx::addc(acc[15], prod[15]);
+}
+
+ZOLT_HD void wide_mul_add(uint32_t* acc, const uint32_t* a, const uint32_t* b) {
+  uint32_t prod[16];
+  wide_mul(prod, a, b);
+  wide_add(acc, prod);
+}
+
+template <class P>
+ZOLT_HD void wide_normalize(uint32_t* acc) {
+  while (acc[15] & 0x80000000u) {
+    acc[8] = ptx::sub_cc(acc[8], P::mod2(0));
+#pragma unroll
+    for (int i = 1; i < 7; i++) acc[8 + i] = ptx::subc_cc(acc[8 + i], P::mod2(i));
+    acc[15] = ptx::subc(acc[15], P::mod2(7));
+  }
+}
+
+ZOLT_HD void wide_zero(uint32_t* acc) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = 0;
+}
+
+// canonical  acc * 2^-256 mod p  for acc < 2^511 (runs once per thread per kernel: written for
+// clarity, not speed).  (acc + M*p) / 2^256 < 2^255 + p < 4p, hence three conditional subtractions.
+template <class P>
+ZOLT_HD Fp<P> wide_reduce(const uint32_t* acc_in) {
+  uint32_t t[17];
+#pragma unroll
+  for (int i = 0; i < 16; i++) t[i] = acc_in[i];
+  t[16] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t m = t[i] * P::INV;
+    uint64_t carry = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint64_t x = (uint64_t)m * P::mod(j) + t[i + j] + carry;
+      t[i + j] = (uint32_t)x;
+      carry = x >> 32;
+    }
+#pragma unroll
+    for (int k = i + 8; k < 17; k++) {
+      const uint64_t x = (uint64_t)t[k] + carry;
+      t[k] = (uint32_t)x;
+      carry = x >> 32;
+    }
+  }
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[8 + i];
+  fp_reduce_once<P>(r.v);
+  fp_reduce_once<P>(r.v);
+  fp_reduce_once<P>(r.v);
+  return r;
 }
 
 using Fr = Fp<FrParams>;

@@ -63,76 +63,239 @@ __device__ __forceinline__ Fr bind_pair(const Fr& lo, const Fr& hi, const Fr& r)
   return fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
 }
 
-// ---- combiners: accumulate one pair (lo[], hi[]) into the running evaluations -----------------------
+// ---- combiners ------------------------------------------------------------------------------------
+// Every product combiner keeps its running sums as UNREDUCED 512-bit accumulators (field.cuh wide_*):
+// the last multiplication of each term costs a plain product, and the Montgomery reduction happens
+// once per thread.  The round polynomial is sampled at X = 0, 2 and "infinity" (its leading
+// coefficient); p(1) comes from the sumcheck identity p(0) + p(1) = claim and p(3) from the third
+// finite difference, both exact in the field, so the four evaluations handed to the host are the
+// canonical values the reference computes by direct summation (e.g. output_check.zig:399-432).
+//
+// Raw sums leave the kernel as 4 field elements:
+//   cubic      [p(0), p(1) or 0, p(2), lead]     quadratic [p(0), p(1) or 0, lead, 0]
+//   SUM/Gruen  [s0, s1, 0, 0]
 template <int COMB> struct CombTraits;
-template <> struct CombTraits<ZOLT_SC_SUM> { static constexpr int K = 1, NE = 2; static constexpr bool GRUEN = false; };
-template <> struct CombTraits<ZOLT_SC_PROD2> { static constexpr int K = 2, NE = 4; static constexpr bool GRUEN = false; };
-template <> struct CombTraits<ZOLT_SC_PROD3> { static constexpr int K = 3, NE = 4; static constexpr bool GRUEN = false; };
-template <> struct CombTraits<ZOLT_SC_EQ_A_BMC> { static constexpr int K = 4, NE = 4; static constexpr bool GRUEN = false; };
-template <> struct CombTraits<ZOLT_SC_EQ_AB_MINUS_C> { static constexpr int K = 4, NE = 4; static constexpr bool GRUEN = false; };
-template <> struct CombTraits<ZOLT_SC_GRUEN_AB> { static constexpr int K = 2, NE = 2; static constexpr bool GRUEN = true; };
-template <> struct CombTraits<ZOLT_SC_GRUEN_AB_MINUS_C> { static constexpr int K = 3, NE = 2; static constexpr bool GRUEN = true; };
+template <> struct CombTraits<ZOLT_SC_SUM> { static constexpr int K = 1, NE = 2, NW = 0, DEG = 0; static constexpr bool GRUEN = false; };
+template <> struct CombTraits<ZOLT_SC_PROD2> { static constexpr int K = 2, NE = 4, NW = 2, DEG = 2; static constexpr bool GRUEN = false; };
+template <> struct CombTraits<ZOLT_SC_PROD3> { static constexpr int K = 3, NE = 4, NW = 3, DEG = 3; static constexpr bool GRUEN = false; };
+template <> struct CombTraits<ZOLT_SC_EQ_A_BMC> { static constexpr int K = 4, NE = 4, NW = 3, DEG = 3; static constexpr bool GRUEN = false; };
+template <> struct CombTraits<ZOLT_SC_EQ_AB_MINUS_C> { static constexpr int K = 4, NE = 4, NW = 3, DEG = 3; static constexpr bool GRUEN = false; };
+template <> struct CombTraits<ZOLT_SC_GRUEN_AB> { static constexpr int K = 2, NE = 2, NW = 2, DEG = 0; static constexpr bool GRUEN = true; };
+template <> struct CombTraits<ZOLT_SC_GRUEN_AB_MINUS_C> { static constexpr int K = 3, NE = 2, NW = 2, DEG = 0; static constexpr bool GRUEN = true; };
 
-template <int COMB>
-__device__ __forceinline__ void accumulate_pair(Fr* acc, const Fr* lo, const Fr* hi, const Fr& w) {
+constexpr int kRaw = 4;  // field elements per partial result
+
+// ---- per-thread shared-memory scratch --------------------------------------------------------------
+// Every thread of a round kernel owns 512 bytes of shared memory, addressed in 16-byte units laid out
+// [unit][thread] so that a warp's 128-bit accesses are conflict-free.  It is PRIVATE to the thread (no
+// barrier is ever needed) and serves as
+//   * the landing zone of cp.async prefetches: the source elements a thread needs next are copied
+//     global -> shared while it is still multiplying, so no register is spent on loads in flight and
+//     the HBM latency is off the critical path;
+//   * the stash of the bound (lo, hi) values of every table between the bind loop, which is rolled over
+//     the tables to keep the kernel's code small enough for the instruction cache, and the evaluation.
+constexpr int kRoundThreads = 128;
+constexpr int kEvalBlocksPerSm = 3;   // MODE 0/1: 32 scratch units (512 B) per thread
+constexpr int kFusedBlocksPerSm = 4;  // MODE 2: 24 scratch units (384 B) per thread
+constexpr int kEvalScratchUnits = 32;
+constexpr int kFusedScratchUnits = 24;
+
+__device__ __forceinline__ Fr scr_ld(const uint4* base, int unit) {
+  const uint4 a = base[unit * kRoundThreads], b = base[(unit + 1) * kRoundThreads];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void scr_st(uint4* base, int unit, const Fr& x) {
+  base[unit * kRoundThreads] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  base[(unit + 1) * kRoundThreads] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+// one field element global -> this thread's scratch (two 16-byte asynchronous copies, L2 only)
+__device__ __forceinline__ void scr_prefetch(uint4* base, int unit, const Fr* g) {
+  const unsigned s0 = (unsigned)__cvta_generic_to_shared(base + unit * kRoundThreads);
+  const unsigned s1 = (unsigned)__cvta_generic_to_shared(base + (unit + 1) * kRoundThreads);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(g) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(reinterpret_cast<const char*>(g) + 16) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// acc += a * b (unreduced), then restore acc < 2^511
+__device__ __forceinline__ void wide_acc(uint32_t* acc, const Fr& a, const Fr& b) {
+  wide_mul_add(acc, a.v, b.v);
+  wide_normalize<FrParams>(acc);
+}
+
+// One pair of every combiner table; the values sit in the thread's stash at units 4k (lo) and 4k+2 (hi).
+// wacc: NW (+1 when P1) wide accumulators, facc: SUM only.
+template <int COMB, bool P1>
+__device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, const uint4* st, const Fr& w) {
+#define LO(k) scr_ld(st, 4 * (k))
+#define HI(k) scr_ld(st, 4 * (k) + 2)
   if constexpr (COMB == ZOLT_SC_SUM) {
-    acc[0] = fr_add(acc[0], lo[0]);
-    acc[1] = fr_add(acc[1], hi[0]);
+    facc[0] = fr_add(facc[0], LO(0));
+    facc[1] = fr_add(facc[1], HI(0));
   } else if constexpr (COMB == ZOLT_SC_PROD2) {
-    // a(X) = lo + X*(hi-lo); evaluations at X = 0,1,2,3 by repeated addition of the slope
-    Fr da = fr_sub(hi[0], lo[0]), db = fr_sub(hi[1], lo[1]);
-    acc[0] = fr_add(acc[0], fr_mul(lo[0], lo[1]));
-    acc[1] = fr_add(acc[1], fr_mul(hi[0], hi[1]));
-    Fr a = fr_add(hi[0], da), b = fr_add(hi[1], db);
-    acc[2] = fr_add(acc[2], fr_mul(a, b));
-    a = fr_add(a, da);
-    b = fr_add(b, db);
-    acc[3] = fr_add(acc[3], fr_mul(a, b));
+    // a(X) b(X): p(0) = a0 b0, lead = (a1-a0)(b1-b0)
+    const Fr a0 = LO(0), b0 = LO(1), a1 = HI(0), b1 = HI(1);
+    wide_acc(wacc[0], a0, b0);
+    if constexpr (P1) wide_acc(wacc[2], a1, b1);
+    wide_acc(wacc[1], fr_sub(a1, a0), fr_sub(b1, b0));
   } else if constexpr (COMB == ZOLT_SC_PROD3 || COMB == ZOLT_SC_EQ_A_BMC) {
-    Fr a0 = lo[0], a1 = hi[0], b0 = lo[1], b1 = hi[1], c0, c1;
+    // x(X) y(X) z(X);  eq*a*(b-c) is the same shape with z = b - c
+    Fr m0, m2, ml, m1;
+    {
+      const Fr x0 = LO(0), y0 = LO(1), x1 = HI(0), y1 = HI(1);
+      m0 = fr_mul(x0, y0);
+      if constexpr (P1) m1 = fr_mul(x1, y1);
+      const Fr dx = fr_sub(x1, x0), dy = fr_sub(y1, y0);
+      ml = fr_mul(dx, dy);
+      m2 = fr_mul(fr_add(x1, dx), fr_add(y1, dy));
+    }
+    Fr z0, z1;
     if constexpr (COMB == ZOLT_SC_PROD3) {
-      c0 = lo[2];
-      c1 = hi[2];
-    } else {  // eq * a * (b - c)
-      c0 = fr_sub(lo[2], lo[3]);
-      c1 = fr_sub(hi[2], hi[3]);
+      z0 = LO(2);
+      z1 = HI(2);
+    } else {
+      z0 = fr_sub(LO(2), LO(3));
+      z1 = fr_sub(HI(2), HI(3));
     }
-    Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0), dc = fr_sub(c1, c0);
-    acc[0] = fr_add(acc[0], fr_mul(fr_mul(a0, b0), c0));
-    acc[1] = fr_add(acc[1], fr_mul(fr_mul(a1, b1), c1));
-    Fr a = fr_add(a1, da), b = fr_add(b1, db), c = fr_add(c1, dc);
-    acc[2] = fr_add(acc[2], fr_mul(fr_mul(a, b), c));
-    a = fr_add(a, da);
-    b = fr_add(b, db);
-    c = fr_add(c, dc);
-    acc[3] = fr_add(acc[3], fr_mul(fr_mul(a, b), c));
+    wide_acc(wacc[0], m0, z0);
+    if constexpr (P1) wide_acc(wacc[3], m1, z1);
+    const Fr dz = fr_sub(z1, z0);
+    wide_acc(wacc[2], ml, dz);
+    wide_acc(wacc[1], m2, fr_add(z1, dz));
   } else if constexpr (COMB == ZOLT_SC_EQ_AB_MINUS_C) {
-    // eq(X) * (az(X)*bz(X) - cz(X))
-    Fr e = lo[0], a = lo[1], b = lo[2], c = lo[3];
-    Fr de = fr_sub(hi[0], e), da = fr_sub(hi[1], a), db = fr_sub(hi[2], b), dc = fr_sub(hi[3], c);
-    acc[0] = fr_add(acc[0], fr_mul(e, fr_sub(fr_mul(a, b), c)));
-#pragma unroll
-    for (int x = 1; x < 4; x++) {
-      e = fr_add(e, de);
-      a = fr_add(a, da);
-      b = fr_add(b, db);
-      c = fr_add(c, dc);
-      acc[x] = fr_add(acc[x], fr_mul(e, fr_sub(fr_mul(a, b), c)));
+    // e(X) * (a(X) b(X) - c(X)): the leading coefficient has no c term
+    Fr t0, t2, ml, t1;
+    {
+      const Fr a0 = LO(1), b0 = LO(2), a1 = HI(1), b1 = HI(2);
+      t0 = fr_mul(a0, b0);
+      if constexpr (P1) t1 = fr_mul(a1, b1);
+      const Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0);
+      ml = fr_mul(da, db);
+      t2 = fr_mul(fr_add(a1, da), fr_add(b1, db));
     }
-  } else if constexpr (COMB == ZOLT_SC_GRUEN_AB) {
-    Fr p0 = fr_mul(lo[0], lo[1]);
-    Fr slope = fr_mul(fr_sub(hi[0], lo[0]), fr_sub(hi[1], lo[1]));
-    acc[0] = fr_add(acc[0], fr_mul(w, p0));
-    acc[1] = fr_add(acc[1], fr_mul(w, slope));
-  } else {  // ZOLT_SC_GRUEN_AB_MINUS_C
-    Fr p0 = fr_sub(fr_mul(lo[0], lo[1]), lo[2]);
-    Fr slope = fr_mul(fr_sub(hi[0], lo[0]), fr_sub(hi[1], lo[1]));
-    acc[0] = fr_add(acc[0], fr_mul(w, p0));
-    acc[1] = fr_add(acc[1], fr_mul(w, slope));
+    {
+      const Fr c0 = LO(3), c1 = HI(3);
+      t0 = fr_sub(t0, c0);
+      if constexpr (P1) t1 = fr_sub(t1, c1);
+      t2 = fr_sub(t2, fr_add(c1, fr_sub(c1, c0)));
+    }
+    const Fr e0 = LO(0), e1 = HI(0);
+    wide_acc(wacc[0], e0, t0);
+    if constexpr (P1) wide_acc(wacc[3], e1, t1);
+    const Fr de = fr_sub(e1, e0);
+    wide_acc(wacc[2], de, ml);
+    wide_acc(wacc[1], fr_add(e1, de), t2);
+  } else if constexpr (COMB == ZOLT_SC_GRUEN_AB || COMB == ZOLT_SC_GRUEN_AB_MINUS_C) {
+    const Fr l0 = LO(0), r0 = LO(1), l1 = HI(0), r1 = HI(1);
+    Fr p0 = fr_mul(l0, r0);
+    if constexpr (COMB == ZOLT_SC_GRUEN_AB_MINUS_C) p0 = fr_sub(p0, LO(2));
+    wide_acc(wacc[0], w, p0);
+    wide_acc(wacc[1], w, fr_mul(fr_sub(l1, l0), fr_sub(r1, r0)));
+  }
+#undef LO
+#undef HI
+}
+
+// thread-local accumulators -> the 4 raw sums
+template <int COMB, bool P1>
+__device__ __forceinline__ void collapse(uint32_t (*wacc)[16], const Fr* facc, Fr* raw) {
+  constexpr int NW = CombTraits<COMB>::NW;
+  constexpr int DEG = CombTraits<COMB>::DEG;
+#pragma unroll
+  for (int i = 0; i < kRaw; i++) raw[i] = Fr::zero();
+  if constexpr (COMB == ZOLT_SC_SUM) {
+    raw[0] = facc[0];
+    raw[1] = facc[1];
+  } else if constexpr (DEG == 3) {
+    raw[0] = wide_reduce<FrParams>(wacc[0]);
+    raw[2] = wide_reduce<FrParams>(wacc[1]);
+    raw[3] = wide_reduce<FrParams>(wacc[2]);
+    if constexpr (P1) raw[1] = wide_reduce<FrParams>(wacc[NW]);
+  } else if constexpr (DEG == 2) {
+    raw[0] = wide_reduce<FrParams>(wacc[0]);
+    raw[2] = wide_reduce<FrParams>(wacc[1]);
+    if constexpr (P1) raw[1] = wide_reduce<FrParams>(wacc[NW]);
+  } else {
+    raw[0] = wide_reduce<FrParams>(wacc[0]);
+    raw[1] = wide_reduce<FrParams>(wacc[1]);
   }
 }
 
-// ---- block / grid reduction of NE field accumulators -------------------------------------------------
+// ---- raw sums -> the evaluations at X = 0..3 -------------------------------------------------------
+enum { CLAIM_NONE = 0 /* p(1) was summed directly */, CLAIM_PREV = 1 /* claim = p_prev(r) */, CLAIM_HOST = 2 /* *d_claim */ };
+
+__device__ __forceinline__ Fr fr_const(uint32_t (*f)(int)) {
+  Fr x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = f(i);
+  return x;
+}
+
+// p(r) for the cubic through (0,p0) (1,p1) (2,p2) (3,p3): Newton forward differences
+__device__ __noinline__ Fr newton_eval4(const Fr* p, const Fr& r) {
+  const Fr d1 = fr_sub(p[1], p[0]);
+  const Fr d1b = fr_sub(p[2], p[1]);
+  const Fr d1c = fr_sub(p[3], p[2]);
+  const Fr d2 = fr_sub(d1b, d1);
+  const Fr d2b = fr_sub(d1c, d1b);
+  const Fr d3 = fr_sub(d2b, d2);
+  Fr inv2, inv6;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    inv2.v[i] = FrParams::inv2(i);
+    inv6.v[i] = FrParams::inv6(i);
+  }
+  const Fr rm1 = fr_sub(r, Fr::one());
+  const Fr rm2 = fr_sub(rm1, Fr::one());
+  const Fr c2 = fr_mul(fr_mul(r, rm1), inv2);          // r(r-1)/2
+  const Fr c3 = fr_mul(fr_mul(fr_mul(r, rm1), rm2), inv6);  // r(r-1)(r-2)/6
+  Fr acc = fr_add(p[0], fr_mul(r, d1));
+  acc = fr_add(acc, fr_mul(c2, d2));
+  acc = fr_add(acc, fr_mul(c3, d3));
+  return acc;
+}
+
+// deg: 0 (raw sums are the evaluations), 2 or 3.  prev: the previous round's 4 evaluations (CLAIM_PREV).
+__device__ __noinline__ void sc_finalize(int deg, int claim_src, const Fr* raw, const Fr* prev, const Fr& r,
+                                         const Fr* d_claim, Fr* out) {
+  if (deg == 0) {
+#pragma unroll
+    for (int i = 0; i < kRaw; i++) out[i] = raw[i];
+    return;
+  }
+  const Fr p0 = raw[0];
+  Fr p1;
+  if (claim_src == CLAIM_NONE) p1 = raw[1];
+  else if (claim_src == CLAIM_PREV) p1 = fr_sub(newton_eval4(prev, r), p0);
+  else p1 = fr_sub(ld_fr(d_claim), p0);
+  Fr p2, p3;
+  if (deg == 3) {
+    p2 = raw[2];
+    const Fr lead = raw[3];
+    Fr t = fr_add(fr_add(lead, lead), lead);  // 3*lead
+    t = fr_add(t, t);                          // 6*lead = third finite difference
+    const Fr d = fr_sub(p2, p1);
+    p3 = fr_add(fr_add(t, fr_add(fr_add(d, d), d)), p0);  // p3 = 6 lead + 3 (p2 - p1) + p0
+  } else {
+    const Fr lead = raw[2];
+    const Fr l2 = fr_add(lead, lead);
+    const Fr s = fr_sub(p1, p0);                             // c1 + c2
+    p2 = fr_add(fr_add(p1, s), l2);                          // 2 p1 - p0 + 2 c2
+    p3 = fr_add(fr_add(fr_add(p1, s), s), fr_add(fr_add(l2, l2), l2));  // 3 p1 - 2 p0 + 6 c2
+  }
+  out[0] = p0;
+  out[1] = p1;
+  out[2] = p2;
+  out[3] = p3;
+}
+
+// ---- block / grid reduction of the raw sums -----------------------------------------------------------
 __device__ __forceinline__ Fr shfl_down_fr(const Fr& x, int delta) {
   Fr r;
 #pragma unroll
@@ -166,18 +329,29 @@ __device__ __forceinline__ void block_reduce(Fr* acc, Fr* smem) {
   __syncthreads();
 }
 
-// Each block publishes its partial; the last block to arrive folds all partials and writes the
-// round evaluations to device memory and to the mapped host mailbox.
+struct ScOut {
+  Fr* partials;       // gridDim.x * kRaw
+  unsigned* ticket;
+  Fr* d_raw;          // kRaw raw sums of this launch (what a sharded run all-gathers)
+  Fr* d_evals;        // 4 evaluations: read as "previous round" (CLAIM_PREV), then overwritten
+  Fr* h_evals;        // mapped pinned host copy of d_evals
+  const Fr* d_claim;  // CLAIM_HOST
+  int deg;            // 0 / 2 / 3
+  int claim_src;
+  int finalize;       // 0: sharded run, stop at the raw sums
+};
+
+// Each block publishes its partial; the last block to arrive folds all partials, turns the raw sums into
+// the round evaluations and writes them to device memory and to the mapped host mailbox.
 template <int NE>
-__device__ __forceinline__ void grid_finish(Fr* acc, Fr* smem, Fr* partials, unsigned* ticket, Fr* d_evals,
-                                            Fr* h_evals) {
+__device__ __forceinline__ void grid_finish(Fr* acc, Fr* smem, const ScOut& o, const Fr& r) {
   __shared__ bool is_last;
   block_reduce<NE>(acc, smem);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int e = 0; e < NE; e++) st_fr(&partials[(size_t)blockIdx.x * NE + e], acc[e]);
+    for (int e = 0; e < NE; e++) st_fr(&o.partials[(size_t)blockIdx.x * NE + e], acc[e]);
     __threadfence();
-    unsigned t = atomicAdd(ticket, 1u);
+    unsigned t = atomicAdd(o.ticket, 1u);
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
@@ -189,7 +363,7 @@ __device__ __forceinline__ void grid_finish(Fr* acc, Fr* smem, Fr* partials, uns
   for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
 #pragma unroll
     for (int e = 0; e < NE; e++) {
-      const uint4* q = reinterpret_cast<const uint4*>(&partials[(size_t)b * NE + e]);
+      const uint4* q = reinterpret_cast<const uint4*>(&o.partials[(size_t)b * NE + e]);
       uint4 lo4 = __ldcg(q), hi4 = __ldcg(q + 1);  // bypass L1: written by other SMs
       Fr x;
       x.v[0] = lo4.x; x.v[1] = lo4.y; x.v[2] = lo4.z; x.v[3] = lo4.w;
@@ -200,86 +374,173 @@ __device__ __forceinline__ void grid_finish(Fr* acc, Fr* smem, Fr* partials, uns
   block_reduce<NE>(tot, smem);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int e = 0; e < NE; e++) {
-      st_fr(&d_evals[e], tot[e]);
-      st_fr(&h_evals[e], tot[e]);
+    for (int e = 0; e < NE; e++) st_fr(&o.d_raw[e], tot[e]);
+    if (o.finalize) {
+      Fr prev[4], ev[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) prev[e] = o.claim_src == CLAIM_PREV ? ld_fr(&o.d_evals[e]) : Fr::zero();
+      Fr raw4[kRaw];
+#pragma unroll
+      for (int e = 0; e < kRaw; e++) raw4[e] = e < NE ? tot[e < NE ? e : 0] : Fr::zero();
+      sc_finalize(o.deg, o.claim_src, raw4, prev, r, o.d_claim, ev);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        st_fr(&o.d_evals[e], ev[e]);
+        st_fr(&o.h_evals[e], ev[e]);
+      }
     }
-    *ticket = 0;
+    *o.ticket = 0;
     __threadfence_system();
   }
 }
 
 // ---- the round kernel ------------------------------------------------------------------------------
-// FUSED == false: evaluate the round polynomial of the current tables (src, length n).
-// FUSED == true : bind src (length n) to r into dst (length n/2) and evaluate the NEXT round's
-//                 polynomial over dst in the same pass.  n_extra tables after the K combiner tables
-//                 are bound only.
-template <int COMB, int PAIR, bool FUSED>
-__global__ void __launch_bounds__(kScThreads)
-sc_round_kernel(ScPtrs t, int n_extra, size_t n, Fr r, SplitEqDev sq, Fr* partials, unsigned* ticket,
-                Fr* d_evals, Fr* h_evals) {
+// MODE 0: evaluate the round polynomial of the current tables (src, length n), p(1) summed directly.
+// MODE 1: the same, p(1) from the claim the host supplied (zolt_sc_set_claim).
+// MODE 2: FUSED -- bind src (length n) to r into dst (length n/2) and evaluate the NEXT round's
+//         polynomial over dst in the same pass; its claim is the previous polynomial at r.  n_extra tables
+//         after the K combiner tables are bound only.
+template <int COMB, int PAIR, int MODE>
+__global__ void __launch_bounds__(kRoundThreads, MODE == 2 ? kFusedBlocksPerSm : kEvalBlocksPerSm)
+sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const __grid_constant__ Fr r, SplitEqDev sq,
+                const __grid_constant__ ScOut out) {
   constexpr int K = CombTraits<COMB>::K;
-  constexpr int NE = CombTraits<COMB>::NE;
-  __shared__ Fr smem[NE * 32];
-  Fr acc[NE];
+  constexpr int NW = CombTraits<COMB>::NW;
+  constexpr bool FUSED = MODE == 2;
+  constexpr bool P1 = MODE == 0 && CombTraits<COMB>::DEG != 0;
+  constexpr int NACC = NW + (P1 ? 1 : 0);
+  __shared__ Fr smem[kRaw * 32];
+  extern __shared__ uint4 scratch[];  // [units][kRoundThreads], dynamic: exceeds the 48 KB static limit
+  uint4* const scr = scratch + threadIdx.x;
+  uint32_t wacc[NACC > 0 ? NACC : 1][16];
+  Fr facc[2] = {Fr::zero(), Fr::zero()};
 #pragma unroll
-  for (int e = 0; e < NE; e++) acc[e] = Fr::zero();
+  for (int i = 0; i < NACC; i++) wide_zero(wacc[i]);
 
   const size_t n_cur = FUSED ? n / 2 : n;  // length of the table the evaluations are taken over
   const size_t pairs = n_cur / 2;
   const size_t half_old = n / 2;           // HALF pairing: distance between bind partners in src
   const size_t half_cur = n_cur / 2;       // HALF pairing: distance between eval partners
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
 
-  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < pairs;
-       g += (size_t)gridDim.x * blockDim.x) {
-    const size_t i_lo = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * g : g;
-    const size_t i_hi = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * g + 1 : g + half_cur;
-    Fr lo[K], hi[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      if constexpr (FUSED) {
-        const Fr* s = t.src[k];
-        Fr a0, a1, b0, b1;
-        if constexpr (PAIR == ZOLT_PAIR_ADJACENT) {
-          a0 = ld_fr(s + 2 * i_lo); a1 = ld_fr(s + 2 * i_lo + 1);
-          b0 = ld_fr(s + 2 * i_hi); b1 = ld_fr(s + 2 * i_hi + 1);
-        } else {
-          a0 = ld_fr(s + i_lo); a1 = ld_fr(s + i_lo + half_old);
-          b0 = ld_fr(s + i_hi); b1 = ld_fr(s + i_hi + half_old);
-        }
-        lo[k] = bind_pair(a0, a1, r);
-        hi[k] = bind_pair(b0, b1, r);
-        st_fr(t.dst[k] + i_lo, lo[k]);
-        st_fr(t.dst[k] + i_hi, hi[k]);
+  if constexpr (FUSED) {
+    // scratch units 0..15: stash of the bound values (unit 4k lo, 4k+2 hi of table k);
+    // units 16..23: two prefetch slots of one bind's two source elements each.
+    // Work items are linearised as (pair, table, half): item q binds one output element.
+    const int kt = K + n_extra;
+    auto prefetch_item = [&](size_t gi, int k, int h, int slot) {
+      const Fr* s = t.src[k];
+      const size_t idx = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * gi + h : gi + (h ? half_cur : 0);
+      const int u = 16 + 4 * slot;
+      if constexpr (PAIR == ZOLT_PAIR_ADJACENT) {
+        scr_prefetch(scr, u, s + 2 * idx);
+        scr_prefetch(scr, u + 2, s + 2 * idx + 1);
       } else {
-        lo[k] = ld_fr(t.src[k] + i_lo);
-        hi[k] = ld_fr(t.src[k] + i_hi);
+        scr_prefetch(scr, u, s + idx);
+        scr_prefetch(scr, u + 2, s + idx + half_old);
       }
+    };
+    // The cp.async ring runs one bind ahead, which hides an L2 hit but not an HBM access; a second,
+    // register- and smem-free stage pulls the lines of the table two steps ahead into L2.
+    auto prefetch_table_l2 = [&](size_t gi, int k) {
+      const Fr* s = t.src[k];
+      if constexpr (PAIR == ZOLT_PAIR_ADJACENT) {
+        prefetch_l2(s + 4 * gi);  // the 128-byte line holding all four source elements of the pair
+      } else {
+        prefetch_l2(s + gi);
+        prefetch_l2(s + gi + half_old);
+        prefetch_l2(s + gi + half_cur);
+        prefetch_l2(s + gi + half_cur + half_old);
+      }
+    };
+    if (g < pairs) {
+      prefetch_item(g, 0, 0, 0);
+      for (int k = 0; k < kt && k < 2; k++) prefetch_table_l2(g, k);
     }
-    if constexpr (FUSED) {
-      for (int k = K; k < K + n_extra; k++) {
-        const Fr* s = t.src[k];
-        Fr a0, a1, b0, b1;
-        if constexpr (PAIR == ZOLT_PAIR_ADJACENT) {
-          a0 = ld_fr(s + 2 * i_lo); a1 = ld_fr(s + 2 * i_lo + 1);
-          b0 = ld_fr(s + 2 * i_hi); b1 = ld_fr(s + 2 * i_hi + 1);
-        } else {
-          a0 = ld_fr(s + i_lo); a1 = ld_fr(s + i_lo + half_old);
-          b0 = ld_fr(s + i_hi); b1 = ld_fr(s + i_hi + half_old);
+    cp_async_commit();
+    int slot = 0;
+    for (; g < pairs; g += stride) {
+#pragma unroll 1
+      for (int q = 0; q < 2 * kt; q++) {
+        const int k = q >> 1, h = q & 1;
+        if (h == 0) {
+          const int k2 = k + 2 >= kt ? k + 2 - kt : k + 2;
+          const size_t g2 = k + 2 >= kt ? g + stride : g;
+          if (k2 < kt && g2 < pairs) prefetch_table_l2(g2, k2);
         }
-        st_fr(t.dst[k] + i_lo, bind_pair(a0, a1, r));
-        st_fr(t.dst[k] + i_hi, bind_pair(b0, b1, r));
+        // start the copy of the next item, then wait for the current one
+        const bool wrap = (q + 1 == 2 * kt);
+        const size_t g_nxt = wrap ? g + stride : g;
+        if (g_nxt < pairs) prefetch_item(g_nxt, wrap ? 0 : (q + 1) >> 1, (q + 1) & 1, slot ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        const int u = 16 + 4 * slot;
+        const size_t idx = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * g + h : g + (h ? half_cur : 0);
+        const Fr a0 = scr_ld(scr, u), a1 = scr_ld(scr, u + 2);
+        const Fr v = bind_pair(a0, a1, r);
+        st_fr(t.dst[k] + idx, v);
+        if (k < K) scr_st(scr, 2 * q, v);
+        slot ^= 1;
       }
+      Fr w;
+      if constexpr (CombTraits<COMB>::GRUEN) {
+        // g = (x_out << in_bits) | x_in  (src/zkvm/spartan/product_remainder.zig:293-296)
+        const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
+        w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+      }
+      accumulate_pair<COMB, P1>(wacc, facc, scr, w);
     }
-    Fr w;
-    if constexpr (CombTraits<COMB>::GRUEN) {
-      // g = (x_out << in_bits) | x_in  (src/zkvm/spartan/product_remainder.zig:293-296)
-      const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
-      w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+  } else {
+    // no bind: the (lo, hi) values of every table are copied straight into the stash layout, double
+    // buffered (units 0..15 and 16..31) one pair ahead.
+    auto prefetch_pair = [&](size_t gi, int buf) {
+      const size_t i_lo = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * gi : gi;
+      const size_t i_hi = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * gi + 1 : gi + half_cur;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        scr_prefetch(scr, 16 * buf + 4 * k, t.src[k] + i_lo);
+        scr_prefetch(scr, 16 * buf + 4 * k + 2, t.src[k] + i_hi);
+      }
+    };
+    if (g < pairs) prefetch_pair(g, 0);
+    cp_async_commit();
+    int buf = 0;
+    for (; g < pairs; g += stride) {
+      if (g + stride < pairs) prefetch_pair(g + stride, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      Fr w;
+      if constexpr (CombTraits<COMB>::GRUEN) {
+        const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
+        w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+      }
+      accumulate_pair<COMB, P1>(wacc, facc, scr + 16 * buf * kRoundThreads, w);
+      buf ^= 1;
     }
-    accumulate_pair<COMB>(acc, lo, hi, w);
   }
-  grid_finish<NE>(acc, smem, partials, ticket, d_evals, h_evals);
+  cp_async_wait<0>();
+  Fr raw[kRaw];
+  collapse<COMB, P1>(wacc, facc, raw);
+  grid_finish<kRaw>(raw, smem, out, r);
+}
+
+// Sharded runs: fold the all-gathered raw sums of every rank (rows x kRaw) and finish the round.
+__global__ void sc_finish_rows_kernel(const Fr* rows, size_t n_rows, ScOut out, Fr r) {
+  if (threadIdx.x != 0) return;
+  Fr raw[kRaw], prev[4], ev[4];
+  for (int c = 0; c < kRaw; c++) {
+    Fr acc = Fr::zero();
+    for (size_t i = 0; i < n_rows; i++) acc = fr_add(acc, ld_fr(rows + i * kRaw + c));
+    raw[c] = acc;
+  }
+  for (int e = 0; e < 4; e++) prev[e] = out.claim_src == CLAIM_PREV ? ld_fr(&out.d_evals[e]) : Fr::zero();
+  sc_finalize(out.deg, out.claim_src, raw, prev, r, out.d_claim, ev);
+  for (int e = 0; e < 4; e++) {
+    st_fr(&out.d_evals[e], ev[e]);
+    st_fr(&out.h_evals[e], ev[e]);
+  }
+  __threadfence_system();
 }
 
 // Final bind (n == 2 -> 1) and stand-alone binds: dst[i] = bind(src pair i).
@@ -297,13 +558,12 @@ __global__ void __launch_bounds__(kScThreads) bind_kernel(Fr* dst, const Fr* src
 // honoured by the host wrapper through a scratch buffer.
 
 // Sum of a table (initial claim).
-__global__ void __launch_bounds__(kScThreads) sum_kernel(const Fr* src, size_t n, Fr* partials,
-                                                         unsigned* ticket, Fr* d_evals, Fr* h_evals) {
+__global__ void __launch_bounds__(kScThreads) sum_kernel(const Fr* src, size_t n, ScOut out) {
   __shared__ Fr smem[32];
   Fr acc[1] = {Fr::zero()};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     acc[0] = fr_add(acc[0], ld_fr(src + i));
-  grid_finish<1>(acc, smem, partials, ticket, d_evals, h_evals);
+  grid_finish<1>(acc, smem, out, Fr::zero());
 }
 
 // rows x cols matrix of Fr -> column sums (multi-GPU fold of gathered partial evaluations)
@@ -360,8 +620,8 @@ inline Fr fr_from_host(const uint64_t* p) {
   return r;
 }
 
-inline unsigned grid_for(const zolt_ctx* ctx, size_t work_items, int per_sm) {
-  size_t blocks = (work_items + kScThreads - 1) / kScThreads;
+inline unsigned grid_for(const zolt_ctx* ctx, size_t work_items, int per_sm, int threads = kScThreads) {
+  size_t blocks = (work_items + threads - 1) / threads;
   size_t cap = (size_t)ctx->num_sms * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
@@ -384,7 +644,14 @@ struct zolt_sc {
   Fr* buf[2][kMaxTables] = {};
   size_t buf_bytes[2] = {0, 0}, in_bytes = 0;
   int cur = -1;  // -1: current tables are tab_in; 0/1: buf[cur]
-  bool evals_valid = false;
+  bool evals_valid = false;   // a round kernel for the current tables has been launched
+  bool evals_final = false;   // ... and its raw sums have been turned into d_evals (always true unless sharded)
+  bool sharded = false;       // multi-GPU: kernels stop at the raw sums, zolt_sc_finish_partials completes the round
+  bool have_claim = false;    // zolt_sc_set_claim: round 0 derives p(1) from it
+  int pending_claim_src = 0;  // how the launched-but-unfinished round (sharded) gets p(1)
+  Fr last_r;                  // challenge of the most recent bind
+  Fr* d_raw = nullptr;
+  Fr* d_claim = nullptr;
   Fr* d_partials = nullptr;
   unsigned* d_ticket = nullptr;
   Fr* d_evals = nullptr;
@@ -433,6 +700,18 @@ SplitEqDev split_eq_for(const zolt_sc* sc, size_t n_cur) {
   return s;
 }
 
+int combiner_deg(int comb) {
+  switch (comb) {
+    case ZOLT_SC_PROD2: return 2;
+    case ZOLT_SC_PROD3:
+    case ZOLT_SC_EQ_A_BMC:
+    case ZOLT_SC_EQ_AB_MINUS_C: return 3;
+    default: return 0;
+  }
+}
+
+constexpr int kBlocksPerSm = kFusedBlocksPerSm;  // upper bound, sizes the partials buffer
+
 template <int COMB, int PAIR>
 void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   ScPtrs t{};
@@ -442,17 +721,38 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
     t.dst[i] = sc->buf[sc->cur < 0 ? 0 : (sc->cur ^ 1)][i];
   }
   const size_t n_cur = fused ? sc->n / 2 : sc->n;
-  const unsigned grid = grid_for(sc->ctx, n_cur / 2, 4);
+  const unsigned grid = grid_for(sc->ctx, n_cur / 2, fused ? kFusedBlocksPerSm : kEvalBlocksPerSm, kRoundThreads);
   SplitEqDev sq = split_eq_for(sc, n_cur);
+  ScOut out{};
+  out.partials = sc->d_partials;
+  out.ticket = sc->d_ticket;
+  out.d_raw = sc->d_raw;
+  out.d_evals = sc->d_evals;
+  out.h_evals = sc->h_evals_dev;
+  out.d_claim = sc->d_claim;
+  out.deg = combiner_deg(sc->combiner);
+  out.finalize = sc->sharded ? 0 : 1;
+  const int mode = fused ? 2 : (sc->have_claim && sc->cur < 0 && out.deg != 0 ? 1 : 0);
+  out.claim_src = mode == 2 ? CLAIM_PREV : (mode == 1 ? CLAIM_HOST : CLAIM_NONE);
+  sc->pending_claim_src = out.claim_src;
+  const size_t kDynSmem = (size_t)(fused ? kFusedScratchUnits : kEvalScratchUnits) * kRoundThreads * sizeof(uint4);
+  static bool attr_set[3] = {false, false, false};  // per (COMB, PAIR) instantiation of this function
+  if (!attr_set[mode]) {
+    if (mode == 2) cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+    else if (mode == 1) cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+    else cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+    attr_set[mode] = true;
+  }
   const int ps = prof_begin(sc->ctx, fused ? PROF_SC_FUSED : PROF_SC_EVAL);
-  if (fused)
-    sc_round_kernel<COMB, PAIR, true><<<grid, kScThreads, 0, sc->ctx->stream>>>(
-        t, sc->n_extra, sc->n, r, sq, sc->d_partials, sc->d_ticket, sc->d_evals, sc->h_evals_dev);
+  if (mode == 2)
+    sc_round_kernel<COMB, PAIR, 2><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out);
+  else if (mode == 1)
+    sc_round_kernel<COMB, PAIR, 1><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out);
   else
-    sc_round_kernel<COMB, PAIR, false><<<grid, kScThreads, 0, sc->ctx->stream>>>(
-        t, sc->n_extra, sc->n, r, sq, sc->d_partials, sc->d_ticket, sc->d_evals, sc->h_evals_dev);
+    sc_round_kernel<COMB, PAIR, 0><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out);
   prof_end(sc->ctx, ps);
   sc->ctx->launches++;
+  sc->evals_final = !sc->sharded;
 }
 
 template <int COMB>
@@ -500,8 +800,10 @@ int sc_alloc(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, 
     ZOLT_CUDA_TRY(pool_alloc(ctx, sc->buf_bytes[0], (void**)&sc->buf[0][i]));
     ZOLT_CUDA_TRY(pool_alloc(ctx, sc->buf_bytes[1], (void**)&sc->buf[1][i]));
   }
-  sc->max_grid = (unsigned)ctx->num_sms * 4;
+  sc->max_grid = (unsigned)ctx->num_sms * kBlocksPerSm;
   ZOLT_CUDA_TRY(pool_alloc(ctx, (size_t)sc->max_grid * 4 * sizeof(Fr), (void**)&sc->d_partials));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(Fr), (void**)&sc->d_raw));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(Fr), (void**)&sc->d_claim));
   ZOLT_CUDA_TRY(pool_alloc(ctx, 256, (void**)&sc->d_ticket));
   ZOLT_CUDA_TRY(cudaMemsetAsync(sc->d_ticket, 0, sizeof(unsigned), ctx->stream));
   ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(Fr), (void**)&sc->d_evals));
@@ -582,8 +884,26 @@ static int sc_ensure_evals(zolt_sc* sc) {
   return ZOLT_OK;
 }
 
+extern "C" int zolt_sc_set_claim(zolt_sc* sc, const uint64_t claim[4]) {
+  if (!sc || !claim) return ZOLT_ERR_ARG;
+  if (sc->cur >= 0 || sc->evals_valid) return ZOLT_ERR_STATE;  // only before the first round is evaluated
+  ZOLT_CUDA_TRY(cudaSetDevice(sc->ctx->device));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(sc->d_claim, claim, sizeof(Fr), cudaMemcpyHostToDevice, sc->ctx->stream));
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));  // claim is a borrowed host buffer
+  sc->have_claim = true;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_sc_set_sharded(zolt_sc* sc, int on) {
+  if (!sc) return ZOLT_ERR_ARG;
+  if (sc->evals_valid && !sc->evals_final) return ZOLT_ERR_STATE;
+  sc->sharded = on != 0;
+  return ZOLT_OK;
+}
+
 extern "C" int zolt_sc_round_evals(zolt_sc* sc, uint64_t* evals_out) {
   if (!sc || !evals_out) return ZOLT_ERR_ARG;
+  if (sc->sharded && !(sc->evals_valid && sc->evals_final)) return ZOLT_ERR_STATE;  // use the partials protocol
   ZOLT_TRY(sc_ensure_evals(sc));
   ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
   memcpy(evals_out, sc->h_evals, (size_t)sc->ne * sizeof(Fr));
@@ -592,8 +912,31 @@ extern "C" int zolt_sc_round_evals(zolt_sc* sc, uint64_t* evals_out) {
 
 extern "C" int zolt_sc_round_partials_dev(zolt_sc* sc, const void** d_ptr) {
   if (!sc || !d_ptr) return ZOLT_ERR_ARG;
+  if (!sc->sharded) return ZOLT_ERR_STATE;
   ZOLT_TRY(sc_ensure_evals(sc));
-  *d_ptr = sc->d_evals;
+  *d_ptr = sc->d_raw;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_sc_finish_partials(zolt_sc* sc, const void* d_rows, size_t rows, uint64_t* evals_out) {
+  if (!sc || !d_rows || !evals_out || rows == 0) return ZOLT_ERR_ARG;
+  if (!sc->sharded || !sc->evals_valid) return ZOLT_ERR_STATE;
+  zolt_ctx* ctx = sc->ctx;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!sc->evals_final) {
+    ScOut out{};
+    out.d_evals = sc->d_evals;
+    out.h_evals = sc->h_evals_dev;
+    out.d_claim = sc->d_claim;
+    out.deg = combiner_deg(sc->combiner);
+    out.claim_src = sc->pending_claim_src;
+    sc_finish_rows_kernel<<<1, 32, 0, ctx->stream>>>((const Fr*)d_rows, rows, out, sc->last_r);
+    ctx->launches++;
+    ZOLT_CUDA_TRY(cudaGetLastError());
+    sc->evals_final = true;
+  }
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(evals_out, sc->h_evals, (size_t)sc->ne * sizeof(Fr));
   return ZOLT_OK;
 }
 
@@ -605,6 +948,13 @@ extern "C" int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]) {
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   const Fr r = fr_from_host(challenge);
   if (sc->n >= 4) {
+    // the fused pass derives p(1) of the next round from this round's polynomial at r
+    if (!sc->evals_valid) {
+      if (sc->sharded) return ZOLT_ERR_STATE;
+      ZOLT_TRY(sc_ensure_evals(sc));
+    }
+    if (!sc->evals_final) return ZOLT_ERR_STATE;  // sharded: zolt_sc_finish_partials has not run
+    sc->last_r = r;
     launch_round_any(sc, true, r);
     sc->evals_valid = true;
   } else {
@@ -660,6 +1010,8 @@ extern "C" int zolt_sc_free(zolt_sc* sc) {
   if (sc->d_partials) pool_release(ctx, sc->d_partials, (size_t)sc->max_grid * 4 * sizeof(Fr));
   if (sc->d_ticket) pool_release(ctx, sc->d_ticket, 256);
   if (sc->d_evals) pool_release(ctx, sc->d_evals, 4 * sizeof(Fr));
+  if (sc->d_raw) pool_release(ctx, sc->d_raw, 4 * sizeof(Fr));
+  if (sc->d_claim) pool_release(ctx, sc->d_claim, 4 * sizeof(Fr));
   pinned_mailbox_release(ctx, sc->h_evals);
   if (sc->d_e_out) cudaFree(sc->d_e_out);
   if (sc->d_e_in) cudaFree(sc->d_e_in);
@@ -749,8 +1101,14 @@ extern "C" int zolt_poly_sum(zolt_ctx* ctx, const void* d_src, size_t n, uint64_
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   Scratch s;
   ZOLT_TRY(scratch_alloc(ctx, &s));
-  sum_kernel<<<grid_for(ctx, n, 4), kScThreads, 0, ctx->stream>>>((const Fr*)d_src, n, s.partials, s.ticket, s.d_out,
-                                                                  (Fr*)ctx->d_mailbox);
+  ScOut so{};
+  so.partials = s.partials;
+  so.ticket = s.ticket;
+  so.d_raw = s.d_out + 8;
+  so.d_evals = s.d_out;
+  so.h_evals = (Fr*)ctx->d_mailbox;
+  so.finalize = 1;
+  sum_kernel<<<grid_for(ctx, n, 4), kScThreads, 0, ctx->stream>>>((const Fr*)d_src, n, so);
   ctx->launches++;
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

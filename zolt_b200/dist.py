@@ -70,6 +70,8 @@ class GpuSumcheckBackend:
         self.ev_part, self.ev_gath = ev_part, ev_gath
         self.combiner, self.k = combiner, k
         self.ne = inst.num_evals
+        if world > 1:
+            inst.set_sharded(True)
 
     def local_evals(self):
         import torch
@@ -77,12 +79,13 @@ class GpuSumcheckBackend:
 
         if self.world == 1:
             return self.inst.compute_round_poly()
-        d_ptr = self.inst.partials_dev()  # this rank's partial evaluations, left on the device
+        d_ptr = self.inst.partials_dev()  # this rank's 4 raw partial sums, left on the device
         with torch.cuda.stream(self.stream):
             # stage into the torch tensor NCCL gathers from (device-to-device, 128 bytes)
-            _lib.check(self.ctx.lib.zolt_dev_copy(self.ctx.handle, self.ev_part.data_ptr(), d_ptr, self.ne * 32), "zolt_dev_copy")
+            _lib.check(self.ctx.lib.zolt_dev_copy(self.ctx.handle, self.ev_part.data_ptr(), d_ptr, 128), "zolt_dev_copy")
             dist.all_gather_into_tensor(self.ev_gath, self.ev_part)
-            return self.ctx.fr_sum_rows(self.ev_gath.data_ptr(), self.world, 4)[: self.ne]
+            # fold the rows mod r and complete the round polynomial on the device (every rank alike)
+            return self.inst.finish_partials(self.ev_gath.data_ptr(), self.world)
 
     def bind(self, r):
         self.inst.bind_challenge(r)
