@@ -441,43 +441,40 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
         scr_prefetch(scr, u + 2, s + idx + half_old);
       }
     };
-    // The cp.async ring runs one bind ahead, which hides an L2 hit but not an HBM access; a second,
-    // register- and smem-free stage pulls the lines of the table two steps ahead into L2.
-    auto prefetch_table_l2 = [&](size_t gi, int k) {
-      const Fr* s = t.src[k];
-      if constexpr (PAIR == ZOLT_PAIR_ADJACENT) {
-        prefetch_l2(s + 4 * gi);  // the 128-byte line holding all four source elements of the pair
-      } else {
-        prefetch_l2(s + gi);
-        prefetch_l2(s + gi + half_old);
-        prefetch_l2(s + gi + half_cur);
-        prefetch_l2(s + gi + half_cur + half_old);
-      }
+    // The ring runs TWO binds ahead with only two slots: the slot of item q is read into registers and then
+    // immediately re-armed with item q+2 (the copy needs a round trip to L2/HBM before it can overwrite what
+    // the same thread read earlier in program order).  128 bytes in flight per thread, 64 KB per SM.
+    auto item_at = [&](size_t gi, int q, size_t& g_out, int& k_out, int& h_out) {
+      // item q (may exceed 2*kt by less than 2*kt) of pair gi -> normalised (pair, table, half)
+      const bool wrap = q >= 2 * kt;
+      const int qq = wrap ? q - 2 * kt : q;
+      g_out = wrap ? gi + stride : gi;
+      k_out = qq >> 1;
+      h_out = qq & 1;
     };
-    if (g < pairs) {
-      prefetch_item(g, 0, 0, 0);
-      for (int k = 0; k < kt && k < 2; k++) prefetch_table_l2(g, k);
+    {
+      size_t g1; int k1, h1;
+      if (g < pairs) prefetch_item(g, 0, 0, 0);
+      cp_async_commit();
+      item_at(g, 1, g1, k1, h1);
+      if (g1 < pairs) prefetch_item(g1, k1, h1, 1);
+      cp_async_commit();
     }
-    cp_async_commit();
     int slot = 0;
     for (; g < pairs; g += stride) {
 #pragma unroll 1
       for (int q = 0; q < 2 * kt; q++) {
         const int k = q >> 1, h = q & 1;
-        if (h == 0) {
-          const int k2 = k + 2 >= kt ? k + 2 - kt : k + 2;
-          const size_t g2 = k + 2 >= kt ? g + stride : g;
-          if (k2 < kt && g2 < pairs) prefetch_table_l2(g2, k2);
-        }
-        // start the copy of the next item, then wait for the current one
-        const bool wrap = (q + 1 == 2 * kt);
-        const size_t g_nxt = wrap ? g + stride : g;
-        if (g_nxt < pairs) prefetch_item(g_nxt, wrap ? 0 : (q + 1) >> 1, (q + 1) & 1, slot ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
+        cp_async_wait<1>();  // item q has landed (item q+1 may still be in flight)
         const int u = 16 + 4 * slot;
         const size_t idx = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * g + h : g + (h ? half_cur : 0);
         const Fr a0 = scr_ld(scr, u), a1 = scr_ld(scr, u + 2);
+        {
+          size_t g2; int k2, h2;
+          item_at(g, q + 2, g2, k2, h2);
+          if (g2 < pairs) prefetch_item(g2, k2, h2, slot);
+          cp_async_commit();
+        }
         const Fr v = bind_pair(a0, a1, r);
         st_fr(t.dst[k] + idx, v);
         if (k < K) scr_st(scr, 2 * q, v);
