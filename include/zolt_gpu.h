@@ -80,6 +80,14 @@ int zolt_field_batch_op(zolt_ctx* ctx, int field, int op, const uint64_t* a, con
 int zolt_msm_bases_upload(zolt_ctx* ctx, const uint64_t* xy /* n*8 */, const uint8_t* inf /* n or NULL */,
                           size_t n, zolt_bases** out);
 int zolt_msm_bases_free(zolt_bases* bases);
+/* Optional, once per SRS: build the window-level table 2^(c*j) * base[i] (j < ceil(255/c)) on the device.
+ * Every later MSM over these bases (any offset / length, zolt_msm*, zolt_msm_batch) then runs as ONE
+ * window over the table: c = 20 -> 13 mixed additions per point instead of 16, no per-window bucket
+ * reduction.  window_bits = 0 picks c from the length (20 from 2^20 points, 16 from 2^15, none below).
+ * Costs (W-1)*c doublings per base and W*n*64 bytes of HBM (13.9 GB at 2^24); results are unchanged
+ * (the same group element, canonical affine).  The SRS is long-lived in the reference
+ * (SetupParams.powers_of_tau_g1, src/poly/commitment/mod.zig:122-140), which is what makes this pay. */
+int zolt_msm_bases_precompute(zolt_bases* bases, int window_bits);
 int zolt_msm_bases_len(const zolt_bases* bases, size_t* n);
 int zolt_msm_bases_download(const zolt_bases* bases, size_t offset, size_t n, uint64_t* xy, uint8_t* inf);
 

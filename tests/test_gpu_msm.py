@@ -159,3 +159,58 @@ def test_msm_large_closed_form(ctx, log_n):
     xy, inf = Z.MSM.compute(bases, fr_arr(scalars))
     assert point_from_out(xy, inf) == B.msm_closed_form(logs, scalars)
     bases.free()
+
+
+@pytest.mark.parametrize("n,c", [(64, 8), (300, 9), (1000, 10), (4096, 13), (1 << 14, 18), (1 << 16, 22)])
+def test_msm_precomputed_levels(ctx, n, c):
+    """zolt_msm_bases_precompute: the window-level table changes the algorithm (one bucket set, W*n table
+    points), never the result.  Small windows force the table path at small n (threshold 2^(c-6))."""
+    logs = [k or 1 for k in rand_fr(4000 + n, n)]
+    scalars = rand_fr(5000 + n, n)
+    scalars[0], scalars[1] = P - 1, 0  # top-window carry, skipped digit
+    bases = _bases_from_logs(ctx, logs)
+    plain = Z.MSM.compute(bases, fr_arr(scalars))
+    bases.precompute(c)
+    xy, inf = Z.MSM.compute(bases, fr_arr(scalars))
+    assert point_from_out(xy, inf) == B.msm_closed_form(logs, scalars)
+    assert (xy == plain[0]).all() and inf == plain[1]
+    # sub-range and batch over the same table
+    off = n // 4
+    sub = scalars[: n - off]
+    xy, inf = Z.MSM.compute(bases, fr_arr(sub), offset=off)
+    assert point_from_out(xy, inf) == B.msm_closed_form(logs[off:], sub)
+    if n <= 4096:
+        batch = [rand_fr(6000 + j, n) for j in range(3)]
+        oxy, oinf = Z.MSM.compute_batch(bases, np.concatenate([fr_arr(b) for b in batch]), 3, n)
+        for j in range(3):
+            assert point_from_out(oxy[j], oinf[j]) == B.msm_closed_form(logs, batch[j])
+    bases.free()
+
+
+def test_msm_precomputed_special_points(ctx):
+    """Table path with identity bases (flagged), repeated bases (P + P inside a bucket) and P, -P pairs."""
+    n = 256
+    logs = rand_fr(41, n)
+    pts = [B.g1_mul(B.G1_GEN, k) for k in logs]
+    pts[5] = None
+    pts[100] = None
+    for i in range(20, 40):
+        pts[i] = pts[20]  # equal points
+        logs[i] = logs[20]
+    xy, inf = B.points_to_arrays(pts)
+    bases = Z.Bases.upload(ctx, xy, inf).precompute(8)
+    scalars = rand_fr(42, n)
+    for i in range(20, 40):
+        scalars[i] = scalars[20]  # same digits -> same buckets -> doubling path
+    out, oinf = Z.MSM.compute(bases, fr_arr(scalars))
+    exp_logs = [0 if p is None else k for p, k in zip(pts, logs)]
+    assert point_from_out(out, oinf) == B.msm_closed_form(exp_logs, scalars)
+    bases.free()
+    logs2, sc2 = [], []
+    for k, s in zip(rand_fr(43, n // 2), rand_fr(44, n // 2)):
+        logs2 += [k, P - k]
+        sc2 += [s, s]
+    b2 = _bases_from_logs(ctx, logs2).precompute(8)
+    out, oinf = Z.MSM.compute(b2, fr_arr(sc2))
+    assert oinf == 1 and not out.any()
+    b2.free()

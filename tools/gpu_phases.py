@@ -37,6 +37,20 @@ def main():
         ctx.prof_enable(False)
         out[f"msm_2^{log_n}"] = {"total_ms": round(total, 3), **ph}
         print(f"msm 2^{log_n}: total {total:.3f} ms", ph, flush=True)
+        for c in [int(x) for x in os.environ.get("PHASE_PRE", "22").split(",") if x]:
+            import time
+            t0 = time.time()
+            bases.precompute(c)
+            t_pre = time.time() - t0
+            r0 = Z.MSM.compute_dev(bases, d_s.ptr, n)  # warm-up (workspace growth)
+            ctx.prof_enable(True)
+            ctx.timer_start()
+            r1 = Z.MSM.compute_dev(bases, d_s.ptr, n)
+            total = ctx.timer_stop_ms()
+            ph = {TAGS[t]: round(ms, 4) for t, ms in ctx.prof_read()}
+            ctx.prof_enable(False)
+            out[f"msm_2^{log_n}_pre{c}"] = {"total_ms": round(total, 3), "precompute_s": round(t_pre, 3), **ph}
+            print(f"msm 2^{log_n} table c={c}: total {total:.3f} ms (table built in {t_pre:.2f} s)", ph, flush=True)
         d_s.free()
         bases.free()
     for name, comb, k, log_n in [("eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4, 24), ("prod2", Z.SC_PROD2, 2, 20)]:

@@ -52,6 +52,7 @@ SIGNATURES = {
     "zolt_msm_bases_download": [_vp, _sz, _sz, _vp, _vp],
     "zolt_msm": [_vp, _vp, _sz, _vp, _sz, _vp, _vp],
     "zolt_msm_dev": [_vp, _vp, _sz, _vp, _sz, _vp, _vp],
+    "zolt_msm_bases_precompute": [_vp, _i],
     "zolt_msm_batch": [_vp, _vp, _vp, _sz, _sz, _vp, _vp],
     "zolt_msm_partial_dev": [_vp, _vp, _sz, _vp, _sz, _vp],
     "zolt_g1_sum_partials": [_vp, _vp, _sz, _vp, _vp],

@@ -167,6 +167,11 @@ class Bases:
         check(ctx.lib.zolt_g1_fixed_base_mul(ctx.handle, _ptr(s), s.shape[0], C.byref(h)), "zolt_g1_fixed_base_mul")
         return cls(ctx, h)
 
+    def precompute(self, window_bits: int = 0) -> "Bases":
+        """zolt_msm_bases_precompute: build the window-level table (once per SRS); MSM results are unchanged."""
+        check(self.ctx.lib.zolt_msm_bases_precompute(self.handle, window_bits), "zolt_msm_bases_precompute")
+        return self
+
     def __len__(self) -> int:
         n = C.c_size_t()
         check(self.ctx.lib.zolt_msm_bases_len(self.handle, C.byref(n)), "zolt_msm_bases_len")

@@ -32,6 +32,13 @@ struct zolt_bases {
   size_t n = 0;
   AffineG1* d_xy = nullptr;
   uint8_t* d_inf = nullptr;  // nullptr: no point at infinity in the set
+  // Optional window-level table (zolt_msm_bases_precompute): d_pre[j*n + i] = 2^(pre_c*j) * base[i], affine,
+  // j < pre_w.  With it every window's digit indexes ONE shared bucket set: a W-window MSM over n points
+  // becomes a single-window MSM over W*n table points -- no per-window bucket reduction, no Horner
+  // doublings, and a window width chosen for the addition count alone (22 bits -> 12 additions per point
+  // instead of 16).  12.9 GB at n = 2^24: HBM3e capacity is what buys the 25 % of integer work.
+  AffineG1* d_pre = nullptr;
+  int pre_c = 0, pre_w = 0;
 };
 
 namespace {
@@ -120,7 +127,7 @@ __device__ __forceinline__ void st_xyzz(XYZZ* p, const XYZZ& v) {
 // one conversion per scalar.
 __global__ void __launch_bounds__(256)
 msm_digits_kernel(const Fr* __restrict__ scalars, const uint8_t* __restrict__ inf, size_t n, size_t k,
-                  MsmGeom g, uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
+                  MsmGeom g, int pre, uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
   const size_t total = n * k;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const size_t batch = t / n, i = t - batch * n;
@@ -145,8 +152,9 @@ msm_digits_kernel(const Fr* __restrict__ scalars, const uint8_t* __restrict__ in
       }
       if (skip) d = 0;
       const size_t row = batch * g.windows + w;
+      const size_t krow = pre ? batch : row;  // precomputed levels: all windows share one bucket set
       digits[row * n + i] = d ? (d | (neg << 31)) : 0u;
-      if (d) atomicAdd(&counts[row * g.B + (d - 1)], 1u);
+      if (d) atomicAdd(&counts[krow * g.B + (d - 1)], 1u);
     }
   }
 }
@@ -226,17 +234,22 @@ scan_apply_kernel(const uint32_t* in, size_t n, const uint32_t* tile_offsets, ui
 
 // ---- 3. scatter ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, MsmGeom g,
-                   const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
-                   uint32_t* __restrict__ sorted) {
+msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, MsmGeom g, int pre, size_t pre_n,
+                   size_t pre_offset, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   const size_t total = n * rows;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const uint32_t d = digits[t];
     if (!d) continue;
-    const size_t row = t / n, i = t - row * n;
-    const size_t key = row * g.B + ((d & 0x7fffffffu) - 1);
-    const uint32_t pos = offsets[key] + atomicAdd(&cursor[key], 1u);
-    sorted[pos] = (uint32_t)i | (d & 0x80000000u);
+    const size_t row = t / n, i = t - row * n;  // row = batch * windows + w
+    size_t krow = row, pidx = i;
+    if (pre) {
+      const size_t batch = row / g.windows, w = row - batch * g.windows;
+      krow = batch;
+      pidx = w * pre_n + pre_offset + i;  // index into the level table
+    }
+    const size_t key = krow * g.B + ((d & 0x7fffffffu) - 1);
+    const uint32_t pos = atomicAdd(&cursor[key], 1u);  // cursor starts as a copy of the bucket offsets
+    sorted[pos] = (uint32_t)pidx | (d & 0x80000000u);
   }
 }
 
@@ -490,6 +503,51 @@ __global__ void __launch_bounds__(256) tau_powers_kernel(Fr* __restrict__ out, s
   }
 }
 
+// ---- window-level table ------------------------------------------------------------------------------------------
+// pre[j*n + i] = 2^(c*j) * base[i] for j = 1..W-1 (level 0 is a copy of the bases).  One thread per base
+// point of the current chunk; the W-1 new points are normalised with ONE inversion per thread
+// (Montgomery's trick over their ZZZ coordinates).  tmp / prefix: (W-1) * chunk scratch, [level][point].
+__global__ void __launch_bounds__(128)
+msm_precompute_kernel(const AffineG1* __restrict__ bases, const uint8_t* __restrict__ inf, size_t n, size_t first,
+                      size_t chunk, int c, int W, AffineG1* __restrict__ pre, XYZZ* __restrict__ tmp,
+                      Fq* __restrict__ prefix) {
+  const size_t ii = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (ii >= chunk) return;
+  const size_t i = first + ii;
+  const AffineG1 b = ld_affine(bases + i);
+  st_fq(&pre[i].x, b.x);
+  st_fq(&pre[i].y, b.y);
+  if (inf != nullptr && inf[i] != 0) {  // identity stays the identity; its digits are never scattered
+    for (int j = 1; j < W; j++) {
+      st_fq(&pre[(size_t)j * n + i].x, Fq::zero());
+      st_fq(&pre[(size_t)j * n + i].y, Fq::zero());
+    }
+    return;
+  }
+  XYZZ p = xyzz_from_affine(b);
+  Fq prod = Fq::one();
+  for (int j = 1; j < W; j++) {
+    for (int t = 0; t < c; t++) p = xyzz_dbl(p);
+    st_xyzz(&tmp[(size_t)(j - 1) * chunk + ii], p);
+    st_fq(&prefix[(size_t)(j - 1) * chunk + ii], prod);
+    prod = fq_mul(prod, p.zzz);
+  }
+  Fq inv = fp_inv<FqParams>(prod);  // a finite point of a prime-order group never doubles to the identity
+  for (int j = W - 1; j >= 1; j--) {
+    const XYZZ q = ld_xyzz_cg(&tmp[(size_t)(j - 1) * chunk + ii]);
+    const uint4* pq = reinterpret_cast<const uint4*>(&prefix[(size_t)(j - 1) * chunk + ii]);
+    const uint4 lo4 = __ldcg(pq), hi4 = __ldcg(pq + 1);
+    Fq pf;
+    pf.v[0] = lo4.x; pf.v[1] = lo4.y; pf.v[2] = lo4.z; pf.v[3] = lo4.w;
+    pf.v[4] = hi4.x; pf.v[5] = hi4.y; pf.v[6] = hi4.z; pf.v[7] = hi4.w;
+    const Fq izzz = fq_mul(inv, pf);  // 1 / q.zzz
+    inv = fq_mul(inv, q.zzz);
+    const Fq izz = fq_mul(fq_sqr(izzz), fq_sqr(q.zz));  // ZZZ^-2 * ZZ^2 = ZZ^-1
+    st_fq(&pre[(size_t)j * n + i].x, fq_mul(q.x, izz));
+    st_fq(&pre[(size_t)j * n + i].y, fq_mul(q.y, izzz));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
@@ -526,11 +584,20 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
     if (k) ZOLT_CUDA_TRY(cudaMemsetAsync(d_out, 0, k * sizeof(XYZZ), st));  // identity (ZZ == 0)
     return ZOLT_OK;
   }
-  const MsmGeom g = choose_geom(n);
-  const size_t rows = k * (size_t)g.windows;
-  const size_t num_keys = rows * g.B;
+  // Use the window-level table when the bases carry one and the MSM is large enough to fill its buckets.
+  const bool pre = bases->d_pre != nullptr && n >= (size_t(1) << (bases->pre_c - 6));
+  MsmGeom g = choose_geom(n);
+  if (pre) {
+    g.c = bases->pre_c;
+    g.windows = bases->pre_w;
+    g.B = 1u << (g.c - 1);
+  }
+  const size_t rows = k * (size_t)g.windows;       // digit rows: (batch, window)
+  const size_t krows = pre ? k : rows;             // bucket sets
+  const size_t num_keys = krows * g.B;
   const size_t max_entries = rows * n;
   if (num_keys >= 0xfffffff0ull || max_entries >= 0xfffffff0ull || n >= 0x7fffffffull) return ZOLT_ERR_ARG;
+  if (pre && (size_t)g.windows * bases->n >= 0x7fffffffull) return ZOLT_ERR_ARG;
 
   const size_t slices0 = (max_entries + kSlice0 - 1) / kSlice0;
   const size_t L0 = 2 * slices0;
@@ -545,7 +612,9 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   bytes += align256((num_tiles + 1) * 4);
   bytes += align256(num_keys * sizeof(XYZZ));                 // buckets
   bytes += align256(edge_total * 4) + align256(edge_total * sizeof(XYZZ));
-  bytes += align256(rows * chunks_per_row * sizeof(XYZZ)) + align256(rows * sizeof(XYZZ));
+  const uint32_t tree_parts = chunks_per_row > 1024 ? chunks_per_row / 256 : 1;  // two-stage row tree
+  bytes += align256(krows * chunks_per_row * sizeof(XYZZ)) + align256(krows * sizeof(XYZZ));
+  bytes += align256(krows * tree_parts * sizeof(XYZZ));
   bytes += 4096;
   if (ctx->ws_bytes < bytes) {
     if (ctx->ws) {
@@ -568,8 +637,9 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   XYZZ* buckets = ar.take<XYZZ>(num_keys);
   uint32_t* edge_keys = ar.take<uint32_t>(edge_total);
   XYZZ* edge_pts = ar.take<XYZZ>(edge_total);
-  XYZZ* chunk_sums = ar.take<XYZZ>(rows * chunks_per_row);
-  XYZZ* row_sums = ar.take<XYZZ>(rows);
+  XYZZ* chunk_sums = ar.take<XYZZ>(krows * chunks_per_row);
+  XYZZ* row_sums = ar.take<XYZZ>(krows);
+  XYZZ* part_sums = ar.take<XYZZ>(krows * tree_parts);
 
   int status = ZOLT_OK;
   auto fail = [&](cudaError_t e, const char* what) {
@@ -583,7 +653,7 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   } while (0)
 
   {
-    const AffineG1* d_pts = bases->d_xy + offset;
+    const AffineG1* d_pts = pre ? bases->d_pre : bases->d_xy + offset;
     const uint8_t* d_inf = bases->d_inf ? bases->d_inf + offset : nullptr;
     const unsigned sm = (unsigned)ctx->num_sms;
 
@@ -593,7 +663,7 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
       size_t blocks = (k * n + 255) / 256;
       if (blocks > (size_t)sm * 16) blocks = (size_t)sm * 16;
       const int ps = prof_begin(ctx, PROF_MSM_DIGITS);
-      msm_digits_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_scalars, d_inf, n, k, g, digits, counts);
+      msm_digits_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_scalars, d_inf, n, k, g, pre ? 1 : 0, digits, counts);
       prof_end(ctx, ps);
       ctx->launches++;
     }
@@ -603,12 +673,13 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
     scan_apply_kernel<<<(unsigned)num_tiles, kScanThreads, 0, st>>>(counts, num_keys, tiles, offsets);
     prof_end(ctx, ps);
     ctx->launches += 3;
-    MSM_CHECK(cudaMemsetAsync(counts, 0, num_keys * 4, st));  // reused as the scatter cursor
+    // counts is reused as the scatter cursor, pre-loaded with the offsets: one random access per entry
+    MSM_CHECK(cudaMemcpyAsync(counts, offsets, num_keys * 4, cudaMemcpyDeviceToDevice, st));
     {
       size_t blocks = (max_entries + 255) / 256;
       if (blocks > (size_t)sm * 16) blocks = (size_t)sm * 16;
       ps = prof_begin(ctx, PROF_MSM_SCATTER);
-      msm_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(digits, n, rows, g, offsets, counts, sorted);
+      msm_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(digits, n, rows, g, pre ? 1 : 0, bases->n, offset, counts, sorted);
       prof_end(ctx, ps);
       ctx->launches++;
     }
@@ -639,13 +710,22 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
     // bucket reduction
     ps = prof_begin(ctx, PROF_MSM_REDUCE);
     {
-      const size_t threads = rows * chunks_per_row;
-      msm_chunk_sums_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(buckets, g.B, Lc, chunks_per_row, rows,
+      const size_t threads = krows * chunks_per_row;
+      msm_chunk_sums_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(buckets, g.B, Lc, chunks_per_row, krows,
                                                                              chunk_sums);
-      unsigned tb = ((chunks_per_row + 1) / 2 + 31) / 32 * 32;
-      if (tb > 256) tb = 256;
-      msm_row_tree_kernel<<<(unsigned)rows, tb, 0, st>>>(chunk_sums, chunks_per_row, row_sums);
-      msm_horner_kernel<<<(unsigned)((k + 31) / 32), 32, 0, st>>>(row_sums, g.windows, g.c, k, d_out);
+      auto tree_threads = [](uint32_t chunks) {
+        unsigned tb = ((chunks + 1) / 2 + 31) / 32 * 32;
+        return tb > 256 ? 256u : (tb ? tb : 32u);
+      };
+      if (tree_parts > 1) {
+        // a row's chunk sums only need to be added up: first 256 at a time over many blocks, then the parts
+        msm_row_tree_kernel<<<(unsigned)(krows * tree_parts), tree_threads(256), 0, st>>>(chunk_sums, 256, part_sums);
+        msm_row_tree_kernel<<<(unsigned)krows, tree_threads(tree_parts), 0, st>>>(part_sums, tree_parts, row_sums);
+        ctx->launches++;
+      } else {
+        msm_row_tree_kernel<<<(unsigned)krows, tree_threads(chunks_per_row), 0, st>>>(chunk_sums, chunks_per_row, row_sums);
+      }
+      msm_horner_kernel<<<(unsigned)((k + 31) / 32), 32, 0, st>>>(row_sums, pre ? 1 : g.windows, pre ? 0 : g.c, k, d_out);
       ctx->launches += 3;
     }
     prof_end(ctx, ps);
@@ -723,7 +803,48 @@ extern "C" int zolt_msm_bases_free(zolt_bases* b) {
   cudaStreamSynchronize(b->ctx->stream);
   if (b->d_xy) cudaFree(b->d_xy);
   if (b->d_inf) cudaFree(b->d_inf);
+  if (b->d_pre) cudaFree(b->d_pre);
   delete b;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_msm_bases_precompute(zolt_bases* b, int window_bits) {
+  if (!b) return ZOLT_ERR_ARG;
+  zolt_ctx* ctx = b->ctx;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  // measured on B200 (tools/gpu_phases.py): 2^24 points 51.5 -> 43.4 ms at c = 20 (c = 22 saves additions but its
+  // counting-sort scatter spreads over a larger array), 2^21 9.0 -> 6.9 ms at c = 20, 2^18 3.8 -> 2.2 ms at c = 16
+  if (window_bits == 0) window_bits = b->n >= (size_t(1) << 20) ? 20 : (b->n >= (size_t(1) << 15) ? 16 : 0);
+  if (window_bits == 0 || b->n == 0) return ZOLT_OK;  // too small to profit: MSMs keep the per-window path
+  if (window_bits < 8 || window_bits > 26) return ZOLT_ERR_ARG;
+  const int W = (255 + window_bits - 1) / window_bits;
+  if ((size_t)W * b->n >= 0x7fffffffull) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (b->d_pre) {
+    cudaFree(b->d_pre);
+    b->d_pre = nullptr;
+  }
+  AffineG1* pre = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&pre, (size_t)W * b->n * sizeof(AffineG1)));
+  const size_t chunk_max = size_t(1) << 20;
+  const size_t chunk_alloc = b->n < chunk_max ? b->n : chunk_max;
+  XYZZ* tmp = nullptr;
+  Fq* prefix = nullptr;
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&tmp, (size_t)(W - 1) * chunk_alloc * sizeof(XYZZ)));
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&prefix, (size_t)(W - 1) * chunk_alloc * sizeof(Fq)));
+  for (size_t first = 0; first < b->n; first += chunk_alloc) {
+    const size_t chunk = b->n - first < chunk_alloc ? b->n - first : chunk_alloc;
+    msm_precompute_kernel<<<(unsigned)((chunk + 127) / 128), 128, 0, ctx->stream>>>(b->d_xy, b->d_inf, b->n, first, chunk,
+                                                                                   window_bits, W, pre, tmp, prefix);
+    ctx->launches++;
+  }
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(tmp);
+  cudaFree(prefix);
+  b->d_pre = pre;
+  b->pre_c = window_bits;
+  b->pre_w = W;
   return ZOLT_OK;
 }
 
