@@ -202,7 +202,25 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
 #undef HI
 }
 
+// ---- cold-path helpers ---------------------------------------------------------------------------------
+// Everything that runs once per thread or once per launch is kept OUT OF LINE with rolled loops.  Inlined,
+// the epilogue of a round kernel was ~60 KB of straight-line code that a single warp stepped through once:
+// an instruction-cache miss every 128 bytes, ~40 us per launch whatever the table size (ncu: r1 v3 launch
+// list, the 2-entry rounds took as long as the 2^13-entry ones).  One copy of each primitive stays cached.
+struct Wide { uint32_t v[16]; };
+__device__ __noinline__ Fr wide_reduce_cold(Wide w) { return wide_reduce<FrParams>(w.v); }
+__device__ __noinline__ Fr fr_add_cold(Fr a, Fr b) { return fr_add(a, b); }
+__device__ __noinline__ Fr fr_sub_cold(Fr a, Fr b) { return fr_sub(a, b); }
+__device__ __noinline__ Fr fr_mul_cold(Fr a, Fr b) { return fr_mul(a, b); }
+
 // thread-local accumulators -> the 4 raw sums
+__device__ __forceinline__ Fr wide_collapse(const uint32_t* acc) {
+  Wide w;
+#pragma unroll
+  for (int i = 0; i < 16; i++) w.v[i] = acc[i];
+  return wide_reduce_cold(w);
+}
+
 template <int COMB, bool P1>
 __device__ __forceinline__ void collapse(uint32_t (*wacc)[16], const Fr* facc, Fr* raw) {
   constexpr int NW = CombTraits<COMB>::NW;
@@ -213,17 +231,17 @@ __device__ __forceinline__ void collapse(uint32_t (*wacc)[16], const Fr* facc, F
     raw[0] = facc[0];
     raw[1] = facc[1];
   } else if constexpr (DEG == 3) {
-    raw[0] = wide_reduce<FrParams>(wacc[0]);
-    raw[2] = wide_reduce<FrParams>(wacc[1]);
-    raw[3] = wide_reduce<FrParams>(wacc[2]);
-    if constexpr (P1) raw[1] = wide_reduce<FrParams>(wacc[NW]);
+    raw[0] = wide_collapse(wacc[0]);
+    raw[2] = wide_collapse(wacc[1]);
+    raw[3] = wide_collapse(wacc[2]);
+    if constexpr (P1) raw[1] = wide_collapse(wacc[NW]);
   } else if constexpr (DEG == 2) {
-    raw[0] = wide_reduce<FrParams>(wacc[0]);
-    raw[2] = wide_reduce<FrParams>(wacc[1]);
-    if constexpr (P1) raw[1] = wide_reduce<FrParams>(wacc[NW]);
+    raw[0] = wide_collapse(wacc[0]);
+    raw[2] = wide_collapse(wacc[1]);
+    if constexpr (P1) raw[1] = wide_collapse(wacc[NW]);
   } else {
-    raw[0] = wide_reduce<FrParams>(wacc[0]);
-    raw[1] = wide_reduce<FrParams>(wacc[1]);
+    raw[0] = wide_collapse(wacc[0]);
+    raw[1] = wide_collapse(wacc[1]);
   }
 }
 
@@ -239,55 +257,54 @@ __device__ __forceinline__ Fr fr_const(uint32_t (*f)(int)) {
 
 // p(r) for the cubic through (0,p0) (1,p1) (2,p2) (3,p3): Newton forward differences
 __device__ __noinline__ Fr newton_eval4(const Fr* p, const Fr& r) {
-  const Fr d1 = fr_sub(p[1], p[0]);
-  const Fr d1b = fr_sub(p[2], p[1]);
-  const Fr d1c = fr_sub(p[3], p[2]);
-  const Fr d2 = fr_sub(d1b, d1);
-  const Fr d2b = fr_sub(d1c, d1b);
-  const Fr d3 = fr_sub(d2b, d2);
+  const Fr d1 = fr_sub_cold(p[1], p[0]);
+  const Fr d1b = fr_sub_cold(p[2], p[1]);
+  const Fr d1c = fr_sub_cold(p[3], p[2]);
+  const Fr d2 = fr_sub_cold(d1b, d1);
+  const Fr d2b = fr_sub_cold(d1c, d1b);
+  const Fr d3 = fr_sub_cold(d2b, d2);
   Fr inv2, inv6;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     inv2.v[i] = FrParams::inv2(i);
     inv6.v[i] = FrParams::inv6(i);
   }
-  const Fr rm1 = fr_sub(r, Fr::one());
-  const Fr rm2 = fr_sub(rm1, Fr::one());
-  const Fr c2 = fr_mul(fr_mul(r, rm1), inv2);          // r(r-1)/2
-  const Fr c3 = fr_mul(fr_mul(fr_mul(r, rm1), rm2), inv6);  // r(r-1)(r-2)/6
-  Fr acc = fr_add(p[0], fr_mul(r, d1));
-  acc = fr_add(acc, fr_mul(c2, d2));
-  acc = fr_add(acc, fr_mul(c3, d3));
+  const Fr rm1 = fr_sub_cold(r, Fr::one());
+  const Fr rm2 = fr_sub_cold(rm1, Fr::one());
+  const Fr rr1 = fr_mul_cold(r, rm1);
+  const Fr c2 = fr_mul_cold(rr1, inv2);                    // r(r-1)/2
+  const Fr c3 = fr_mul_cold(fr_mul_cold(rr1, rm2), inv6);  // r(r-1)(r-2)/6
+  Fr acc = fr_add_cold(p[0], fr_mul_cold(r, d1));
+  acc = fr_add_cold(acc, fr_mul_cold(c2, d2));
+  acc = fr_add_cold(acc, fr_mul_cold(c3, d3));
   return acc;
 }
 
-// deg: 0 (raw sums are the evaluations), 2 or 3.  prev: the previous round's 4 evaluations (CLAIM_PREV).
-__device__ __noinline__ void sc_finalize(int deg, int claim_src, const Fr* raw, const Fr* prev, const Fr& r,
-                                         const Fr* d_claim, Fr* out) {
+// Raw sums -> evaluations at X = 0..3.  deg: 0 (raw sums are the evaluations), 2 or 3.  `claim` is
+// p(0) + p(1) (ignored when have_claim is false: p(1) was summed directly and sits in raw[1]).
+__device__ __noinline__ void sc_finalize(int deg, bool have_claim, const Fr* raw, const Fr& claim, Fr* out) {
   if (deg == 0) {
 #pragma unroll
     for (int i = 0; i < kRaw; i++) out[i] = raw[i];
     return;
   }
   const Fr p0 = raw[0];
-  Fr p1;
-  if (claim_src == CLAIM_NONE) p1 = raw[1];
-  else if (claim_src == CLAIM_PREV) p1 = fr_sub(newton_eval4(prev, r), p0);
-  else p1 = fr_sub(ld_fr(d_claim), p0);
+  const Fr p1 = have_claim ? fr_sub_cold(claim, p0) : raw[1];
   Fr p2, p3;
   if (deg == 3) {
     p2 = raw[2];
     const Fr lead = raw[3];
-    Fr t = fr_add(fr_add(lead, lead), lead);  // 3*lead
-    t = fr_add(t, t);                          // 6*lead = third finite difference
-    const Fr d = fr_sub(p2, p1);
-    p3 = fr_add(fr_add(t, fr_add(fr_add(d, d), d)), p0);  // p3 = 6 lead + 3 (p2 - p1) + p0
+    Fr t = fr_add_cold(fr_add_cold(lead, lead), lead);  // 3*lead
+    t = fr_add_cold(t, t);                               // 6*lead = third finite difference
+    const Fr d = fr_sub_cold(p2, p1);
+    p3 = fr_add_cold(fr_add_cold(t, fr_add_cold(fr_add_cold(d, d), d)), p0);  // p3 = 6 lead + 3 (p2 - p1) + p0
   } else {
     const Fr lead = raw[2];
-    const Fr l2 = fr_add(lead, lead);
-    const Fr s = fr_sub(p1, p0);                             // c1 + c2
-    p2 = fr_add(fr_add(p1, s), l2);                          // 2 p1 - p0 + 2 c2
-    p3 = fr_add(fr_add(fr_add(p1, s), s), fr_add(fr_add(l2, l2), l2));  // 3 p1 - 2 p0 + 6 c2
+    const Fr l2 = fr_add_cold(lead, lead);
+    const Fr s = fr_sub_cold(p1, p0);                                  // c1 + c2
+    const Fr p1s = fr_add_cold(p1, s);
+    p2 = fr_add_cold(p1s, l2);                                         // 2 p1 - p0 + 2 c2
+    p3 = fr_add_cold(fr_add_cold(p1s, s), fr_add_cold(fr_add_cold(l2, l2), l2));  // 3 p1 - 2 p0 + 6 c2
   }
   out[0] = p0;
   out[1] = p1;
@@ -335,11 +352,47 @@ struct ScOut {
   Fr* d_raw;          // kRaw raw sums of this launch (what a sharded run all-gathers)
   Fr* d_evals;        // 4 evaluations: read as "previous round" (CLAIM_PREV), then overwritten
   Fr* h_evals;        // mapped pinned host copy of d_evals
-  const Fr* d_claim;  // CLAIM_HOST
+  const Fr* d_claim;  // CLAIM_HOST: p(0) + p(1) supplied by the host
+  Fr* d_claim_cur;    // CLAIM_PREV: previous round polynomial at r, written by block 0 at kernel start
   int deg;            // 0 / 2 / 3
   int claim_src;
   int finalize;       // 0: sharded run, stop at the raw sums
 };
+
+__device__ __forceinline__ Fr ldcg_fr(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 lo4 = __ldcg(q), hi4 = __ldcg(q + 1);  // bypass L1: written by other SMs
+  Fr x;
+  x.v[0] = lo4.x; x.v[1] = lo4.y; x.v[2] = lo4.z; x.v[3] = lo4.w;
+  x.v[4] = hi4.x; x.v[5] = hi4.y; x.v[6] = hi4.z; x.v[7] = hi4.w;
+  return x;
+}
+
+// sum over the 32 lanes of a warp, valid in lane 0
+__device__ __noinline__ Fr warp_sum_cold(Fr x) {
+#pragma unroll 1
+  for (int d = 16; d > 0; d >>= 1) x = fr_add(x, shfl_down_fr(x, d));
+  return x;
+}
+
+// raw sums -> round evaluations, written to device memory and to the mapped host mailbox (one thread)
+__device__ __noinline__ void sc_publish(const ScOut& o, const Fr* tot) {
+#pragma unroll 1
+  for (int e = 0; e < kRaw; e++) st_fr(&o.d_raw[e], tot[e]);
+  if (o.finalize) {
+    Fr claim = Fr::zero();
+    if (o.claim_src == CLAIM_PREV) claim = ldcg_fr(o.d_claim_cur);
+    else if (o.claim_src == CLAIM_HOST) claim = ld_fr(o.d_claim);
+    Fr ev[4];
+    sc_finalize(o.deg, o.claim_src != CLAIM_NONE, tot, claim, ev);
+#pragma unroll 1
+    for (int e = 0; e < 4; e++) {
+      st_fr(&o.d_evals[e], ev[e]);
+      st_fr(&o.h_evals[e], ev[e]);
+    }
+  }
+  __threadfence_system();
+}
 
 // Each block publishes its partial; the last block to arrive folds all partials, turns the raw sums into
 // the round evaluations and writes them to device memory and to the mapped host mailbox.
@@ -362,35 +415,56 @@ __device__ __forceinline__ void grid_finish(Fr* acc, Fr* smem, const ScOut& o, c
   for (int e = 0; e < NE; e++) tot[e] = Fr::zero();
   for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
 #pragma unroll
-    for (int e = 0; e < NE; e++) {
-      const uint4* q = reinterpret_cast<const uint4*>(&o.partials[(size_t)b * NE + e]);
-      uint4 lo4 = __ldcg(q), hi4 = __ldcg(q + 1);  // bypass L1: written by other SMs
-      Fr x;
-      x.v[0] = lo4.x; x.v[1] = lo4.y; x.v[2] = lo4.z; x.v[3] = lo4.w;
-      x.v[4] = hi4.x; x.v[5] = hi4.y; x.v[6] = hi4.z; x.v[7] = hi4.w;
-      tot[e] = fr_add(tot[e], x);
-    }
+    for (int e = 0; e < NE; e++) tot[e] = fr_add(tot[e], ldcg_fr(&o.partials[(size_t)b * NE + e]));
   }
   block_reduce<NE>(tot, smem);
   if (threadIdx.x == 0) {
+    Fr raw4[kRaw];
 #pragma unroll
-    for (int e = 0; e < NE; e++) st_fr(&o.d_raw[e], tot[e]);
-    if (o.finalize) {
-      Fr prev[4], ev[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) prev[e] = o.claim_src == CLAIM_PREV ? ld_fr(&o.d_evals[e]) : Fr::zero();
-      Fr raw4[kRaw];
-#pragma unroll
-      for (int e = 0; e < kRaw; e++) raw4[e] = e < NE ? tot[e < NE ? e : 0] : Fr::zero();
-      sc_finalize(o.deg, o.claim_src, raw4, prev, r, o.d_claim, ev);
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        st_fr(&o.d_evals[e], ev[e]);
-        st_fr(&o.h_evals[e], ev[e]);
-      }
-    }
+    for (int e = 0; e < kRaw; e++) raw4[e] = e < NE ? tot[e < NE ? e : 0] : Fr::zero();
     *o.ticket = 0;
-    __threadfence_system();
+    sc_publish(o, raw4);
+  }
+}
+
+// The round kernels' version (kRoundThreads = 4 warps, kRaw = 4 sums): warp e owns sum e.  `vals` is the
+// block's dynamic scratch, re-used as [kRaw][kRoundThreads] field elements once every thread has left its loop.
+__device__ __noinline__ void round_finish(const Fr* raw, Fr* vals, const ScOut& o) {
+  __shared__ bool is_last;
+  __shared__ Fr fin[kRaw];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
+#pragma unroll 1
+  for (int e = 0; e < kRaw; e++) st_fr(&vals[e * kRoundThreads + tid], raw[e]);
+  __syncthreads();
+  Fr x = vals[warp * kRoundThreads + lane];
+#pragma unroll 1
+  for (int j = 1; j < kRoundThreads / 32; j++) x = fr_add(x, vals[warp * kRoundThreads + lane + 32 * j]);
+  x = warp_sum_cold(x);
+  if (gridDim.x > 1) {
+    if (lane == 0) {
+      st_fr(&o.partials[(size_t)blockIdx.x * kRaw + warp], x);
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      const unsigned t = atomicAdd(o.ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Fr tot = Fr::zero();
+#pragma unroll 1
+    for (unsigned b = lane; b < gridDim.x; b += 32) tot = fr_add(tot, ldcg_fr(&o.partials[(size_t)b * kRaw + warp]));
+    x = warp_sum_cold(tot);
+  }
+  if (lane == 0) fin[warp] = x;
+  __syncthreads();
+  if (tid == 0) {
+    if (gridDim.x > 1) *o.ticket = 0;
+    sc_publish(o, fin);
   }
 }
 
@@ -409,9 +483,19 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
   constexpr bool FUSED = MODE == 2;
   constexpr bool P1 = MODE == 0 && CombTraits<COMB>::DEG != 0;
   constexpr int NACC = NW + (P1 ? 1 : 0);
-  __shared__ Fr smem[kRaw * 32];
   extern __shared__ uint4 scratch[];  // [units][kRoundThreads], dynamic: exceeds the 48 KB static limit
   uint4* const scr = scratch + threadIdx.x;
+  if constexpr (FUSED) {
+    // this round's claim p(0) + p(1) is the previous round polynomial at r: one thread evaluates it while the
+    // grid streams the tables, so it is off the serial tail of the launch
+    if (blockIdx.x == 0 && threadIdx.x == 0 && out.finalize) {
+      Fr prev[4];
+#pragma unroll 1
+      for (int e = 0; e < 4; e++) prev[e] = ld_fr(&out.d_evals[e]);
+      st_fr(out.d_claim_cur, newton_eval4(prev, r));
+      __threadfence();
+    }
+  }
   uint32_t wacc[NACC > 0 ? NACC : 1][16];
   Fr facc[2] = {Fr::zero(), Fr::zero()};
 #pragma unroll
@@ -519,7 +603,7 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
   cp_async_wait<0>();
   Fr raw[kRaw];
   collapse<COMB, P1>(wacc, facc, raw);
-  grid_finish<kRaw>(raw, smem, out, r);
+  round_finish(raw, reinterpret_cast<Fr*>(scratch), out);
 }
 
 // Sharded runs: fold the all-gathered raw sums of every rank (rows x kRaw) and finish the round.
@@ -531,8 +615,14 @@ __global__ void sc_finish_rows_kernel(const Fr* rows, size_t n_rows, ScOut out, 
     for (size_t i = 0; i < n_rows; i++) acc = fr_add(acc, ld_fr(rows + i * kRaw + c));
     raw[c] = acc;
   }
-  for (int e = 0; e < 4; e++) prev[e] = out.claim_src == CLAIM_PREV ? ld_fr(&out.d_evals[e]) : Fr::zero();
-  sc_finalize(out.deg, out.claim_src, raw, prev, r, out.d_claim, ev);
+  Fr claim = Fr::zero();
+  if (out.claim_src == CLAIM_PREV) {
+    for (int e = 0; e < 4; e++) prev[e] = ld_fr(&out.d_evals[e]);
+    claim = newton_eval4(prev, r);
+  } else if (out.claim_src == CLAIM_HOST) {
+    claim = ld_fr(out.d_claim);
+  }
+  sc_finalize(out.deg, out.claim_src != CLAIM_NONE, raw, claim, ev);
   for (int e = 0; e < 4; e++) {
     st_fr(&out.d_evals[e], ev[e]);
     st_fr(&out.h_evals[e], ev[e]);
@@ -727,6 +817,7 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   out.d_evals = sc->d_evals;
   out.h_evals = sc->h_evals_dev;
   out.d_claim = sc->d_claim;
+  out.d_claim_cur = sc->d_claim + 1;
   out.deg = combiner_deg(sc->combiner);
   out.finalize = sc->sharded ? 0 : 1;
   const int mode = fused ? 2 : (sc->have_claim && sc->cur < 0 && out.deg != 0 ? 1 : 0);
@@ -925,6 +1016,8 @@ extern "C" int zolt_sc_finish_partials(zolt_sc* sc, const void* d_rows, size_t r
     out.d_evals = sc->d_evals;
     out.h_evals = sc->h_evals_dev;
     out.d_claim = sc->d_claim;
+    out.d_claim_cur = sc->d_claim + 1;
+  out.d_claim_cur = sc->d_claim + 1;
     out.deg = combiner_deg(sc->combiner);
     out.claim_src = sc->pending_claim_src;
     sc_finish_rows_kernel<<<1, 32, 0, ctx->stream>>>((const Fr*)d_rows, rows, out, sc->last_r);
