@@ -264,6 +264,8 @@ def run_b200(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, which must carry the JSON line only
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -300,9 +302,19 @@ def run_b200(args):
     ev_part = torch.zeros(128, dtype=torch.uint8, device="cuda")
     ev_gath = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
 
+    # multi-GPU exchange: NVLink peer mailboxes written by the kernels themselves (default), or NCCL all-gathers
+    # driven from the host (--nccl-exchange, the baseline the mailbox replaces)
+    box = None
+    if world > 1 and not args.nccl_exchange:
+        from zolt_b200 import dist as ZD
+
+        box = ZD.connect_peer_box(ctx, rank, world)
+
     def msm_resident():
         if world == 1:
             return Z.MSM.compute_dev(bases, d_scalars.ptr, n_local)
+        if box is not None:
+            return Z.MSM.compute_sharded_dev(bases, d_scalars.ptr, n_local, box)
         with torch.cuda.stream(stream):
             Z.MSM.partial_dev(bases, d_scalars.ptr, n_local, part.data_ptr())
             dist.all_gather_into_tensor(gathered, part)
@@ -311,6 +323,8 @@ def run_b200(args):
     def sumcheck_resident():
         if world == 1:
             return H.sumcheck_prove_dev(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, d_tab_ptrs, sc_local_log)
+        if box is not None:
+            return H.sumcheck_prove_sharded(ctx, box, Z.SC_EQ_AB_MINUS_C, d_tab_ptrs, sc_local_log)
         from zolt_b200 import dist as ZD
 
         return ZD.sharded_sumcheck_gpu(ctx, stream, Z.SC_EQ_AB_MINUS_C, d_tab_ptrs, sc_local_log, world, ev_part, ev_gath)
@@ -318,6 +332,9 @@ def run_b200(args):
     def msm_e2e():
         if world == 1:
             return Z.MSM.compute(bases, h_scalars)
+        if box is not None:
+            d_scalars.upload(h_scalars)
+            return Z.MSM.compute_sharded_dev(bases, d_scalars.ptr, n_local, box)
         with torch.cuda.stream(stream):
             d_scalars.upload(h_scalars)
             Z.MSM.partial_dev(bases, d_scalars.ptr, n_local, part.data_ptr())
@@ -419,7 +436,9 @@ def run_b200(args):
             "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
             "config": {
                 "workload": f"BN254 G1 MSM 2^{log_n} points (HyperKZG commit shape) + degree-3 sumcheck eq*(Az*Bz-Cz) over 2^{sc_log_n} entries with host Keccak transcript (BASELINE configs 4 and 3)",
-                "sharding": "MSM by point range, sumcheck by contiguous hypercube blocks" if world > 1 else "single GPU",
+                "sharding": ("MSM by point range, sumcheck by contiguous hypercube blocks; exchange: "
+                             + ("NVLink peer mailboxes written by the kernels (no collective library on the data path)" if box is not None
+                                else "NCCL all-gather per round")) if world > 1 else "single GPU",
                 "l2": "inputs (1.5 GiB MSM, 2 GiB sumcheck) exceed the 126 MB L2; no flush needed",
                 "msm_bases": "window-level table built once per SRS in setup (zolt_msm_bases_precompute, c=20, 13 windows)" if not args.no_table else "plain bases (16 windows)",
             },
@@ -443,6 +462,7 @@ def run_b200(args):
                 "e2e_ms": v_e2e_sc, "e2e_fr_elems_per_s": K_TABLES * n_sc / (v_e2e_sc * 1e-3),
             },
             "msm_phases_ms": {k: round(v, 4) for k, v in phase_ms.items() if not k.startswith("sc_")},
+            "sc_round_kernel_ms": [round(ms, 4) for tag, ms in phase_log[-1] if tag in (16, 17)] if phase_log else [],
             "e2e": {"value": v_e2e_msm, "unit": "ms", "h2d_bytes_per_step": int(n_local * 32 + K_TABLES * (1 << sc_local_log) * 32),
                     "d2h_bytes_per_step": int(65 + sc_log_n * (128 + 32) + K_TABLES * 32), "sumcheck_ms": v_e2e_sc},
             "gpu_launches": int(launches),
@@ -463,6 +483,9 @@ def run_b200(args):
                 "host_cores_available": cores,
             }
         print(json.dumps(line), flush=True)
+    if box is not None:
+        barrier()
+        box.free()
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
@@ -477,6 +500,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=24, help="MSM size (log2 points)")
     ap.add_argument("--sc-log-n", type=int, default=24, help="sumcheck table size (log2 entries)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: host-driven NCCL all-gathers instead of the NVLink mailboxes")
     ap.add_argument("--no-table", action="store_true", help="MSM without the precomputed window-level table")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -33,10 +33,12 @@ extern "C" {
 #define ZOLT_ERR_ARG 2   /* invalid argument (null pointer, size not a power of two, ...) */
 #define ZOLT_ERR_STATE 3 /* call sequence violated (e.g. bind after the last round) */
 #define ZOLT_ERR_NOGPU 4 /* no CUDA device: there is no CPU path */
+#define ZOLT_ERR_PEER 5  /* a peer GPU never delivered its part of an exchange (timeout) */
 
 typedef struct zolt_ctx zolt_ctx;     /* one device + one stream */
 typedef struct zolt_bases zolt_bases; /* device-resident G1 bases (an SRS) */
 typedef struct zolt_sc zolt_sc;       /* one sumcheck instance: k device-resident tables */
+typedef struct zolt_peer_box zolt_peer_box; /* this rank's NVLink mailbox + the mapped mailboxes of its peers */
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* `stream` is a cudaStream_t to launch on (borrowed), or NULL to create a private one. */
@@ -46,6 +48,11 @@ int zolt_gpu_sync(zolt_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int zolt_gpu_launch_count(zolt_ctx* ctx, unsigned long long* out);
 const char* zolt_gpu_version(void);
+/* Tuning knobs (tests use them to force a code path; defaults are what bench.py measures).
+ *   ZOLT_TUNE_SC_SMALL_PAIRS  rounds whose current table has at most this many pairs run on the
+ *                             latency-oriented small-round kernel (default 2^14; 0 = always stream) */
+#define ZOLT_TUNE_SC_SMALL_PAIRS 1
+int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value);
 
 /* raw device buffers, so a host without CUDA bindings can keep tables resident */
 int zolt_dev_alloc(zolt_ctx* ctx, size_t bytes, void** dptr);
@@ -207,7 +214,34 @@ int zolt_sc_round_partials_dev(zolt_sc* sc, const void** d_ptr);
 int zolt_sc_finish_partials(zolt_sc* sc, const void* d_rows /* rows*16 u64 */, size_t rows,
                             uint64_t* evals_out /* num_evals*4 */);
 int zolt_fr_sum_rows(zolt_ctx* ctx, const void* d_rows, size_t rows, size_t cols, uint64_t* out /* cols*4 */);
+/* Multi-GPU, fused exchange (preferred): after zolt_sc_set_peers(sc, box) every round kernel pushes its 4 raw
+ * sums into the mailbox of every rank over NVLink and folds all ranks' rows itself, so zolt_sc_round_evals /
+ * zolt_sc_bind behave exactly as on one GPU while each rank holds only its hypercube block.  Every rank
+ * must make the same sequence of calls.  zolt_sc_gather_tail: once the local block is down to one entry per
+ * table, all-gather those entries into d_out laid out [table][rank] (the tables of the last log2(world)
+ * rounds, which every rank then runs redundantly). */
+int zolt_sc_set_peers(zolt_sc* sc, zolt_peer_box* box);
+int zolt_sc_gather_tail(zolt_sc* sc, void* d_out /* (k+n_extra) * world * 4 u64, device */);
 int zolt_sc_free(zolt_sc* sc);
+
+/* ---- NVLink peer mailbox (multi-GPU exchange without a collective library) ---------------------------
+ * One process per GPU.  zolt_peer_box_create allocates this rank's mailbox and returns its 64-byte CUDA IPC
+ * handle; the caller exchanges the handles of all ranks by any means (bench.py: torch.distributed
+ * all_gather at start-up) and passes them, rank-ordered, to zolt_peer_box_connect, which maps every peer's
+ * mailbox (P2P over NVLink/NVSwitch).  From then on kernels exchange small results by storing straight into
+ * the peers' mailboxes (csrc/peer.cuh); a peer that never shows up makes the waiting call fail with
+ * ZOLT_ERR_PEER after 4 s.  world <= 8.
+ *   zolt_peer_allgather    n_fr (<= 8) field-sized elements per rank; d_out is [rank][n_fr] (transpose 0) or
+ *                          [n_fr][rank] (transpose 1), device memory; synchronises the stream.
+ *   zolt_msm_sharded_dev   MSM over point-range shards (ParallelMSM.compute's split, src/msm/mod.zig:608-653,
+ *                          across GPUs): this rank's partial over its bases/scalars, exchanged and summed on
+ *                          the device by one kernel; every rank returns the same affine result. */
+int zolt_peer_box_create(zolt_ctx* ctx, zolt_peer_box** out, unsigned char handle_out[64]);
+int zolt_peer_box_connect(zolt_peer_box* box, const unsigned char* handles /* world*64 */, int rank, int world);
+int zolt_peer_box_free(zolt_peer_box* box);
+int zolt_peer_allgather(zolt_peer_box* box, const void* d_src, int n_fr, void* d_out, int transpose);
+int zolt_msm_sharded_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const void* d_scalars, size_t n,
+                         zolt_peer_box* box, uint64_t out_xy[8], uint8_t* out_inf);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------
  * Integer-pipe micro-benchmarks (the MSM roofline denominator).  `kind`: 0 = IMAD (3-reg),

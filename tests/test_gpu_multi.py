@@ -54,7 +54,37 @@ r_evals, r_chal, r_final = R.sc_prove("eq_ab_minus_c", 0, full)
 assert (chal == r_chal).all(), "challenges differ"
 assert (evals == r_evals).all(), "round evaluations differ"
 assert all((final[t] == r_final[t][0]).all() for t in range(k)), "final values differ"
+
+# --- the same two paths with the exchange fused into the kernels (NVLink peer mailboxes, no NCCL on the data path) ---
+from zolt_b200 import host as H
+box = ZD.connect_peer_box(ctx, rank, world)
+xy2, inf2 = Z.MSM.compute_sharded_dev(bases, d_s.ptr, (1 << 13) // world, box)
+assert (xy2 == xy).all() and inf2 == inf, "mailbox-sharded MSM differs"
+e2, c2, f2 = H.sumcheck_prove_sharded(ctx, box, Z.SC_EQ_AB_MINUS_C, [b.ptr for b in d_tabs], log_n - ZD.log2_exact(world))
+assert (c2 == r_chal).all() and (e2 == r_evals).all(), "mailbox-sharded sumcheck: round polynomials differ"
+assert all((f2[t] == r_final[t][0]).all() for t in range(k)), "mailbox-sharded sumcheck: final values differ"
+# larger block: streaming round kernels first, then the small-round kernel, then the gathered tail; degree 2 and 3
+for comb, name, kk, lg in ((Z.SC_EQ_AB_MINUS_C, "eq_ab_minus_c", 4, 17), (Z.SC_PROD2, "prod2", 2, 16)):
+    full = [fr_arr(rand_fr(500 + 10 * lg + t, 1 << lg)) for t in range(kk)]
+    lo, hi = ZD.shard_range(1 << lg, rank, world)
+    d_big = [Z.DeviceBuffer.from_host(ctx, t[lo:hi]) for t in full]
+    e3, c3, f3 = H.sumcheck_prove_sharded(ctx, box, comb, [b.ptr for b in d_big], lg - ZD.log2_exact(world))
+    r_e, r_c, r_f = R.sc_prove(name, 0, full)
+    ne = 3 if comb == Z.SC_PROD2 else 4
+    assert (c3 == r_c).all() and (e3[:, :ne] == r_e[:, :ne]).all(), f"mailbox-sharded {name} 2^{lg}: round polynomials differ"
+    assert all((f3[t] == r_f[t][0]).all() for t in range(kk)), f"mailbox-sharded {name} 2^{lg}: final values differ"
+    for b in d_big:
+        b.free()
+# all-gather primitive, both layouts
+src = torch.arange(rank * 16, rank * 16 + 16, dtype=torch.int64, device="cuda")  # 4 field-sized elements
+out = torch.zeros(16 * world, dtype=torch.int64, device="cuda")
+box.allgather(src.data_ptr(), 4, out.data_ptr(), False)
+assert out.cpu().tolist() == list(range(16 * world))
+box.allgather(src.data_ptr(), 4, out.data_ptr(), True)
+exp = [g * 16 + i * 4 + j for i in range(4) for g in range(world) for j in range(4)]
+assert out.cpu().tolist() == exp
 dist.barrier()
+box.free()
 if rank == 0:
     print("MULTI_GPU_OK")
 dist.destroy_process_group()

@@ -19,6 +19,15 @@ COMBINERS = [
 ]
 
 
+@pytest.fixture(params=["small_rounds", "streaming"])
+def ctx(ctx, request):
+    """Every sumcheck test runs twice: with the default dispatch (the latency-oriented small-round kernel below
+    2^14 pairs) and with the streaming round kernels forced at every size."""
+    ctx.set_tuning(Z.TUNE_SC_SMALL_PAIRS, (1 << 14) if request.param == "small_rounds" else 0)
+    yield ctx
+    ctx.set_tuning(Z.TUNE_SC_SMALL_PAIRS, 1 << 14)
+
+
 def _run_and_compare(ctx, kind, comb, k, pairing, log_n, seed, n_extra=0):
     n = 1 << log_n
     tables = [rand_fr(seed * 100 + t, n) for t in range(k + n_extra)]
@@ -43,6 +52,12 @@ def _run_and_compare(ctx, kind, comb, k, pairing, log_n, seed, n_extra=0):
 @pytest.mark.parametrize("log_n", [1, 2, 3, 7, 11])
 def test_dense_rounds_and_tables(ctx, kind, comb, k, pairing, log_n):
     _run_and_compare(ctx, kind, comb, k, pairing, log_n, seed=log_n + 17 * comb + pairing)
+
+
+def test_dispatch_crossover(ctx):
+    # 2^16 entries: rounds 0-1 stream, the rest run on the small-round kernel (several chunks per block)
+    _run_and_compare(ctx, "eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4, Z.PAIR_ADJACENT, 16, seed=31)
+    _run_and_compare(ctx, "prod2", Z.SC_PROD2, 2, Z.PAIR_HALF, 16, seed=32)
 
 
 def test_extra_tables_are_bound_in_lockstep(ctx):

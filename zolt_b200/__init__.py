@@ -29,6 +29,7 @@ from ._lib import (  # noqa: F401
     SC_PROD2,
     SC_PROD3,
     SC_SUM,
+    TUNE_SC_SMALL_PAIRS,
     ZoltGpuError,
     load_library,
 )
@@ -40,6 +41,7 @@ from .api import (  # noqa: F401
     DeviceBuffer,
     EqPolynomial,
     HyperKZG,
+    PeerBox,
     SumcheckInstance,
 )
 

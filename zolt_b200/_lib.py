@@ -13,13 +13,14 @@ LIB_DIR = Path(__file__).resolve().parent / "lib"
 LIB_PATH = LIB_DIR / "libzolt_gpu.so"
 HOST_LIB_PATH = LIB_DIR / "libzolt_host.so"
 
-ZOLT_OK, ZOLT_ERR_CUDA, ZOLT_ERR_ARG, ZOLT_ERR_STATE, ZOLT_ERR_NOGPU = 0, 1, 2, 3, 4
-_ERR_NAMES = {1: "ZOLT_ERR_CUDA", 2: "ZOLT_ERR_ARG", 3: "ZOLT_ERR_STATE", 4: "ZOLT_ERR_NOGPU"}
+ZOLT_OK, ZOLT_ERR_CUDA, ZOLT_ERR_ARG, ZOLT_ERR_STATE, ZOLT_ERR_NOGPU, ZOLT_ERR_PEER = 0, 1, 2, 3, 4, 5
+_ERR_NAMES = {1: "ZOLT_ERR_CUDA", 2: "ZOLT_ERR_ARG", 3: "ZOLT_ERR_STATE", 4: "ZOLT_ERR_NOGPU", 5: "ZOLT_ERR_PEER"}
 
 FIELD_FR, FIELD_FQ = 0, 1
 OP_MUL, OP_ADD, OP_SUB, OP_INV, OP_FROM_MONT, OP_TO_MONT, OP_NEG = range(7)
 PAIR_ADJACENT, PAIR_HALF = 0, 1
 SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN_AB_MINUS_C = range(7)
+TUNE_SC_SMALL_PAIRS = 1
 
 
 class ZoltGpuError(RuntimeError):
@@ -40,6 +41,7 @@ SIGNATURES = {
     "zolt_gpu_shutdown": [_vp],
     "zolt_gpu_sync": [_vp],
     "zolt_gpu_launch_count": [_vp, C.POINTER(C.c_ulonglong)],
+    "zolt_gpu_set_tuning": [_vp, _i, C.c_longlong],
     "zolt_dev_alloc": [_vp, _sz, C.POINTER(_vp)],
     "zolt_dev_free": [_vp, _vp],
     "zolt_dev_upload": [_vp, _vp, _vp, _sz],
@@ -73,6 +75,13 @@ SIGNATURES = {
     "zolt_sc_table_dev": [_vp, _i, C.POINTER(_vp)],
     "zolt_sc_set_claim": [_vp, _vp],
     "zolt_sc_set_sharded": [_vp, _i],
+    "zolt_sc_set_peers": [_vp, _vp],
+    "zolt_sc_gather_tail": [_vp, _vp],
+    "zolt_peer_box_create": [_vp, C.POINTER(_vp), _vp],
+    "zolt_peer_box_connect": [_vp, _vp, _i, _i],
+    "zolt_peer_box_free": [_vp],
+    "zolt_peer_allgather": [_vp, _vp, _i, _vp, _i],
+    "zolt_msm_sharded_dev": [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp],
     "zolt_sc_round_partials_dev": [_vp, C.POINTER(_vp)],
     "zolt_sc_finish_partials": [_vp, _vp, _sz, _vp],
     "zolt_fr_sum_rows": [_vp, _vp, _sz, _sz, _vp],

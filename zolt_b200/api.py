@@ -64,6 +64,9 @@ class Context:
         check(self.lib.zolt_gpu_launch_count(self.handle, C.byref(out)), "zolt_gpu_launch_count")
         return out.value
 
+    def set_tuning(self, key: int, value: int):
+        check(self.lib.zolt_gpu_set_tuning(self.handle, key, value), "zolt_gpu_set_tuning")
+
     def timer_start(self):
         check(self.lib.zolt_timer_start(self.handle), "zolt_timer_start")
 
@@ -227,11 +230,48 @@ class MSM:
         check(ctx.lib.zolt_msm_partial_dev(ctx.handle, bases.handle, offset, C.c_void_p(d_scalars), n, C.c_void_p(d_out)), "zolt_msm_partial_dev")
 
     @staticmethod
+    def compute_sharded_dev(bases: Bases, d_scalars: int, n: int, box: "PeerBox", offset: int = 0):
+        """ParallelMSM's point-range split across GPUs: this rank's range, partials exchanged through the NVLink
+        mailboxes and summed on the device; every rank returns the same affine point."""
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_uint8()
+        ctx = bases.ctx
+        check(ctx.lib.zolt_msm_sharded_dev(ctx.handle, bases.handle, offset, C.c_void_p(d_scalars), n, box.handle, _ptr(out), C.byref(inf)),
+              "zolt_msm_sharded_dev")
+        return out, int(inf.value)
+
+    @staticmethod
     def sum_partials(ctx: Context, d_partials: int, count: int):
         out = np.zeros(8, dtype=np.uint64)
         inf = C.c_uint8()
         check(ctx.lib.zolt_g1_sum_partials(ctx.handle, C.c_void_p(d_partials), count, _ptr(out), C.byref(inf)), "zolt_g1_sum_partials")
         return out, int(inf.value)
+
+
+class PeerBox:
+    """This rank's NVLink mailbox and the mapped mailboxes of its peers (csrc/peer.cuh).  `exchange` is any
+    callable that all-gathers one 64-byte blob per rank, rank-ordered (zolt_b200.dist.connect_peer_box uses
+    torch.distributed once at start-up); after that no collective library is on the data path."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, exchange):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        check(ctx.lib.zolt_peer_box_create(ctx.handle, C.byref(h), C.cast(handle, C.c_void_p)), "zolt_peer_box_create")
+        self.handle = h
+        blobs = exchange(bytes(handle))
+        if len(blobs) != world or any(len(b) != 64 for b in blobs):
+            raise ValueError("exchange must return one 64-byte handle per rank")
+        allh = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(blobs))
+        check(ctx.lib.zolt_peer_box_connect(self.handle, C.cast(allh, C.c_void_p), rank, world), "zolt_peer_box_connect")
+
+    def allgather(self, d_src: int, n_fr: int, d_out: int, transpose: bool = False):
+        check(self.ctx.lib.zolt_peer_allgather(self.handle, C.c_void_p(d_src), n_fr, C.c_void_p(d_out), int(transpose)), "zolt_peer_allgather")
+
+    def free(self):
+        if self.handle:
+            check(self.ctx.lib.zolt_peer_box_free(self.handle), "zolt_peer_box_free")
+            self.handle = None
 
 
 class HyperKZG:

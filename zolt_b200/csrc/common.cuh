@@ -54,6 +54,8 @@ struct zolt_ctx {
   std::vector<void*> pinned_free;  // recycled 256-byte mapped pinned mailboxes (one per live instance)
   // counters for the bench's "gpu_launches" claim
   unsigned long long launches = 0;
+  // tuning (zolt_gpu_set_tuning)
+  long long sc_small_pairs = 1 << 14;
   // phase profiling (CUDA events on `stream`): begin/end pairs tagged by the caller
   static constexpr int kMaxProf = 96;
   cudaEvent_t prof_ev[2 * kMaxProf] = {};

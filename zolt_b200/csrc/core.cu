@@ -77,6 +77,14 @@ extern "C" int zolt_gpu_launch_count(zolt_ctx* ctx, unsigned long long* out) {
   return ZOLT_OK;
 }
 
+extern "C" int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value) {
+  if (!ctx || value < 0) return ZOLT_ERR_ARG;
+  switch (key) {
+    case ZOLT_TUNE_SC_SMALL_PAIRS: ctx->sc_small_pairs = value > (1 << 14) ? (1 << 14) : value; return ZOLT_OK;
+    default: return ZOLT_ERR_ARG;
+  }
+}
+
 extern "C" int zolt_dev_alloc(zolt_ctx* ctx, size_t bytes, void** dptr) {
   if (!ctx || !dptr) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));

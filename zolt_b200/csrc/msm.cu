@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "curve.cuh"
+#include "peer.cuh"
 
 using namespace zolt;
 
@@ -445,6 +446,25 @@ __global__ void g1_sum_partials_kernel(const XYZZ* __restrict__ parts, size_t co
   XYZZ acc = XYZZ::identity();
   for (size_t i = 0; i < count; i++) {
     XYZZ p = ld_xyzz(&parts[i]);
+    xyzz_add(acc, p);
+  }
+  st_xyzz(out, acc);
+}
+
+// Point-range shards across GPUs: publish this rank's partial (128 bytes) into every rank's NVLink mailbox,
+// wait for all of them, add the rows in rank order.  One thread; the additions are 8 full XYZZ adds at most.
+__global__ void g1_peer_sum_kernel(const XYZZ* __restrict__ part, const __grid_constant__ PeerDev peer, XYZZ* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  Fr vals[4];
+  const Fr* src = reinterpret_cast<const Fr*>(part);  // XYZZ = four 32-byte elements
+#pragma unroll 1
+  for (int i = 0; i < 4; i++) vals[i] = src[i];
+  peer_publish(peer, vals, 4);
+  if (!peer_wait(peer)) return;
+  XYZZ acc = XYZZ::identity();
+#pragma unroll 1
+  for (int g = 0; g < peer.world; g++) {
+    XYZZ p = ld_xyzz_cg(reinterpret_cast<const XYZZ*>(peer_row(peer.box[peer.rank], peer.seq, g)));
     xyzz_add(acc, p);
   }
   st_xyzz(out, acc);
@@ -884,6 +904,24 @@ extern "C" int zolt_g1_sum_partials(zolt_ctx* ctx, const void* d_partials, size_
   ctx->launches++;
   int s = finish_affine(ctx, d_sum, 1, out_xy, out_inf);
   pool_release(ctx, d_sum, sizeof(XYZZ));
+  return s;
+}
+
+extern "C" int zolt_msm_sharded_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const void* d_scalars, size_t n,
+                                    zolt_peer_box* box, uint64_t out_xy[8], uint8_t* out_inf) {
+  if (!ctx || !bases || !box || !box->connected || box->ctx != ctx || !out_xy || !out_inf || (n && !d_scalars) || offset + n > bases->n)
+    return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 2 * sizeof(XYZZ), (void**)&d_res));
+  int s = msm_core(ctx, bases, offset, (const Fr*)d_scalars, 1, n, d_res);
+  if (s == ZOLT_OK) {
+    g1_peer_sum_kernel<<<1, 32, 0, ctx->stream>>>(d_res, peer_next(box), d_res + 1);
+    ctx->launches++;
+    s = finish_affine(ctx, d_res + 1, 1, out_xy, out_inf);
+    if (s == ZOLT_OK) s = peer_check(box);
+  }
+  pool_release(ctx, d_res, 2 * sizeof(XYZZ));
   return s;
 }
 

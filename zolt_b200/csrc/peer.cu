@@ -1,0 +1,127 @@
+// NVLink peer mailbox management (CUDA IPC) and the stand-alone mailbox all-gather.  See peer.cuh.
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "peer.cuh"
+
+using namespace zolt;
+
+namespace {
+
+struct GatherSrc {
+  const Fr* p[kPeerSlotFr];
+};
+
+// Publish n_fr elements (one pointer each), wait for every rank, write all rows to `out`:
+// transpose == 0: out[g * n_fr + i] (rank-major), transpose == 1: out[i * world + g] (one table per element).
+__global__ void peer_allgather_kernel(const __grid_constant__ GatherSrc src, int n_fr, const __grid_constant__ PeerDev peer, Fr* out,
+                                      int transpose) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    Fr vals[kPeerSlotFr];
+#pragma unroll 1
+    for (int i = 0; i < n_fr; i++) vals[i] = src.p[i][0];
+    peer_publish(peer, vals, n_fr);
+    ok = peer_wait(peer) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!ok) return;
+  for (int j = threadIdx.x; j < peer.world * n_fr; j += blockDim.x) {
+    const int g = j / n_fr, i = j % n_fr;
+    const Fr v = peer_load(peer, g, i);
+    Fr* dst = out + (transpose ? (size_t)i * peer.world + g : (size_t)g * n_fr + i);
+    uint4* q = reinterpret_cast<uint4*>(dst);
+    q[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    q[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+  }
+}
+
+}  // namespace
+
+namespace zolt {
+int peer_allgather_ptrs(zolt_peer_box* box, const Fr* const* d_src, int n_fr, Fr* d_out, int transpose) {
+  if (!box || !box->connected || !d_src || !d_out || n_fr < 1 || n_fr > kPeerSlotFr) return ZOLT_ERR_ARG;
+  zolt_ctx* ctx = box->ctx;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  GatherSrc s{};
+  for (int i = 0; i < n_fr; i++) s.p[i] = d_src[i];
+  const PeerDev p = peer_next(box);
+  peer_allgather_kernel<<<1, 64, 0, ctx->stream>>>(s, n_fr, p, d_out, transpose);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  return ZOLT_OK;
+}
+int peer_check(zolt_peer_box* box) {
+  if (box && box->h_err && *box->h_err) {
+    fprintf(stderr, "[zolt_gpu] peer mailbox: rank %d never saw rank %d's data (timeout)\n", box->rank, *box->h_err - 1);
+    return ZOLT_ERR_PEER;
+  }
+  return ZOLT_OK;
+}
+}  // namespace zolt
+
+extern "C" int zolt_peer_box_create(zolt_ctx* ctx, zolt_peer_box** out, unsigned char handle_out[64]) {
+  if (!ctx || !out || !handle_out) return ZOLT_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  *out = nullptr;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  zolt_peer_box* box = new (std::nothrow) zolt_peer_box();
+  if (!box) return ZOLT_ERR_ARG;
+  box->ctx = ctx;
+  // plain cudaMalloc (not a pool): IPC export needs a whole allocation
+  ZOLT_CUDA_TRY(cudaMalloc((void**)&box->d_local, kPeerBoxBytes));
+  ZOLT_CUDA_TRY(cudaMemset(box->d_local, 0, kPeerBoxBytes));
+  ZOLT_CUDA_TRY(cudaHostAlloc((void**)&box->h_err, 64, cudaHostAllocMapped));
+  ZOLT_CUDA_TRY(cudaHostGetDevicePointer((void**)&box->d_err, box->h_err, 0));
+  *box->h_err = 0;
+  cudaIpcMemHandle_t h;
+  ZOLT_CUDA_TRY(cudaIpcGetMemHandle(&h, box->d_local));
+  memcpy(handle_out, &h, 64);
+  ZOLT_CUDA_TRY(cudaDeviceSynchronize());
+  *out = box;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_peer_box_connect(zolt_peer_box* box, const unsigned char* handles, int rank, int world) {
+  if (!box || !handles || world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || box->connected) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(box->ctx->device));
+  for (int g = 0; g < world; g++) {
+    if (g == rank) {
+      box->mapped[g] = box->d_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)g, 64);
+    void* p = nullptr;
+    ZOLT_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    box->mapped[g] = (unsigned char*)p;
+    box->opened[g] = true;
+  }
+  box->rank = rank;
+  box->world = world;
+  box->seq = 0;
+  box->connected = true;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_peer_box_free(zolt_peer_box* box) {
+  if (!box) return ZOLT_ERR_ARG;
+  cudaSetDevice(box->ctx->device);
+  cudaStreamSynchronize(box->ctx->stream);
+  for (int g = 0; g < kPeerMaxWorld; g++)
+    if (box->opened[g]) cudaIpcCloseMemHandle(box->mapped[g]);
+  if (box->d_local) cudaFree(box->d_local);
+  if (box->h_err) cudaFreeHost(box->h_err);
+  delete box;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_peer_allgather(zolt_peer_box* box, const void* d_src, int n_fr, void* d_out, int transpose) {
+  if (!box || !d_src || n_fr < 1 || n_fr > kPeerSlotFr) return ZOLT_ERR_ARG;
+  const Fr* ptrs[kPeerSlotFr];
+  for (int i = 0; i < n_fr; i++) ptrs[i] = (const Fr*)d_src + i;
+  ZOLT_TRY(peer_allgather_ptrs(box, ptrs, n_fr, (Fr*)d_out, transpose));
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(box->ctx->stream));
+  return peer_check(box);
+}

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "field.cuh"
+#include "peer.cuh"
 
 using namespace zolt;
 
@@ -356,7 +357,8 @@ struct ScOut {
   Fr* d_claim_cur;    // CLAIM_PREV: previous round polynomial at r, written by block 0 at kernel start
   int deg;            // 0 / 2 / 3
   int claim_src;
-  int finalize;       // 0: sharded run, stop at the raw sums
+  int finalize;       // 0: sharded run (host-driven exchange), stop at the raw sums
+  PeerDev peer;       // world > 1: the raw sums of all ranks are exchanged through the NVLink mailboxes right here
 };
 
 __device__ __forceinline__ Fr ldcg_fr(const Fr* p) {
@@ -376,7 +378,23 @@ __device__ __noinline__ Fr warp_sum_cold(Fr x) {
 }
 
 // raw sums -> round evaluations, written to device memory and to the mapped host mailbox (one thread)
-__device__ __noinline__ void sc_publish(const ScOut& o, const Fr* tot) {
+__device__ __noinline__ void sc_publish(const ScOut& o, const Fr* tot_local) {
+  Fr tot[kRaw];
+#pragma unroll 1
+  for (int e = 0; e < kRaw; e++) tot[e] = tot_local[e];
+  if (o.peer.world > 1) {
+    // hypercube shards: push this rank's sums into every rank's mailbox over NVLink, wait for everybody's,
+    // fold the rows in rank order -- every rank ends the launch holding the same global round polynomial
+    peer_publish(o.peer, tot_local, kRaw);
+    if (!peer_wait(o.peer)) return;
+#pragma unroll 1
+    for (int e = 0; e < kRaw; e++) {
+      Fr acc = Fr::zero();
+#pragma unroll 1
+      for (int g = 0; g < o.peer.world; g++) acc = fr_add_cold(acc, peer_load(o.peer, g, e));
+      tot[e] = acc;
+    }
+  }
 #pragma unroll 1
   for (int e = 0; e < kRaw; e++) st_fr(&o.d_raw[e], tot[e]);
   if (o.finalize) {
@@ -427,22 +445,15 @@ __device__ __forceinline__ void grid_finish(Fr* acc, Fr* smem, const ScOut& o, c
   }
 }
 
-// The round kernels' version (kRoundThreads = 4 warps, kRaw = 4 sums): warp e owns sum e.  `vals` is the
-// block's dynamic scratch, re-used as [kRaw][kRoundThreads] field elements once every thread has left its loop.
-__device__ __noinline__ void round_finish(const Fr* raw, Fr* vals, const ScOut& o) {
+// Grid-level fold of the raw sums and publication.  `x` is the block's sum number `warp`, valid in lane 0 of
+// warps 0..kRaw-1 (a block may have more warps; they only take part in the barriers).  Each block stores its
+// four sums and takes a ticket; the last block to arrive folds all partials (warp e owns sum e) and publishes.
+__device__ __noinline__ void grid_fold_publish(Fr x, const ScOut& o) {
   __shared__ bool is_last;
   __shared__ Fr fin[kRaw];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __syncthreads();
-#pragma unroll 1
-  for (int e = 0; e < kRaw; e++) st_fr(&vals[e * kRoundThreads + tid], raw[e]);
-  __syncthreads();
-  Fr x = vals[warp * kRoundThreads + lane];
-#pragma unroll 1
-  for (int j = 1; j < kRoundThreads / 32; j++) x = fr_add(x, vals[warp * kRoundThreads + lane + 32 * j]);
-  x = warp_sum_cold(x);
   if (gridDim.x > 1) {
-    if (lane == 0) {
+    if (warp < kRaw && lane == 0) {
       st_fr(&o.partials[(size_t)blockIdx.x * kRaw + warp], x);
       __threadfence();
     }
@@ -455,17 +466,34 @@ __device__ __noinline__ void round_finish(const Fr* raw, Fr* vals, const ScOut& 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    Fr tot = Fr::zero();
+    if (warp < kRaw) {
+      Fr tot = Fr::zero();
 #pragma unroll 1
-    for (unsigned b = lane; b < gridDim.x; b += 32) tot = fr_add(tot, ldcg_fr(&o.partials[(size_t)b * kRaw + warp]));
-    x = warp_sum_cold(tot);
+      for (unsigned b = lane; b < gridDim.x; b += 32) tot = fr_add(tot, ldcg_fr(&o.partials[(size_t)b * kRaw + warp]));
+      x = warp_sum_cold(tot);
+    }
   }
-  if (lane == 0) fin[warp] = x;
+  if (warp < kRaw && lane == 0) fin[warp] = x;
   __syncthreads();
   if (tid == 0) {
     if (gridDim.x > 1) *o.ticket = 0;
     sc_publish(o, fin);
   }
+}
+
+// The streaming round kernels' epilogue (kRoundThreads = 4 warps, kRaw = 4 sums): warp e owns sum e.  `vals` is the
+// block's dynamic scratch, re-used as [kRaw][kRoundThreads] field elements once every thread has left its loop.
+__device__ __noinline__ void round_finish(const Fr* raw, Fr* vals, const ScOut& o) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
+#pragma unroll 1
+  for (int e = 0; e < kRaw; e++) st_fr(&vals[e * kRoundThreads + tid], raw[e]);
+  __syncthreads();
+  Fr x = vals[warp * kRoundThreads + lane];
+#pragma unroll 1
+  for (int j = 1; j < kRoundThreads / 32; j++) x = fr_add(x, vals[warp * kRoundThreads + lane + 32 * j]);
+  x = warp_sum_cold(x);
+  grid_fold_publish(x, o);
 }
 
 // ---- the round kernel ------------------------------------------------------------------------------
@@ -604,6 +632,123 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
   Fr raw[kRaw];
   collapse<COMB, P1>(wacc, facc, raw);
   round_finish(raw, reinterpret_cast<Fr*>(scratch), out);
+}
+
+// ---- small rounds --------------------------------------------------------------------------------------
+// Below ~2^14 pairs the streaming kernel is pure latency: one thread walks 2k binds, the whole combiner and
+// three reductions in sequence (~25 us whatever the size; r1 v4 launch list).  This kernel spreads the same
+// arithmetic over threads instead: ONE bound element per thread, then ONE (pair, sample point) term per
+// thread, every field primitive called out of line so the code stays a few KB.  The raw sums it produces are
+// the same field elements (sums of the same canonical terms), so it feeds sc_publish unchanged.
+constexpr int kSmallWorkWarps = 4;                            // warp e evaluates raw sum e
+constexpr int kSmallThreads = 32 * (kSmallWorkWarps + 1);     // + one warp for the claim p_prev(r)
+constexpr int kSmallPairs = 16;                               // pairs of the current table per chunk
+constexpr size_t kSmallMaxPairs = size_t(1) << 14;
+
+struct SmallArgs {
+  int comb, k, n_extra, deg, fused, p1_direct;
+};
+
+__device__ __noinline__ Fr bind_pair_cold(Fr lo, Fr hi, Fr r) { return fr_add(lo, fr_mul(r, fr_sub(hi, lo))); }
+
+enum { PT_NONE = 0, PT_0, PT_1, PT_2, PT_LEAD };
+
+// the term of pair p of this chunk that belongs to raw sum e (layout of the raw sums: see the combiners above)
+__device__ __noinline__ Fr small_term(const SmallArgs& a, int e, const Fr (*stash)[2][kSmallPairs], int p, const SplitEqDev& sq,
+                                      size_t g) {
+  const bool gruen = a.comb == ZOLT_SC_GRUEN_AB || a.comb == ZOLT_SC_GRUEN_AB_MINUS_C;
+  int pt = PT_NONE;
+  if (a.deg == 3) pt = e == 0 ? PT_0 : (e == 1 ? (a.p1_direct ? PT_1 : PT_NONE) : (e == 2 ? PT_2 : PT_LEAD));
+  else if (a.deg == 2) pt = e == 0 ? PT_0 : (e == 1 ? (a.p1_direct ? PT_1 : PT_NONE) : (e == 2 ? PT_LEAD : PT_NONE));
+  else if (gruen) pt = e == 0 ? PT_0 : (e == 1 ? PT_LEAD : PT_NONE);
+  else pt = e == 0 ? PT_0 : (e == 1 ? PT_1 : PT_NONE);
+  if (pt == PT_NONE) return Fr::zero();
+  Fr v[4];
+#pragma unroll 1
+  for (int k = 0; k < a.k; k++) {
+    const Fr lo = stash[k][0][p], hi = stash[k][1][p];
+    if (pt == PT_0) v[k] = lo;
+    else if (pt == PT_1) v[k] = hi;
+    else {
+      const Fr d = fr_sub_cold(hi, lo);
+      v[k] = pt == PT_LEAD ? d : fr_add_cold(hi, d);
+    }
+  }
+  const bool lead = pt == PT_LEAD;
+  switch (a.comb) {
+    case ZOLT_SC_SUM: return v[0];
+    case ZOLT_SC_PROD2: return fr_mul_cold(v[0], v[1]);
+    case ZOLT_SC_PROD3: return fr_mul_cold(fr_mul_cold(v[0], v[1]), v[2]);
+    case ZOLT_SC_EQ_A_BMC: return fr_mul_cold(fr_mul_cold(v[0], v[1]), fr_sub_cold(v[2], v[3]));
+    case ZOLT_SC_EQ_AB_MINUS_C: {
+      Fr t = fr_mul_cold(v[1], v[2]);
+      if (!lead) t = fr_sub_cold(t, v[3]);  // c(X) is linear: no cubic term
+      return fr_mul_cold(v[0], t);
+    }
+    default: {  // Gruen: weight * (l r [- c])
+      const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
+      const Fr w = fr_mul_cold(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+      Fr t = fr_mul_cold(v[0], v[1]);
+      if (a.comb == ZOLT_SC_GRUEN_AB_MINUS_C && !lead) t = fr_sub_cold(t, v[2]);
+      return fr_mul_cold(w, t);
+    }
+  }
+}
+
+template <int PAIR>
+__global__ void __launch_bounds__(kSmallThreads)
+sc_small_kernel(const __grid_constant__ ScPtrs t, const SmallArgs a, size_t n, const __grid_constant__ Fr r, const SplitEqDev sq,
+                const __grid_constant__ ScOut out) {
+  __shared__ Fr stash[4][2][kSmallPairs];  // [table][half][pair of the chunk]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.fused && warp == kSmallWorkWarps && blockIdx.x == 0 && lane == 0 && out.finalize) {
+    Fr prev[4];
+#pragma unroll 1
+    for (int e = 0; e < 4; e++) prev[e] = ld_fr(&out.d_evals[e]);
+    st_fr(out.d_claim_cur, newton_eval4(prev, r));
+    __threadfence();
+  }
+  const size_t n_cur = a.fused ? n / 2 : n;
+  const size_t pairs = n_cur / 2, half_old = n / 2, half_cur = n_cur / 2;
+  const int kt = a.k + a.n_extra;
+  const size_t n_chunks = (pairs + kSmallPairs - 1) / kSmallPairs;
+  Fr x = Fr::zero();
+  for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    if (warp < kSmallWorkWarps) {
+#pragma unroll 1
+      for (int it = tid; it < kSmallPairs * 2 * kt; it += 32 * kSmallWorkWarps) {
+        const int p = it % kSmallPairs, h = (it / kSmallPairs) & 1, k = it / (2 * kSmallPairs);
+        const size_t g = c * kSmallPairs + p;
+        if (g >= pairs) continue;
+        const size_t idx = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * g + h : g + (h ? half_cur : 0);
+        Fr v;
+        if (a.fused) {
+          const Fr* s = t.src[k];
+          const Fr lo = (PAIR == ZOLT_PAIR_ADJACENT) ? ld_fr(s + 2 * idx) : ld_fr(s + idx);
+          const Fr hi = (PAIR == ZOLT_PAIR_ADJACENT) ? ld_fr(s + 2 * idx + 1) : ld_fr(s + idx + half_old);
+          v = bind_pair_cold(lo, hi, r);
+          st_fr(t.dst[k] + idx, v);
+        } else {
+          v = ld_fr(t.src[k] + idx);
+        }
+        if (k < a.k) stash[k][h][p] = v;
+      }
+    }
+    __syncthreads();
+    if (warp < kSmallWorkWarps && lane < kSmallPairs) {
+      const size_t g = c * kSmallPairs + lane;
+      if (g < pairs) x = fr_add_cold(x, small_term(a, warp, stash, lane, sq, g));
+    }
+    __syncthreads();
+  }
+  if (warp < kSmallWorkWarps) x = warp_sum_cold(x);
+  grid_fold_publish(x, out);
+}
+
+// last variable (n == 2): bind every table's single pair, nothing left to evaluate
+__global__ void bind_last_kernel(const __grid_constant__ ScPtrs t, int kt, const __grid_constant__ Fr r) {
+  const int k = threadIdx.x;
+  if (k < kt) st_fr(t.dst[k], bind_pair_cold(ld_fr(t.src[k]), ld_fr(t.src[k] + 1), r));
 }
 
 // Sharded runs: fold the all-gathered raw sums of every rank (rows x kRaw) and finish the round.
@@ -750,6 +895,7 @@ struct zolt_sc {
   Fr* d_tau = nullptr;
   int n_tau = 0;
   unsigned max_grid = 0;
+  zolt_peer_box* box = nullptr;  // zolt_sc_set_peers: rounds exchange their sums through the NVLink mailboxes
 };
 
 namespace {
@@ -820,6 +966,7 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   out.d_claim_cur = sc->d_claim + 1;
   out.deg = combiner_deg(sc->combiner);
   out.finalize = sc->sharded ? 0 : 1;
+  out.peer = peer_next(sc->sharded ? nullptr : sc->box);
   const int mode = fused ? 2 : (sc->have_claim && sc->cur < 0 && out.deg != 0 ? 1 : 0);
   out.claim_src = mode == 2 ? CLAIM_PREV : (mode == 1 ? CLAIM_HOST : CLAIM_NONE);
   sc->pending_claim_src = out.claim_src;
@@ -832,7 +979,14 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
     attr_set[mode] = true;
   }
   const int ps = prof_begin(sc->ctx, fused ? PROF_SC_FUSED : PROF_SC_EVAL);
-  if (mode == 2)
+  if (n_cur / 2 <= (size_t)sc->ctx->sc_small_pairs) {
+    // latency-bound sizes: one element / one term per thread (sc_small_kernel)
+    SmallArgs a{sc->combiner, sc->k, sc->n_extra, out.deg, fused ? 1 : 0, mode == 0 ? 1 : 0};
+    size_t chunks = (n_cur / 2 + kSmallPairs - 1) / kSmallPairs;
+    if (chunks > sc->max_grid) chunks = sc->max_grid;
+    if (chunks == 0) chunks = 1;
+    sc_small_kernel<PAIR><<<(unsigned)chunks, kSmallThreads, 0, sc->ctx->stream>>>(t, a, sc->n, r, sq, out);
+  } else if (mode == 2)
     sc_round_kernel<COMB, PAIR, 2><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out);
   else if (mode == 1)
     sc_round_kernel<COMB, PAIR, 1><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out);
@@ -994,8 +1148,27 @@ extern "C" int zolt_sc_round_evals(zolt_sc* sc, uint64_t* evals_out) {
   if (sc->sharded && !(sc->evals_valid && sc->evals_final)) return ZOLT_ERR_STATE;  // use the partials protocol
   ZOLT_TRY(sc_ensure_evals(sc));
   ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  ZOLT_TRY(peer_check(sc->box));
   memcpy(evals_out, sc->h_evals, (size_t)sc->ne * sizeof(Fr));
   return ZOLT_OK;
+}
+
+extern "C" int zolt_sc_set_peers(zolt_sc* sc, zolt_peer_box* box) {
+  if (!sc || !box || !box->connected || box->ctx != sc->ctx) return ZOLT_ERR_ARG;
+  if (sc->evals_valid || sc->cur >= 0 || sc->sharded) return ZOLT_ERR_STATE;  // before the first round
+  sc->box = box;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_sc_gather_tail(zolt_sc* sc, void* d_out) {
+  if (!sc || !d_out || !sc->box) return ZOLT_ERR_ARG;
+  if (sc->n != 1) return ZOLT_ERR_STATE;  // every local variable must be bound
+  const Fr* ptrs[kMaxTables];
+  const int total = sc->k + sc->n_extra;
+  for (int i = 0; i < total; i++) ptrs[i] = sc->cur < 0 ? sc->tab_in[i] : sc->buf[sc->cur][i];
+  ZOLT_TRY(peer_allgather_ptrs(sc->box, ptrs, total, (Fr*)d_out, 1));
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  return peer_check(sc->box);
 }
 
 extern "C" int zolt_sc_round_partials_dev(zolt_sc* sc, const void** d_ptr) {
@@ -1017,7 +1190,6 @@ extern "C" int zolt_sc_finish_partials(zolt_sc* sc, const void* d_rows, size_t r
     out.h_evals = sc->h_evals_dev;
     out.d_claim = sc->d_claim;
     out.d_claim_cur = sc->d_claim + 1;
-  out.d_claim_cur = sc->d_claim + 1;
     out.deg = combiner_deg(sc->combiner);
     out.claim_src = sc->pending_claim_src;
     sc_finish_rows_kernel<<<1, 32, 0, ctx->stream>>>((const Fr*)d_rows, rows, out, sc->last_r);
@@ -1048,16 +1220,15 @@ extern "C" int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]) {
     launch_round_any(sc, true, r);
     sc->evals_valid = true;
   } else {
-    // last variable: bind only, nothing left to evaluate
-    for (int i = 0; i < sc->k + sc->n_extra; i++) {
-      const Fr* src = sc->cur < 0 ? sc->tab_in[i] : sc->buf[sc->cur][i];
-      Fr* dst = sc->buf[sc->cur < 0 ? 0 : (sc->cur ^ 1)][i];
-      if (sc->pairing == ZOLT_PAIR_ADJACENT)
-        bind_kernel<ZOLT_PAIR_ADJACENT><<<1, kScThreads, 0, ctx->stream>>>(dst, src, sc->n, r);
-      else
-        bind_kernel<ZOLT_PAIR_HALF><<<1, kScThreads, 0, ctx->stream>>>(dst, src, sc->n, r);
-      ctx->launches++;
+    // last variable: bind only, nothing left to evaluate (both pairings pair elements 0 and 1)
+    ScPtrs t{};
+    const int total = sc->k + sc->n_extra;
+    for (int i = 0; i < total; i++) {
+      t.src[i] = sc->cur < 0 ? sc->tab_in[i] : sc->buf[sc->cur][i];
+      t.dst[i] = sc->buf[sc->cur < 0 ? 0 : (sc->cur ^ 1)][i];
     }
+    bind_last_kernel<<<1, 32, 0, ctx->stream>>>(t, total, r);
+    ctx->launches++;
     sc->evals_valid = false;
   }
   ZOLT_CUDA_TRY(cudaGetLastError());

@@ -126,6 +126,26 @@ def sharded_sumcheck_gpu(ctx, stream, combiner: int, d_tab_ptrs, local_log: int,
     return out
 
 
+def connect_peer_box(ctx, rank: int, world: int):
+    """Create this rank's NVLink mailbox and map every peer's (one torch.distributed all_gather of the 64-byte
+    CUDA IPC handles at start-up; nothing on the data path uses the process group afterwards)."""
+    import torch
+    import torch.distributed as dist
+
+    from .api import PeerBox
+
+    def exchange(blob: bytes):
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+        allb = torch.zeros(64 * world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allb, mine)
+        host = bytes(allb.cpu().numpy().tobytes())
+        return [host[64 * g:64 * (g + 1)] for g in range(world)]
+
+    box = PeerBox(ctx, rank, world, exchange)
+    dist.barrier()  # every rank has mapped every mailbox before anybody publishes
+    return box
+
+
 def run_sharded_msm(partial_fn, allgather_fn, combine_fn):
     """MSM over point-range shards: partial_fn() -> this rank's partial; allgather_fn(p) -> all partials;
     combine_fn(parts) -> affine result.  (Kept as three callables so the CPU gloo test can exercise the

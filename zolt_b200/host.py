@@ -38,6 +38,8 @@ def load_host() -> C.CDLL:
         _host.zolt_host_sumcheck_prove_gruen.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
                                                          C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p,
                                                          C.c_void_p, C.c_void_p]
+        _host.zolt_host_sumcheck_prove_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                                           C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_hyperkzg_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     return _host
 
@@ -115,6 +117,22 @@ def sumcheck_prove_dev(ctx: Context, combiner: int, pairing: int, d_tables, log_
     st = load_host().zolt_host_sumcheck_prove_dev(ctx.handle, combiner, pairing, log_n, len(d_tables), n_extra, arr, domain,
                                                   len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
     _lib.check(st, "zolt_host_sumcheck_prove_dev")
+    return evals, chal, final
+
+
+def sumcheck_prove_sharded(ctx: Context, box, combiner: int, d_tables, local_log: int, domain: bytes = b"bench",
+                           label: bytes = b"round"):
+    """One rank of the dense LowToHigh sumcheck over contiguous hypercube blocks (zolt_host.hpp proveSumcheckSharded):
+    the round kernels exchange their sums through the NVLink mailboxes, every rank returns the whole proof."""
+    world = box.world
+    rounds = local_log + (world - 1).bit_length()
+    arr = (C.c_void_p * len(d_tables))(*d_tables)
+    evals = np.zeros((rounds, 4, 4), dtype=np.uint64)
+    chal = np.zeros((rounds, 4), dtype=np.uint64)
+    final = np.zeros((len(d_tables), 4), dtype=np.uint64)
+    st = load_host().zolt_host_sumcheck_prove_sharded(ctx.handle, box.handle, world, combiner, local_log, len(d_tables), arr, domain,
+                                                      len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
+    _lib.check(st, "zolt_host_sumcheck_prove_sharded")
     return evals, chal, final
 
 

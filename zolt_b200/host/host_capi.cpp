@@ -81,6 +81,22 @@ int zolt_host_sumcheck_prove_dev(zolt_ctx* ctx, int combiner, int pairing, int l
   return ZOLT_OK;
 }
 
+// One rank of the sharded dense sumcheck (contiguous hypercube blocks, NVLink mailbox exchange inside the round
+// kernels).  evals_out / challenges_out hold local_log + log2(world) rounds.
+int zolt_host_sumcheck_prove_sharded(zolt_ctx* ctx, zolt_peer_box* box, int world, int combiner, int local_log, int n_tables,
+                                     const void* const* d_tables, const char* domain, size_t dn, const char* label, size_t ln,
+                                     uint64_t* evals_out, uint64_t* challenges_out, uint64_t* final_out) {
+  Context c(ctx);
+  std::vector<const void*> tabs(d_tables, d_tables + n_tables);
+  Transcript tr(std::string_view(domain, dn));
+  std::vector<Fr> fin;
+  SumcheckProof proof = proveSumcheckSharded(c, box, world, combiner, tabs, local_log, tr, std::string_view(label, ln), &fin);
+  store_proof(proof, evals_out, challenges_out);
+  if (final_out)
+    for (int t = 0; t < n_tables; t++) fin[t].store(final_out + 4 * t);
+  return ZOLT_OK;
+}
+
 // Gruen split-eq degree-3 sumcheck (ProductVirtualRemainderProver shape); claim = initial claim.
 int zolt_host_sumcheck_prove_gruen(zolt_ctx* ctx, int with_c, int log_n, int n_tables, const uint64_t* const* tables,
                                    const uint64_t* tau, const uint64_t* claim, const char* domain, size_t dn,

@@ -367,6 +367,59 @@ struct SumcheckProof {
 
 // The stage loop of MultiStageProver (src/zkvm/prover.zig:405-428): per round absorb the first
 // degree+1 evaluations as "round_poly_j", squeeze `challenge_label`, bind.
+// Appends inst's rounds to `proof` (the transcript carries over from whatever ran before).
+inline void proveSumcheckInto(SumcheckProof& proof, SumcheckInstance& inst, Transcript& transcript, std::string_view challenge_label) {
+  const size_t n_absorb = inst.degree() + 1;
+  for (size_t round = 0; round < inst.numRounds(); round++) {
+    const auto evals = inst.computeRoundPoly(round);
+    for (size_t j = 0; j < n_absorb; j++) {
+      char label[24];
+      const int ln = std::snprintf(label, sizeof label, "round_poly_%zu", j);
+      transcript.appendScalar(std::string_view(label, (size_t)ln), evals[j]);
+    }
+    const Fr r = transcript.challengeScalar(challenge_label);
+    inst.bindChallenge(r);
+    proof.round_polys.push_back(evals);
+    proof.challenges.push_back(r);
+  }
+}
+
+// One rank of a dense LowToHigh sumcheck whose tables are sharded over `world` GPUs in contiguous hypercube
+// blocks.  Every rank runs this with its own block; the round kernels exchange their sums through
+// the NVLink mailboxes, so each rank sees the global round polynomials, runs the same Keccak transcript and
+// derives the same challenges.  When the local block is down to one entry per table those `world` entries are
+// all-gathered and the last log2(world) rounds run on every rank alike.  Returns the whole proof; final_out
+// receives the k fully bound table values.
+inline SumcheckProof proveSumcheckSharded(Context& ctx, zolt_peer_box* box, int world, int combiner,
+                                          const std::vector<const void*>& d_tables, int local_log, Transcript& transcript,
+                                          std::string_view challenge_label, std::vector<Fr>* final_out) {
+  SumcheckProof proof;
+  const int k = (int)d_tables.size();
+  int tail_log = 0;
+  while ((1 << tail_log) < world) tail_log++;
+  DenseSumcheckProver local(ctx, DenseSumcheckProver::DeviceTables{}, combiner, ZOLT_PAIR_ADJACENT, d_tables, local_log);
+  if (world > 1) must(zolt_sc_set_peers(local.raw(), box), "zolt_sc_set_peers");
+  proveSumcheckInto(proof, local, transcript, challenge_label);
+  if (world == 1) {
+    if (final_out)
+      for (int t = 0; t < k; t++) final_out->push_back(local.table(t)[0]);
+    return proof;
+  }
+  void* d_tail = nullptr;
+  must(zolt_dev_alloc(ctx.raw(), (size_t)k * world * 32, &d_tail), "zolt_dev_alloc");
+  must(zolt_sc_gather_tail(local.raw(), d_tail), "zolt_sc_gather_tail");
+  std::vector<const void*> tail_tabs;
+  for (int t = 0; t < k; t++) tail_tabs.push_back(static_cast<const char*>(d_tail) + (size_t)t * world * 32);
+  {
+    DenseSumcheckProver tail(ctx, DenseSumcheckProver::DeviceTables{}, combiner, ZOLT_PAIR_ADJACENT, tail_tabs, tail_log);
+    proveSumcheckInto(proof, tail, transcript, challenge_label);
+    if (final_out)
+      for (int t = 0; t < k; t++) final_out->push_back(tail.table(t)[0]);
+  }
+  must(zolt_dev_free(ctx.raw(), d_tail), "zolt_dev_free");
+  return proof;
+}
+
 inline SumcheckProof proveSumcheck(SumcheckInstance& inst, Transcript& transcript, std::string_view challenge_label) {
   SumcheckProof proof;
   const size_t n_absorb = inst.degree() + 1;
