@@ -95,3 +95,23 @@ extern "C" void shim_wide_dot(int field, const uint32_t* a, const uint32_t* b, s
   if (field == 0) wide_dot<FrParams>(a, b, n, out);
   else wide_dot<FqParams>(a, b, n, out);
 }
+
+// fp_bind_fixed: out[i] = lo[i] + r * (hi[i] - lo[i]) through the per-launch table of r (raw limbs in, raw limbs out;
+// the arithmetic is agnostic of what the limbs stand for: out = lo + r_std * (hi - lo) mod p with r_std = r / 2^256).
+template <class P>
+static void bind_fixed(const uint32_t* r, const uint32_t* lo, const uint32_t* hi, size_t n, uint32_t* out) {
+  Fp<P> rr;
+  memcpy(rr.v, r, 32);
+  const FixedMulTable t = fixed_mul_table<P>(rr);
+  for (size_t i = 0; i < n; i++) {
+    Fp<P> a, b;
+    memcpy(a.v, lo + 8 * i, 32);
+    memcpy(b.v, hi + 8 * i, 32);
+    const Fp<P> v = fp_bind_fixed<P>(a, b, t);
+    memcpy(out + 8 * i, v.v, 32);
+  }
+}
+extern "C" void shim_bind_fixed(int field, const uint32_t* r, const uint32_t* lo, const uint32_t* hi, size_t n, uint32_t* out) {
+  if (field == 0) bind_fixed<FrParams>(r, lo, hi, n, out);
+  else bind_fixed<FqParams>(r, lo, hi, n, out);
+}

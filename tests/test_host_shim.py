@@ -100,3 +100,28 @@ def test_wide_accumulator(host_shim, field, mod):
                                 out.ctypes.data_as(C.c_void_p))
         want = sum(x * y for x, y in zip(av, bv)) * rinv % mod
         assert B.raw_array_to_ints(out.reshape(1, 4)) == [want], (n, kind)
+
+
+@pytest.mark.parametrize("field,mod", [(0, B.FR_MOD), (1, B.FQ_MOD)])
+def test_fixed_multiplier_bind(host_shim, field, mod):
+    """fp_bind_fixed (the streaming sumcheck kernels' bind: table of r * 2^(32 i) mod p, plain 8 x 8 product, one Barrett
+    step) returns the canonical lo + r (hi - lo), i.e. exactly what the Montgomery-product form returns, for random and
+    extreme operands (0, p-1, all-ones limbs in the difference, r = 0, 1, p-1)."""
+    rng = np.random.default_rng(11)
+    rinv = pow(1 << 256, -1, mod)
+    n = 400
+    los = [v % mod for v in B.random_fr(rng, n)]
+    his = [v % mod for v in B.random_fr(rng, n)]
+    edge = [0, 1, mod - 1, mod - 2, (1 << 253), (1 << 224) - 1, mod >> 1]
+    for i, a in enumerate(edge):
+        for j, b in enumerate(edge):
+            los[(7 * i + j) % n], his[(7 * i + j) % n] = a, b
+    lo, hi = B.ints_to_raw_array(los), B.ints_to_raw_array(his)
+    for r in [0, 1, mod - 1, (1 << 256) % mod, (1 << 253) + 5, 0xFFFFFFFF, ((1 << 125) - 1) << 128] + [v % mod for v in B.random_fr(rng, 6)]:
+        rr = B.ints_to_raw_array([r % mod])
+        out = np.zeros((n, 4), dtype=np.uint64)
+        host_shim.shim_bind_fixed(field, rr.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
+                                  C.c_size_t(n), out.ctypes.data_as(C.c_void_p))
+        r_std = (r % mod) * rinv % mod
+        want = [(a + r_std * (b - a)) % mod for a, b in zip(los, his)]
+        assert B.raw_array_to_ints(out) == want, hex(r)

@@ -99,6 +99,7 @@ struct FrParams {
   ZOLT_FIELD_TABLE(inv6, 0x0aaaaaaau, 0x7d695c48u, 0xaed9b4f4u, 0x3a880fcfu, 0xa9a9c517u, 0xda7526dbu,
                    0x69deea8eu, 0x0a67cbb3u)
   static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32 (low word of 0xc2e1f593efffffff)
+  static constexpr unsigned long long MU288 = 0x54a474626ull;  // floor(2^288 / r) (Barrett, fp_fixed_mul_add)
 };
 
 struct FqParams {
@@ -116,6 +117,7 @@ struct FqParams {
   ZOLT_FIELD_TABLE(inv6, 0x1a575726u, 0xd7ea4d46u, 0x0fb423a1u, 0xf054639fu, 0xa9a9c516u, 0xda7526dbu,
                    0x69deea8eu, 0x0a67cbb3u)
   static constexpr uint32_t INV = 0xe4866389u;  // -q^-1 mod 2^32 (low word of 0x87d20782e4866389)
+  static constexpr unsigned long long MU288 = 0x54a474626ull;  // floor(2^288 / q)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -484,6 +486,152 @@ ZOLT_HD Fp<P> wide_reduce(const uint32_t* acc_in) {
   fp_reduce_once<P>(r.v);
   fp_reduce_once<P>(r.v);
   return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multiplication by a per-launch constant (the sumcheck bind: every element of every table is
+// multiplied by the same challenge r).
+//
+// With c[i] = (r_std * 2^(32 i)) mod p precomputed once per launch (r_std = the plain integer the
+// Montgomery limbs of r stand for),  sum_i d_i * c[i]  is congruent to r_std * d for ANY 256-bit d, so for
+// d = Montgomery limbs of a field element it is the Montgomery form of the product -- the value
+// montgomeryMul (src/field/mod.zig:735-779) returns -- reached with the 64 wide multiplies of a plain
+// 8 x 8 product and NO interleaved reduction rows.  The sum (plus an addend < p) is below 2^289 and is
+// brought back to [0, p) by one Barrett step on its top 65 bits (quotient estimate short by at most 3) and
+// two conditional subtractions: 128 + 28 + ~8 integer multiply-adds instead of 264.
+// Table rows are kernel parameters, i.e. constant-bank operands of the multiply instructions.
+// ---------------------------------------------------------------------------------------------
+struct FixedMulTable {
+  uint32_t c[8][8];
+};
+
+// c[i] = mont_mul(r, 2^(32 i) as a raw integer) = r_std * 2^(32 i) mod p
+template <class P>
+ZOLT_HD FixedMulTable fixed_mul_table(const Fp<P>& r) {
+  FixedMulTable t;
+  for (int i = 0; i < 8; i++) {
+    Fp<P> e = Fp<P>::zero();
+    e.v[i] = 1u;
+    const Fp<P> ci = fp_mul<P>(r, e);
+    for (int j = 0; j < 8; j++) t.c[i][j] = ci.v[j];
+  }
+  return t;
+}
+
+// acc[0..7] += (m0, m1, m2, m3) * d as four (lo, hi) pairs, carry into acc[8]
+ZOLT_HD void fixed_chain(uint32_t* acc, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t d) {
+  acc[0] = ptx::mad_lo_cc(m0, d, acc[0]);
+  acc[1] = ptx::madc_hi_cc(m0, d, acc[1]);
+  acc[2] = ptx::madc_lo_cc(m1, d, acc[2]);
+  acc[3] = ptx::madc_hi_cc(m1, d, acc[3]);
+  acc[4] = ptx::madc_lo_cc(m2, d, acc[4]);
+  acc[5] = ptx::madc_hi_cc(m2, d, acc[5]);
+  acc[6] = ptx::madc_lo_cc(m3, d, acc[6]);
+  acc[7] = ptx::madc_hi_cc(m3, d, acc[7]);
+  acc[8] = ptx::addc(acc[8], 0u);
+}
+
+// canonical (addend + r * d) for the table of r;  addend < p canonical, d any 256-bit representative.
+template <class P>
+ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) {
+  // x = addend + sum_i d_i * c[i] = E + (O << 32): E takes the even limbs of c[i], O the odd ones
+  uint32_t e[9], o[9];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    e[j] = addend.v[j];
+    o[j] = 0;
+  }
+  e[8] = o[8] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    fixed_chain(e, t.c[i][0], t.c[i][2], t.c[i][4], t.c[i][6], d[i]);
+    fixed_chain(o, t.c[i][1], t.c[i][3], t.c[i][5], t.c[i][7], d[i]);
+  }
+  uint32_t x[10];
+  x[0] = e[0];
+  x[1] = ptx::add_cc(e[1], o[0]);
+#pragma unroll
+  for (int j = 2; j < 9; j++) x[j] = ptx::addc_cc(e[j], o[j - 1]);
+  x[9] = ptx::addc(o[8], 0u);
+  // Barrett: q = floor(floor(x / 2^224) * floor(2^288 / p) / 2^64) in [floor(x/p) - 3, floor(x/p)]
+  const unsigned long long H = ((unsigned long long)x[8] << 32) | x[7];
+  const unsigned long long MU = P::MU288;
+#if defined(__CUDA_ARCH__)
+  const unsigned long long hi64 = __umul64hi(H, MU);
+#else
+  const unsigned long long hi64 = (unsigned long long)(((unsigned __int128)H * MU) >> 64);
+#endif
+  const unsigned long long q = hi64 + (unsigned long long)x[9] * MU;
+  const uint32_t q0 = (uint32_t)q, q1 = (uint32_t)(q >> 32);
+  // q * p mod 2^256 = TE + (TO << 32)
+  uint32_t te[8], to[7];
+  te[0] = ptx::mul_lo(P::mod(0), q0);
+  te[1] = ptx::mul_hi(P::mod(0), q0);
+  te[2] = ptx::mul_lo(P::mod(2), q0);
+  te[3] = ptx::mul_hi(P::mod(2), q0);
+  te[4] = ptx::mul_lo(P::mod(4), q0);
+  te[5] = ptx::mul_hi(P::mod(4), q0);
+  te[6] = ptx::mul_lo(P::mod(6), q0);
+  te[7] = ptx::mul_hi(P::mod(6), q0);
+  to[0] = ptx::mul_lo(P::mod(1), q0);
+  to[1] = ptx::mul_hi(P::mod(1), q0);
+  to[2] = ptx::mul_lo(P::mod(3), q0);
+  to[3] = ptx::mul_hi(P::mod(3), q0);
+  to[4] = ptx::mul_lo(P::mod(5), q0);
+  to[5] = ptx::mul_hi(P::mod(5), q0);
+  to[6] = ptx::mul_lo(P::mod(7), q0);
+  // + q1 * p * 2^32: even limbs of p land on the TO alignment, odd limbs on TE two limbs up
+  to[0] = ptx::mad_lo_cc(P::mod(0), q1, to[0]);
+  to[1] = ptx::madc_hi_cc(P::mod(0), q1, to[1]);
+  to[2] = ptx::madc_lo_cc(P::mod(2), q1, to[2]);
+  to[3] = ptx::madc_hi_cc(P::mod(2), q1, to[3]);
+  to[4] = ptx::madc_lo_cc(P::mod(4), q1, to[4]);
+  to[5] = ptx::madc_hi_cc(P::mod(4), q1, to[5]);
+  to[6] = ptx::madc_lo_cc(P::mod(6), q1, to[6]);
+  te[2] = ptx::mad_lo_cc(P::mod(1), q1, te[2]);
+  te[3] = ptx::madc_hi_cc(P::mod(1), q1, te[3]);
+  te[4] = ptx::madc_lo_cc(P::mod(3), q1, te[4]);
+  te[5] = ptx::madc_hi_cc(P::mod(3), q1, te[5]);
+  te[6] = ptx::madc_lo_cc(P::mod(5), q1, te[6]);
+  te[7] = ptx::madc_hi(P::mod(5), q1, te[7]);
+  // rem = x - q p  (true value in [0, 4p) < 2^256: the low 8 limbs are exact)
+  Fp<P> r;
+  r.v[0] = ptx::sub_cc(x[0], te[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) r.v[j] = ptx::subc_cc(x[j], te[j]);
+  r.v[7] = ptx::subc(x[7], te[7]);
+  r.v[1] = ptx::sub_cc(r.v[1], to[0]);
+#pragma unroll
+  for (int j = 2; j < 7; j++) r.v[j] = ptx::subc_cc(r.v[j], to[j - 1]);
+  r.v[7] = ptx::subc(r.v[7], to[6]);
+  // [0, 4p) -> [0, p)
+  {
+    uint32_t s2[8];
+    s2[0] = ptx::sub_cc(r.v[0], P::mod2(0));
+#pragma unroll
+    for (int j = 1; j < 8; j++) s2[j] = ptx::subc_cc(r.v[j], P::mod2(j));
+    const uint32_t borrow = ptx::subc(0u, 0u);
+#pragma unroll
+    for (int j = 0; j < 8; j++) r.v[j] = borrow ? r.v[j] : s2[j];
+  }
+  fp_reduce_once<P>(r.v);
+  return r;
+}
+
+// lo + r * (hi - lo)  (DensePolynomial.bindLow, src/poly/mod.zig:171) through the table of r.  The difference
+// is taken as hi + (p - lo), a non-canonical representative below 2p: the table product accepts any limbs.
+template <class P>
+ZOLT_HD Fp<P> fp_bind_fixed(const Fp<P>& lo, const Fp<P>& hi, const FixedMulTable& t) {
+  uint32_t d[8];
+  d[0] = ptx::sub_cc(P::mod(0), lo.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) d[j] = ptx::subc_cc(P::mod(j), lo.v[j]);
+  d[7] = ptx::subc(P::mod(7), lo.v[7]);
+  d[0] = ptx::add_cc(d[0], hi.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) d[j] = ptx::addc_cc(d[j], hi.v[j]);
+  d[7] = ptx::addc(d[7], hi.v[7]);
+  return fp_fixed_mul_add<P>(lo, d, t);
 }
 
 using Fr = Fp<FrParams>;

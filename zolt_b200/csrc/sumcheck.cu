@@ -505,7 +505,7 @@ __device__ __noinline__ void round_finish(const Fr* raw, Fr* vals, const ScOut& 
 template <int COMB, int PAIR, int MODE>
 __global__ void __launch_bounds__(kRoundThreads, MODE == 2 ? kFusedBlocksPerSm : kEvalBlocksPerSm)
 sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const __grid_constant__ Fr r, SplitEqDev sq,
-                const __grid_constant__ ScOut out) {
+                const __grid_constant__ ScOut out, const __grid_constant__ FixedMulTable rt) {
   constexpr int K = CombTraits<COMB>::K;
   constexpr int NW = CombTraits<COMB>::NW;
   constexpr bool FUSED = MODE == 2;
@@ -587,7 +587,7 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
           if (g2 < pairs) prefetch_item(g2, k2, h2, slot);
           cp_async_commit();
         }
-        const Fr v = bind_pair(a0, a1, r);
+        const Fr v = fp_bind_fixed<FrParams>(a0, a1, rt);  // lo + r (hi - lo): multiplier table in the constant bank
         st_fr(t.dst[k] + idx, v);
         if (k < K) scr_st(scr, 2 * q, v);
         slot ^= 1;
@@ -986,12 +986,14 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
     if (chunks > sc->max_grid) chunks = sc->max_grid;
     if (chunks == 0) chunks = 1;
     sc_small_kernel<PAIR><<<(unsigned)chunks, kSmallThreads, 0, sc->ctx->stream>>>(t, a, sc->n, r, sq, out);
-  } else if (mode == 2)
-    sc_round_kernel<COMB, PAIR, 2><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out);
-  else if (mode == 1)
-    sc_round_kernel<COMB, PAIR, 1><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out);
-  else
-    sc_round_kernel<COMB, PAIR, 0><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out);
+  } else if (mode == 2) {
+    const FixedMulTable rt = fixed_mul_table<FrParams>(r);  // 8 host-side products per launch (O(1) glue)
+    sc_round_kernel<COMB, PAIR, 2><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, rt);
+  } else if (mode == 1) {
+    sc_round_kernel<COMB, PAIR, 1><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, FixedMulTable{});
+  } else {
+    sc_round_kernel<COMB, PAIR, 0><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, FixedMulTable{});
+  }
   prof_end(sc->ctx, ps);
   sc->ctx->launches++;
   sc->evals_final = !sc->sharded;
