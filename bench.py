@@ -372,6 +372,8 @@ def run_b200(args):
     msm_ms, sc_ms, phase_log = [], [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        if box is not None:
+            box.barrier()  # align the ranks' streams: time the MSM, not the arrival skew of the previous phase
         a = ev()
         r_msm = msm_resident()
         b = ev()
@@ -391,6 +393,8 @@ def run_b200(args):
     barrier()
     e2e_msm, e2e_sc = [], []
     for _ in range(args.steps):
+        if box is not None:
+            box.barrier()
         a = ev()
         msm_e2e()
         b = ev()

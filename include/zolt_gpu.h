@@ -240,6 +240,8 @@ int zolt_peer_box_create(zolt_ctx* ctx, zolt_peer_box** out, unsigned char handl
 int zolt_peer_box_connect(zolt_peer_box* box, const unsigned char* handles /* world*64 */, int rank, int world);
 int zolt_peer_box_free(zolt_peer_box* box);
 int zolt_peer_allgather(zolt_peer_box* box, const void* d_src, int n_fr, void* d_out, int transpose);
+/* stream-ordered barrier across the ranks (an empty exchange); asynchronous */
+int zolt_peer_barrier(zolt_peer_box* box);
 int zolt_msm_sharded_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const void* d_scalars, size_t n,
                          zolt_peer_box* box, uint64_t out_xy[8], uint8_t* out_inf);
 

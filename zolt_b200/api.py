@@ -268,6 +268,10 @@ class PeerBox:
     def allgather(self, d_src: int, n_fr: int, d_out: int, transpose: bool = False):
         check(self.ctx.lib.zolt_peer_allgather(self.handle, C.c_void_p(d_src), n_fr, C.c_void_p(d_out), int(transpose)), "zolt_peer_allgather")
 
+    def barrier(self):
+        """Stream-ordered barrier across the ranks (asynchronous)."""
+        check(self.ctx.lib.zolt_peer_barrier(self.handle), "zolt_peer_barrier")
+
     def free(self):
         if self.handle:
             check(self.ctx.lib.zolt_peer_box_free(self.handle), "zolt_peer_box_free")

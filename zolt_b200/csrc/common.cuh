@@ -56,6 +56,7 @@ struct zolt_ctx {
   unsigned long long launches = 0;
   // tuning (zolt_gpu_set_tuning)
   long long sc_small_pairs = 1 << 14;
+  unsigned mail_seq = 0;  // last sequence number handed to a kernel that reports through a mapped host mailbox
   // phase profiling (CUDA events on `stream`): begin/end pairs tagged by the caller
   static constexpr int kMaxProf = 96;
   cudaEvent_t prof_ev[2 * kMaxProf] = {};

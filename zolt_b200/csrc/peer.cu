@@ -117,6 +117,19 @@ extern "C" int zolt_peer_box_free(zolt_peer_box* box) {
   return ZOLT_OK;
 }
 
+// Stream-ordered barrier across the ranks: an empty exchange.  Returns at once; work queued behind it on this
+// rank's stream starts only after every rank's stream has reached its own barrier.
+extern "C" int zolt_peer_barrier(zolt_peer_box* box) {
+  if (!box || !box->connected) return ZOLT_ERR_ARG;
+  zolt_ctx* ctx = box->ctx;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  GatherSrc s{};
+  peer_allgather_kernel<<<1, 32, 0, ctx->stream>>>(s, 0, peer_next(box), nullptr, 0);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  return ZOLT_OK;
+}
+
 extern "C" int zolt_peer_allgather(zolt_peer_box* box, const void* d_src, int n_fr, void* d_out, int transpose) {
   if (!box || !d_src || n_fr < 1 || n_fr > kPeerSlotFr) return ZOLT_ERR_ARG;
   const Fr* ptrs[kPeerSlotFr];
