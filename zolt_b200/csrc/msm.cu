@@ -234,23 +234,42 @@ scan_apply_kernel(const uint32_t* in, size_t n, const uint32_t* tile_offsets, ui
 }
 
 // ---- 3. scatter ----------------------------------------------------------------------------------------
+// Each thread keeps kScatterE independent (load, atomic, store) chains in flight: the kernel is bound by the
+// round trip of the returning atomic, not by bandwidth (ncu r1 v9: long-scoreboard stalls, DRAM at 10 %).
+constexpr int kScatterE = 4;
 __global__ void __launch_bounds__(256)
 msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, MsmGeom g, int pre, size_t pre_n,
                    size_t pre_offset, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   const size_t total = n * rows;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t d = digits[t];
-    if (!d) continue;
-    const size_t row = t / n, i = t - row * n;  // row = batch * windows + w
-    size_t krow = row, pidx = i;
-    if (pre) {
-      const size_t batch = row / g.windows, w = row - batch * g.windows;
-      krow = batch;
-      pidx = w * pre_n + pre_offset + i;  // index into the level table
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t0 < total; t0 += stride * kScatterE) {
+    uint32_t d[kScatterE], val[kScatterE], pos[kScatterE];
+    size_t key[kScatterE];
+#pragma unroll
+    for (int j = 0; j < kScatterE; j++) {
+      const size_t t = t0 + (size_t)j * stride;
+      d[j] = t < total ? __ldcs(digits + t) : 0u;
     }
-    const size_t key = krow * g.B + ((d & 0x7fffffffu) - 1);
-    const uint32_t pos = atomicAdd(&cursor[key], 1u);  // cursor starts as a copy of the bucket offsets
-    sorted[pos] = (uint32_t)pidx | (d & 0x80000000u);
+#pragma unroll
+    for (int j = 0; j < kScatterE; j++) {
+      if (!d[j]) continue;
+      const size_t t = t0 + (size_t)j * stride;
+      const size_t row = t / n, i = t - row * n;  // row = batch * windows + w
+      size_t krow = row, pidx = i;
+      if (pre) {
+        const size_t batch = row / g.windows, w = row - batch * g.windows;
+        krow = batch;
+        pidx = w * pre_n + pre_offset + i;  // index into the level table
+      }
+      key[j] = krow * g.B + ((d[j] & 0x7fffffffu) - 1);
+      val[j] = (uint32_t)pidx | (d[j] & 0x80000000u);
+    }
+#pragma unroll
+    for (int j = 0; j < kScatterE; j++)
+      if (d[j]) pos[j] = atomicAdd(&cursor[key[j]], 1u);  // cursor starts as a copy of the bucket offsets
+#pragma unroll
+    for (int j = 0; j < kScatterE; j++)
+      if (d[j]) sorted[pos[j]] = val[j];
   }
 }
 
