@@ -124,6 +124,18 @@ int zolt_g1_fixed_base_mul(zolt_ctx* ctx, const uint64_t* scalars /* n*4 Montgom
                            zolt_bases** out);
 /* HyperKZG.setup(max_degree): mock SRS with tau = 0x12345678 (commitment/mod.zig:189) built on device. */
 int zolt_hyperkzg_setup(zolt_ctx* ctx, size_t max_degree, zolt_bases** out);
+/* HyperKZG.open (commitment/mod.zig:261-324): fold the table variable by variable (half-split order); per level
+ * the quotient hi - lo is committed (an MSM over the first len/2 powers) and the table is folded with point[i].
+ * Everything stays on the device between levels.  Outputs: quotient commitments (affine, n_quotients of them:
+ * num_vars unless the table has fewer than 2^num_vars entries) and final_eval (the fully folded value; for
+ * num_vars == 0 the caller keeps `value`, as the reference does).  The _dev variant borrows a device table
+ * (not modified). */
+int zolt_hyperkzg_open(zolt_ctx* ctx, const zolt_bases* params, const uint64_t* evals /* n*4, host */, size_t n,
+                       const uint64_t* point /* num_vars*4 */, int num_vars, uint64_t* quotients_xy /* num_vars*8 */,
+                       uint8_t* quotients_inf /* num_vars */, int* n_quotients, uint64_t final_eval[4]);
+int zolt_hyperkzg_open_dev(zolt_ctx* ctx, const zolt_bases* params, const void* d_evals, size_t n, const uint64_t* point,
+                           int num_vars, uint64_t* quotients_xy, uint8_t* quotients_inf, int* n_quotients,
+                           uint64_t final_eval[4]);
 
 /* ---- dense multilinear tables ------------------------------------------------------------------
  * Device-resident tables of 2^v Fr elements (32 B each, same layout as []F). */

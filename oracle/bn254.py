@@ -339,6 +339,26 @@ def hyperkzg_commit_closed_form(evals):
     return g1_mul(G1_GEN, acc)
 
 
+def hyperkzg_open(powers, evals, point, value):
+    """HyperKZG.open (src/poly/commitment/mod.zig:261-324): per variable, commit the quotient hi - lo
+    (:296-303), then fold new[j] = (1 - r) * low[j] + r * high[j] (:305-312), half-split order; stops early when
+    the table runs out (:289).  Returns (quotient commitments, final_eval); num_vars == 0 keeps `value` (:270-276).
+    `powers` may be None: commitments are then taken from the closed form (sum_j q_j tau^j) G of the mock SRS."""
+    if not point:
+        return [], value % FR_MOD
+    cur = [e % FR_MOD for e in evals]
+    quotients = []
+    for r in point:
+        half = len(cur) // 2
+        if half == 0:
+            break
+        q = [(cur[j + half] - cur[j]) % FR_MOD for j in range(half)]
+        quotients.append(hyperkzg_commit(powers, q) if powers is not None else hyperkzg_commit_closed_form(q))
+        one_minus_r = (1 - r) % FR_MOD
+        cur = [(cur[j] * one_minus_r + cur[j + half] * r) % FR_MOD for j in range(half)]
+    return quotients, (cur[0] if cur else 0)
+
+
 # --- affine point <-> C-ABI layout --------------------------------------------------
 def points_to_arrays(points):
     """Affine tuples/None -> (xy (n,8) uint64 Montgomery Fq limbs, inf (n,) uint8).

@@ -164,3 +164,23 @@ def test_transcript_is_deterministic_and_sensitive():
     st = bytearray(200)
     OT.keccak_f(st)
     assert int.from_bytes(st[:8], "little") == 0xF1258F7940E1DDE7
+
+
+def test_hyperkzg_open_oracle_consistency():
+    """HyperKZG.open restatement (src/poly/commitment/mod.zig:261-324): the final evaluation is the multilinear
+    extension at the point (top variable first) and the literal MSM commits agree with the mock-SRS closed form
+    (sum_j q_j tau^j) G; edge cases of :270-276 (no variables) and :289 (table runs out)."""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    evals, point = B.random_fr(rng, 8), B.random_fr(rng, 3)
+    powers = B.hyperkzg_setup(8)
+    q_lit, fin = B.hyperkzg_open(powers, evals, point, 0)
+    q_cf, fin2 = B.hyperkzg_open(None, evals, point, 0)
+    assert q_lit == q_cf and fin == fin2 and len(q_lit) == 3
+    cur = evals
+    for r in point:
+        cur = OP.bind_first(cur, r)
+    assert fin == cur[0]
+    assert B.hyperkzg_open(powers, evals, [], 42) == ([], 42)
+    assert len(B.hyperkzg_open(powers, evals[:2], point, 0)[0]) == 1

@@ -295,6 +295,34 @@ class HyperKZG:
         return MSM.compute(params, e[:n])
 
 
+def _hyperkzg_open(params: Bases, fn_name: str, evals_arg, n: int, point):
+    ctx = params.ctx
+    pt = _as_u64(point, 4) if len(point) else np.empty((0, 4), dtype=np.uint64)
+    nv = pt.shape[0]
+    qxy = np.zeros((max(nv, 1), 8), dtype=np.uint64)
+    qinf = np.zeros(max(nv, 1), dtype=np.uint8)
+    nq = C.c_int()
+    final = np.zeros(4, dtype=np.uint64)
+    check(getattr(ctx.lib, fn_name)(ctx.handle, params.handle, evals_arg, n, _ptr(pt), nv, _ptr(qxy), _ptr(qinf), C.byref(nq), _ptr(final)),
+          fn_name)
+    return qxy[: nq.value], qinf[: nq.value], final
+
+
+def hyperkzg_open(params: Bases, evals, point):
+    """HyperKZG.open (src/poly/commitment/mod.zig:261-324) from a host table -> (quotient xy (q,8), infinity flags (q,),
+    final_eval (4,))."""
+    e = _as_u64(evals, 4) if len(evals) else np.empty((0, 4), dtype=np.uint64)
+    return _hyperkzg_open(params, "zolt_hyperkzg_open", _ptr(e), e.shape[0], point)
+
+
+def hyperkzg_open_dev(params: Bases, d_evals: int, n: int, point):
+    return _hyperkzg_open(params, "zolt_hyperkzg_open_dev", C.c_void_p(d_evals), n, point)
+
+
+HyperKZG.open = staticmethod(hyperkzg_open)
+HyperKZG.open_dev = staticmethod(hyperkzg_open_dev)
+
+
 class DensePolynomial:
     """DensePolynomial(F) with its evaluation table resident on the device (src/poly/mod.zig:23-182)."""
 

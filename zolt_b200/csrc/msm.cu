@@ -1018,6 +1018,88 @@ extern "C" int zolt_g1_fixed_base_mul(zolt_ctx* ctx, const uint64_t* scalars, si
   return s;
 }
 
+// ---- HyperKZG.open (src/poly/commitment/mod.zig:261-324) -----------------------------------------------------
+// One level of the fold: q[j] = hi[j] - lo[j] (the quotient that gets committed) and, in place,
+// cur[j] = (1 - r) lo[j] + r hi[j] = lo[j] + r q[j] (the same canonical element; multiplier table as in the sumcheck bind).
+__global__ void __launch_bounds__(256)
+hk_quotient_fold_kernel(Fr* __restrict__ cur, size_t half, Fr* __restrict__ q, const __grid_constant__ FixedMulTable rt) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < half; j += (size_t)gridDim.x * blockDim.x) {
+    const Fr lo = cur[j], hi = cur[j + half];
+    q[j] = fp_sub<FrParams>(hi, lo);
+    cur[j] = fp_bind_fixed<FrParams>(lo, hi, rt);
+  }
+}
+
+static int hyperkzg_open_core(zolt_ctx* ctx, const zolt_bases* params, Fr* d_cur /* owned copy, n */, size_t n, const uint64_t* point,
+                              int num_vars, uint64_t* quotients_xy, uint8_t* quotients_inf, int* n_quotients, uint64_t final_eval[4]) {
+  cudaStream_t st = ctx->stream;
+  Fr* d_q = nullptr;
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, (n / 2 ? n / 2 : 1) * sizeof(Fr), (void**)&d_q));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, (size_t)(num_vars ? num_vars : 1) * sizeof(XYZZ), (void**)&d_res));
+  int done = 0, status = ZOLT_OK;
+  size_t len = n;
+  for (int i = 0; i < num_vars && status == ZOLT_OK; i++) {
+    const size_t half = len / 2;
+    if (half == 0) break;  // fewer entries than 2^num_vars: the reference stops folding here (mod.zig:289)
+    Fr r;
+    for (int j = 0; j < 4; j++) {
+      r.v[2 * j] = (uint32_t)point[4 * i + j];
+      r.v[2 * j + 1] = (uint32_t)(point[4 * i + j] >> 32);
+    }
+    size_t blocks = (half + 255) / 256;
+    if (blocks > (size_t)ctx->num_sms * 8) blocks = (size_t)ctx->num_sms * 8;
+    hk_quotient_fold_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_cur, half, d_q, fixed_mul_table<FrParams>(r));
+    ctx->launches++;
+    const size_t m = half < params->n ? half : params->n;  // commit(): n = min(len(evals), len(powers)) (mod.zig:241-249)
+    status = msm_core(ctx, params, 0, d_q, 1, m, d_res + done);
+    done++;
+    len = half;
+  }
+  if (status == ZOLT_OK && done) status = finish_affine(ctx, d_res, (size_t)done, quotients_xy, quotients_inf);
+  if (status == ZOLT_OK) {
+    if (len > 0) {
+      cudaError_t e = cudaMemcpyAsync(final_eval, d_cur, sizeof(Fr), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) status = ZOLT_ERR_CUDA;
+    } else {
+      memset(final_eval, 0, 32);
+    }
+  }
+  if (n_quotients) *n_quotients = done;
+  pool_release(ctx, d_q, (n / 2 ? n / 2 : 1) * sizeof(Fr));
+  pool_release(ctx, d_res, (size_t)(num_vars ? num_vars : 1) * sizeof(XYZZ));
+  return status;
+}
+
+extern "C" int zolt_hyperkzg_open_dev(zolt_ctx* ctx, const zolt_bases* params, const void* d_evals, size_t n, const uint64_t* point,
+                                      int num_vars, uint64_t* quotients_xy, uint8_t* quotients_inf, int* n_quotients,
+                                      uint64_t final_eval[4]) {
+  if (!ctx || !params || !final_eval || num_vars < 0 || (n && !d_evals) || (num_vars && (!point || !quotients_xy || !quotients_inf)))
+    return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Fr* d_cur = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, (n ? n : 1) * sizeof(Fr), (void**)&d_cur));
+  if (n) ZOLT_CUDA_TRY(cudaMemcpyAsync(d_cur, d_evals, n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+  const int s = hyperkzg_open_core(ctx, params, d_cur, n, point, num_vars, quotients_xy, quotients_inf, n_quotients, final_eval);
+  pool_release(ctx, d_cur, (n ? n : 1) * sizeof(Fr));
+  return s;
+}
+
+extern "C" int zolt_hyperkzg_open(zolt_ctx* ctx, const zolt_bases* params, const uint64_t* evals, size_t n, const uint64_t* point,
+                                  int num_vars, uint64_t* quotients_xy, uint8_t* quotients_inf, int* n_quotients,
+                                  uint64_t final_eval[4]) {
+  if (!ctx || !params || !final_eval || num_vars < 0 || (n && !evals) || (num_vars && (!point || !quotients_xy || !quotients_inf)))
+    return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Fr* d_cur = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, (n ? n : 1) * sizeof(Fr), (void**)&d_cur));
+  if (n) ZOLT_CUDA_TRY(cudaMemcpyAsync(d_cur, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  const int s = hyperkzg_open_core(ctx, params, d_cur, n, point, num_vars, quotients_xy, quotients_inf, n_quotients, final_eval);
+  pool_release(ctx, d_cur, (n ? n : 1) * sizeof(Fr));
+  return s;
+}
+
 extern "C" int zolt_hyperkzg_setup(zolt_ctx* ctx, size_t max_degree, zolt_bases** out) {
   if (!ctx || !out) return ZOLT_ERR_ARG;
   *out = nullptr;

@@ -131,6 +131,34 @@ struct HyperKZG {
     std::vector<Fr> head(evals.begin(), evals.begin() + n);
     return MSM::compute(*params.powers_of_tau_g1, head);
   }
+  // open(params, evals, point, value) (commitment/mod.zig:261-324): quotient commitments per variable + final_eval
+  struct Proof {
+    std::vector<AffinePoint> quotient_commitments;
+    Fr final_eval;
+  };
+  static Proof open(const SetupParams& params, const std::vector<Fr>& evals, const std::vector<Fr>& point, const Fr& value) {
+    Proof pr;
+    pr.final_eval = value;
+    const int nv = (int)point.size();
+    if (nv == 0) return pr;
+    std::vector<uint64_t> xy((size_t)nv * 8);
+    std::vector<uint8_t> inf((size_t)nv);
+    int nq = 0;
+    uint64_t fin[4];
+    must(zolt_hyperkzg_open(params.powers_of_tau_g1->ctx().raw(), params.powers_of_tau_g1->raw(),
+                            reinterpret_cast<const uint64_t*>(evals.data()), evals.size(), reinterpret_cast<const uint64_t*>(point.data()),
+                            nv, xy.data(), inf.data(), &nq, fin),
+         "zolt_hyperkzg_open");
+    for (int i = 0; i < nq; i++) {
+      AffinePoint p;
+      std::memcpy(p.x, &xy[8 * i], 32);
+      std::memcpy(p.y, &xy[8 * i + 4], 32);
+      p.infinity = inf[i] != 0;
+      pr.quotient_commitments.push_back(p);
+    }
+    pr.final_eval = Fr::fromRaw(fin);
+    return pr;
+  }
   static std::vector<AffinePoint> batchCommit(const SetupParams& params, const std::vector<std::vector<Fr>>& polys) {
     std::vector<AffinePoint> out;
     for (const auto& p : polys) out.push_back(commit(params, p));
