@@ -1030,14 +1030,24 @@ hk_quotient_fold_kernel(Fr* __restrict__ cur, size_t half, Fr* __restrict__ q, c
   }
 }
 
+// Levels whose quotient has at most kOpenBatchN entries are committed together: their MSMs are all launch latency
+// (~1.5 ms each for ~45 kernels), so the quotients are parked as zero-padded rows of one [levels][nb] matrix and
+// committed by ONE batched MSM over the first nb powers (zero digits are skipped; BatchMSM shape, src/msm/mod.zig:551-563).
+constexpr size_t kOpenBatchN = 4096;
+
 static int hyperkzg_open_core(zolt_ctx* ctx, const zolt_bases* params, Fr* d_cur /* owned copy, n */, size_t n, const uint64_t* point,
                               int num_vars, uint64_t* quotients_xy, uint8_t* quotients_inf, int* n_quotients, uint64_t final_eval[4]) {
   cudaStream_t st = ctx->stream;
-  Fr* d_q = nullptr;
+  Fr *d_q = nullptr, *d_qb = nullptr;
   XYZZ* d_res = nullptr;
-  ZOLT_CUDA_TRY(pool_alloc(ctx, (n / 2 ? n / 2 : 1) * sizeof(Fr), (void**)&d_q));
+  const size_t q_bytes = (n / 2 ? n / 2 : 1) * sizeof(Fr);
+  const size_t qb_bytes = 16 * kOpenBatchN * sizeof(Fr);  // log2(kOpenBatchN) + 1 = 13 rows at most
+  ZOLT_CUDA_TRY(pool_alloc(ctx, q_bytes, (void**)&d_q));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, qb_bytes, (void**)&d_qb));
   ZOLT_CUDA_TRY(pool_alloc(ctx, (size_t)(num_vars ? num_vars : 1) * sizeof(XYZZ), (void**)&d_res));
   int done = 0, status = ZOLT_OK;
+  int batch_first = -1, batch_rows = 0;
+  size_t batch_n = 0;
   size_t len = n;
   for (int i = 0; i < num_vars && status == ZOLT_OK; i++) {
     const size_t half = len / 2;
@@ -1047,15 +1057,27 @@ static int hyperkzg_open_core(zolt_ctx* ctx, const zolt_bases* params, Fr* d_cur
       r.v[2 * j] = (uint32_t)point[4 * i + j];
       r.v[2 * j + 1] = (uint32_t)(point[4 * i + j] >> 32);
     }
+    const size_t m = half < params->n ? half : params->n;  // commit(): n = min(len(evals), len(powers)) (mod.zig:241-249)
+    Fr* q_dst = d_q;
+    const bool batched = half <= kOpenBatchN && params->n >= half;  // an SRS shorter than the quotient: per-level path
+    if (batched) {
+      if (batch_first < 0) {
+        batch_first = done;
+        batch_n = m;
+        if (cudaMemsetAsync(d_qb, 0, qb_bytes, st) != cudaSuccess) { status = ZOLT_ERR_CUDA; break; }
+      }
+      q_dst = d_qb + (size_t)batch_rows * batch_n;  // rows shorter than batch_n stay zero-padded
+      batch_rows++;
+    }
     size_t blocks = (half + 255) / 256;
     if (blocks > (size_t)ctx->num_sms * 8) blocks = (size_t)ctx->num_sms * 8;
-    hk_quotient_fold_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_cur, half, d_q, fixed_mul_table<FrParams>(r));
+    hk_quotient_fold_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_cur, half, q_dst, fixed_mul_table<FrParams>(r));
     ctx->launches++;
-    const size_t m = half < params->n ? half : params->n;  // commit(): n = min(len(evals), len(powers)) (mod.zig:241-249)
-    status = msm_core(ctx, params, 0, d_q, 1, m, d_res + done);
+    if (!batched) status = msm_core(ctx, params, 0, d_q, 1, m, d_res + done);
     done++;
     len = half;
   }
+  if (status == ZOLT_OK && batch_rows) status = msm_core(ctx, params, 0, d_qb, (size_t)batch_rows, batch_n, d_res + batch_first);
   if (status == ZOLT_OK && done) status = finish_affine(ctx, d_res, (size_t)done, quotients_xy, quotients_inf);
   if (status == ZOLT_OK) {
     if (len > 0) {
@@ -1067,7 +1089,8 @@ static int hyperkzg_open_core(zolt_ctx* ctx, const zolt_bases* params, Fr* d_cur
     }
   }
   if (n_quotients) *n_quotients = done;
-  pool_release(ctx, d_q, (n / 2 ? n / 2 : 1) * sizeof(Fr));
+  pool_release(ctx, d_q, q_bytes);
+  pool_release(ctx, d_qb, qb_bytes);
   pool_release(ctx, d_res, (size_t)(num_vars ? num_vars : 1) * sizeof(XYZZ));
   return status;
 }
