@@ -150,6 +150,16 @@ int zolt_eq_evals(zolt_ctx* ctx, const uint64_t* r /* n_vars*4 */, int n_vars, c
                   void* d_out);
 /* sum of all entries (initial sumcheck claim, src/subprotocols/mod.zig:306-309) */
 int zolt_poly_sum(zolt_ctx* ctx, const void* d_src, size_t n, uint64_t out[4]);
+/* Element-wise construction of device-resident tables (asynchronous on the context's stream):
+ *   ZOLT_VEC_MUL            out = a o b
+ *   ZOLT_VEC_EQ_AB_MINUS_C  out = e * (a * b - c)   JoltSpartanInterface's combined table (jolt_r1cs.zig:352-360)
+ *   ZOLT_VEC_AXPY           out = out + s * a       gamma-power combination of batchOpen (commitment/mod.zig:648-656)
+ * Unused operands may be NULL. */
+#define ZOLT_VEC_MUL 0
+#define ZOLT_VEC_EQ_AB_MINUS_C 1
+#define ZOLT_VEC_AXPY 2
+int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d_a, const void* d_b, const void* d_c, const void* d_e,
+                    const uint64_t* s /* 4, AXPY only */, size_t n);
 
 /* ---- sumcheck prover inner loop ----------------------------------------------------------------
  * One instance = k dense tables bound in lock-step.  The call pattern is the reference's:

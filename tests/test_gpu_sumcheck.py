@@ -130,3 +130,42 @@ def test_call_sequence_errors(ctx):
     with pytest.raises(Z.ZoltGpuError):
         inst.compute_round_poly()
     inst.free()
+
+
+def test_device_table_construction_and_spartan_stage1(ctx):
+    """JoltSpartanInterface builds combined = eq * (Az * Bz - Cz) (jolt_r1cs.zig:352-360) and runs
+    a linear sumcheck over it with adjacent pairs (:436-477).  Here the eq table, the combined table and the rounds are all
+    produced on the device; nothing but tau, the challenges and the round sums crosses the bus."""
+    log_n = 10
+    n = 1 << log_n
+    tau = rand_fr(61, log_n)
+    az, bz, cz = rand_fr(62, n), rand_fr(63, n), rand_fr(64, n)
+    eq = OP.eq_evals(tau)
+    want = [e * (a * b - c) % P for e, a, b, c in zip(eq, az, bz, cz)]
+    d_eq = Z.DeviceBuffer(ctx, n * 32)
+    ctx_lib = ctx.lib
+    import ctypes as C
+
+    from zolt_b200._lib import check
+    check(ctx_lib.zolt_eq_evals(ctx.handle, fr_arr(tau).ctypes.data_as(C.c_void_p), log_n, None, C.c_void_p(d_eq.ptr)), "zolt_eq_evals")
+    d_a, d_b, d_c = (Z.DeviceBuffer.from_host(ctx, fr_arr(t)) for t in (az, bz, cz))
+    d_out = Z.DeviceBuffer(ctx, n * 32)
+    ctx.fr_vec_dev(Z.VEC_EQ_AB_MINUS_C, d_out.ptr, d_a.ptr, d_b.ptr, d_c.ptr, d_eq.ptr, n=n)
+    assert fr_ints(d_out.download((n, 4))) == want
+    # out = a o b, then out += s * c
+    ctx.fr_vec_dev(Z.VEC_MUL, d_out.ptr, d_a.ptr, d_b.ptr, n=n)
+    s = rand_fr(65, 1)[0]
+    ctx.fr_vec_dev(Z.VEC_AXPY, d_out.ptr, d_c.ptr, s=fr_arr([s]), n=n)
+    assert fr_ints(d_out.download((n, 4))) == [(a * b + s * c) % P for a, b, c in zip(az, bz, cz)]
+    # stage 1 rounds over the combined table straight from device memory
+    ctx.fr_vec_dev(Z.VEC_EQ_AB_MINUS_C, d_out.ptr, d_a.ptr, d_b.ptr, d_c.ptr, d_eq.ptr, n=n)
+    challenges = rand_fr(66, log_n)
+    exp_evals, exp_bound = OS.run_dense("sum", [want], Z.PAIR_ADJACENT, challenges)
+    inst = Z.SumcheckInstance.from_device(ctx, Z.SC_SUM, Z.PAIR_ADJACENT, [d_out.ptr], log_n)
+    for rnd, r in enumerate(challenges):
+        assert fr_ints(inst.compute_round_poly()) == exp_evals[rnd]
+        inst.bind_challenge(fr_arr([r]))
+        assert fr_ints(inst.table(0)) == exp_bound[rnd][0]
+    inst.free()
+    for b in (d_eq, d_a, d_b, d_c, d_out):
+        b.free()

@@ -30,6 +30,9 @@ from ._lib import (  # noqa: F401
     SC_PROD3,
     SC_SUM,
     TUNE_SC_SMALL_PAIRS,
+    VEC_AXPY,
+    VEC_EQ_AB_MINUS_C,
+    VEC_MUL,
     ZoltGpuError,
     load_library,
 )

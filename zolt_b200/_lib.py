@@ -21,6 +21,7 @@ OP_MUL, OP_ADD, OP_SUB, OP_INV, OP_FROM_MONT, OP_TO_MONT, OP_NEG = range(7)
 PAIR_ADJACENT, PAIR_HALF = 0, 1
 SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN_AB_MINUS_C = range(7)
 TUNE_SC_SMALL_PAIRS = 1
+VEC_MUL, VEC_EQ_AB_MINUS_C, VEC_AXPY = range(3)
 
 
 class ZoltGpuError(RuntimeError):
@@ -58,6 +59,7 @@ SIGNATURES = {
     "zolt_msm_batch": [_vp, _vp, _vp, _sz, _sz, _vp, _vp],
     "zolt_hyperkzg_open": [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, C.POINTER(_i), _vp],
     "zolt_hyperkzg_open_dev": [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, C.POINTER(_i), _vp],
+    "zolt_fr_vec_dev": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
     "zolt_msm_partial_dev": [_vp, _vp, _sz, _vp, _sz, _vp],
     "zolt_g1_sum_partials": [_vp, _vp, _sz, _vp, _vp],
     "zolt_g1_fixed_base_mul": [_vp, _vp, _sz, C.POINTER(_vp)],

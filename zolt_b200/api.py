@@ -109,6 +109,12 @@ class Context:
         )
         return out
 
+    def fr_vec_dev(self, op: int, d_out: int, d_a: int, d_b: int = 0, d_c: int = 0, d_e: int = 0, s=None, n: int = 0):
+        """Element-wise table construction on device-resident tables (zolt_fr_vec_dev)."""
+        sv = _as_u64(s, 4) if s is not None else None
+        check(self.lib.zolt_fr_vec_dev(self.handle, op, C.c_void_p(d_out), C.c_void_p(d_a), C.c_void_p(d_b or None), C.c_void_p(d_c or None),
+                                       C.c_void_p(d_e or None), _ptr(sv), n), "zolt_fr_vec_dev")
+
     def fr_sum_rows(self, d_rows: int, rows: int, cols: int) -> np.ndarray:
         out = np.empty((cols, 4), dtype=np.uint64)
         check(self.lib.zolt_fr_sum_rows(self.handle, C.c_void_p(d_rows), rows, cols, _ptr(out)), "zolt_fr_sum_rows")

@@ -826,6 +826,27 @@ __global__ void __launch_bounds__(kScThreads) eq_level_kernel(Fr* res, size_t si
 
 __global__ void set_one_kernel(Fr* p, Fr v) { st_fr(p, v); }
 
+// Element-wise construction of device-resident tables, one pass over HBM each.
+template <int OP>
+__global__ void __launch_bounds__(kScThreads)
+vec_kernel(Fr* __restrict__ out, const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c, const Fr* __restrict__ e,
+           const __grid_constant__ FixedMulTable st, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr v;
+    if constexpr (OP == ZOLT_VEC_MUL) {
+      v = fr_mul(ld_fr(a + i), ld_fr(b + i));
+    } else if constexpr (OP == ZOLT_VEC_EQ_AB_MINUS_C) {
+      // combined[i] = eq[i] * (Az[i] * Bz[i] - Cz[i])  (src/zkvm/r1cs/jolt_r1cs.zig:352-360)
+      v = fr_mul(ld_fr(e + i), fr_sub(fr_mul(ld_fr(a + i), ld_fr(b + i)), ld_fr(c + i)));
+    } else {
+      // out[i] += s * a[i]: the gamma-power combination of batchOpen (src/poly/commitment/mod.zig:648-656)
+      const Fr x = ld_fr(a + i);
+      v = fp_fixed_mul_add<FrParams>(out[i], x.v, st);
+    }
+    st_fr(out + i, v);
+  }
+}
+
 // GruenSplitEqPolynomial prefix tables (src/poly/split_eq.zig:131-171): level k+1 from level k,
 // next[2i] = prev[i]*(1-tau_k), next[2i+1] = prev[i]*tau_k.  Tables are stored back to back, level
 // L at offset 2^L - 1.  One block walks all levels (tables are ~sqrt(N) long).
@@ -1425,6 +1446,26 @@ extern "C" int zolt_eq_evals(zolt_ctx* ctx, const uint64_t* r, int n_vars, const
     ctx->launches++;
     size *= 2;
   }
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d_a, const void* d_b, const void* d_c, const void* d_e,
+                               const uint64_t* s, size_t n) {
+  if (!ctx || !d_out || !d_a) return ZOLT_ERR_ARG;
+  if (op == ZOLT_VEC_MUL && !d_b) return ZOLT_ERR_ARG;
+  if (op == ZOLT_VEC_EQ_AB_MINUS_C && (!d_b || !d_c || !d_e)) return ZOLT_ERR_ARG;
+  if (op == ZOLT_VEC_AXPY && !s) return ZOLT_ERR_ARG;
+  if (op < ZOLT_VEC_MUL || op > ZOLT_VEC_AXPY) return ZOLT_ERR_ARG;
+  if (n == 0) return ZOLT_OK;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  const unsigned grid = grid_for(ctx, n, 8);
+  Fr* o = (Fr*)d_out;
+  const Fr *a = (const Fr*)d_a, *b = (const Fr*)d_b, *c = (const Fr*)d_c, *e = (const Fr*)d_e;
+  if (op == ZOLT_VEC_MUL) vec_kernel<ZOLT_VEC_MUL><<<grid, kScThreads, 0, ctx->stream>>>(o, a, b, c, e, FixedMulTable{}, n);
+  else if (op == ZOLT_VEC_EQ_AB_MINUS_C) vec_kernel<ZOLT_VEC_EQ_AB_MINUS_C><<<grid, kScThreads, 0, ctx->stream>>>(o, a, b, c, e, FixedMulTable{}, n);
+  else vec_kernel<ZOLT_VEC_AXPY><<<grid, kScThreads, 0, ctx->stream>>>(o, a, b, c, e, fixed_mul_table_host(fr_from_host(s)), n);
+  ctx->launches++;
   ZOLT_CUDA_TRY(cudaGetLastError());
   return ZOLT_OK;
 }
