@@ -134,6 +134,41 @@ def run_dense(kind: str, tables, pairing: int, challenges, n_extra: int = 0):
     return evals, bound
 
 
+def run_batched(instances, coeffs, challenges):
+    """BatchedSumcheckProver + generateBatchedProof (src/zkvm/batched_sumcheck.zig:158-171, :189-257, :330-420), adjacent
+    pairs.  instances: list of (kind, tables).  Returns (compressed round polynomials [c0, c2, c3] per round, final claim,
+    input claims).  An instance of n_i rounds starts at round max - n_i; before that it contributes its input claim scaled
+    by 2^(rounds still to wait) as a constant polynomial (:206-218).
+    Restated AS WRITTEN: the reference scales the waiting constant by 2^(start - round), one doubling more than the
+    2^(start - round - 1) that would keep s(0) + s(1) equal to the instance's share of the claim (Jolt's convention); because
+    only [c0, c2, c3] travel and c1 is recovered from the running claim (:389), the proof stays self-consistent round by
+    round.  With equal numbers of rounds (no waiting instance) the final claim equals sum_i coeff_i * combiner_i(bound
+    values), which tests/test_oracle_golden.py checks."""
+    from . import poly as OP
+
+    rounds = [len(ts[0]).bit_length() - 1 for _, ts in instances]
+    mx = max(rounds)
+    per_inst, claims = [], []
+    for (kind, ts), n_r in zip(instances, rounds):
+        ev, _ = run_dense(kind, ts, 0, challenges[mx - n_r:])
+        ev = [list(e) + ([(2 * e[1] - e[0]) % P, (3 * e[1] - 2 * e[0]) % P] if len(e) == 2 else []) for e in ev]
+        per_inst.append(ev)
+        claims.append((ev[0][0] + ev[0][1]) % P)
+    claim = sum(cf * cl * pow(2, mx - n_r, P) for cf, cl, n_r in zip(coeffs, claims, rounds)) % P
+    out = []
+    for rnd in range(mx):
+        comb = [0, 0, 0, 0]
+        for ev, cf, cl, n_r in zip(per_inst, coeffs, claims, rounds):
+            start = mx - n_r
+            for j in range(4):
+                term = ev[rnd - start][j] if rnd >= start else cl * pow(2, start - rnd, P)
+                comb[j] = (comb[j] + cf * term) % P
+        c0, c2, c3 = OP.evals_to_compressed(comb)
+        out.append([c0, c2, c3])
+        claim = OP.compressed_claim_update(claim, c0, c2, c3, challenges[rnd])
+    return out, claim, claims
+
+
 def run_gruen(tables, tau, challenges, with_c: bool = False):
     tabs = [list(t) for t in tables]
     sq = GruenSplitEq(tau)

@@ -89,3 +89,22 @@ def test_gruen_prove_matches_oracle(ctx, with_c):
         tabs = OS.bind_tables(tabs, r, OS.ADJACENT)
         sq.bind(r)
     assert fr_ints(final_claim) == [cur]
+
+
+def test_batched_sumcheck_prover_rlc(ctx):
+    """S6: BatchedSumcheckProver (src/zkvm/batched_sumcheck.zig:77-430) over three GPU instances with different numbers of
+    rounds (front-padded by scaled constant polynomials), caller-supplied batching coefficients: compressed round
+    polynomials and the final claim match the oracle restatement."""
+    from oracle import sumcheck as OS
+    from tests.util import rand_fr
+
+    inst = [("prod3", [rand_fr(300 + t, 1 << 9) for t in range(3)]),
+            ("eq_ab_minus_c", [rand_fr(310 + t, 1 << 6) for t in range(4)]),
+            ("sum", [rand_fr(320, 1 << 3)])]
+    coeffs, challenges = rand_fr(330, 3), rand_fr(331, 9)
+    want, want_final, claims = OS.run_batched(inst, coeffs, challenges)
+    comb = {"prod3": Z.SC_PROD3, "eq_ab_minus_c": Z.SC_EQ_AB_MINUS_C, "sum": Z.SC_SUM}
+    got, final = H.batched_sumcheck(ctx, [(comb[k], [fr_arr(t) for t in ts]) for k, ts in inst], fr_arr(claims), fr_arr(coeffs),
+                                    fr_arr(challenges))
+    assert [fr_ints(g) for g in got] == want
+    assert fr_ints(final) == [want_final]

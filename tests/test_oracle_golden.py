@@ -184,3 +184,20 @@ def test_hyperkzg_open_oracle_consistency():
     assert fin == cur[0]
     assert B.hyperkzg_open(powers, evals, [], 42) == ([], 42)
     assert len(B.hyperkzg_open(powers, evals[:2], point, 0)[0]) == 1
+
+
+def test_batched_sumcheck_restatement_final_claim():
+    """BatchedSumcheckProver restatement (src/zkvm/batched_sumcheck.zig:158-257, :330-420): with instances of equal
+    length the final claim is the batching-coefficient combination of the instances' combiners at the bound point; the
+    claim chain uses the compressed update pinned by the logs/zolt.log KATs above."""
+    import numpy as np
+
+    rng = np.random.default_rng(1)
+    inst = [("prod3", [B.random_fr(rng, 16) for _ in range(3)]), ("sum", [B.random_fr(rng, 16)])]
+    coeffs, ch = B.random_fr(rng, 2), B.random_fr(rng, 4)
+    out, final, claims = OS.run_batched(inst, coeffs, ch)
+    _, b0 = OS.run_dense("prod3", inst[0][1], 0, ch)
+    _, b1 = OS.run_dense("sum", inst[1][1], 0, ch)
+    f0, f1 = [t[0] for t in b0[-1]], b1[-1][0][0]
+    assert final == (coeffs[0] * f0[0] * f0[1] * f0[2] + coeffs[1] * f1) % P
+    assert len(out) == 4 and all(len(c) == 3 for c in out)

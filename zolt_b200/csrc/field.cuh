@@ -99,7 +99,7 @@ struct FrParams {
   ZOLT_FIELD_TABLE(inv6, 0x0aaaaaaau, 0x7d695c48u, 0xaed9b4f4u, 0x3a880fcfu, 0xa9a9c517u, 0xda7526dbu,
                    0x69deea8eu, 0x0a67cbb3u)
   static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32 (low word of 0xc2e1f593efffffff)
-  static constexpr unsigned long long MU288 = 0x54a474626ull;  // floor(2^288 / r) (Barrett, fp_fixed_mul_add)
+  static constexpr unsigned long long MU320_HI = 0x5ull, MU320_LO = 0x4a47462623a04a7aull;  // floor(2^320 / r) (Barrett, fp_fixed_mul_add)
 };
 
 struct FqParams {
@@ -117,7 +117,7 @@ struct FqParams {
   ZOLT_FIELD_TABLE(inv6, 0x1a575726u, 0xd7ea4d46u, 0x0fb423a1u, 0xf054639fu, 0xa9a9c516u, 0xda7526dbu,
                    0x69deea8eu, 0x0a67cbb3u)
   static constexpr uint32_t INV = 0xe4866389u;  // -q^-1 mod 2^32 (low word of 0x87d20782e4866389)
-  static constexpr unsigned long long MU288 = 0x54a474626ull;  // floor(2^288 / q)
+  static constexpr unsigned long long MU320_HI = 0x5ull, MU320_LO = 0x4a47462623a04a7aull;  // floor(2^320 / q)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -497,8 +497,8 @@ ZOLT_HD Fp<P> wide_reduce(const uint32_t* acc_in) {
 // d = Montgomery limbs of a field element it is the Montgomery form of the product -- the value
 // montgomeryMul (src/field/mod.zig:735-779) returns -- reached with the 64 wide multiplies of a plain
 // 8 x 8 product and NO interleaved reduction rows.  The sum (plus an addend < p) is below 2^289 and is
-// brought back to [0, p) by one Barrett step on its top 65 bits (quotient estimate short by at most 3) and
-// two conditional subtractions: 128 + 28 + ~8 integer multiply-adds instead of 264.
+// brought back to [0, p) by one Barrett step on its top 65 bits (quotient estimate short by at most 1) and
+// one conditional subtraction: 128 + 28 + ~12 integer multiply-adds instead of 264.
 // Table rows are kernel parameters, i.e. constant-bank operands of the multiply instructions.
 // ---------------------------------------------------------------------------------------------
 struct FixedMulTable {
@@ -553,15 +553,17 @@ ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const Fix
 #pragma unroll
   for (int j = 2; j < 9; j++) x[j] = ptx::addc_cc(e[j], o[j - 1]);
   x[9] = ptx::addc(o[8], 0u);
-  // Barrett: q = floor(floor(x / 2^224) * floor(2^288 / p) / 2^64) in [floor(x/p) - 3, floor(x/p)]
+  // Barrett: q = floor(h * mu / 2^96), h = floor(x / 2^224) = x[9] 2^64 + H, mu = floor(2^320 / p) = MU_HI 2^64 + MU_LO.
+  // Both truncations together cost less than 2^-29 of a unit, so q is floor(x / p) or one less.  The low 64 bits of
+  // H * MU_LO cannot change floor(. / 2^96):  q = x[9] MU_HI 2^32 + floor((x[9] MU_LO + H MU_HI + hi64(H MU_LO)) / 2^32).
   const unsigned long long H = ((unsigned long long)x[8] << 32) | x[7];
-  const unsigned long long MU = P::MU288;
 #if defined(__CUDA_ARCH__)
-  const unsigned long long hi64 = __umul64hi(H, MU);
+  const unsigned long long hi64 = __umul64hi(H, P::MU320_LO);
 #else
-  const unsigned long long hi64 = (unsigned long long)(((unsigned __int128)H * MU) >> 64);
+  const unsigned long long hi64 = (unsigned long long)(((unsigned __int128)H * P::MU320_LO) >> 64);
 #endif
-  const unsigned long long q = hi64 + (unsigned long long)x[9] * MU;
+  const unsigned __int128 bsum = (unsigned __int128)H * P::MU320_HI + hi64 + (x[9] ? (unsigned __int128)x[9] * P::MU320_LO : 0);
+  const unsigned long long q = (unsigned long long)(bsum >> 32) + (((unsigned long long)x[9] * P::MU320_HI) << 32);
   const uint32_t q0 = (uint32_t)q, q1 = (uint32_t)(q >> 32);
   // q * p mod 2^256 = TE + (TO << 32)
   uint32_t te[8], to[7];
@@ -594,7 +596,7 @@ ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const Fix
   te[5] = ptx::madc_hi_cc(P::mod(3), q1, te[5]);
   te[6] = ptx::madc_lo_cc(P::mod(5), q1, te[6]);
   te[7] = ptx::madc_hi(P::mod(5), q1, te[7]);
-  // rem = x - q p  (true value in [0, 4p) < 2^256: the low 8 limbs are exact)
+  // rem = x - q p  (true value in [0, 2p) < 2^256: the low 8 limbs are exact)
   Fp<P> r;
   r.v[0] = ptx::sub_cc(x[0], te[0]);
 #pragma unroll
@@ -604,17 +606,7 @@ ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const Fix
 #pragma unroll
   for (int j = 2; j < 7; j++) r.v[j] = ptx::subc_cc(r.v[j], to[j - 1]);
   r.v[7] = ptx::subc(r.v[7], to[6]);
-  // [0, 4p) -> [0, p)
-  {
-    uint32_t s2[8];
-    s2[0] = ptx::sub_cc(r.v[0], P::mod2(0));
-#pragma unroll
-    for (int j = 1; j < 8; j++) s2[j] = ptx::subc_cc(r.v[j], P::mod2(j));
-    const uint32_t borrow = ptx::subc(0u, 0u);
-#pragma unroll
-    for (int j = 0; j < 8; j++) r.v[j] = borrow ? r.v[j] : s2[j];
-  }
-  fp_reduce_once<P>(r.v);
+  fp_reduce_once<P>(r.v);  // [0, 2p) -> [0, p)
   return r;
 }
 

@@ -40,6 +40,8 @@ def load_host() -> C.CDLL:
                                                          C.c_void_p, C.c_void_p]
         _host.zolt_host_sumcheck_prove_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                                            C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _host.zolt_host_batched_sumcheck.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                                     C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_hyperkzg_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     return _host
 
@@ -134,6 +136,24 @@ def sumcheck_prove_sharded(ctx: Context, box, combiner: int, d_tables, local_log
                                                       len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
     _lib.check(st, "zolt_host_sumcheck_prove_sharded")
     return evals, chal, final
+
+
+def batched_sumcheck(ctx: Context, instances, claims, coeffs, challenges):
+    """BatchedSumcheckProver (src/zkvm/batched_sumcheck.zig:77-430) over dense instances: `instances` is a list of
+    (combiner, [host tables]); returns (compressed round polynomials (rounds, 3, 4), final claim (4,))."""
+    n_inst = len(instances)
+    combs = (C.c_int * n_inst)(*[c for c, _ in instances])
+    tabs_flat = [_as_u64(t, 4) for _, ts in instances for t in ts]
+    log_ns = (C.c_int * n_inst)(*[(_as_u64(ts[0], 4).shape[0]).bit_length() - 1 for _, ts in instances])
+    n_tabs = (C.c_int * n_inst)(*[len(ts) for _, ts in instances])
+    arr = (C.c_void_p * len(tabs_flat))(*[t.ctypes.data for t in tabs_flat])
+    rounds = max(log_ns)
+    cl, cf, ch = _as_u64(claims, 4), _as_u64(coeffs, 4), _as_u64(challenges, 4)
+    comp = np.zeros((rounds, 3, 4), dtype=np.uint64)
+    final = np.zeros(4, dtype=np.uint64)
+    st = load_host().zolt_host_batched_sumcheck(ctx.handle, n_inst, combs, log_ns, n_tabs, arr, _ptr(cl), _ptr(cf), _ptr(ch), _ptr(comp), _ptr(final))
+    _lib.check(st, "zolt_host_batched_sumcheck")
+    return comp, final
 
 
 def sumcheck_prove_gruen(ctx: Context, tables, tau, claim, with_c: bool = False, domain: bytes = b"bench",

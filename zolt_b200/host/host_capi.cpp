@@ -97,6 +97,43 @@ int zolt_host_sumcheck_prove_sharded(zolt_ctx* ctx, zolt_peer_box* box, int worl
   return ZOLT_OK;
 }
 
+// BatchedSumcheckProver over n_inst dense instances (host tables, adjacent pairs) with caller-supplied batching
+// coefficients, input claims and per-round challenges.  Outputs per round the compressed polynomial [c0, c2, c3]
+// (generateBatchedProof, batched_sumcheck.zig:330-420: c1 is recovered from the running claim, the claim is updated from
+// the re-expanded evaluations) and the final claim.
+int zolt_host_batched_sumcheck(zolt_ctx* ctx, int n_inst, const int* combiners, const int* log_ns, const int* n_tables,
+                               const uint64_t* const* tables /* all instances, concatenated */, const uint64_t* claims,
+                               const uint64_t* coeffs, const uint64_t* challenges, uint64_t* compressed_out /* rounds*3*4 */,
+                               uint64_t* final_claim_out) {
+  Context c(ctx);
+  std::vector<std::unique_ptr<DenseSumcheckProver>> provers;
+  BatchedSumcheckProver batch;
+  size_t t0 = 0;
+  for (int i = 0; i < n_inst; i++) {
+    std::vector<const uint64_t*> tabs(tables + t0, tables + t0 + n_tables[i]);
+    t0 += (size_t)n_tables[i];
+    provers.push_back(std::make_unique<DenseSumcheckProver>(c, combiners[i], ZOLT_PAIR_ADJACENT, tabs, log_ns[i]));
+    batch.addInstance(provers.back().get(), Fr::fromRaw(claims + 4 * i));
+  }
+  std::vector<Fr> cf;
+  for (int i = 0; i < n_inst; i++) cf.push_back(Fr::fromRaw(coeffs + 4 * i));
+  batch.setBatchingCoeffs(cf);
+  for (size_t round = 0; round < batch.maxNumRounds(); round++) {
+    const auto comp = batch.computeRoundPolynomial();
+    for (int j = 0; j < 3; j++) comp[j].store(compressed_out + 12 * round + 4 * j);
+    const Fr r = Fr::fromRaw(challenges + 4 * round);
+    const Fr c0 = comp[0], c2 = comp[1], c3 = comp[2];
+    const Fr c1 = batch.current_claim.sub(c0).sub(c0).sub(c2).sub(c3);  // :389
+    const Fr s1 = c0.add(c1).add(c2).add(c3);
+    const Fr s2 = c0.add(c1.mul(Fr::fromU64(2))).add(c2.mul(Fr::fromU64(4))).add(c3.mul(Fr::fromU64(8)));
+    const Fr s3 = c0.add(c1.mul(Fr::fromU64(3))).add(c2.mul(Fr::fromU64(9))).add(c3.mul(Fr::fromU64(27)));
+    batch.updateClaim({c0, s1, s2, s3}, r);
+    batch.bindChallenge(r);
+  }
+  batch.current_claim.store(final_claim_out);
+  return ZOLT_OK;
+}
+
 // Gruen split-eq degree-3 sumcheck (ProductVirtualRemainderProver shape); claim = initial claim.
 int zolt_host_sumcheck_prove_gruen(zolt_ctx* ctx, int with_c, int log_n, int n_tables, const uint64_t* const* tables,
                                    const uint64_t* tau, const uint64_t* claim, const char* domain, size_t dn,

@@ -412,6 +412,62 @@ inline void proveSumcheckInto(SumcheckProof& proof, SumcheckInstance& inst, Tran
   }
 }
 
+// batched_sumcheck.BatchedSumcheckProver (src/zkvm/batched_sumcheck.zig:77-262): random linear combination of several
+// instances with different numbers of rounds.  Pure O(#instances) glue per round around the instances' device kernels.
+// The reference samples the batching coefficients from its Blake2b transcript (:150-156), which is outside this tier;
+// here the caller supplies them (and the per-round challenges come from whatever transcript drives the proof).
+class BatchedSumcheckProver {
+ public:
+  void addInstance(SumcheckInstance* inst, const Fr& input_claim) {  // :117-122
+    instances_.push_back(inst);
+    claims_.push_back(input_claim);
+    if (inst->numRounds() > max_rounds_) max_rounds_ = inst->numRounds();
+  }
+  // coefficients + initial batched claim  sum_i coeff_i * claim_i * 2^(max_rounds - rounds_i)  (:158-171)
+  void setBatchingCoeffs(const std::vector<Fr>& coeffs) {
+    coeffs_ = coeffs;
+    current_claim = Fr::zero();
+    for (size_t i = 0; i < instances_.size(); i++)
+      current_claim = current_claim.add(scaled(claims_[i], max_rounds_ - instances_[i]->numRounds()).mul(coeffs_[i]));
+  }
+  size_t maxNumRounds() const { return max_rounds_; }
+  // combined evaluations at X = 0..3 of this round (:189-220)
+  std::array<Fr, 4> computeRoundEvals() {
+    std::array<Fr, 4> combined{Fr::zero(), Fr::zero(), Fr::zero(), Fr::zero()};
+    for (size_t i = 0; i < instances_.size(); i++) {
+      const size_t start = max_rounds_ - instances_[i]->numRounds();
+      if (current_round_ >= start) {
+        const auto evals = instances_[i]->computeRoundPoly(current_round_ - start);
+        for (int j = 0; j < 4; j++) combined[j] = combined[j].add(evals[j].mul(coeffs_[i]));
+      } else {
+        // not started yet: constant polynomial, the input claim scaled by the rounds still to wait (:206-218)
+        const Fr w = scaled(claims_[i], start - current_round_).mul(coeffs_[i]);
+        for (int j = 0; j < 4; j++) combined[j] = combined[j].add(w);
+      }
+    }
+    return combined;
+  }
+  std::array<Fr, 3> computeRoundPolynomial() { return UniPoly::evalsToCompressed(computeRoundEvals()); }  // :223
+  void updateClaim(const std::array<Fr, 4>& round_evals, const Fr& challenge) {  // :242-245
+    current_claim = evaluateCubicAtPoint(round_evals, challenge);
+  }
+  void bindChallenge(const Fr& challenge) {  // :227-239
+    for (auto* inst : instances_)
+      if (current_round_ >= max_rounds_ - inst->numRounds()) inst->bindChallenge(challenge);
+    current_round_++;
+  }
+  Fr current_claim = Fr::zero();
+
+ private:
+  static Fr scaled(Fr c, size_t doublings) {
+    for (size_t k = 0; k < doublings; k++) c = c.add(c);
+    return c;
+  }
+  std::vector<SumcheckInstance*> instances_;
+  std::vector<Fr> claims_, coeffs_;
+  size_t max_rounds_ = 0, current_round_ = 0;
+};
+
 // One rank of a dense LowToHigh sumcheck whose tables are sharded over `world` GPUs in contiguous hypercube
 // blocks.  Every rank runs this with its own block; the round kernels exchange their sums through
 // the NVLink mailboxes, so each rank sees the global round polynomials, runs the same Keccak transcript and
