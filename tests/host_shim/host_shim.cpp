@@ -20,6 +20,7 @@ static void binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, s
       case 4: r = fp_from_mont<P>(x); break;
       case 5: r = fp_to_mont<P>(x); break;
       case 6: r = fp_neg<P>(x); break;
+      case 7: r = fp_inv_vartime<P>(x); break;
       default: r = Fp<P>::zero();
     }
     memcpy(out + 8 * i, r.v, 32);

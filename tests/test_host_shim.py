@@ -37,6 +37,12 @@ def test_field_algorithms(host_shim, field, mod):
     R = (1 << 256) % mod
     got = B.raw_array_to_ints(_run(host_shim, field, 3, a[:100], b[:100]))
     assert got == [0 if x == 0 else pow(x * rinv % mod, -1, mod) * R % mod for x in av[:100]]
+    # binary-GCD inversion (one thread normalising one MSM result): same canonical value, incl. 0 -> 0, 1, p-1, 2^k
+    av2 = av[:3000]
+    av2[6:12] = [2, 4, 1 << 253, (1 << 200) + 1, 3, mod - 3]
+    a2 = B.ints_to_raw_array(av2)
+    got = B.raw_array_to_ints(_run(host_shim, field, 7, a2, a2))
+    assert got == [0 if x == 0 else pow(x * rinv % mod, -1, mod) * R % mod for x in av2]
 
 
 def _fold(shim, mode, pts, neg=None, dbl=0):

@@ -190,7 +190,7 @@ ZOLT_HD bool xyzz_to_affine(const XYZZ& p, AffineG1& out) {
     return false;
   }
   // one inversion: ZZ^3 == ZZZ^2, hence ZZ^-1 = ZZZ^-2 * ZZ^2
-  Fq izzz = fp_inv<FqParams>(p.zzz);
+  Fq izzz = fp_inv_vartime<FqParams>(p.zzz);
   Fq izz = fq_mul(fq_sqr(izzz), fq_sqr(p.zz));  // ZZZ^-2 * ZZ^2 = ZZ^-3 * ZZ^2 = ZZ^-1
   out.x = fq_mul(p.x, izz);
   out.y = fq_mul(p.y, izzz);

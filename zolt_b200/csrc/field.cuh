@@ -354,6 +354,76 @@ ZOLT_HD Fp<P> fp_inv(const Fp<P>& a) {
   return acc;
 }
 
+// a^-1 by the binary extended Euclidean algorithm: same value as fp_inv (0 -> 0), about 4x less latency on a single
+// thread (shifts and subtractions instead of 380 dependent Montgomery products).  Variable time and divergent, so it is
+// used where ONE thread normalises ONE result (xyzz_to_affine at the end of an MSM), not in batch kernels.
+template <class P>
+ZOLT_HD Fp<P> fp_inv_vartime(const Fp<P>& a) {
+  if (a.is_zero()) return a;
+  uint32_t u[8], v[8], x1[8], x2[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u[i] = a.v[i];
+    v[i] = P::mod(i);
+    x1[i] = i == 0 ? 1u : 0u;
+    x2[i] = 0u;
+  }
+  auto is_one = [](const uint32_t* z) {
+    uint32_t o = z[0] ^ 1u;
+    for (int i = 1; i < 8; i++) o |= z[i];
+    return o == 0;
+  };
+  auto shr1 = [](uint32_t* z) {
+    for (int i = 0; i < 7; i++) z[i] = (z[i] >> 1) | (z[i + 1] << 31);
+    z[7] >>= 1;
+  };
+  auto add_mod = [](uint32_t* z) {  // z += p  (z < p < 2^254: no overflow)
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+      c += (uint64_t)z[i] + P::mod(i);
+      z[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  };
+  auto geq = [](const uint32_t* x, const uint32_t* y) {
+    for (int i = 7; i >= 0; i--) {
+      if (x[i] != y[i]) return x[i] > y[i];
+    }
+    return true;
+  };
+  auto sub = [](uint32_t* x, const uint32_t* y) {  // x -= y, returns the borrow
+    uint64_t b = 0;
+    for (int i = 0; i < 8; i++) {
+      const uint64_t d = (uint64_t)x[i] - y[i] - b;
+      x[i] = (uint32_t)d;
+      b = (d >> 32) & 1;
+    }
+    return (uint32_t)b;
+  };
+  auto halve = [&](uint32_t* z, uint32_t* x) {  // z even: z /= 2, x /= 2 mod p
+    shr1(z);
+    if (x[0] & 1u) add_mod(x);
+    shr1(x);
+  };
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1u)) halve(u, x1);
+    while (!(v[0] & 1u)) halve(v, x2);
+    if (geq(u, v)) {
+      sub(u, v);
+      if (sub(x1, x2)) add_mod(x1);
+    } else {
+      sub(v, u);
+      if (sub(x2, x1)) add_mod(x2);
+    }
+  }
+  // y = (a * 2^256)^-1 as a plain integer; the Montgomery form of a^-1 is y * 2^512 = mont(mont(y, R^2), R^2)
+  Fp<P> y;
+  const uint32_t* res = is_one(u) ? x1 : x2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) y.v[i] = res[i];
+  return fp_mul<P>(fp_mul<P>(y, Fp<P>::r2()), Fp<P>::r2());
+}
+
 // ---------------------------------------------------------------------------------------------
 // Delayed reduction: sums of products kept as unreduced 512-bit integers.
 //
