@@ -151,10 +151,16 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
     {
       const Fr x0 = LO(0), y0 = LO(1), x1 = HI(0), y1 = HI(1);
       m0 = fr_mul(x0, y0);
-      if constexpr (P1) m1 = fr_mul(x1, y1);
       const Fr dx = fr_sub(x1, x0), dy = fr_sub(y1, y0);
       ml = fr_mul(dx, dy);
-      m2 = fr_mul(fr_add(x1, dx), fr_add(y1, dy));
+      if constexpr (P1) {
+        // with x1 y1 at hand the product at X = 2 needs no multiplication: (2x1-x0)(2y1-y0) = 2 dx dy + 2 x1 y1 - x0 y0
+        m1 = fr_mul(x1, y1);
+        const Fr s = fr_add(ml, m1);
+        m2 = fr_sub(fr_add(s, s), m0);
+      } else {
+        m2 = fr_mul(fr_add(x1, dx), fr_add(y1, dy));
+      }
     }
     Fr z0, z1;
     if constexpr (COMB == ZOLT_SC_PROD3) {
@@ -175,10 +181,16 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
     {
       const Fr a0 = LO(1), b0 = LO(2), a1 = HI(1), b1 = HI(2);
       t0 = fr_mul(a0, b0);
-      if constexpr (P1) t1 = fr_mul(a1, b1);
       const Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0);
       ml = fr_mul(da, db);
-      t2 = fr_mul(fr_add(a1, da), fr_add(b1, db));
+      if constexpr (P1) {
+        // (2a1-a0)(2b1-b0) = 2 da db + 2 a1 b1 - a0 b0: no fourth multiplication when a1 b1 is needed anyway
+        t1 = fr_mul(a1, b1);
+        const Fr s = fr_add(ml, t1);
+        t2 = fr_sub(fr_add(s, s), t0);
+      } else {
+        t2 = fr_mul(fr_add(a1, da), fr_add(b1, db));
+      }
     }
     {
       const Fr c0 = LO(3), c1 = HI(3);
