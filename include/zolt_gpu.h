@@ -154,10 +154,13 @@ int zolt_poly_sum(zolt_ctx* ctx, const void* d_src, size_t n, uint64_t out[4]);
  *   ZOLT_VEC_MUL            out = a o b
  *   ZOLT_VEC_EQ_AB_MINUS_C  out = e * (a * b - c)   JoltSpartanInterface's combined table (jolt_r1cs.zig:352-360)
  *   ZOLT_VEC_AXPY           out = out + s * a       gamma-power combination of batchOpen (commitment/mod.zig:648-656)
- * Unused operands may be NULL. */
+ *   ZOLT_VEC_AFFINE_INDEX   out[i] = s[0] + s[1] * i   UnmapPolynomial as a table (ram/raf_checking.zig:206-209): with it
+ *                           RafEvaluationProver (:335-409) is the PROD2 combiner over (ra, unmap) with zolt_sc_set_claim
+ * Unused operands may be NULL; s holds one scalar (AXPY) or two (AFFINE_INDEX). */
 #define ZOLT_VEC_MUL 0
 #define ZOLT_VEC_EQ_AB_MINUS_C 1
 #define ZOLT_VEC_AXPY 2
+#define ZOLT_VEC_AFFINE_INDEX 3
 int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d_a, const void* d_b, const void* d_c, const void* d_e,
                     const uint64_t* s /* 4, AXPY only */, size_t n);
 

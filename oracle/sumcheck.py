@@ -134,6 +134,49 @@ def run_dense(kind: str, tables, pairing: int, challenges, n_extra: int = 0):
     return evals, bound
 
 
+def run_raf(ra, start_address: int, challenges, initial_claim: int):
+    """RafEvaluationProver (src/zkvm/ram/raf_checking.zig:335-409, bind :162-174, claim update :420-445) restated as
+    written: the unmap factor is implicit, unmap(x) = base + x * current_power + remaining(i) with
+    base = start_address + sum_j bound_j * 8 * 2^j (:345-351); s0 = sum ra_lo * unmap(0), s2 = sum (2 ra_hi - ra_lo) * unmap(2),
+    s1 = claim - s0, s3 = s0 - 3 s1 + 3 s2.  Returns (evals per round, bound ra tables per round, final claim)."""
+    from . import poly as OP
+
+    ra = [v % P for v in ra]
+    log_k = len(ra).bit_length() - 1
+    claim = initial_claim % P
+    bound, evals_all, tables = [], [], []
+    for rnd, r in enumerate(challenges):
+        half = len(ra) // 2
+        base = start_address % P
+        power = 8
+        for v in bound:
+            base = (base + v * power) % P
+            power *= 2
+        current_power = power
+        s0 = s2 = 0
+        remaining_vars = log_k - rnd - 1
+        for i in range(half):
+            ra_lo, ra_hi = ra[2 * i], ra[2 * i + 1]
+            ra_at_2 = (2 * ra_hi - ra_lo) % P
+            remaining, rp, idx = 0, current_power * 2, i
+            for _ in range(remaining_vars):
+                if idx & 1:
+                    remaining += rp
+                idx >>= 1
+                rp *= 2
+            s0 = (s0 + ra_lo * (base + remaining)) % P
+            s2 = (s2 + ra_at_2 * (base + current_power * 2 + remaining)) % P
+        s1 = (claim - s0) % P
+        s3 = (s0 - 3 * s1 + 3 * s2) % P
+        ev = [s0, s1, s2, s3]
+        evals_all.append(ev)
+        ra = [((1 - r) * ra[2 * i] + r * ra[2 * i + 1]) % P for i in range(half)]
+        tables.append(list(ra))
+        bound.append(r)
+        claim = OP.evaluate_cubic_at_point(ev, r)
+    return evals_all, tables, claim
+
+
 def run_batched(instances, coeffs, challenges):
     """BatchedSumcheckProver + generateBatchedProof (src/zkvm/batched_sumcheck.zig:158-171, :189-257, :330-420), adjacent
     pairs.  instances: list of (kind, tables).  Returns (compressed round polynomials [c0, c2, c3] per round, final claim,

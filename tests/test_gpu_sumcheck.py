@@ -169,3 +169,29 @@ def test_device_table_construction_and_spartan_stage1(ctx):
     inst.free()
     for b in (d_eq, d_a, d_b, d_c, d_out):
         b.free()
+
+
+@pytest.mark.parametrize("log_k", [1, 4, 10])
+def test_raf_evaluation_prover_shape(ctx, log_k):
+    """S3: RafEvaluationProver (src/zkvm/ram/raf_checking.zig:335-409) keeps `unmap` implicit; on the device it is the
+    PROD2 combiner over (ra, unmap table) with the prover's running claim supplying s(1).  The unmap table
+    start_address + 8 k is generated on the device (ZOLT_VEC_AFFINE_INDEX)."""
+    k = 1 << log_k
+    ra = rand_fr(1200 + log_k, k)
+    start = 0x8000_0000
+    challenges = rand_fr(1300 + log_k, log_k)
+    claim = sum(a * (start + 8 * i) for i, a in enumerate(ra)) % P  # computeInitialClaim (:316-324)
+    exp_evals, exp_tables, exp_final = OS.run_raf(ra, start, challenges, claim)
+    d_unmap = Z.DeviceBuffer(ctx, k * 32)
+    ctx.fr_vec_dev(Z.VEC_AFFINE_INDEX, d_unmap.ptr, s=fr_arr([start, 8]), n=k)
+    assert fr_ints(d_unmap.download((k, 4))) == [start + 8 * i for i in range(k)]
+    d_ra = Z.DeviceBuffer.from_host(ctx, fr_arr(ra))
+    inst = Z.SumcheckInstance.from_device(ctx, Z.SC_PROD2, Z.PAIR_ADJACENT, [d_ra.ptr, d_unmap.ptr], log_k)
+    inst.set_claim(fr_arr([claim]))
+    for rnd, r in enumerate(challenges):
+        assert fr_ints(inst.compute_round_poly()) == exp_evals[rnd], f"round {rnd}"
+        inst.bind_challenge(fr_arr([r]))
+        assert fr_ints(inst.table(0)) == exp_tables[rnd]
+    inst.free()
+    d_ra.free()
+    d_unmap.free()

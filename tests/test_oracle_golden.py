@@ -201,3 +201,19 @@ def test_batched_sumcheck_restatement_final_claim():
     f0, f1 = [t[0] for t in b0[-1]], b1[-1][0][0]
     assert final == (coeffs[0] * f0[0] * f0[1] * f0[2] + coeffs[1] * f1) % P
     assert len(out) == 4 and all(len(c) == 3 for c in out)
+
+
+def test_raf_restatement_equals_dense_product():
+    """RafEvaluationProver as written (implicit unmap, src/zkvm/ram/raf_checking.zig:335-409) == the dense degree-2
+    product over (ra, unmap table): the identity the device path relies on (tests/test_gpu_sumcheck.py)."""
+    import numpy as np
+
+    rng = np.random.default_rng(2)
+    k, start = 16, 0x8000_0000
+    ra, ch = B.random_fr(rng, k), B.random_fr(rng, 4)
+    claim = sum(a * (start + 8 * i) for i, a in enumerate(ra)) % P
+    ev, tabs, fin = OS.run_raf(ra, start, ch, claim)
+    ev2, b2 = OS.run_dense("prod2", [ra, [start + 8 * i for i in range(k)]], 0, ch)
+    assert ev == [list(e) for e in ev2]
+    assert [t for t in tabs] == [b[0] for b in b2]
+    assert fin == b2[-1][0][0] * b2[-1][1][0] % P

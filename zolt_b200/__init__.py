@@ -30,6 +30,7 @@ from ._lib import (  # noqa: F401
     SC_PROD3,
     SC_SUM,
     TUNE_SC_SMALL_PAIRS,
+    VEC_AFFINE_INDEX,
     VEC_AXPY,
     VEC_EQ_AB_MINUS_C,
     VEC_MUL,

@@ -109,10 +109,10 @@ class Context:
         )
         return out
 
-    def fr_vec_dev(self, op: int, d_out: int, d_a: int, d_b: int = 0, d_c: int = 0, d_e: int = 0, s=None, n: int = 0):
+    def fr_vec_dev(self, op: int, d_out: int, d_a: int = 0, d_b: int = 0, d_c: int = 0, d_e: int = 0, s=None, n: int = 0):
         """Element-wise table construction on device-resident tables (zolt_fr_vec_dev)."""
         sv = _as_u64(s, 4) if s is not None else None
-        check(self.lib.zolt_fr_vec_dev(self.handle, op, C.c_void_p(d_out), C.c_void_p(d_a), C.c_void_p(d_b or None), C.c_void_p(d_c or None),
+        check(self.lib.zolt_fr_vec_dev(self.handle, op, C.c_void_p(d_out), C.c_void_p(d_a or None), C.c_void_p(d_b or None), C.c_void_p(d_c or None),
                                        C.c_void_p(d_e or None), _ptr(sv), n), "zolt_fr_vec_dev")
 
     def fr_sum_rows(self, d_rows: int, rows: int, cols: int) -> np.ndarray:

@@ -45,7 +45,8 @@ struct zolt_bases {
 namespace {
 
 constexpr uint32_t kInvalidKey = 0xffffffffu;
-constexpr int kSlice0 = 128;  // level-0 slice length (mixed additions per thread)
+constexpr int kSlice0 = 128;     // level-0 slice length (mixed additions per thread)
+constexpr int kSlice0Big = 256;  // ... for lists of 2^26 entries and more: half the edge entries, still >= 14 waves of blocks
 constexpr int kSliceE = 8;    // edge-level slice length (full additions per thread)
 constexpr int kChunk = 32;    // buckets per thread in the running-sum reduction
 
@@ -279,14 +280,14 @@ msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, M
 __global__ void __launch_bounds__(128)
 msm_accum_points_kernel(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets, uint32_t num_keys,
                         const AffineG1* __restrict__ bases, XYZZ* __restrict__ buckets,
-                        uint32_t* __restrict__ edge_keys, XYZZ* __restrict__ edge_pts, size_t num_slices) {
+                        uint32_t* __restrict__ edge_keys, XYZZ* __restrict__ edge_pts, size_t num_slices, uint32_t slice_len) {
   const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t >= num_slices) return;
   const uint32_t total = offsets[num_keys];
-  const uint64_t p0 = (uint64_t)t * kSlice0;
+  const uint64_t p0 = (uint64_t)t * slice_len;
   uint32_t ek0 = kInvalidKey, ek1 = kInvalidKey;
   if (p0 < total) {
-    const uint32_t p1 = (uint32_t)min((uint64_t)total, p0 + kSlice0);
+    const uint32_t p1 = (uint32_t)min((uint64_t)total, p0 + slice_len);
     // largest k with offsets[k] <= p0 (skips empty buckets automatically)
     uint32_t lo = 0, hi = num_keys;  // invariant: offsets[lo] <= p0 < offsets[hi]
     while (hi - lo > 1) {
@@ -638,7 +639,8 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   if (num_keys >= 0xfffffff0ull || max_entries >= 0xfffffff0ull || n >= 0x7fffffffull) return ZOLT_ERR_ARG;
   if (pre && (size_t)g.windows * bases->n >= 0x7fffffffull) return ZOLT_ERR_ARG;
 
-  const size_t slices0 = (max_entries + kSlice0 - 1) / kSlice0;
+  const uint32_t slice_len = max_entries >= (size_t(1) << 26) ? kSlice0Big : kSlice0;
+  const size_t slices0 = (max_entries + slice_len - 1) / slice_len;
   const size_t L0 = 2 * slices0;
   const size_t edge_total = L0 + edge_levels_total(L0);
   const uint32_t Lc = kChunk;
@@ -725,7 +727,7 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
     // level 0
     ps = prof_begin(ctx, PROF_MSM_ACCUM0);
     msm_accum_points_kernel<<<(unsigned)((slices0 + 127) / 128), 128, 0, st>>>(
-        sorted, offsets, (uint32_t)num_keys, d_pts, buckets, edge_keys, edge_pts, slices0);
+        sorted, offsets, (uint32_t)num_keys, d_pts, buckets, edge_keys, edge_pts, slices0, slice_len);
     prof_end(ctx, ps);
     ctx->launches++;
     // edge levels

@@ -850,6 +850,13 @@ vec_kernel(Fr* __restrict__ out, const Fr* __restrict__ a, const Fr* __restrict_
     } else if constexpr (OP == ZOLT_VEC_EQ_AB_MINUS_C) {
       // combined[i] = eq[i] * (Az[i] * Bz[i] - Cz[i])  (src/zkvm/r1cs/jolt_r1cs.zig:352-360)
       v = fr_mul(ld_fr(e + i), fr_sub(fr_mul(ld_fr(a + i), ld_fr(b + i)), ld_fr(c + i)));
+    } else if constexpr (OP == ZOLT_VEC_AFFINE_INDEX) {
+      // out[i] = s0 + s1 * i: UnmapPolynomial (start_address + 8 k, src/zkvm/ram/raf_checking.zig:206-209) as a dense table;
+      // `a` carries the two scalars, i enters Montgomery form through one product by R^2
+      Fr idx = Fr::zero();
+      idx.v[0] = (uint32_t)i;
+      idx.v[1] = (uint32_t)((unsigned long long)i >> 32);
+      v = fr_add(a[0], fr_mul(a[1], fr_mul(Fr::r2(), idx)));
     } else {
       // out[i] += s * a[i]: the gamma-power combination of batchOpen (src/poly/commitment/mod.zig:648-656)
       const Fr x = ld_fr(a + i);
@@ -1464,7 +1471,23 @@ extern "C" int zolt_eq_evals(zolt_ctx* ctx, const uint64_t* r, int n_vars, const
 
 extern "C" int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d_a, const void* d_b, const void* d_c, const void* d_e,
                                const uint64_t* s, size_t n) {
-  if (!ctx || !d_out || !d_a) return ZOLT_ERR_ARG;
+  if (!ctx || !d_out) return ZOLT_ERR_ARG;
+  if (op == ZOLT_VEC_AFFINE_INDEX) {
+    if (!s) return ZOLT_ERR_ARG;
+    if (n == 0) return ZOLT_OK;
+    ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+    Fr* d_s = nullptr;
+    ZOLT_CUDA_TRY(pool_alloc(ctx, 2 * sizeof(Fr), (void**)&d_s));
+    ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, s, 2 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    vec_kernel<ZOLT_VEC_AFFINE_INDEX><<<grid_for(ctx, n, 8), kScThreads, 0, ctx->stream>>>((Fr*)d_out, d_s, nullptr, nullptr, nullptr,
+                                                                                         FixedMulTable{}, n);
+    ctx->launches++;
+    ZOLT_CUDA_TRY(cudaGetLastError());
+    ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // s is a borrowed host buffer
+    pool_release(ctx, d_s, 2 * sizeof(Fr));
+    return ZOLT_OK;
+  }
+  if (!d_a) return ZOLT_ERR_ARG;
   if (op == ZOLT_VEC_MUL && !d_b) return ZOLT_ERR_ARG;
   if (op == ZOLT_VEC_EQ_AB_MINUS_C && (!d_b || !d_c || !d_e)) return ZOLT_ERR_ARG;
   if (op == ZOLT_VEC_AXPY && !s) return ZOLT_ERR_ARG;
