@@ -308,7 +308,12 @@ def run_b200(args):
     if world > 1 and not args.nccl_exchange:
         from zolt_b200 import dist as ZD
 
-        box = ZD.connect_peer_box(ctx, rank, world)
+        try:
+            box = ZD.connect_peer_box(ctx, rank, world)  # raises on every rank alike if any rank cannot map its peers
+        except RuntimeError as e:  # e.g. CUDA IPC unavailable in this container: fall back to the NCCL exchange, visibly
+            box = None
+            if rank == 0:
+                print(f"[bench] {e}; using the NCCL exchange", file=sys.stderr, flush=True)
 
     def msm_resident():
         if world == 1:

@@ -263,11 +263,16 @@ class PeerBox:
         self.ctx, self.rank, self.world = ctx, rank, world
         h = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        check(ctx.lib.zolt_peer_box_create(ctx.handle, C.byref(h), C.cast(handle, C.c_void_p)), "zolt_peer_box_create")
-        self.handle = h
-        blobs = exchange(bytes(handle))
+        st = ctx.lib.zolt_peer_box_create(ctx.handle, C.byref(h), C.cast(handle, C.c_void_p))
+        self.handle = h if st == 0 else None
+        # always take part in the exchange (an all-zero blob tells the peers this rank has no mailbox)
+        blobs = exchange(bytes(handle) if st == 0 else bytes(64))
+        check(st, "zolt_peer_box_create")
         if len(blobs) != world or any(len(b) != 64 for b in blobs):
             raise ValueError("exchange must return one 64-byte handle per rank")
+        if any(b == bytes(64) for b in blobs):
+            self.free()
+            raise RuntimeError("a peer rank could not create its mailbox")
         allh = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(blobs))
         check(ctx.lib.zolt_peer_box_connect(self.handle, C.cast(allh, C.c_void_p), rank, world), "zolt_peer_box_connect")
 

@@ -141,8 +141,18 @@ def connect_peer_box(ctx, rank: int, world: int):
         host = bytes(allb.cpu().numpy().tobytes())
         return [host[64 * g:64 * (g + 1)] for g in range(world)]
 
-    box = PeerBox(ctx, rank, world, exchange)
-    dist.barrier()  # every rank has mapped every mailbox before anybody publishes
+    box, err = None, None
+    try:
+        box = PeerBox(ctx, rank, world, exchange)
+    except Exception as e:  # noqa: BLE001 - reported below, on every rank alike
+        err = e
+    # every rank has mapped every mailbox before anybody publishes -- or nobody uses the mailboxes at all
+    ok = torch.tensor([0 if err is not None else 1], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        if box is not None:
+            box.free()
+        raise RuntimeError(f"peer mailboxes unavailable on at least one rank ({err!r} on rank {rank})")
     return box
 
 
