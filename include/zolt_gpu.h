@@ -242,11 +242,14 @@ int zolt_fr_sum_rows(zolt_ctx* ctx, const void* d_rows, size_t rows, size_t cols
 /* Multi-GPU, fused exchange (preferred): after zolt_sc_set_peers(sc, box) every round kernel pushes its 4 raw
  * sums into the mailbox of every rank over NVLink and folds all ranks' rows itself, so zolt_sc_round_evals /
  * zolt_sc_bind behave exactly as on one GPU while each rank holds only its hypercube block.  Every rank
- * must make the same sequence of calls.  zolt_sc_gather_tail: once the local block is down to one entry per
- * table, all-gather those entries into d_out laid out [table][rank] (the tables of the last log2(world)
- * rounds, which every rank then runs redundantly). */
+ * must make the same sequence of calls.  zolt_sc_gather_tail: once the local block is down to ZOLT_SC_TAIL_ENTRIES
+ * entries per table or fewer, all-gather the blocks over NVLink: d_tables_out[t] then points at the GLOBAL table t
+ * (*n_out = world * local length, blocked order) inside this rank's mailbox, valid until the box's next but one
+ * gather; every rank runs the remaining rounds on those tables redundantly, without further exchanges (small rounds
+ * are latency-bound: one exchange less per round matters more than the duplicated arithmetic). */
+#define ZOLT_SC_TAIL_ENTRIES 1024
 int zolt_sc_set_peers(zolt_sc* sc, zolt_peer_box* box);
-int zolt_sc_gather_tail(zolt_sc* sc, void* d_out /* (k+n_extra) * world * 4 u64, device */);
+int zolt_sc_gather_tail(zolt_sc* sc, const void** d_tables_out /* k+n_extra device pointers */, size_t* n_out);
 int zolt_sc_free(zolt_sc* sc);
 
 /* ---- NVLink peer mailbox (multi-GPU exchange without a collective library) ---------------------------

@@ -80,7 +80,7 @@ SIGNATURES = {
     "zolt_sc_set_claim": [_vp, _vp],
     "zolt_sc_set_sharded": [_vp, _i],
     "zolt_sc_set_peers": [_vp, _vp],
-    "zolt_sc_gather_tail": [_vp, _vp],
+    "zolt_sc_gather_tail": [_vp, C.POINTER(_vp), C.POINTER(_sz)],
     "zolt_peer_box_create": [_vp, C.POINTER(_vp), _vp],
     "zolt_peer_box_connect": [_vp, _vp, _i, _i],
     "zolt_peer_box_free": [_vp],

@@ -37,9 +37,53 @@ __global__ void peer_allgather_kernel(const __grid_constant__ GatherSrc src, int
   }
 }
 
+// Every rank stores its k local tables into the tail buffer of every rank (its own included) over NVLink, then the
+// usual fence + flag + wait.  Table t of the gathered set starts at entry t * world * n_local of the buffer.
+__global__ void __launch_bounds__(256)
+peer_gather_tables_kernel(const __grid_constant__ GatherSrc src, int k, unsigned n_local, const __grid_constant__ PeerDev peer,
+                          size_t buf_offset) {
+  __shared__ int ok;
+  const unsigned total = (unsigned)k * n_local;
+  for (unsigned idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const unsigned t = idx / n_local, i = idx - t * n_local;
+    const uint4* s = reinterpret_cast<const uint4*>(src.p[t] + i);
+    const uint4 a = s[0], b = s[1];
+    const size_t dst_entry = (size_t)t * peer.world * n_local + (size_t)peer.rank * n_local + i;
+#pragma unroll 1
+    for (int g = 0; g < peer.world; g++) {
+      uint4* d = reinterpret_cast<uint4*>(peer.box[g] + buf_offset) + 2 * dst_entry;
+      d[0] = a;
+      d[1] = b;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    peer_publish(peer, nullptr, 0);
+    ok = peer_wait(peer) ? 1 : 0;
+  }
+  __syncthreads();
+}
+
 }  // namespace
 
 namespace zolt {
+int peer_gather_tables(zolt_peer_box* box, const Fr* const* d_src, int k, size_t n_local, const Fr** d_tables_out) {
+  if (!box || !box->connected || !d_src || !d_tables_out || k < 1 || k > kPeerTailTables || n_local < 1 || n_local > kPeerTailEntries)
+    return ZOLT_ERR_ARG;
+  zolt_ctx* ctx = box->ctx;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  GatherSrc s{};
+  for (int i = 0; i < k; i++) s.p[i] = d_src[i];
+  const size_t buf_offset = kPeerHeaderBytes + (size_t)(box->gathers++ & 1u) * kPeerTailBufBytes;
+  const PeerDev p = peer_next(box);
+  peer_gather_tables_kernel<<<1, 256, 0, ctx->stream>>>(s, k, (unsigned)n_local, p, buf_offset);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  const Fr* base = reinterpret_cast<const Fr*>(box->d_local + buf_offset);
+  for (int t = 0; t < k; t++) d_tables_out[t] = base + (size_t)t * box->world * n_local;
+  return ZOLT_OK;
+}
 int peer_allgather_ptrs(zolt_peer_box* box, const Fr* const* d_src, int n_fr, Fr* d_out, int transpose) {
   if (!box || !box->connected || !d_src || !d_out || n_fr < 1 || n_fr > kPeerSlotFr) return ZOLT_ERR_ARG;
   zolt_ctx* ctx = box->ctx;
@@ -64,6 +108,7 @@ int peer_check(zolt_peer_box* box) {
 extern "C" int zolt_peer_box_create(zolt_ctx* ctx, zolt_peer_box** out, unsigned char handle_out[64]) {
   if (!ctx || !out || !handle_out) return ZOLT_ERR_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  static_assert(kPeerTailTables <= kPeerSlotFr, "GatherSrc holds kPeerSlotFr pointers");
   *out = nullptr;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   zolt_peer_box* box = new (std::nothrow) zolt_peer_box();

@@ -22,7 +22,15 @@ namespace zolt {
 constexpr int kPeerMaxWorld = 8;  // one NVSwitch node of B200s
 constexpr int kPeerSlotFr = 8;    // 256 bytes per (slot, sender)
 constexpr size_t kPeerDataBytes = 2ull * kPeerMaxWorld * kPeerSlotFr * 32;
-constexpr size_t kPeerBoxBytes = kPeerDataBytes + 2ull * kPeerMaxWorld * sizeof(unsigned);
+constexpr size_t kPeerHeaderBytes = 8192;  // rows + flags, padded
+// Table-gather area (the tail of a sharded sumcheck): two buffers of kPeerTailTables tables, each table holding
+// kPeerTailEntries entries per rank, laid out [table][rank][entry] = the global table in blocked order.
+constexpr int kPeerTailTables = 8;
+constexpr size_t kPeerTailEntries = 1024;
+constexpr size_t kPeerTailTableStride = (size_t)kPeerMaxWorld * kPeerTailEntries;             // entries
+constexpr size_t kPeerTailBufBytes = (size_t)kPeerTailTables * kPeerTailTableStride * 32;   // 2 MiB
+constexpr size_t kPeerBoxBytes = kPeerHeaderBytes + 2 * kPeerTailBufBytes;
+static_assert(kPeerDataBytes + 2ull * kPeerMaxWorld * sizeof(unsigned) <= kPeerHeaderBytes, "mailbox header");
 constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;
 
 struct PeerDev {
@@ -51,11 +59,13 @@ static __device__ __noinline__ void peer_publish(const PeerDev& p, const Fr* val
       dst[2 * i + 1] = make_uint4(vals[i].v[4], vals[i].v[5], vals[i].v[6], vals[i].v[7]);
     }
   }
+  // ONE system-scope fence orders all the row stores above before all the flag stores below; the flags themselves
+  // are relaxed stores (a release per flag would pay the NVLink round trip once per peer)
   __threadfence_system();
 #pragma unroll 1
   for (int g = 0; g < p.world; g++) {
     unsigned* f = peer_flag(p.box[g], p.seq, p.rank);
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(p.seq) : "memory");
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(f), "r"(p.seq) : "memory");
   }
 }
 
@@ -69,7 +79,7 @@ static __device__ __noinline__ bool peer_wait(const PeerDev& p) {
     unsigned spins = 0;
     while (true) {
       unsigned v;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if (v == p.seq) break;
       if ((++spins & 1023u) == 0) {
         unsigned long long t1;
@@ -82,6 +92,7 @@ static __device__ __noinline__ bool peer_wait(const PeerDev& p) {
       }
     }
   }
+  __threadfence_system();  // acquire side: the rows are read (from L2) only after every flag has been seen
   return true;
 }
 
@@ -106,6 +117,7 @@ struct zolt_peer_box {
   bool opened[zolt::kPeerMaxWorld] = {};
   int rank = 0, world = 1;
   unsigned seq = 0;
+  unsigned gathers = 0;  // table gathers so far (selects the tail buffer)
   int* h_err = nullptr;  // mapped pinned
   int* d_err = nullptr;
   bool connected = false;
@@ -127,5 +139,8 @@ inline PeerDev peer_next(zolt_peer_box* box) {
 }
 // peer.cu
 int peer_allgather_ptrs(zolt_peer_box* box, const Fr* const* d_src, int n_fr, Fr* d_out, int transpose);
+// All-gather k local tables of n_local (<= kPeerTailEntries) entries each: afterwards d_tables_out[t] points at the
+// global table t (world * n_local entries, rank-major = blocked order) inside THIS rank's mailbox.  Asynchronous.
+int peer_gather_tables(zolt_peer_box* box, const Fr* const* d_src, int k, size_t n_local, const Fr** d_tables_out);
 int peer_check(zolt_peer_box* box);
 }  // namespace zolt

@@ -1272,15 +1272,19 @@ extern "C" int zolt_sc_set_peers(zolt_sc* sc, zolt_peer_box* box) {
   return ZOLT_OK;
 }
 
-extern "C" int zolt_sc_gather_tail(zolt_sc* sc, void* d_out) {
-  if (!sc || !d_out || !sc->box) return ZOLT_ERR_ARG;
-  if (sc->n != 1) return ZOLT_ERR_STATE;  // every local variable must be bound
+extern "C" int zolt_sc_gather_tail(zolt_sc* sc, const void** d_tables_out, size_t* n_out) {
+  if (!sc || !d_tables_out || !n_out || !sc->box) return ZOLT_ERR_ARG;
+  if (sc->n < 1 || sc->n > kPeerTailEntries) return ZOLT_ERR_STATE;  // bind further first
   const Fr* ptrs[kMaxTables];
+  const Fr* outs[kMaxTables];
   const int total = sc->k + sc->n_extra;
   for (int i = 0; i < total; i++) ptrs[i] = sc->cur < 0 ? sc->tab_in[i] : sc->buf[sc->cur][i];
-  ZOLT_TRY(peer_allgather_ptrs(sc->box, ptrs, total, (Fr*)d_out, 1));
+  ZOLT_TRY(peer_gather_tables(sc->box, ptrs, total, sc->n, outs));
   ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
-  return peer_check(sc->box);
+  ZOLT_TRY(peer_check(sc->box));
+  for (int i = 0; i < total; i++) d_tables_out[i] = outs[i];
+  *n_out = sc->n * (size_t)sc->box->world;
+  return ZOLT_OK;
 }
 
 extern "C" int zolt_sc_round_partials_dev(zolt_sc* sc, const void** d_ptr) {

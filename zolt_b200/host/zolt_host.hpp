@@ -396,9 +396,10 @@ struct SumcheckProof {
 // The stage loop of MultiStageProver (src/zkvm/prover.zig:405-428): per round absorb the first
 // degree+1 evaluations as "round_poly_j", squeeze `challenge_label`, bind.
 // Appends inst's rounds to `proof` (the transcript carries over from whatever ran before).
-inline void proveSumcheckInto(SumcheckProof& proof, SumcheckInstance& inst, Transcript& transcript, std::string_view challenge_label) {
+inline void proveSumcheckInto(SumcheckProof& proof, SumcheckInstance& inst, Transcript& transcript, std::string_view challenge_label,
+                              size_t max_rounds = ~size_t(0)) {
   const size_t n_absorb = inst.degree() + 1;
-  for (size_t round = 0; round < inst.numRounds(); round++) {
+  for (size_t round = 0; round < inst.numRounds() && round < max_rounds; round++) {
     const auto evals = inst.computeRoundPoly(round);
     for (size_t j = 0; j < n_absorb; j++) {
       char label[24];
@@ -471,36 +472,36 @@ class BatchedSumcheckProver {
 // One rank of a dense LowToHigh sumcheck whose tables are sharded over `world` GPUs in contiguous hypercube
 // blocks.  Every rank runs this with its own block; the round kernels exchange their sums through
 // the NVLink mailboxes, so each rank sees the global round polynomials, runs the same Keccak transcript and
-// derives the same challenges.  When the local block is down to one entry per table those `world` entries are
-// all-gathered and the last log2(world) rounds run on every rank alike.  Returns the whole proof; final_out
+// derives the same challenges.  When the local block is down to ZOLT_SC_TAIL_ENTRIES entries per table the blocks are
+// all-gathered over NVLink and the remaining rounds run on every rank alike, without exchanges.  Returns the whole proof; final_out
 // receives the k fully bound table values.
 inline SumcheckProof proveSumcheckSharded(Context& ctx, zolt_peer_box* box, int world, int combiner,
                                           const std::vector<const void*>& d_tables, int local_log, Transcript& transcript,
                                           std::string_view challenge_label, std::vector<Fr>* final_out) {
   SumcheckProof proof;
   const int k = (int)d_tables.size();
-  int tail_log = 0;
-  while ((1 << tail_log) < world) tail_log++;
   DenseSumcheckProver local(ctx, DenseSumcheckProver::DeviceTables{}, combiner, ZOLT_PAIR_ADJACENT, d_tables, local_log);
-  if (world > 1) must(zolt_sc_set_peers(local.raw(), box), "zolt_sc_set_peers");
-  proveSumcheckInto(proof, local, transcript, challenge_label);
   if (world == 1) {
+    proveSumcheckInto(proof, local, transcript, challenge_label);
     if (final_out)
       for (int t = 0; t < k; t++) final_out->push_back(local.table(t)[0]);
     return proof;
   }
-  void* d_tail = nullptr;
-  must(zolt_dev_alloc(ctx.raw(), (size_t)k * world * 32, &d_tail), "zolt_dev_alloc");
-  must(zolt_sc_gather_tail(local.raw(), d_tail), "zolt_sc_gather_tail");
-  std::vector<const void*> tail_tabs;
-  for (int t = 0; t < k; t++) tail_tabs.push_back(static_cast<const char*>(d_tail) + (size_t)t * world * 32);
-  {
-    DenseSumcheckProver tail(ctx, DenseSumcheckProver::DeviceTables{}, combiner, ZOLT_PAIR_ADJACENT, tail_tabs, tail_log);
-    proveSumcheckInto(proof, tail, transcript, challenge_label);
-    if (final_out)
-      for (int t = 0; t < k; t++) final_out->push_back(tail.table(t)[0]);
-  }
-  must(zolt_dev_free(ctx.raw(), d_tail), "zolt_dev_free");
+  must(zolt_sc_set_peers(local.raw(), box), "zolt_sc_set_peers");
+  // exchange rounds while the block is larger than the tail threshold ...
+  int tail_local_log = 0;
+  while ((size_t(2) << tail_local_log) <= (size_t)ZOLT_SC_TAIL_ENTRIES && tail_local_log < local_log) tail_local_log++;
+  proveSumcheckInto(proof, local, transcript, challenge_label, (size_t)(local_log - tail_local_log));
+  // ... then one all-gather of the blocks and the remaining rounds on every rank alike
+  std::vector<const void*> tail_tabs((size_t)k);
+  size_t tail_n = 0;
+  must(zolt_sc_gather_tail(local.raw(), tail_tabs.data(), &tail_n), "zolt_sc_gather_tail");
+  int tail_log = 0;
+  while ((size_t(1) << tail_log) < tail_n) tail_log++;
+  DenseSumcheckProver tail(ctx, DenseSumcheckProver::DeviceTables{}, combiner, ZOLT_PAIR_ADJACENT, tail_tabs, tail_log);
+  proveSumcheckInto(proof, tail, transcript, challenge_label);
+  if (final_out)
+    for (int t = 0; t < k; t++) final_out->push_back(tail.table(t)[0]);
   return proof;
 }
 
