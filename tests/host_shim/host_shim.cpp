@@ -116,3 +116,22 @@ extern "C" void shim_bind_fixed(int field, const uint32_t* r, const uint32_t* lo
   if (field == 0) bind_fixed<FrParams>(r, lo, hi, n, out);
   else bind_fixed<FqParams>(r, lo, hi, n, out);
 }
+
+// fp_mul2_sub: out = (a * b - c * d) * 2^-256 mod p with one shared reduction (the MSM's y3)
+template <class P>
+static void mul2_sub(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, size_t n, uint32_t* out) {
+  for (size_t i = 0; i < n; i++) {
+    Fp<P> x, y, z, w;
+    memcpy(x.v, a + 8 * i, 32);
+    memcpy(y.v, b + 8 * i, 32);
+    memcpy(z.v, c + 8 * i, 32);
+    memcpy(w.v, d + 8 * i, 32);
+    const Fp<P> r = fp_mul2_sub<P>(x, y, z, w);
+    memcpy(out + 8 * i, r.v, 32);
+  }
+}
+extern "C" void shim_mul2_sub(int field, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, size_t n,
+                              uint32_t* out) {
+  if (field == 0) mul2_sub<FrParams>(a, b, c, d, n, out);
+  else mul2_sub<FqParams>(a, b, c, d, n, out);
+}

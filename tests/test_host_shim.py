@@ -131,3 +131,27 @@ def test_fixed_multiplier_bind(host_shim, field, mod):
         r_std = (r % mod) * rinv % mod
         want = [(a + r_std * (b - a)) % mod for a, b in zip(los, his)]
         assert B.raw_array_to_ints(out) == want, hex(r)
+
+
+@pytest.mark.parametrize("field,mod", [(0, B.FR_MOD), (1, B.FQ_MOD)])
+def test_two_products_one_reduction(host_shim, field, mod):
+    """fp_mul2_sub (y3 = r (q - x3) - y1 ppp of the MSM's mixed addition with ONE Montgomery reduction): equal to the
+    difference of the two reduced products for random operands and for the extremes (0, 1, p-1 in every position, which
+    drive the shared accumulator to its 3p bound and the subtrahend's complement to p itself)."""
+    rng = np.random.default_rng(21)
+    n = 4000
+    vals = [[v % mod for v in B.random_fr(rng, n)] for _ in range(4)]
+    ext = [0, 1, mod - 1, mod - 2, (1 << 253), mod >> 1]
+    k = 0
+    for a in ext:
+        for b in ext:
+            for c in ext:
+                for d in (0, mod - 1, 1):
+                    vals[0][k], vals[1][k], vals[2][k], vals[3][k] = a, b, c, d
+                    k += 1
+    arrs = [B.ints_to_raw_array(v) for v in vals]
+    out = np.zeros((n, 4), dtype=np.uint64)
+    host_shim.shim_mul2_sub(field, *[x.ctypes.data_as(C.c_void_p) for x in arrs], C.c_size_t(n), out.ctypes.data_as(C.c_void_p))
+    rinv = pow(1 << 256, -1, mod)
+    want = [(a * b - c * d) * rinv % mod for a, b, c, d in zip(*vals)]
+    assert B.raw_array_to_ints(out) == want

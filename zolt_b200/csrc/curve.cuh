@@ -33,6 +33,8 @@ ZOLT_HD Fq fq_add(const Fq& a, const Fq& b) { return fp_add<FqParams>(a, b); }
 ZOLT_HD Fq fq_sub(const Fq& a, const Fq& b) { return fp_sub<FqParams>(a, b); }
 ZOLT_HD Fq fq_mul(const Fq& a, const Fq& b) { return fp_mul<FqParams>(a, b); }
 ZOLT_HD Fq fq_sqr(const Fq& a) { return fp_sqr<FqParams>(a); }
+// a * b - c * d with one shared Montgomery reduction (field.cuh): the y coordinate of every addition / doubling
+ZOLT_HD Fq fq_mul2_sub(const Fq& a, const Fq& b, const Fq& c, const Fq& d) { return fp_mul2_sub<FqParams>(a, b, c, d); }
 
 ZOLT_HD XYZZ xyzz_from_affine(const AffineG1& p) {
   XYZZ r;
@@ -53,7 +55,7 @@ ZOLT_HD XYZZ xyzz_dbl_affine(const AffineG1& p) {
   Fq xx = fq_sqr(p.x);
   Fq m = fq_add(fq_add(xx, xx), xx);
   r.x = fq_sub(fq_sqr(m), fq_add(s, s));
-  r.y = fq_sub(fq_mul(m, fq_sub(s, r.x)), fq_mul(w, p.y));
+  r.y = fq_mul2_sub(m, fq_sub(s, r.x), w, p.y);
   r.zz = v;
   r.zzz = w;
   return r;
@@ -70,7 +72,7 @@ ZOLT_HD XYZZ xyzz_dbl(const XYZZ& p) {
   Fq xx = fq_sqr(p.x);
   Fq m = fq_add(fq_add(xx, xx), xx);
   r.x = fq_sub(fq_sqr(m), fq_add(s, s));
-  r.y = fq_sub(fq_mul(m, fq_sub(s, r.x)), fq_mul(w, p.y));
+  r.y = fq_mul2_sub(m, fq_sub(s, r.x), w, p.y);
   r.zz = fq_mul(v, p.zz);
   r.zzz = fq_mul(w, p.zzz);
   return r;
@@ -95,7 +97,7 @@ ZOLT_HD void xyzz_madd(XYZZ& acc, const AffineG1& q) {
   Fq ppp = fq_mul(p, pp);
   Fq qq = fq_mul(acc.x, pp);
   Fq x3 = fq_sub(fq_sub(fq_sqr(r), ppp), fq_add(qq, qq));
-  Fq y3 = fq_sub(fq_mul(r, fq_sub(qq, x3)), fq_mul(acc.y, ppp));
+  Fq y3 = fq_mul2_sub(r, fq_sub(qq, x3), acc.y, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fq_mul(acc.zz, pp);
@@ -115,7 +117,7 @@ ZOLT_HD void xyzz_madd_uniform(XYZZ& acc, const AffineG1& q) {
   Fq ppp = fq_mul(p, pp);
   Fq qq = fq_mul(acc.x, pp);
   Fq x3 = fq_sub(fq_sub(fq_sqr(r), ppp), fq_add(qq, qq));
-  Fq y3 = fq_sub(fq_mul(r, fq_sub(qq, x3)), fq_mul(acc.y, ppp));
+  Fq y3 = fq_mul2_sub(r, fq_sub(qq, x3), acc.y, ppp);
   Fq zz3 = fq_mul(acc.zz, pp);
   Fq zzz3 = fq_mul(acc.zzz, ppp);
   if (!ident && p.is_zero()) {  // same x: P + P or P + (-P)
@@ -157,7 +159,7 @@ ZOLT_HD void xyzz_add(XYZZ& acc, const XYZZ& b) {
   Fq ppp = fq_mul(p, pp);
   Fq qq = fq_mul(u1, pp);
   Fq x3 = fq_sub(fq_sub(fq_sqr(r), ppp), fq_add(qq, qq));
-  Fq y3 = fq_sub(fq_mul(r, fq_sub(qq, x3)), fq_mul(s1, ppp));
+  Fq y3 = fq_mul2_sub(r, fq_sub(qq, x3), s1, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fq_mul(fq_mul(acc.zz, b.zz), pp);

@@ -299,6 +299,107 @@ ZOLT_HD void mont_mul_raw(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   r[7] = ptx::addc(x[7], y[8]);
 }
 
+// ---- two products, one reduction -------------------------------------------------------------------------
+// (a * b + c * d) * 2^-256 mod p with the reduction rows shared between the two products: 8 x (8 + 8 + 8) wide
+// multiplies instead of 2 x 8 x (8 + 8).  Requires a, c < 2^254 (canonical elements, or p itself); b, d arbitrary.
+// Bounds: every odd-limb partial (a_odd * b_i, c_odd * d_i, m * p_odd) is below 2^254 because the top limbs of a, c, p
+// are below 2^30, so O = carried-in (< 2^224) + three of them stays below 2^256 and never carries out of o[7]; E gains
+// at most three carries per row in e[8].  The result is below a + c + p + 1 <= 3p.
+template <class P>
+ZOLT_HD void mont_row_extra(uint32_t* e, uint32_t* o, const uint32_t* c, uint32_t di) {
+  o[0] = ptx::mad_lo_cc(c[1], di, o[0]);
+  o[1] = ptx::madc_hi_cc(c[1], di, o[1]);
+  o[2] = ptx::madc_lo_cc(c[3], di, o[2]);
+  o[3] = ptx::madc_hi_cc(c[3], di, o[3]);
+  o[4] = ptx::madc_lo_cc(c[5], di, o[4]);
+  o[5] = ptx::madc_hi_cc(c[5], di, o[5]);
+  o[6] = ptx::madc_lo_cc(c[7], di, o[6]);
+  o[7] = ptx::madc_hi(c[7], di, o[7]);
+  e[0] = ptx::mad_lo_cc(c[0], di, e[0]);
+  e[1] = ptx::madc_hi_cc(c[0], di, e[1]);
+  e[2] = ptx::madc_lo_cc(c[2], di, e[2]);
+  e[3] = ptx::madc_hi_cc(c[2], di, e[3]);
+  e[4] = ptx::madc_lo_cc(c[4], di, e[4]);
+  e[5] = ptx::madc_hi_cc(c[4], di, e[5]);
+  e[6] = ptx::madc_lo_cc(c[6], di, e[6]);
+  e[7] = ptx::madc_hi_cc(c[6], di, e[7]);
+  e[8] = ptx::addc(e[8], 0u);
+}
+
+// the product rows of mont_row_first / mont_row_next without their reduction step
+template <class P>
+ZOLT_HD void mont_row_first_noreduce(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    o[2 * t] = ptx::mul_lo(a[2 * t + 1], bi);
+    o[2 * t + 1] = ptx::mul_hi(a[2 * t + 1], bi);
+    e[2 * t] = ptx::mul_lo(a[2 * t], bi);
+    e[2 * t + 1] = ptx::mul_hi(a[2 * t], bi);
+  }
+  e[8] = 0;
+}
+template <class P>
+ZOLT_HD void mont_row_next_noreduce(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
+  e[0] = ptx::add_cc(e[0], o[1]);
+  o[0] = ptx::madc_lo_cc(a[1], bi, o[2]);
+  o[1] = ptx::madc_hi_cc(a[1], bi, o[3]);
+  o[2] = ptx::madc_lo_cc(a[3], bi, o[4]);
+  o[3] = ptx::madc_hi_cc(a[3], bi, o[5]);
+  o[4] = ptx::madc_lo_cc(a[5], bi, o[6]);
+  o[5] = ptx::madc_hi_cc(a[5], bi, o[7]);
+  o[6] = ptx::madc_lo_cc(a[7], bi, o[8]);
+  o[7] = ptx::madc_hi(a[7], bi, 0u);
+  e[0] = ptx::mad_lo_cc(a[0], bi, e[0]);
+  e[1] = ptx::madc_hi_cc(a[0], bi, e[1]);
+  e[2] = ptx::madc_lo_cc(a[2], bi, e[2]);
+  e[3] = ptx::madc_hi_cc(a[2], bi, e[3]);
+  e[4] = ptx::madc_lo_cc(a[4], bi, e[4]);
+  e[5] = ptx::madc_hi_cc(a[4], bi, e[5]);
+  e[6] = ptx::madc_lo_cc(a[6], bi, e[6]);
+  e[7] = ptx::madc_hi_cc(a[6], bi, e[7]);
+  e[8] = ptx::addc(0u, 0u);
+}
+
+// canonical a * b + c * d (Montgomery); a, c canonical (c may also be p)
+template <class P>
+ZOLT_HD Fp<P> fp_mul2_add(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+  uint32_t x[9], y[9];
+  mont_row_first_noreduce<P>(x, y, a.v, b.v[0]);
+  mont_row_extra<P>(x, y, c.v, d.v[0]);
+  mont_row_reduce<P>(x, y);
+#define ZOLT_ROW2(E, O, I)                          \
+  mont_row_next_noreduce<P>(E, O, a.v, b.v[I]);     \
+  mont_row_extra<P>(E, O, c.v, d.v[I]);             \
+  mont_row_reduce<P>(E, O);
+  ZOLT_ROW2(y, x, 1)
+  ZOLT_ROW2(x, y, 2)
+  ZOLT_ROW2(y, x, 3)
+  ZOLT_ROW2(x, y, 4)
+  ZOLT_ROW2(y, x, 5)
+  ZOLT_ROW2(x, y, 6)
+  ZOLT_ROW2(y, x, 7)
+#undef ZOLT_ROW2
+  Fp<P> r;
+  r.v[0] = ptx::add_cc(x[0], y[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(x[i], y[i + 1]);
+  r.v[7] = ptx::addc(x[7], y[8]);
+  fp_reduce_once<P>(r.v);  // [0, 3p) -> [0, p)
+  fp_reduce_once<P>(r.v);
+  return r;
+}
+
+// canonical a * b - c * d:  the subtrahend enters as (p - c) * d
+template <class P>
+ZOLT_HD Fp<P> fp_mul2_sub(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+  Fp<P> nc;
+  nc.v[0] = ptx::sub_cc(P::mod(0), c.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) nc.v[i] = ptx::subc_cc(P::mod(i), c.v[i]);
+  nc.v[7] = ptx::subc(P::mod(7), c.v[7]);
+  return fp_mul2_add<P>(a, b, nc, d);
+}
+
 // canonical Montgomery product (reference montgomeryMul, src/field/mod.zig:269-308, :735-779)
 template <class P>
 ZOLT_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
