@@ -21,6 +21,7 @@ static void binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, s
       case 5: r = fp_to_mont<P>(x); break;
       case 6: r = fp_neg<P>(x); break;
       case 7: r = fp_inv_vartime<P>(x); break;
+      case 8: r = fp_sqr<P>(x); break;
       default: r = Fp<P>::zero();
     }
     memcpy(out + 8 * i, r.v, 32);

@@ -37,6 +37,13 @@ def test_field_algorithms(host_shim, field, mod):
     R = (1 << 256) % mod
     got = B.raw_array_to_ints(_run(host_shim, field, 3, a[:100], b[:100]))
     assert got == [0 if x == 0 else pow(x * rinv % mod, -1, mod) * R % mod for x in av[:100]]
+    # dedicated squaring (36 instead of 64 partial products): same canonical value as mul(a, a), incl. all-ones limbs
+    av3 = list(av)
+    av3[6:14] = [2, mod - 3, (1 << 253) + (1 << 31), 0xFFFFFFFF, (0xFFFFFFFF << 32) | 0x80000000, (1 << 254) - 1 - (1 << 254) % 1 if (1 << 254) - 1 < mod else mod - 5,
+                 int("80000000" * 7, 16), int("7fffffff" + "ffffffff" * 6, 16)]
+    av3 = [v % mod for v in av3]
+    a3 = B.ints_to_raw_array(av3)
+    assert B.raw_array_to_ints(_run(host_shim, field, 8, a3, a3)) == [x * x * rinv % mod for x in av3]
     # binary-GCD inversion (one thread normalising one MSM result): same canonical value, incl. 0 -> 0, 1, p-1, 2^k
     av2 = av[:3000]
     av2[6:12] = [2, 4, 1 << 253, (1 << 200) + 1, 3, mod - 3]

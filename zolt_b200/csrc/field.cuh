@@ -409,9 +409,83 @@ ZOLT_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// ---- squaring ---------------------------------------------------------------------------------------------
+// a^2 = sum_i a_i * (a_i 2^(32 i) + 2 sum_{j > i} a_j 2^(32 j)) 2^(32 i): row i of the interleaved product only needs the
+// partial products at limb positions k >= i, taken against V_i = (a_i at k = i, the limbs of 2a above: D[i+1] with its
+// lowest bit -- the bit shifted in from a_i -- cleared, D[k] for k > i+1).  36 wide multiplies for the product part
+// instead of 64; the reduction rows are those of mont_mul_raw.  Positions below i only move the accumulator down (adds).
+// Odd-position partials are below 2^255 (doubled limbs) and m * p_odd below 2^254, so O still never carries out of o[7].
+template <class P, int I>
+ZOLT_HD void sqr_row_next(uint32_t* e, uint32_t* o, const uint32_t* v, uint32_t ai) {
+  e[0] = ptx::add_cc(e[0], o[1]);
+  // O' = (previous E >> 64) + carry + odd positions of V_i * a_i
+  if constexpr (1 >= I) { o[0] = ptx::madc_lo_cc(v[1], ai, o[2]); o[1] = ptx::madc_hi_cc(v[1], ai, o[3]); }
+  else { o[0] = ptx::addc_cc(o[2], 0u); o[1] = ptx::addc_cc(o[3], 0u); }
+  if constexpr (3 >= I) { o[2] = ptx::madc_lo_cc(v[3], ai, o[4]); o[3] = ptx::madc_hi_cc(v[3], ai, o[5]); }
+  else { o[2] = ptx::addc_cc(o[4], 0u); o[3] = ptx::addc_cc(o[5], 0u); }
+  if constexpr (5 >= I) { o[4] = ptx::madc_lo_cc(v[5], ai, o[6]); o[5] = ptx::madc_hi_cc(v[5], ai, o[7]); }
+  else { o[4] = ptx::addc_cc(o[6], 0u); o[5] = ptx::addc_cc(o[7], 0u); }
+  o[6] = ptx::madc_lo_cc(v[7], ai, o[8]);
+  o[7] = ptx::madc_hi(v[7], ai, 0u);
+  // E += even positions of V_i * a_i (first present pair opens the chain)
+  constexpr int kFirstEven = (I + 1) / 2 * 2;  // smallest even k >= I
+  if constexpr (kFirstEven <= 6) {
+    if constexpr (0 >= I) {
+      e[0] = ptx::mad_lo_cc(v[0], ai, e[0]);
+      e[1] = ptx::madc_hi_cc(v[0], ai, e[1]);
+    }
+    if constexpr (2 >= I) {
+      e[2] = (kFirstEven == 2) ? ptx::mad_lo_cc(v[2], ai, e[2]) : ptx::madc_lo_cc(v[2], ai, e[2]);
+      e[3] = ptx::madc_hi_cc(v[2], ai, e[3]);
+    }
+    if constexpr (4 >= I) {
+      e[4] = (kFirstEven == 4) ? ptx::mad_lo_cc(v[4], ai, e[4]) : ptx::madc_lo_cc(v[4], ai, e[4]);
+      e[5] = ptx::madc_hi_cc(v[4], ai, e[5]);
+    }
+    e[6] = (kFirstEven == 6) ? ptx::mad_lo_cc(v[6], ai, e[6]) : ptx::madc_lo_cc(v[6], ai, e[6]);
+    e[7] = ptx::madc_hi_cc(v[6], ai, e[7]);
+    e[8] = ptx::addc(0u, 0u);
+  } else {
+    e[8] = 0u;
+  }
+  mont_row_reduce<P>(e, o);
+}
+
+// canonical a^2 (Montgomery); a canonical
 template <class P>
 ZOLT_HD Fp<P> fp_sqr(const Fp<P>& a) {
-  return fp_mul<P>(a, a);
+  // D = 2a (a < 2^254: no overflow)
+  uint32_t d[8];
+  d[0] = a.v[0] << 1;
+#pragma unroll
+  for (int k = 1; k < 8; k++) d[k] = (a.v[k] << 1) | (a.v[k - 1] >> 31);
+  uint32_t x[9], y[9], v[8];
+  // row 0: V_0 = (a_0, D[1] & ~1, D[2..7])
+  v[0] = a.v[0];
+  v[1] = d[1] & ~1u;
+#pragma unroll
+  for (int k = 2; k < 8; k++) v[k] = d[k];
+  mont_row_first<P>(x, y, v, a.v[0]);
+  // rows 1..7: V_i differs from V_(i-1) at positions i and i+1 only; positions below i are never read
+#define ZOLT_SQR_ROW(E, O, I)                         \
+  v[I] = a.v[I];                                      \
+  if (I + 1 < 8) v[(I + 1) & 7] = d[(I + 1) & 7] & ~1u; \
+  sqr_row_next<P, I>(E, O, v, a.v[I]);
+  ZOLT_SQR_ROW(y, x, 1)
+  ZOLT_SQR_ROW(x, y, 2)
+  ZOLT_SQR_ROW(y, x, 3)
+  ZOLT_SQR_ROW(x, y, 4)
+  ZOLT_SQR_ROW(y, x, 5)
+  ZOLT_SQR_ROW(x, y, 6)
+  ZOLT_SQR_ROW(y, x, 7)
+#undef ZOLT_SQR_ROW
+  Fp<P> r;
+  r.v[0] = ptx::add_cc(x[0], y[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(x[i], y[i + 1]);
+  r.v[7] = ptx::addc(x[7], y[8]);
+  fp_reduce_once<P>(r.v);
+  return r;
 }
 
 // Montgomery -> standard integer limbs (reference fromMontgomery, src/field/mod.zig:642-645)
