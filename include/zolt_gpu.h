@@ -266,6 +266,8 @@ int zolt_sc_free(zolt_sc* sc);
  *                          the device by one kernel; every rank returns the same affine result. */
 int zolt_peer_box_create(zolt_ctx* ctx, zolt_peer_box** out, unsigned char handle_out[64]);
 int zolt_peer_box_connect(zolt_peer_box* box, const unsigned char* handles /* world*64 */, int rank, int world);
+/* ranks that live in one process (one context each): address the mailboxes directly instead of through IPC handles */
+int zolt_peer_box_connect_local(zolt_peer_box* box, zolt_peer_box* const* boxes /* world, rank-ordered */, int rank, int world);
 int zolt_peer_box_free(zolt_peer_box* box);
 int zolt_peer_allgather(zolt_peer_box* box, const void* d_src, int n_fr, void* d_out, int transpose);
 /* stream-ordered barrier across the ranks (an empty exchange); asynchronous */

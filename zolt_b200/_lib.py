@@ -83,6 +83,7 @@ SIGNATURES = {
     "zolt_sc_gather_tail": [_vp, C.POINTER(_vp), C.POINTER(_sz)],
     "zolt_peer_box_create": [_vp, C.POINTER(_vp), _vp],
     "zolt_peer_box_connect": [_vp, _vp, _i, _i],
+    "zolt_peer_box_connect_local": [_vp, C.POINTER(_vp), _i, _i],
     "zolt_peer_box_free": [_vp],
     "zolt_peer_allgather": [_vp, _vp, _i, _vp, _i],
     "zolt_peer_barrier": [_vp],

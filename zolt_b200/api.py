@@ -276,6 +276,24 @@ class PeerBox:
         allh = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(blobs))
         check(ctx.lib.zolt_peer_box_connect(self.handle, C.cast(allh, C.c_void_p), rank, world), "zolt_peer_box_connect")
 
+    @classmethod
+    def local_group(cls, ctxs):
+        """Mailboxes of several contexts of THIS process (one per rank), connected without IPC."""
+        world = len(ctxs)
+        boxes = []
+        for rank, ctx in enumerate(ctxs):
+            b = cls.__new__(cls)
+            b.ctx, b.rank, b.world = ctx, rank, world
+            h = C.c_void_p()
+            handle = (C.c_ubyte * 64)()
+            check(ctx.lib.zolt_peer_box_create(ctx.handle, C.byref(h), C.cast(handle, C.c_void_p)), "zolt_peer_box_create")
+            b.handle = h
+            boxes.append(b)
+        arr = (C.c_void_p * world)(*[b.handle for b in boxes])
+        for b in boxes:
+            check(b.ctx.lib.zolt_peer_box_connect_local(b.handle, arr, b.rank, world), "zolt_peer_box_connect_local")
+        return boxes
+
     def allgather(self, d_src: int, n_fr: int, d_out: int, transpose: bool = False):
         check(self.ctx.lib.zolt_peer_allgather(self.handle, C.c_void_p(d_src), n_fr, C.c_void_p(d_out), int(transpose)), "zolt_peer_allgather")
 

@@ -150,6 +150,28 @@ extern "C" int zolt_peer_box_connect(zolt_peer_box* box, const unsigned char* ha
   return ZOLT_OK;
 }
 
+// Ranks that live in ONE process (several contexts, e.g. a multi-GPU host thread pool or the single-GPU test of the
+// protocol): the mailboxes are addressed directly, no IPC handles.  Different devices need peer access.
+extern "C" int zolt_peer_box_connect_local(zolt_peer_box* box, zolt_peer_box* const* boxes, int rank, int world) {
+  if (!box || !boxes || world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || box->connected || boxes[rank] != box)
+    return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(box->ctx->device));
+  for (int g = 0; g < world; g++) {
+    if (!boxes[g] || !boxes[g]->d_local) return ZOLT_ERR_ARG;
+    if (boxes[g]->ctx->device != box->ctx->device) {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(boxes[g]->ctx->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ZOLT_CUDA_TRY(e);
+      (void)cudaGetLastError();
+    }
+    box->mapped[g] = boxes[g]->d_local;
+  }
+  box->rank = rank;
+  box->world = world;
+  box->seq = 0;
+  box->connected = true;
+  return ZOLT_OK;
+}
+
 extern "C" int zolt_peer_box_free(zolt_peer_box* box) {
   if (!box) return ZOLT_ERR_ARG;
   cudaSetDevice(box->ctx->device);
