@@ -184,6 +184,19 @@ ZOLT_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// a + b WITHOUT the final conditional subtraction: a value in [0, 2p) < 2^255 for canonical a, b.  Only for operands of
+// a product whose other factor keeps the result in range: mont_mul_raw accepts a < 2^255 with a * b < p * 2^256, the wide
+// accumulators accept factors below 4p (see their invariants below).
+template <class P>
+ZOLT_HD Fp<P> fp_add_lazy(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+  r.v[7] = ptx::addc(a.v[7], b.v[7]);
+  return r;
+}
+
 // canonical a - b  (reference sub, src/field/mod.zig:801-816)
 template <class P>
 ZOLT_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {

@@ -56,6 +56,8 @@ __device__ __forceinline__ void st_fr(Fr* p, const Fr& x) {
 
 __device__ __forceinline__ Fr fr_add(const Fr& a, const Fr& b) { return fp_add<FrParams>(a, b); }
 __device__ __forceinline__ Fr fr_sub(const Fr& a, const Fr& b) { return fp_sub<FrParams>(a, b); }
+// extrapolation to X = 2 (hi + (hi - lo)) feeding a product: stays below 2p, the product's reduction absorbs it
+__device__ __forceinline__ Fr fr_add_lazy(const Fr& a, const Fr& b) { return fp_add_lazy<FrParams>(a, b); }
 __device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) { return fp_mul<FrParams>(a, b); }
 
 // lo + r*(hi - lo): DensePolynomial.bindLow's form (src/poly/mod.zig:171); equal, as a canonical
@@ -159,7 +161,7 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
         const Fr s = fr_add(ml, m1);
         m2 = fr_sub(fr_add(s, s), m0);
       } else {
-        m2 = fr_mul(fr_add(x1, dx), fr_add(y1, dy));
+        m2 = fr_mul(fr_add_lazy(x1, dx), fr_add_lazy(y1, dy));  // (< 2p) * (< 2p) < p * 2^256
       }
     }
     Fr z0, z1;
@@ -174,7 +176,7 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
     if constexpr (P1) wide_acc(wacc[3], m1, z1);
     const Fr dz = fr_sub(z1, z0);
     wide_acc(wacc[2], ml, dz);
-    wide_acc(wacc[1], m2, fr_add(z1, dz));
+    wide_acc(wacc[1], m2, fr_add_lazy(z1, dz));
   } else if constexpr (COMB == ZOLT_SC_EQ_AB_MINUS_C) {
     // e(X) * (a(X) b(X) - c(X)): the leading coefficient has no c term
     Fr t0, t2, ml, t1;
@@ -189,7 +191,7 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
         const Fr s = fr_add(ml, t1);
         t2 = fr_sub(fr_add(s, s), t0);
       } else {
-        t2 = fr_mul(fr_add(a1, da), fr_add(b1, db));
+        t2 = fr_mul(fr_add_lazy(a1, da), fr_add_lazy(b1, db));  // (< 2p) * (< 2p) < p * 2^256
       }
     }
     {
@@ -203,7 +205,7 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
     if constexpr (P1) wide_acc(wacc[3], e1, t1);
     const Fr de = fr_sub(e1, e0);
     wide_acc(wacc[2], de, ml);
-    wide_acc(wacc[1], fr_add(e1, de), t2);
+    wide_acc(wacc[1], fr_add_lazy(e1, de), t2);
   } else if constexpr (COMB == ZOLT_SC_GRUEN_AB || COMB == ZOLT_SC_GRUEN_AB_MINUS_C) {
     const Fr l0 = LO(0), r0 = LO(1), l1 = HI(0), r1 = HI(1);
     Fr p0 = fr_mul(l0, r0);
