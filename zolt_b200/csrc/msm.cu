@@ -48,7 +48,7 @@ constexpr uint32_t kInvalidKey = 0xffffffffu;
 constexpr int kSlice0 = 128;     // level-0 slice length (mixed additions per thread)
 constexpr int kSlice0Big = 256;  // ... for lists of 2^26 entries and more: half the edge entries, still >= 14 waves of blocks
 constexpr int kSliceE = 8;    // edge-level slice length (full additions per thread)
-constexpr int kChunk = 32;    // buckets per thread in the running-sum reduction
+constexpr int kChunk = 16;    // buckets per thread in the running-sum reduction
 
 struct MsmGeom {
   int c;         // window bits
