@@ -277,7 +277,7 @@ msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, M
 // ---- 4. accumulate, level 0 ---------------------------------------------------------------------------
 // Thread t folds sorted[t*S, (t+1)*S).  Keys are implicit: entry p belongs to the bucket k with
 // offsets[k] <= p < offsets[k+1].
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 msm_accum_points_kernel(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets, uint32_t num_keys,
                         const AffineG1* __restrict__ bases, XYZZ* __restrict__ buckets,
                         uint32_t* __restrict__ edge_keys, XYZZ* __restrict__ edge_pts, size_t num_slices, uint32_t slice_len) {
