@@ -162,3 +162,40 @@ def test_two_products_one_reduction(host_shim, field, mod):
     rinv = pow(1 << 256, -1, mod)
     want = [(a * b - c * d) * rinv % mod for a, b, c, d in zip(*vals)]
     assert B.raw_array_to_ints(out) == want
+
+
+# ---- property tests (hypothesis): limb-pattern-biased operands for the arithmetic added in r1 -----------------------
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+
+def _limb_biased(mod):
+    """Field elements whose 32-bit limbs are drawn from {0, 1, 2^31, 2^32-1, random}: carries and all-ones runs."""
+    limb = st.one_of(st.sampled_from([0, 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF, 0xFFFFFFFE]), st.integers(0, 0xFFFFFFFF))
+    return st.lists(limb, min_size=8, max_size=8).map(lambda ls: sum(v << (32 * i) for i, v in enumerate(ls)) % mod)
+
+
+@settings(max_examples=300, deadline=None)
+@given(data=st.data())
+def test_property_sqr_mul2_bind(host_shim, data):
+    field = data.draw(st.sampled_from([0, 1]))
+    mod = B.FR_MOD if field == 0 else B.FQ_MOD
+    a, b, c, d = (data.draw(_limb_biased(mod)) for _ in range(4))
+    rinv = pow(1 << 256, -1, mod)
+    arr = lambda v: B.ints_to_raw_array([v])  # noqa: E731
+    out = np.zeros((1, 4), dtype=np.uint64)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    A, Bv, Cv, D = arr(a), arr(b), arr(c), arr(d)
+    # squaring
+    host_shim.shim_field_op(field, 8, p(A), p(A), p(out), C.c_size_t(1))
+    assert B.raw_array_to_ints(out) == [a * a * rinv % mod]
+    # two products, one reduction
+    host_shim.shim_mul2_sub(field, p(A), p(Bv), p(Cv), p(D), C.c_size_t(1), p(out))
+    assert B.raw_array_to_ints(out) == [(a * b - c * d) * rinv % mod]
+    # bind through the multiplier table: lo + r (hi - lo), r in Montgomery form
+    host_shim.shim_bind_fixed(field, p(A), p(Bv), p(Cv), C.c_size_t(1), p(out))
+    assert B.raw_array_to_ints(out) == [(b + a * rinv % mod * (c - b)) % mod]
+    # binary-GCD inverse
+    host_shim.shim_field_op(field, 7, p(A), p(A), p(out), C.c_size_t(1))
+    R = (1 << 256) % mod
+    assert B.raw_array_to_ints(out) == [0 if a == 0 else pow(a * rinv % mod, -1, mod) * R % mod]
