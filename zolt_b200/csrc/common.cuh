@@ -56,6 +56,9 @@ struct zolt_ctx {
   unsigned long long launches = 0;
   // tuning (zolt_gpu_set_tuning)
   long long sc_small_pairs = 1 << 14;
+  // second stream + events for the host-scalar MSM: the second half of the scalars crosses PCIe during the first half's MSM
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_gate = nullptr, ev_copied = nullptr;
   unsigned mail_seq = 0;  // last sequence number handed to a kernel that reports through a mapped host mailbox
   // phase profiling (CUDA events on `stream`): begin/end pairs tagged by the caller
   static constexpr int kMaxProf = 96;

@@ -60,6 +60,9 @@ extern "C" int zolt_gpu_shutdown(zolt_ctx* ctx) {
   pool_destroy(ctx);
   for (int i = 0; i < 2 * zolt_ctx::kMaxProf; i++)
     if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_gate) cudaEventDestroy(ctx->ev_gate);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ZOLT_OK;

@@ -964,8 +964,38 @@ extern "C" int zolt_msm(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, c
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   Fr* d_s = nullptr;
   ZOLT_TRY(staging_for(ctx, n * sizeof(Fr), &d_s));
-  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  return zolt_msm_dev(ctx, bases, offset, d_s, n, out_xy, out_inf);
+  if (n < (size_t(1) << 22)) {
+    ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    return zolt_msm_dev(ctx, bases, offset, d_s, n, out_xy, out_inf);
+  }
+  // Large inputs: the scalars take ~10 ms per 2^24 over PCIe.  Split the points in two ranges (ParallelMSM's split,
+  // src/msm/mod.zig:608-653, used here for overlap): the second half is copied on a second stream while the first half
+  // is multiplied, then the two partial sums are added.  Same group element, same canonical affine result.
+  if (!ctx->copy_stream) {
+    ZOLT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ZOLT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_gate, cudaEventDisableTiming));
+    ZOLT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+  }
+  const size_t n0 = (n + 1) / 2, n1 = n - n0;
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(XYZZ), (void**)&d_res));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n0 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  ZOLT_CUDA_TRY(cudaEventRecord(ctx->ev_gate, ctx->stream));  // the second copy queues behind the first on the bus
+  int s = msm_core(ctx, bases, offset, d_s, 1, n0, d_res);
+  if (s == ZOLT_OK) {
+    ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gate, 0));
+    ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s + n0, scalars + 4 * n0, n1 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+    ZOLT_CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+    s = msm_core(ctx, bases, offset + n0, d_s + n0, 1, n1, d_res + 1);
+  }
+  if (s == ZOLT_OK) {
+    g1_sum_partials_kernel<<<1, 1, 0, ctx->stream>>>(d_res, 2, d_res + 2);
+    ctx->launches++;
+    s = finish_affine(ctx, d_res + 2, 1, out_xy, out_inf);
+  }
+  pool_release(ctx, d_res, 4 * sizeof(XYZZ));
+  return s;
 }
 
 extern "C" int zolt_msm_batch(zolt_ctx* ctx, const zolt_bases* bases, const uint64_t* scalars, size_t k, size_t n,
