@@ -238,39 +238,34 @@ scan_apply_kernel(const uint32_t* in, size_t n, const uint32_t* tile_offsets, ui
 // Each thread keeps kScatterE independent (load, atomic, store) chains in flight: the kernel is bound by the
 // round trip of the returning atomic, not by bandwidth (ncu r1 v9: long-scoreboard stalls, DRAM at 10 %).
 constexpr int kScatterE = 4;
+// grid.y = digit row (batch * windows + w): row, batch and w are per-block constants, no 64-bit division per entry
 __global__ void __launch_bounds__(256)
 msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, MsmGeom g, int pre, size_t pre_n,
                    size_t pre_offset, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-  const size_t total = n * rows;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t0 < total; t0 += stride * kScatterE) {
-    uint32_t d[kScatterE], val[kScatterE], pos[kScatterE];
-    size_t key[kScatterE];
-#pragma unroll
-    for (int j = 0; j < kScatterE; j++) {
-      const size_t t = t0 + (size_t)j * stride;
-      d[j] = t < total ? __ldcs(digits + t) : 0u;
+  for (size_t row = blockIdx.y; row < rows; row += gridDim.y) {
+    size_t krow = row, pbase = 0;
+    if (pre) {
+      const size_t batch = row / g.windows, w = row - batch * g.windows;
+      krow = batch;
+      pbase = w * pre_n + pre_offset;  // index of point 0 in the level table of window w
     }
+    const uint32_t* __restrict__ drow = digits + row * n;
+    uint32_t* __restrict__ crow = cursor + krow * g.B;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n; i0 += stride * kScatterE) {
+      uint32_t d[kScatterE], pos[kScatterE];
 #pragma unroll
-    for (int j = 0; j < kScatterE; j++) {
-      if (!d[j]) continue;
-      const size_t t = t0 + (size_t)j * stride;
-      const size_t row = t / n, i = t - row * n;  // row = batch * windows + w
-      size_t krow = row, pidx = i;
-      if (pre) {
-        const size_t batch = row / g.windows, w = row - batch * g.windows;
-        krow = batch;
-        pidx = w * pre_n + pre_offset + i;  // index into the level table
+      for (int j = 0; j < kScatterE; j++) {
+        const size_t i = i0 + (size_t)j * stride;
+        d[j] = i < n ? __ldcs(drow + i) : 0u;
       }
-      key[j] = krow * g.B + ((d[j] & 0x7fffffffu) - 1);
-      val[j] = (uint32_t)pidx | (d[j] & 0x80000000u);
+#pragma unroll
+      for (int j = 0; j < kScatterE; j++)
+        if (d[j]) pos[j] = atomicAdd(&crow[(d[j] & 0x7fffffffu) - 1], 1u);  // cursor starts as a copy of the bucket offsets
+#pragma unroll
+      for (int j = 0; j < kScatterE; j++)
+        if (d[j]) sorted[pos[j]] = (uint32_t)(pbase + i0 + (size_t)j * stride) | (d[j] & 0x80000000u);
     }
-#pragma unroll
-    for (int j = 0; j < kScatterE; j++)
-      if (d[j]) pos[j] = atomicAdd(&cursor[key[j]], 1u);  // cursor starts as a copy of the bucket offsets
-#pragma unroll
-    for (int j = 0; j < kScatterE; j++)
-      if (d[j]) sorted[pos[j]] = val[j];
   }
 }
 
@@ -717,10 +712,16 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
     // counts is reused as the scatter cursor, pre-loaded with the offsets: one random access per entry
     MSM_CHECK(cudaMemcpyAsync(counts, offsets, num_keys * 4, cudaMemcpyDeviceToDevice, st));
     {
-      size_t blocks = (max_entries + 255) / 256;
-      if (blocks > (size_t)sm * 16) blocks = (size_t)sm * 16;
       ps = prof_begin(ctx, PROF_MSM_SCATTER);
-      msm_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(digits, n, rows, g, pre ? 1 : 0, bases->n, offset, counts, sorted);
+      {
+        // 2-D grid: y walks the digit rows, x the points of a row; about 16 blocks per SM in total
+        const unsigned gy = (unsigned)(rows < 1024 ? rows : 1024);
+        size_t gx = ((size_t)sm * 16 + gy - 1) / gy;
+        const size_t gx_max = (n + 255) / 256;
+        if (gx > gx_max) gx = gx_max;
+        if (gx == 0) gx = 1;
+        msm_scatter_kernel<<<dim3((unsigned)gx, gy), 256, 0, st>>>(digits, n, rows, g, pre ? 1 : 0, bases->n, offset, counts, sorted);
+      }
       prof_end(ctx, ps);
       ctx->launches++;
     }
