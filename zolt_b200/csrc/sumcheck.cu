@@ -121,7 +121,6 @@ __device__ __forceinline__ void scr_prefetch(uint4* base, int unit, const Fr* g)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(g) : "memory");
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(reinterpret_cast<const char*>(g) + 16) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -262,13 +261,6 @@ __device__ __forceinline__ void collapse(uint32_t (*wacc)[16], const Fr* facc, F
 
 // ---- raw sums -> the evaluations at X = 0..3 -------------------------------------------------------
 enum { CLAIM_NONE = 0 /* p(1) was summed directly */, CLAIM_PREV = 1 /* claim = p_prev(r) */, CLAIM_HOST = 2 /* *d_claim */ };
-
-__device__ __forceinline__ Fr fr_const(uint32_t (*f)(int)) {
-  Fr x;
-#pragma unroll
-  for (int i = 0; i < 8; i++) x.v[i] = f(i);
-  return x;
-}
 
 // p(r) for the cubic through (0,p0) (1,p1) (2,p2) (3,p3): Newton forward differences
 __device__ __noinline__ Fr newton_eval4(const Fr* p, const Fr& r) {
@@ -661,7 +653,6 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
 constexpr int kSmallWorkWarps = 4;                            // warp e evaluates raw sum e
 constexpr int kSmallThreads = 32 * (kSmallWorkWarps + 1);     // + one warp for the claim p_prev(r)
 constexpr int kSmallPairs = 16;                               // pairs of the current table per chunk
-constexpr size_t kSmallMaxPairs = size_t(1) << 14;
 
 struct SmallArgs {
   int comb, k, n_extra, deg, fused, p1_direct;
