@@ -338,8 +338,7 @@ def run_b200(args):
         if world == 1:
             return Z.MSM.compute(bases, h_scalars)
         if box is not None:
-            d_scalars.upload(h_scalars)
-            return Z.MSM.compute_sharded_dev(bases, d_scalars.ptr, n_local, box)
+            return Z.MSM.compute_sharded(bases, h_scalars, box)
         with torch.cuda.stream(stream):
             d_scalars.upload(h_scalars)
             Z.MSM.partial_dev(bases, d_scalars.ptr, n_local, part.data_ptr())

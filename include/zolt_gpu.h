@@ -274,6 +274,9 @@ int zolt_peer_allgather(zolt_peer_box* box, const void* d_src, int n_fr, void* d
 int zolt_peer_barrier(zolt_peer_box* box);
 int zolt_msm_sharded_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const void* d_scalars, size_t n,
                          zolt_peer_box* box, uint64_t out_xy[8], uint8_t* out_inf);
+/* the same from HOST scalars (this rank's range); the upload overlaps the multiplication as in zolt_msm */
+int zolt_msm_sharded(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars /* n*4, host */, size_t n,
+                     zolt_peer_box* box, uint64_t out_xy[8], uint8_t* out_inf);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------
  * Integer-pipe micro-benchmarks (the MSM roofline denominator).  `kind`: 0 = IMAD (3-reg),

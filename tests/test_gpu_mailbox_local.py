@@ -98,10 +98,14 @@ def test_sharded_msm_and_primitives_two_ranks_one_gpu(ranks):
         d_s = Z.DeviceBuffer.from_host(ctx, fr_arr(scalars[lo:hi]))
         src = Z.DeviceBuffer.from_host(ctx, np.arange(rank * 16, rank * 16 + 16, dtype=np.uint64).reshape(4, 4))
         out = Z.DeviceBuffer(ctx, 16 * WORLD * 8)
+        sc_host = fr_arr(scalars[lo:hi])
         Z.MSM.compute_dev(bases, d_s.ptr, hi - lo)  # warm-up: MSM workspace and pool buffers exist before anybody spins
+        Z.MSM.compute(bases, sc_host)               # ... and the staging buffer of the host-scalar path
         ctx.sync()
         barrier.wait()
         xy, inf = Z.MSM.compute_sharded_dev(bases, d_s.ptr, hi - lo, boxes[rank])
+        xy_h, inf_h = Z.MSM.compute_sharded(bases, sc_host, boxes[rank])  # host scalars, same exchange
+        assert (xy_h == xy).all() and inf_h == inf
         # all-gather primitive (both layouts) and the stream-ordered barrier
         boxes[rank].allgather(src.ptr, 4, out.ptr, False)
         flat = out.download((16 * WORLD,)).tolist()

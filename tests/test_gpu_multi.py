@@ -60,6 +60,8 @@ from zolt_b200 import host as H
 box = ZD.connect_peer_box(ctx, rank, world)
 xy2, inf2 = Z.MSM.compute_sharded_dev(bases, d_s.ptr, (1 << 13) // world, box)
 assert (xy2 == xy).all() and inf2 == inf, "mailbox-sharded MSM differs"
+xy3, inf3 = Z.MSM.compute_sharded(bases, fr_arr(scalars[(1 << 13) // world * rank:(1 << 13) // world * (rank + 1)]), box)
+assert (xy3 == xy).all() and inf3 == inf, "mailbox-sharded MSM from host scalars differs"
 e2, c2, f2 = H.sumcheck_prove_sharded(ctx, box, Z.SC_EQ_AB_MINUS_C, [b.ptr for b in d_tabs], log_n - ZD.log2_exact(world))
 assert (c2 == r_chal).all() and (e2 == r_evals).all(), "mailbox-sharded sumcheck: round polynomials differ"
 assert all((f2[t] == r_final[t][0]).all() for t in range(k)), "mailbox-sharded sumcheck: final values differ"

@@ -88,6 +88,7 @@ SIGNATURES = {
     "zolt_peer_allgather": [_vp, _vp, _i, _vp, _i],
     "zolt_peer_barrier": [_vp],
     "zolt_msm_sharded_dev": [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp],
+    "zolt_msm_sharded": [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp],
     "zolt_sc_round_partials_dev": [_vp, C.POINTER(_vp)],
     "zolt_sc_finish_partials": [_vp, _vp, _sz, _vp],
     "zolt_fr_sum_rows": [_vp, _vp, _sz, _sz, _vp],

@@ -247,6 +247,17 @@ class MSM:
         return out, int(inf.value)
 
     @staticmethod
+    def compute_sharded(bases: Bases, scalars, box: "PeerBox", offset: int = 0):
+        """compute_sharded_dev from HOST scalars of this rank's range (upload overlapped with the multiplication)."""
+        s = _as_u64(scalars, 4)
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_uint8()
+        ctx = bases.ctx
+        check(ctx.lib.zolt_msm_sharded(ctx.handle, bases.handle, offset, _ptr(s), s.shape[0], box.handle, _ptr(out), C.byref(inf)),
+              "zolt_msm_sharded")
+        return out, int(inf.value)
+
+    @staticmethod
     def sum_partials(ctx: Context, d_partials: int, count: int):
         out = np.zeros(8, dtype=np.uint64)
         inf = C.c_uint8()

@@ -959,41 +959,63 @@ extern "C" int zolt_msm_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offse
   return s;
 }
 
-extern "C" int zolt_msm(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n,
-                        uint64_t out_xy[8], uint8_t* out_inf) {
-  if (!ctx || !bases || !out_xy || !out_inf || (n && !scalars) || offset + n > bases->n) return ZOLT_ERR_ARG;
-  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+// sum_i scalars[i] * bases[offset + i] for HOST scalars, left on the device as one XYZZ point (d_out[0]; d_out needs room
+// for 3 points).  Large inputs: the scalars take ~10 ms per 2^24 over PCIe, so the points are split in two ranges
+// (ParallelMSM's split, src/msm/mod.zig:608-653, used here for overlap): the second half is copied on a second stream while
+// the first half is multiplied, then the two partial sums are added.  Same group element either way.
+static int msm_host_partial(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n, XYZZ* d_out) {
   Fr* d_s = nullptr;
   ZOLT_TRY(staging_for(ctx, n * sizeof(Fr), &d_s));
   if (n < (size_t(1) << 22)) {
     ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    return zolt_msm_dev(ctx, bases, offset, d_s, n, out_xy, out_inf);
+    return msm_core(ctx, bases, offset, d_s, 1, n, d_out);
   }
-  // Large inputs: the scalars take ~10 ms per 2^24 over PCIe.  Split the points in two ranges (ParallelMSM's split,
-  // src/msm/mod.zig:608-653, used here for overlap): the second half is copied on a second stream while the first half
-  // is multiplied, then the two partial sums are added.  Same group element, same canonical affine result.
   if (!ctx->copy_stream) {
     ZOLT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     ZOLT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_gate, cudaEventDisableTiming));
     ZOLT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
   }
   const size_t n0 = (n + 1) / 2, n1 = n - n0;
-  XYZZ* d_res = nullptr;
-  ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(XYZZ), (void**)&d_res));
   ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n0 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
   ZOLT_CUDA_TRY(cudaEventRecord(ctx->ev_gate, ctx->stream));  // the second copy queues behind the first on the bus
-  int s = msm_core(ctx, bases, offset, d_s, 1, n0, d_res);
+  ZOLT_TRY(msm_core(ctx, bases, offset, d_s, 1, n0, d_out + 1));
+  ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gate, 0));
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s + n0, scalars + 4 * n0, n1 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+  ZOLT_CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+  ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+  ZOLT_TRY(msm_core(ctx, bases, offset + n0, d_s + n0, 1, n1, d_out + 2));
+  g1_sum_partials_kernel<<<1, 1, 0, ctx->stream>>>(d_out + 1, 2, d_out);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_msm(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n,
+                        uint64_t out_xy[8], uint8_t* out_inf) {
+  if (!ctx || !bases || !out_xy || !out_inf || (n && !scalars) || offset + n > bases->n) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(XYZZ), (void**)&d_res));
+  int s = msm_host_partial(ctx, bases, offset, scalars, n, d_res);
+  if (s == ZOLT_OK) s = finish_affine(ctx, d_res, 1, out_xy, out_inf);
+  pool_release(ctx, d_res, 4 * sizeof(XYZZ));
+  return s;
+}
+
+// zolt_msm_sharded_dev for HOST scalars (this rank's range): upload overlapped as in zolt_msm, then the mailbox exchange.
+extern "C" int zolt_msm_sharded(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n,
+                                zolt_peer_box* box, uint64_t out_xy[8], uint8_t* out_inf) {
+  if (!ctx || !bases || !box || !box->connected || box->ctx != ctx || !out_xy || !out_inf || (n && !scalars) || offset + n > bases->n)
+    return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(XYZZ), (void**)&d_res));
+  int s = msm_host_partial(ctx, bases, offset, scalars, n, d_res);
   if (s == ZOLT_OK) {
-    ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gate, 0));
-    ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s + n0, scalars + 4 * n0, n1 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
-    ZOLT_CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
-    ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
-    s = msm_core(ctx, bases, offset + n0, d_s + n0, 1, n1, d_res + 1);
-  }
-  if (s == ZOLT_OK) {
-    g1_sum_partials_kernel<<<1, 1, 0, ctx->stream>>>(d_res, 2, d_res + 2);
+    g1_peer_sum_kernel<<<1, 32, 0, ctx->stream>>>(d_res, peer_next(box), d_res + 3);
     ctx->launches++;
-    s = finish_affine(ctx, d_res + 2, 1, out_xy, out_inf);
+    s = finish_affine(ctx, d_res + 3, 1, out_xy, out_inf);
+    if (s == ZOLT_OK) s = peer_check(box);
   }
   pool_release(ctx, d_res, 4 * sizeof(XYZZ));
   return s;
