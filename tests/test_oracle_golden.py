@@ -217,3 +217,44 @@ def test_raf_restatement_equals_dense_product():
     assert ev == [list(e) for e in ev2]
     assert [t for t in tabs] == [b[0] for b in b2]
     assert fin == b2[-1][0][0] * b2[-1][1][0] % P
+
+
+def _load_vectors():
+    return json.loads((GOLD / "oracle_vectors.json").read_text())
+
+
+def _ints(xs):
+    return [int(x, 16) for x in xs]
+
+
+def _pt(p):
+    return None if p is None else (int(p[0], 16), int(p[1], 16))
+
+
+def test_oracle_reproduces_committed_vectors():
+    """tests/golden/oracle_vectors.json (written by make_oracle_vectors.py): the Python oracle AND the C++ restatement
+    (oracle/cpu_ref.cpp) still produce the committed outputs -- a drift in either is caught here, on the CPU tier."""
+    import numpy as np
+
+    from oracle import cpu_ref as R
+
+    v = _load_vectors()
+    logs, scalars = _ints(v["msm"]["base_logs"]), _ints(v["msm"]["scalars"])
+    bases = [B.g1_mul(B.G1_GEN, k) for k in logs]
+    assert B.msm(bases, scalars) == _pt(v["msm"]["result"]) == B.msm_closed_form(logs, scalars)
+    xy, inf = B.points_to_arrays(bases)
+    cxy, cinf = R.msm(xy, inf, B.ints_to_mont_array(scalars, P), threads=1)
+    assert B.arrays_to_points(cxy.reshape(1, 8), [cinf])[0] == _pt(v["msm"]["result"])
+    hk = v["hyperkzg"]
+    powers = B.hyperkzg_setup(8)
+    assert B.hyperkzg_commit(powers, _ints(hk["evals"])) == _pt(hk["commitment"])
+    q, fin = B.hyperkzg_open(powers, _ints(hk["evals"]), _ints(hk["point"]), 0)
+    assert q == [_pt(p) for p in hk["quotients"]] and fin == int(hk["final_eval"], 16)
+    for kind, s in v["sumcheck"].items():
+        tabs = [_ints(t) for t in s["tables"]]
+        ev, bound = OS.run_dense(kind, tabs, s["pairing"], _ints(s["challenges"]))
+        assert [list(e) for e in ev] == [_ints(e) for e in s["round_evals"]], kind
+        assert [t[0] for t in bound[-1]] == _ints(s["final_values"]), kind
+    g = v["gruen_ab"]
+    ev, _ = OS.run_gruen([_ints(t) for t in g["tables"]], _ints(g["tau"]), _ints(g["challenges"]), False)
+    assert [list(e) for e in ev] == [_ints(e) for e in g["round_sums"]]
