@@ -150,6 +150,8 @@ int zolt_eq_evals(zolt_ctx* ctx, const uint64_t* r /* n_vars*4 */, int n_vars, c
                   void* d_out);
 /* sum of all entries (initial sumcheck claim, src/subprotocols/mod.zig:306-309) */
 int zolt_poly_sum(zolt_ctx* ctx, const void* d_src, size_t n, uint64_t out[4]);
+/* BatchOps.innerProduct (src/field/mod.zig:1164-1280) over device tables: sum_i a[i] * b[i] */
+int zolt_fr_inner_product_dev(zolt_ctx* ctx, const void* d_a, const void* d_b, size_t n, uint64_t out[4]);
 /* Element-wise construction of device-resident tables (asynchronous on the context's stream):
  *   ZOLT_VEC_MUL            out = a o b
  *   ZOLT_VEC_EQ_AB_MINUS_C  out = e * (a * b - c)   JoltSpartanInterface's combined table (jolt_r1cs.zig:352-360)

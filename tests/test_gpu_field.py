@@ -69,3 +69,16 @@ def test_reference_small_integer_identities(ctx):
     assert B.mont_array_to_ints(ctx.field_op(Z.FIELD_FR, Z.OP_MUL, three, seven), B.FR_MOD) == [21]
     four = ctx.field_op(Z.FIELD_FR, Z.OP_MUL, two, two)
     assert B.mont_array_to_ints(ctx.field_op(Z.FIELD_FR, Z.OP_MUL, four, two), B.FR_MOD) == [8]
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 70001])
+def test_inner_product_dev(ctx, n):
+    """BatchOps.innerProduct (src/field/mod.zig:1164-1280) over device-resident vectors."""
+    from tests.util import fr_arr, fr_ints, rand_fr
+
+    a, b = rand_fr(9100 + n, n), rand_fr(9200 + n, n)
+    a[0], b[0] = B.FR_MOD - 1, B.FR_MOD - 1
+    da, db = Z.DeviceBuffer.from_host(ctx, fr_arr(a)), Z.DeviceBuffer.from_host(ctx, fr_arr(b))
+    assert fr_ints(ctx.fr_inner_product_dev(da.ptr, db.ptr, n)) == [sum(x * y for x, y in zip(a, b)) % B.FR_MOD]
+    da.free()
+    db.free()

@@ -59,6 +59,7 @@ SIGNATURES = {
     "zolt_msm_batch": [_vp, _vp, _vp, _sz, _sz, _vp, _vp],
     "zolt_hyperkzg_open": [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, C.POINTER(_i), _vp],
     "zolt_hyperkzg_open_dev": [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, C.POINTER(_i), _vp],
+    "zolt_fr_inner_product_dev": [_vp, _vp, _vp, _sz, _vp],
     "zolt_fr_vec_dev": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
     "zolt_msm_partial_dev": [_vp, _vp, _sz, _vp, _sz, _vp],
     "zolt_g1_sum_partials": [_vp, _vp, _sz, _vp, _vp],

@@ -115,6 +115,11 @@ class Context:
         check(self.lib.zolt_fr_vec_dev(self.handle, op, C.c_void_p(d_out), C.c_void_p(d_a or None), C.c_void_p(d_b or None), C.c_void_p(d_c or None),
                                        C.c_void_p(d_e or None), _ptr(sv), n), "zolt_fr_vec_dev")
 
+    def fr_inner_product_dev(self, d_a: int, d_b: int, n: int) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        check(self.lib.zolt_fr_inner_product_dev(self.handle, C.c_void_p(d_a), C.c_void_p(d_b), n, _ptr(out)), "zolt_fr_inner_product_dev")
+        return out
+
     def fr_sum_rows(self, d_rows: int, rows: int, cols: int) -> np.ndarray:
         out = np.empty((cols, 4), dtype=np.uint64)
         check(self.lib.zolt_fr_sum_rows(self.handle, C.c_void_p(d_rows), rows, cols, _ptr(out)), "zolt_fr_sum_rows")

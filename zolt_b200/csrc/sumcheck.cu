@@ -807,6 +807,19 @@ __global__ void __launch_bounds__(kScThreads) sum_kernel(const Fr* src, size_t n
   grid_finish<1>(acc, smem, out, Fr::zero());
 }
 
+// BatchOps.innerProduct (src/field/mod.zig:1164-1280): sum_i a[i] * b[i], unreduced 512-bit accumulation per thread
+__global__ void __launch_bounds__(kScThreads) inner_product_kernel(const Fr* a, const Fr* b, size_t n, ScOut out) {
+  __shared__ Fr smem[32];
+  uint32_t w[16];
+  wide_zero(w);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const Fr x = ld_fr(a + i), y = ld_fr(b + i);
+    wide_acc(w, x, y);
+  }
+  Fr acc[1] = {wide_collapse(w)};
+  grid_finish<1>(acc, smem, out, Fr::zero());
+}
+
 // rows x cols matrix of Fr -> column sums (multi-GPU fold of gathered partial evaluations)
 __global__ void sum_rows_kernel(const Fr* rows, size_t n_rows, size_t cols, Fr* d_out, Fr* h_out) {
   const size_t c = threadIdx.x;
@@ -1515,6 +1528,27 @@ extern "C" int zolt_poly_sum(zolt_ctx* ctx, const void* d_src, size_t n, uint64_
   so.h_evals = (Fr*)ctx->d_mailbox;
   so.finalize = 1;
   sum_kernel<<<grid_for(ctx, n, 4), kScThreads, 0, ctx->stream>>>((const Fr*)d_src, n, so);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->h_mailbox, 32);
+  scratch_free(ctx, &s);
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_fr_inner_product_dev(zolt_ctx* ctx, const void* d_a, const void* d_b, size_t n, uint64_t out[4]) {
+  if (!ctx || !d_a || !d_b || !out) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Scratch s;
+  ZOLT_TRY(scratch_alloc(ctx, &s));
+  ScOut so{};
+  so.partials = s.partials;
+  so.ticket = s.ticket;
+  so.d_raw = s.d_out + 8;
+  so.d_evals = s.d_out;
+  so.h_evals = (Fr*)ctx->d_mailbox;
+  so.finalize = 1;
+  inner_product_kernel<<<grid_for(ctx, n, 4), kScThreads, 0, ctx->stream>>>((const Fr*)d_a, (const Fr*)d_b, n, so);
   ctx->launches++;
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
