@@ -50,8 +50,13 @@ int zolt_gpu_launch_count(zolt_ctx* ctx, unsigned long long* out);
 const char* zolt_gpu_version(void);
 /* Tuning knobs (tests use them to force a code path; defaults are what bench.py measures).
  *   ZOLT_TUNE_SC_SMALL_PAIRS  rounds whose current table has at most this many pairs run on the
- *                             latency-oriented small-round kernel (default 2^14; 0 = always stream) */
+ *                             latency-oriented small-round kernel (default 2^14; 0 = always stream)
+ *   ZOLT_TUNE_SC_BIND_F64     bit k set: the fused adjacent-pair passes bind table k on the FP64 pipe (exact 16 x 32-bit
+ *                             limb products in doubles, csrc/field.cuh fp_bind2_fixed_f64) instead of the integer
+ *                             multiplier.  Same values; default 0 (measured on B200: the passes are bound by instruction
+ *                             issue, the idle FP64 pipe buys nothing -- kept as a parity-tested alternative) */
 #define ZOLT_TUNE_SC_SMALL_PAIRS 1
+#define ZOLT_TUNE_SC_BIND_F64 2
 int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value);
 
 /* raw device buffers, so a host without CUDA bindings can keep tables resident */

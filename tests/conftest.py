@@ -24,12 +24,20 @@ def built_lib():
     """Path of libzolt_gpu.so, building it when nvcc is available and the library is stale."""
     from zolt_b200 import build
 
+    import shutil
+
+    so = build.LIB / "libzolt_gpu.so"
+    have_nvcc = bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+    if not have_nvcc:
+        # the only tolerated case: a box without the toolkit runs the library that travelled with the snapshot
+        if not so.exists():
+            pytest.fail("libzolt_gpu.so is missing and nvcc is not installed: nothing to test (there is no CPU path)")
+        return so
     try:
         build.build_all()
-    except Exception as e:  # noqa: BLE001 - surface the reason in the skip/fail message
-        if not build.LIB.joinpath("libzolt_gpu.so").exists():
-            pytest.fail(f"libzolt_gpu.so is missing and could not be built: {e}")
-    return build.LIB / "libzolt_gpu.so"
+    except Exception as e:  # noqa: BLE001 - a broken source tree must never be tested against a stale binary
+        pytest.fail(f"libzolt_gpu.so could not be rebuilt from the current sources: {e}")
+    return so
 
 
 @pytest.fixture(scope="session")

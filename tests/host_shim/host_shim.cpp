@@ -113,6 +113,24 @@ static void bind_fixed(const uint32_t* r, const uint32_t* lo, const uint32_t* hi
     memcpy(out + 8 * i, v.v, 32);
   }
 }
+template <class P>
+static void bind_fixed_f64(const uint32_t* r, const uint32_t* lo, const uint32_t* hi, size_t n, uint32_t* out) {
+  Fp<P> rr;
+  memcpy(rr.v, r, 32);
+  const FixedMulTableF64 t = fixed_mul_table_f64<P>(rr);
+  for (size_t i = 0; i < n; i++) {
+    Fp<P> a, b;
+    memcpy(a.v, lo + 8 * i, 32);
+    memcpy(b.v, hi + 8 * i, 32);
+    const Fp<P> v = fp_bind_fixed_f64<P>(a, b, t);
+    memcpy(out + 8 * i, v.v, 32);
+  }
+}
+// the FP64-pipe form of the same bind (field.cuh fp_bind_fixed_f64)
+extern "C" void shim_bind_fixed_f64(int field, const uint32_t* r, const uint32_t* lo, const uint32_t* hi, size_t n, uint32_t* out) {
+  if (field == 0) bind_fixed_f64<FrParams>(r, lo, hi, n, out);
+  else bind_fixed_f64<FqParams>(r, lo, hi, n, out);
+}
 extern "C" void shim_bind_fixed(int field, const uint32_t* r, const uint32_t* lo, const uint32_t* hi, size_t n, uint32_t* out) {
   if (field == 0) bind_fixed<FrParams>(r, lo, hi, n, out);
   else bind_fixed<FqParams>(r, lo, hi, n, out);

@@ -138,6 +138,11 @@ def test_fixed_multiplier_bind(host_shim, field, mod):
         r_std = (r % mod) * rinv % mod
         want = [(a + r_std * (b - a)) % mod for a, b in zip(los, his)]
         assert B.raw_array_to_ints(out) == want, hex(r)
+        # the FP64-pipe form (16-bit x 32-bit limb products summed exactly in doubles, one-word Barrett): same values
+        out64 = np.zeros((n, 4), dtype=np.uint64)
+        host_shim.shim_bind_fixed_f64(field, rr.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
+                                      C.c_size_t(n), out64.ctypes.data_as(C.c_void_p))
+        assert B.raw_array_to_ints(out64) == want, ("f64", hex(r))
 
 
 @pytest.mark.parametrize("field,mod", [(0, B.FR_MOD), (1, B.FQ_MOD)])
@@ -194,6 +199,8 @@ def test_property_sqr_mul2_bind(host_shim, data):
     assert B.raw_array_to_ints(out) == [(a * b - c * d) * rinv % mod]
     # bind through the multiplier table: lo + r (hi - lo), r in Montgomery form
     host_shim.shim_bind_fixed(field, p(A), p(Bv), p(Cv), C.c_size_t(1), p(out))
+    assert B.raw_array_to_ints(out) == [(b + a * rinv % mod * (c - b)) % mod]
+    host_shim.shim_bind_fixed_f64(field, p(A), p(Bv), p(Cv), C.c_size_t(1), p(out))
     assert B.raw_array_to_ints(out) == [(b + a * rinv % mod * (c - b)) % mod]
     # binary-GCD inverse
     host_shim.shim_field_op(field, 7, p(A), p(A), p(out), C.c_size_t(1))

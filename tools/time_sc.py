@@ -1,0 +1,74 @@
+"""A/B timing of the sumcheck round kernels (device events per launch); not a benchmark of record.
+
+    python tools/time_sc.py [log_n=24] [combiner=eq_ab_minus_c] [reps=3]
+Prints per-setting kernel totals and the per-round list, and writes gpurun_out/time_sc.json.
+"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import zolt_b200 as Z  # noqa: E402
+from zolt_b200 import host as H  # noqa: E402
+
+COMB = {"sum": (Z.SC_SUM, 1), "prod2": (Z.SC_PROD2, 2), "prod3": (Z.SC_PROD3, 3), "eq_a_bmc": (Z.SC_EQ_A_BMC, 4),
+        "eq_ab_minus_c": (Z.SC_EQ_AB_MINUS_C, 4)}
+TUNE_BIND_F64 = 2
+
+
+def main():
+    log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    name = sys.argv[2] if len(sys.argv) > 2 else "eq_ab_minus_c"
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    comb, k = COMB[name]
+    ctx = Z.Context(0)
+    rng = np.random.default_rng(3)
+    n = 1 << log_n
+    bufs = []
+    for _ in range(k):
+        a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 60) - 1)
+        bufs.append(Z.DeviceBuffer.from_host(ctx, a))
+    ptrs = [b.ptr for b in bufs]
+    out = {}
+    ref = None
+    claim = None
+    if os.environ.get("SC_CLAIM"):
+        ev0, _, _ = H.sumcheck_prove_dev(ctx, comb, Z.PAIR_ADJACENT, ptrs, log_n)
+        claim = H.fr_op(1, ev0[0][0:1], ev0[0][1:2])[0]  # p(0) + p(1) of round 0 = the input claim
+    masks = [int(x, 0) for x in os.environ.get('SC_MASKS', '0,0xffff,0,0xffff').split(',')]
+    for setting in masks:
+        ctx.set_tuning(TUNE_BIND_F64, setting)
+        H.sumcheck_prove_dev(ctx, comb, Z.PAIR_ADJACENT, ptrs, log_n, claim=claim)  # warm
+        best = None
+        for _ in range(reps):
+            ctx.prof_enable(True)
+            ctx.timer_start()
+            ev, ch, fin = H.sumcheck_prove_dev(ctx, comb, Z.PAIR_ADJACENT, ptrs, log_n, claim=claim)
+            wall = ctx.timer_stop_ms()
+            log = ctx.prof_read()
+            ctx.prof_enable(False)
+            ks = [ms for tag, ms in log if tag in (16, 17)]
+            if best is None or sum(ks) < sum(best[1]):
+                best = (wall, ks)
+        if ref is None:
+            ref = (ev.copy(), fin.copy())
+        same = bool((ev == ref[0]).all() and (fin == ref[1]).all())
+        gb = 128 * k * n / 1e9
+        key = f"bind_f64={setting:#x}"
+        out.setdefault(key, []).append({"wall_ms": best[0], "kernel_ms": sum(best[1]), "GBps_kernel": gb / (sum(best[1]) * 1e-3),
+                                        "rounds_ms": [round(x, 4) for x in best[1][:8]], "same_as_first": same})
+        print(key, f"wall {best[0]:.3f} ms kernels {sum(best[1]):.3f} ms -> {gb / (sum(best[1]) * 1e-3):.0f} GB/s", [round(x, 3) for x in best[1][:6]], "same:", same, flush=True)
+    os.makedirs(ROOT / "gpurun_out", exist_ok=True)
+    (ROOT / "gpurun_out" / "time_sc.json").write_text(json.dumps(out, indent=1))
+    for b in bufs:
+        b.free()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,7 @@ struct zolt_ctx {
   unsigned long long launches = 0;
   // tuning (zolt_gpu_set_tuning)
   long long sc_small_pairs = 1 << 14;
+  int sc_bind_f64 = 0;  // mask of the tables whose binds run on the FP64 pipe in a fused sumcheck pass (ZOLT_TUNE_SC_BIND_F64; measured: no gain)
   // second stream + events for the host-scalar MSM: the second half of the scalars crosses PCIe during the first half's MSM
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_gate = nullptr, ev_copied = nullptr;

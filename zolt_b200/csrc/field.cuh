@@ -789,28 +789,9 @@ ZOLT_HD void fixed_chain(uint32_t* acc, uint32_t m0, uint32_t m1, uint32_t m2, u
   acc[8] = ptx::addc(acc[8], 0u);
 }
 
-// canonical (addend + r * d) for the table of r;  addend < p canonical, d any 256-bit representative.
+// x[0..9] (< 2^289, the value of a table product plus an addend) -> the canonical representative of x mod p.
 template <class P>
-ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) {
-  // x = addend + sum_i d_i * c[i] = E + (O << 32): E takes the even limbs of c[i], O the odd ones
-  uint32_t e[9], o[9];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    e[j] = addend.v[j];
-    o[j] = 0;
-  }
-  e[8] = o[8] = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    fixed_chain(e, t.c[i][0], t.c[i][2], t.c[i][4], t.c[i][6], d[i]);
-    fixed_chain(o, t.c[i][1], t.c[i][3], t.c[i][5], t.c[i][7], d[i]);
-  }
-  uint32_t x[10];
-  x[0] = e[0];
-  x[1] = ptx::add_cc(e[1], o[0]);
-#pragma unroll
-  for (int j = 2; j < 9; j++) x[j] = ptx::addc_cc(e[j], o[j - 1]);
-  x[9] = ptx::addc(o[8], 0u);
+ZOLT_HD Fp<P> fp_barrett_289(const uint32_t* x) {
   // Barrett: q = floor(h * mu / 2^96), h = floor(x / 2^224) = x[9] 2^64 + H, mu = floor(2^320 / p) = MU_HI 2^64 + MU_LO.
   // Both truncations together cost less than 2^-29 of a unit, so q is floor(x / p) or one less.  The low 64 bits of
   // H * MU_LO cannot change floor(. / 2^96):  q = x[9] MU_HI 2^32 + floor((x[9] MU_LO + H MU_HI + hi64(H MU_LO)) / 2^32).
@@ -868,6 +849,31 @@ ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const Fix
   return r;
 }
 
+// canonical (addend + r * d) for the table of r;  addend < p canonical, d any 256-bit representative.
+template <class P>
+ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) {
+  // x = addend + sum_i d_i * c[i] = E + (O << 32): E takes the even limbs of c[i], O the odd ones
+  uint32_t e[9], o[9];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    e[j] = addend.v[j];
+    o[j] = 0;
+  }
+  e[8] = o[8] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    fixed_chain(e, t.c[i][0], t.c[i][2], t.c[i][4], t.c[i][6], d[i]);
+    fixed_chain(o, t.c[i][1], t.c[i][3], t.c[i][5], t.c[i][7], d[i]);
+  }
+  uint32_t x[10];
+  x[0] = e[0];
+  x[1] = ptx::add_cc(e[1], o[0]);
+#pragma unroll
+  for (int j = 2; j < 9; j++) x[j] = ptx::addc_cc(e[j], o[j - 1]);
+  x[9] = ptx::addc(o[8], 0u);
+  return fp_barrett_289<P>(x);
+}
+
 // lo + r * (hi - lo)  (DensePolynomial.bindLow, src/poly/mod.zig:171) through the table of r.  The difference
 // is taken as hi + (p - lo), a non-canonical representative below 2p: the table product accepts any limbs.
 template <class P>
@@ -882,6 +888,206 @@ ZOLT_HD Fp<P> fp_bind_fixed(const Fp<P>& lo, const Fp<P>& hi, const FixedMulTabl
   for (int j = 1; j < 7; j++) d[j] = ptx::addc_cc(d[j], hi.v[j]);
   d[7] = ptx::addc(d[7], hi.v[7]);
   return fp_fixed_mul_add<P>(lo, d, t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same fixed-multiplier product on the FP64 pipe.
+//
+// On B200 the FP64 pipe (DFMA, 16 lanes / SM sub-partition / clock, the rate of a 32-bit IMAD) sits idle beside
+// the integer multiplier that bounds the sumcheck passes, and it issues in parallel with it.  The bind's product has a
+// per-launch constant on one side, so it maps onto exact double-precision arithmetic with no carry handling at all:
+//   d  = 16 limbs of 16 bits  (d_l < 2^16)
+//   C_l = (r_std * 2^(16 l)) mod p  as 8 limbs of 32 bits, converted to doubles ON THE HOST (kernel parameter, i.e.
+//         uniform-register operands of the DFMAs)
+//   col_j = sum_l d_l * C_l[j]   -- 16 terms below 2^48: every partial sum is an integer below 2^52, exact in a double
+// so  lo + sum_j col_j 2^(32 j)  is congruent to  lo + r_std * d  and below 2^277; eight (low 32, high 20) splits,
+// two carry chains and a one-word Barrett step (quotient < 2^23) bring it to the canonical value -- the same field
+// element fp_fixed_mul_add / montgomeryMul produce.  128 DFMA + 24 DADD + ~50 integer instructions instead of 64 wide
+// integer multiplies (256 multiplier-pipe cycles per warp) + 15 more in the two-word Barrett step.
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) F64Pair {
+  double x, y;
+};
+struct alignas(16) FixedMulTableF64 {
+  F64Pair c[16][4];  // row l: limbs (0,1) (2,3) (4,5) (6,7) of C_l; pairs so that one 128-bit constant load feeds two DFMAs
+};
+
+// table of r for fp_fixed_mul_add_f64: row l = limbs of r_std * 2^(16 l) mod p  (O(1) per launch; host or one thread)
+template <class P>
+ZOLT_HD FixedMulTableF64 fixed_mul_table_f64(const Fp<P>& r) {
+  FixedMulTableF64 t;
+  // r_std * 2^(16 l) = mont_mul(r, 2^(16 l) as a raw integer) for l < 16 (2^(16 l) < 2^256)
+  for (int l = 0; l < 16; l++) {
+    Fp<P> e = Fp<P>::zero();
+    e.v[l >> 1] = (l & 1) ? 0x10000u : 1u;
+    const Fp<P> cl = fp_mul<P>(r, e);
+    for (int j = 0; j < 4; j++) t.c[l][j] = F64Pair{(double)cl.v[2 * j], (double)cl.v[2 * j + 1]};
+  }
+  return t;
+}
+
+namespace f64 {
+#if defined(__CUDA_ARCH__)
+// exact u32 -> double without the conversion unit: 2^52 + x by bit pattern, minus 2^52
+ZOLT_D double from_u32(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
+// integer-valued v in [0, 2^52) -> (low 32 bits, high 20 bits)
+ZOLT_D void split52(double v, uint32_t& lo, uint32_t& hi) {
+  const double y = v + 4503599627370496.0;
+  lo = (uint32_t)__double2loint(y);
+  hi = (uint32_t)__double2hiint(y) & 0xfffffu;
+}
+ZOLT_D double fma_(double a, double b, double c) { return fma(a, b, c); }
+#else
+inline double from_u32(uint32_t x) { return (double)x; }
+inline void split52(double v, uint32_t& lo, uint32_t& hi) {
+  const unsigned long long y = (unsigned long long)v;
+  lo = (uint32_t)y;
+  hi = (uint32_t)(y >> 32);
+}
+inline double fma_(double a, double b, double c) { return __builtin_fma(a, b, c); }
+#endif
+}  // namespace f64
+
+// x[0..8] < 2^277 with floor(x / p) < 2^32 -> canonical x mod p (one-word Barrett: see fp_barrett_289 for the error bound)
+template <class P>
+ZOLT_HD Fp<P> fp_barrett_small(const uint32_t* x) {
+  const unsigned long long H = ((unsigned long long)x[8] << 32) | x[7];  // floor(x / 2^224) < 2^53
+#if defined(__CUDA_ARCH__)
+  const unsigned long long hi64 = __umul64hi(H, P::MU320_LO);
+#else
+  const unsigned long long hi64 = (unsigned long long)(((unsigned __int128)H * P::MU320_LO) >> 64);
+#endif
+  const uint32_t q = (uint32_t)((H * P::MU320_HI + hi64) >> 32);  // floor(x / p) or one less
+  // q * p mod 2^256 = TE + (TO << 32)
+  uint32_t te[8], to[7];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    te[2 * k] = ptx::mul_lo(P::mod(2 * k), q);
+    te[2 * k + 1] = ptx::mul_hi(P::mod(2 * k), q);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    to[2 * k] = ptx::mul_lo(P::mod(2 * k + 1), q);
+    to[2 * k + 1] = ptx::mul_hi(P::mod(2 * k + 1), q);
+  }
+  to[6] = ptx::mul_lo(P::mod(7), q);
+  Fp<P> r;
+  r.v[0] = ptx::sub_cc(x[0], te[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) r.v[j] = ptx::subc_cc(x[j], te[j]);
+  r.v[7] = ptx::subc(x[7], te[7]);
+  r.v[1] = ptx::sub_cc(r.v[1], to[0]);
+#pragma unroll
+  for (int j = 2; j < 7; j++) r.v[j] = ptx::subc_cc(r.v[j], to[j - 1]);
+  r.v[7] = ptx::subc(r.v[7], to[6]);
+  fp_reduce_once<P>(r.v);  // [0, 2p) -> [0, p)
+  return r;
+}
+
+// canonical (addend + r * d) through the FP64 table of r;  addend < p canonical, d any 256-bit value
+template <class P>
+ZOLT_HD Fp<P> fp_fixed_mul_add_f64(const Fp<P>& addend, const uint32_t* d, const FixedMulTableF64& t) {
+  double col[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) col[j] = 0.0;
+#pragma unroll
+  for (int l = 0; l < 16; l++) {
+    const uint32_t w = d[l >> 1];
+    const double x = f64::from_u32((l & 1) ? (w >> 16) : (w & 0xffffu));
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const F64Pair c = t.c[l][j];
+      col[2 * j] = f64::fma_(x, c.x, col[2 * j]);
+      col[2 * j + 1] = f64::fma_(x, c.y, col[2 * j + 1]);
+    }
+  }
+  uint32_t lo[8], hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) f64::split52(col[j], lo[j], hi[j]);
+  // x = addend + sum_j lo[j] 2^(32 j) + sum_j hi[j] 2^(32 (j + 1))
+  uint32_t x[9];
+  x[0] = ptx::add_cc(addend.v[0], lo[0]);
+#pragma unroll
+  for (int j = 1; j < 8; j++) x[j] = ptx::addc_cc(addend.v[j], lo[j]);
+  x[8] = ptx::addc(0u, 0u);
+  x[1] = ptx::add_cc(x[1], hi[0]);
+#pragma unroll
+  for (int j = 2; j < 8; j++) x[j] = ptx::addc_cc(x[j], hi[j - 1]);
+  x[8] = ptx::addc(x[8], hi[7]);
+  return fp_barrett_small<P>(x);
+}
+
+// lo + r * (hi - lo) through the FP64 table of r (see fp_bind_fixed)
+template <class P>
+ZOLT_HD Fp<P> fp_bind_fixed_f64(const Fp<P>& lo, const Fp<P>& hi, const FixedMulTableF64& t) {
+  uint32_t d[8];
+  d[0] = ptx::sub_cc(P::mod(0), lo.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) d[j] = ptx::subc_cc(P::mod(j), lo.v[j]);
+  d[7] = ptx::subc(P::mod(7), lo.v[7]);
+  d[0] = ptx::add_cc(d[0], hi.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) d[j] = ptx::addc_cc(d[j], hi.v[j]);
+  d[7] = ptx::addc(d[7], hi.v[7]);
+  return fp_fixed_mul_add_f64<P>(lo, d, t);
+}
+
+// Two binds against the same table, interleaved: 16 independent DFMA chains instead of 8 and every table constant
+// loaded once for two products.  (lo0, hi0) -> out0, (lo1, hi1) -> out1; same values as two fp_bind_fixed_f64 calls.
+template <class P>
+ZOLT_HD void fp_bind2_fixed_f64(const Fp<P>& lo0, const Fp<P>& hi0, const Fp<P>& lo1, const Fp<P>& hi1,
+                                const FixedMulTableF64& t, Fp<P>& out0, Fp<P>& out1) {
+  uint32_t d0[8], d1[8];
+  d0[0] = ptx::sub_cc(P::mod(0), lo0.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) d0[j] = ptx::subc_cc(P::mod(j), lo0.v[j]);
+  d0[7] = ptx::subc(P::mod(7), lo0.v[7]);
+  d0[0] = ptx::add_cc(d0[0], hi0.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) d0[j] = ptx::addc_cc(d0[j], hi0.v[j]);
+  d0[7] = ptx::addc(d0[7], hi0.v[7]);
+  d1[0] = ptx::sub_cc(P::mod(0), lo1.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) d1[j] = ptx::subc_cc(P::mod(j), lo1.v[j]);
+  d1[7] = ptx::subc(P::mod(7), lo1.v[7]);
+  d1[0] = ptx::add_cc(d1[0], hi1.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) d1[j] = ptx::addc_cc(d1[j], hi1.v[j]);
+  d1[7] = ptx::addc(d1[7], hi1.v[7]);
+  double c0[8], c1[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) c0[j] = c1[j] = 0.0;
+#pragma unroll
+  for (int l = 0; l < 16; l++) {
+    const uint32_t w0 = d0[l >> 1], w1 = d1[l >> 1];
+    const double x0 = f64::from_u32((l & 1) ? (w0 >> 16) : (w0 & 0xffffu));
+    const double x1 = f64::from_u32((l & 1) ? (w1 >> 16) : (w1 & 0xffffu));
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const F64Pair c = t.c[l][j];
+      c0[2 * j] = f64::fma_(x0, c.x, c0[2 * j]);
+      c1[2 * j] = f64::fma_(x1, c.x, c1[2 * j]);
+      c0[2 * j + 1] = f64::fma_(x0, c.y, c0[2 * j + 1]);
+      c1[2 * j + 1] = f64::fma_(x1, c.y, c1[2 * j + 1]);
+    }
+  }
+  auto finish = [](const Fp<P>& addend, const double* col) {
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) f64::split52(col[j], lo[j], hi[j]);
+    uint32_t x[9];
+    x[0] = ptx::add_cc(addend.v[0], lo[0]);
+#pragma unroll
+    for (int j = 1; j < 8; j++) x[j] = ptx::addc_cc(addend.v[j], lo[j]);
+    x[8] = ptx::addc(0u, 0u);
+    x[1] = ptx::add_cc(x[1], hi[0]);
+#pragma unroll
+    for (int j = 2; j < 8; j++) x[j] = ptx::addc_cc(x[j], hi[j - 1]);
+    x[8] = ptx::addc(x[8], hi[7]);
+    return fp_barrett_small<P>(x);
+  };
+  out0 = finish(lo0, c0);
+  out1 = finish(lo1, c1);
 }
 
 using Fr = Fp<FrParams>;

@@ -14,6 +14,10 @@
 // (Montgomery limbs), index bit j <-> variable j.  Every instance owns two buffers per table
 // (sizes N and N/2) used as a ping-pong, so a fused bind+eval pass reads the current table once
 // and writes the half-size table once: 128*k*N algorithmic bytes for a whole sumcheck.
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cudaTypedefs.h>
+
+#include <atomic>
 #include <cstring>
 #include <new>
 
@@ -103,24 +107,88 @@ constexpr int kFusedBlocksPerSm = 4;  // MODE 2: 24 scratch units (384 B) per th
 constexpr int kEvalScratchUnits = 32;
 constexpr int kFusedScratchUnits = 24;
 
+// Unit stride of the scratch, in 16-byte slots: the thread count padded so that it is 4 mod 8.  A thread's own accesses
+// (32 consecutive slots per warp) are conflict-free for any stride; the padding makes the warp-cooperative copies
+// below conflict-free too (their 32 destinations spread over (unit, thread) instead of thread alone).
+constexpr int kScrStride = kRoundThreads + 4;
+
 __device__ __forceinline__ Fr scr_ld(const uint4* base, int unit) {
-  const uint4 a = base[unit * kRoundThreads], b = base[(unit + 1) * kRoundThreads];
+  const uint4 a = base[unit * kScrStride], b = base[(unit + 1) * kScrStride];
   Fr r;
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
   r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
   return r;
 }
 __device__ __forceinline__ void scr_st(uint4* base, int unit, const Fr& x) {
-  base[unit * kRoundThreads] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-  base[(unit + 1) * kRoundThreads] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+  base[unit * kScrStride] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  base[(unit + 1) * kScrStride] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
-// one field element global -> this thread's scratch (two 16-byte asynchronous copies, L2 only)
-__device__ __forceinline__ void scr_prefetch(uint4* base, int unit, const Fr* g) {
-  const unsigned s0 = (unsigned)__cvta_generic_to_shared(base + unit * kRoundThreads);
-  const unsigned s1 = (unsigned)__cvta_generic_to_shared(base + (unit + 1) * kRoundThreads);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(g) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(reinterpret_cast<const char*>(g) + 16) : "memory");
+// ---- coalesced global -> scratch copies ----------------------------------------------------------------------------
+// A thread's source elements are 32-byte values 64 or 128 bytes apart from its neighbour's: copied by their owner, one
+// warp instruction touches 32 different 128-byte lines, 16 bytes each, and every 32-byte sector crosses L2 -> SM twice
+// (r2 v4 ablation: the loads ALONE ran at 3.4 TB/s and bounded every round, whatever the arithmetic did).  Instead the
+// warp copies its contiguous source range cooperatively: instruction j moves the 512 contiguous bytes
+// [512 j, 512 j + 512), lane L the 16-byte piece q = 32 j + L, and drops it into the scratch slot of the thread that
+// owns it.  `pieces_per_thread` consecutive pieces belong to one thread and land in its units unit0, unit0 + 1, ...
+// (piece order == unit order: an element's low half, its high half, the next element ...).  Pieces at or beyond
+// `valid` (the ragged end of the table) are skipped.  Every lane of the warp must call this (converged).
+template <int PIECES_PER_THREAD>
+__device__ __forceinline__ void warp_copy_run(uint4* warp_scr, int unit0, const Fr* src, int valid, int lane) {
+  constexpr int kInstr = PIECES_PER_THREAD;  // 32 threads x PIECES_PER_THREAD pieces / 32 lanes
+  const uint4* g = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int j = 0; j < kInstr; j++) {
+    const int q = 32 * j + lane;
+    const int owner = q / PIECES_PER_THREAD, unit = unit0 + q % PIECES_PER_THREAD;
+    if (q < valid) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(warp_scr + unit * kScrStride + owner);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + q) : "memory");
+    }
+  }
 }
+// ---- TMA global -> shared copies -------------------------------------------------------------------------------------
+// cp.async (LDGSTS) writes shared memory 16 bytes per cycle per SM on this part: 148 x 16 B x 1.965 GHz = 4.6 TB/s is all
+// a kernel can stream through it, well below HBM (r2 v5: the loads ALONE ran at 3.5-3.8 TB/s, coalesced or not, with
+// 32 shared-memory wavefronts per copy instruction).  The adjacent-pair rounds therefore move their sources with TMA
+// tensor copies: a table is described to the TMA unit as a 2-D tensor of ROWS (one row = everything one pair reads
+// from it: 128 bytes in a fused pass, 64 in an evaluation-only round), a warp's 32 consecutive pairs are one box of 32
+// rows, fetched by ONE instruction of one lane and counted in bytes on a per-warp mbarrier.  The box lands in shared
+// memory with the hardware swizzle of its row width (16-byte chunk index XOR row bits), which is exactly what makes the
+// 8 lanes served together by a 128-bit shared load hit 8 different bank groups although their rows are one bank period
+// apart.  Rows past the end of the table are zero-filled by the TMA unit (and never used).  Measured (r2 v8, 2^24 entries,
+// 4 tables): loads alone 6.6 TB/s, loads + bound-table stores 6.0 TB/s -- the memory side of a pass is at the HBM roofline;
+// what is left is the arithmetic.
+//   r2 v6/v7 (1-D bulk copies, 8 per table and warp into padded pieces): same bandwidth, but the issue sequence
+//   (5 R2UR + UBLKCP per piece, serialised) cost 20 % of the pass; the tensor form is one instruction.
+struct alignas(64) TmapArray {
+  CUtensorMap m[kMaxTables];
+};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// box of 32 rows starting at row `row0` of the tensor -> dst (swizzled); completion bytes on `bar`.  One lane.
+__device__ __forceinline__ void tma_rows_g2s(void* dst, const CUtensorMap* tm, int row0, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+               "l"(tm), "r"(0), "r"(row0), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -133,10 +201,41 @@ __device__ __forceinline__ void wide_acc(uint32_t* acc, const Fr& a, const Fr& b
 
 // One pair of every combiner table; the values sit in the thread's stash at units 4k (lo) and 4k+2 (hi).
 // wacc: NW (+1 when P1) wide accumulators, facc: SUM only.
-template <int COMB, bool P1>
-__device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, const uint4* st, const Fr& w) {
-#define LO(k) scr_ld(st, 4 * (k))
-#define HI(k) scr_ld(st, 4 * (k) + 2)
+// Where a thread finds the (lo, hi) values of table k:
+//   UnitStash  [unit][thread] slots of 16 bytes (unit 4k = lo, 4k+2 = hi), thread stride `S` slots
+//   SwizzledRows64  one 64-byte row (lo, hi) per table inside the swizzled TMA boxes of the evaluation-only rounds
+template <int S>
+struct UnitStash {
+  const uint4* base;
+  __device__ __forceinline__ Fr ld(int unit) const {
+    const uint4 a = base[unit * S], b = base[(unit + 1) * S];
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+  __device__ __forceinline__ Fr lo(int k) const { return ld(4 * k); }
+  __device__ __forceinline__ Fr hi(int k) const { return ld(4 * k + 2); }
+};
+struct SwizzledRows64 {
+  const unsigned char* row;  // this thread's 64-byte row (lo, hi) of table 0, inside a 64-byte-swizzled TMA box
+  int sw, pitch;             // chunk c sits at byte (16 c) ^ sw of the row; `pitch` bytes between the boxes of two tables
+  __device__ __forceinline__ Fr ld(int k, int c) const {
+    const uint4 a = *reinterpret_cast<const uint4*>(row + k * pitch + ((16 * c) ^ sw));
+    const uint4 b = *reinterpret_cast<const uint4*>(row + k * pitch + ((16 * (c + 1)) ^ sw));
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+  __device__ __forceinline__ Fr lo(int k) const { return ld(k, 0); }
+  __device__ __forceinline__ Fr hi(int k) const { return ld(k, 2); }
+};
+
+template <int COMB, bool P1, class Stash>
+__device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, const Stash& st, const Fr& w) {
+#define LO(k) st.lo(k)
+#define HI(k) st.hi(k)
   if constexpr (COMB == ZOLT_SC_SUM) {
     facc[0] = fr_add(facc[0], LO(0));
     facc[1] = fr_add(facc[1], HI(0));
@@ -512,17 +611,30 @@ __device__ __noinline__ void round_finish(const Fr* raw, Fr* vals, const ScOut& 
 // MODE 2: FUSED -- bind src (length n) to r into dst (length n/2) and evaluate the NEXT round's
 //         polynomial over dst in the same pass; its claim is the previous polynomial at r.  n_extra tables
 //         after the K combiner tables are bound only.
-template <int COMB, int PAIR, int MODE>
+//
+// BIND selects the multiplier pipe of the bind (MODE 2 only): 0 = integer (fp_bind_fixed, wide IMADs), 1 = FP64
+// (fp_bind_fixed_f64: 128 DFMAs per bound element on the otherwise idle FP64 pipe; the combiner's products keep
+// the integer multiplier to themselves).  Both produce the same canonical elements.
+struct BindTables {
+  FixedMulTable i32;
+  // Two identical copies, used alternately by successive binds: the table (128 doubles) does not fit the 63 uniform
+  // registers, and a loop-invariant table makes ptxas hoist all of it out of the bind loop and spill it to local memory
+  // (r2 v1: LDL + R2UR per DFMA operand, the pass ran 1.6x SLOWER than the integer bind).  An address that changes with
+  // the loop counter keeps the LDCU loads next to their DFMAs.
+  FixedMulTableF64 f64[2];
+  unsigned f64_mask;  // bit k: table k's binds take the FP64 pipe (BIND == 1 kernels)
+};
+
+template <int COMB, int PAIR, int MODE, int BIND = 0>
 __global__ void __launch_bounds__(kRoundThreads, MODE == 2 ? kFusedBlocksPerSm : kEvalBlocksPerSm)
 sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const __grid_constant__ Fr r, SplitEqDev sq,
-                const __grid_constant__ ScOut out, const __grid_constant__ FixedMulTable rt) {
+                const __grid_constant__ ScOut out, const __grid_constant__ BindTables rt, const __grid_constant__ TmapArray tm) {
   constexpr int K = CombTraits<COMB>::K;
   constexpr int NW = CombTraits<COMB>::NW;
   constexpr bool FUSED = MODE == 2;
   constexpr bool P1 = MODE == 0 && CombTraits<COMB>::DEG != 0;
   constexpr int NACC = NW + (P1 ? 1 : 0);
-  extern __shared__ uint4 scratch[];  // [units][kRoundThreads], dynamic: exceeds the 48 KB static limit
-  uint4* const scr = scratch + threadIdx.x;
+  extern __shared__ __align__(128) uint4 scratch[];  // dynamic: exceeds the 48 KB static limit
   if constexpr (FUSED) {
     // this round's claim p(0) + p(1) is the previous round polynomial at r: one thread evaluates it while the
     // grid streams the tables, so it is off the serial tail of the launch
@@ -544,101 +656,221 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
   const size_t half_old = n / 2;           // HALF pairing: distance between bind partners in src
   const size_t half_cur = n_cur / 2;       // HALF pairing: distance between eval partners
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  size_t g0 = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31);  // first pair of this warp's 32
+  // The trip count is the same for every thread of the grid (a ragged last iteration is predicated), so the loops below
+  // are warp-convergent code: warp-cooperative copies, __syncwarp, and -- for the FP64 bind -- multiplier-table constants
+  // as uniform-register operands loaded by LDCU next to their DFMAs.  (Inside a loop whose trip count depends on the
+  // thread ptxas may not touch the uniform datapath: one indexed LDC per DFMA, measured slower than the integer bind.)
+  const size_t iters = (pairs + stride - 1) / stride;
 
-  if constexpr (FUSED) {
-    // scratch units 0..15: stash of the bound values (unit 4k lo, 4k+2 hi of table k);
-    // units 16..23: two prefetch slots of one bind's two source elements each.
-    // Work items are linearised as (pair, table, half): item q binds one output element.
-    const int kt = K + n_extra;
-    auto prefetch_item = [&](size_t gi, int k, int h, int slot) {
-      const Fr* s = t.src[k];
-      const size_t idx = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * gi + h : gi + (h ? half_cur : 0);
-      const int u = 16 + 4 * slot;
-      if constexpr (PAIR == ZOLT_PAIR_ADJACENT) {
-        scr_prefetch(scr, u, s + 2 * idx);
-        scr_prefetch(scr, u + 2, s + 2 * idx + 1);
-      } else {
-        scr_prefetch(scr, u, s + idx);
-        scr_prefetch(scr, u + 2, s + idx + half_old);
+  if constexpr (PAIR == ZOLT_PAIR_ADJACENT) {
+    // ============ adjacent pairs (LowToHigh): TMA boxes of 32 rows per warp and table ===================================
+    // 1024-byte aligned start (the swizzle pattern is a function of the shared-memory address); plain pointer arithmetic on
+    // `scratch` so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
+    unsigned char* const smem = reinterpret_cast<unsigned char*>(scratch) + ((1024u - (smem_u32(scratch) & 1023u)) & 1023u);
+    size_t g = g0 + lane;
+    if constexpr (FUSED) {
+      // per warp: one 4 KB slot for a table's sources (32 rows x 128 B, 128-byte swizzle), then the stash of the bound
+      // values ([unit][lane] 16-byte slots, unit 4k = lo, 4k+2 = hi of table k); mbarriers after the last warp
+      constexpr int kSlot = 32 * 128, kWarpBytes = kSlot + 16 * 32 * 16;
+      unsigned char* const slot = smem + warp * kWarpBytes;
+      uint4* const stash = reinterpret_cast<uint4*>(slot + kSlot) + lane;
+      const unsigned char* const row = slot + lane * 128;
+      const int sw = (lane & 7) << 4;  // chunk c of this lane's row sits at byte (16 c) ^ sw
+      unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem + (kRoundThreads / 32) * kWarpBytes) + warp;
+      if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
-    };
-    // The ring runs TWO binds ahead with only two slots: the slot of item q is read into registers and then
-    // immediately re-armed with item q+2 (the copy needs a round trip to L2/HBM before it can overwrite what
-    // the same thread read earlier in program order).  128 bytes in flight per thread, 64 KB per SM.
-    auto item_at = [&](size_t gi, int q, size_t& g_out, int& k_out, int& h_out) {
-      // item q (may exceed 2*kt by less than 2*kt) of pair gi -> normalised (pair, table, half)
-      const bool wrap = q >= 2 * kt;
-      const int qq = wrap ? q - 2 * kt : q;
-      g_out = wrap ? gi + stride : gi;
-      k_out = qq >> 1;
-      h_out = qq & 1;
-    };
-    {
-      size_t g1; int k1, h1;
-      if (g < pairs) prefetch_item(g, 0, 0, 0);
-      cp_async_commit();
-      item_at(g, 1, g1, k1, h1);
-      if (g1 < pairs) prefetch_item(g1, k1, h1, 1);
-      cp_async_commit();
-    }
-    int slot = 0;
-    for (; g < pairs; g += stride) {
-#pragma unroll 1
-      for (int q = 0; q < 2 * kt; q++) {
-        const int k = q >> 1, h = q & 1;
-        cp_async_wait<1>();  // item q has landed (item q+1 may still be in flight)
-        const int u = 16 + 4 * slot;
-        const size_t idx = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * g + h : g + (h ? half_cur : 0);
-        const Fr a0 = scr_ld(scr, u), a1 = scr_ld(scr, u + 2);
-        {
-          size_t g2; int k2, h2;
-          item_at(g, q + 2, g2, k2, h2);
-          if (g2 < pairs) prefetch_item(g2, k2, h2, slot);
-          cp_async_commit();
+      __syncwarp();
+      const int kt = K + n_extra;
+      // `dep` is always zero but computed from the words just read out of the slot: the copy that overwrites the slot cannot
+      // issue before those shared loads have returned (the TMA unit is not ordered behind the LSU queue the way cp.async is)
+      auto issue = [&](size_t gi, int k, unsigned dep) {
+        if (lane == 0) {
+          if (gi < pairs) {
+            mbar_expect_tx(bar, kSlot);
+            tma_rows_g2s(slot, &tm.m[k], (int)gi + (int)dep, bar);  // row g = sources 4g .. 4g+3 of pair g
+          } else {
+            mbar_expect_tx(bar, 0);
+          }
         }
-        const Fr v = fp_bind_fixed<FrParams>(a0, a1, rt);  // lo + r (hi - lo): multiplier table in the constant bank
-        st_fr(t.dst[k] + idx, v);
-        if (k < K) scr_st(scr, 2 * q, v);
-        slot ^= 1;
+      };
+      auto ld_chunks = [&](int c) {  // the element made of chunks c, c+1 of this lane's row
+        const uint4 a = *reinterpret_cast<const uint4*>(row + ((16 * c) ^ sw));
+        const uint4 b = *reinterpret_cast<const uint4*>(row + ((16 * (c + 1)) ^ sw));
+        Fr x;
+        x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
+        x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
+        return x;
+      };
+      issue(g0, 0, 0u);
+      unsigned parity = 0;
+      for (size_t it = 0; it < iters; it++, g += stride, g0 += stride) {
+        const bool act = g < pairs;
+#pragma unroll 1
+        for (int k = 0; k < kt; k++) {
+          mbar_wait(bar, parity);  // this table's sources have landed
+          parity ^= 1u;
+          const Fr a0 = ld_chunks(0), a1 = ld_chunks(2), b0 = ld_chunks(4), b1 = ld_chunks(6);  // zeros when !act
+          __syncwarp();  // every lane has read its row before the slot is re-armed
+          {
+            // canonical limbs: the top word of every element is below 2^30, so this is 0
+            const unsigned dep = (a0.v[7] | a1.v[7] | b0.v[7] | b1.v[7] | (a0.v[3] & a1.v[3] & b0.v[3] & b1.v[3] & a0.v[7])) >> 31;
+            const bool wrap = k + 1 == kt;
+            issue(wrap ? g0 + stride : g0, wrap ? 0 : k + 1, dep);
+          }
+          Fr v0, v1;  // lo + r (hi - lo): multiplier table in the constant bank
+          if constexpr (BIND == 1) {
+            // bit k of the mask: this table's binds run on the FP64 pipe, else on the integer multiplier
+            if ((rt.f64_mask >> k) & 1u) {
+              fp_bind2_fixed_f64<FrParams>(a0, a1, b0, b1, rt.f64[k & 1], v0, v1);
+            } else {
+              v0 = fp_bind_fixed<FrParams>(a0, a1, rt.i32);
+              v1 = fp_bind_fixed<FrParams>(b0, b1, rt.i32);
+            }
+          } else {
+            v0 = fp_bind_fixed<FrParams>(a0, a1, rt.i32);
+            v1 = fp_bind_fixed<FrParams>(b0, b1, rt.i32);
+          }
+          if (act) {
+            st_fr(t.dst[k] + 2 * g, v0);
+            st_fr(t.dst[k] + 2 * g + 1, v1);
+          }
+          if (k < K) {
+            stash[(4 * k) * 32] = make_uint4(v0.v[0], v0.v[1], v0.v[2], v0.v[3]);
+            stash[(4 * k + 1) * 32] = make_uint4(v0.v[4], v0.v[5], v0.v[6], v0.v[7]);
+            stash[(4 * k + 2) * 32] = make_uint4(v1.v[0], v1.v[1], v1.v[2], v1.v[3]);
+            stash[(4 * k + 3) * 32] = make_uint4(v1.v[4], v1.v[5], v1.v[6], v1.v[7]);
+          }
+        }
+        if (act) {
+          Fr w;
+          if constexpr (CombTraits<COMB>::GRUEN) {
+            // g = (x_out << in_bits) | x_in  (src/zkvm/spartan/product_remainder.zig:293-296)
+            const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
+            w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+          }
+          accumulate_pair<COMB, P1>(wacc, facc, UnitStash<32>{stash}, w);
+        }
       }
-      Fr w;
-      if constexpr (CombTraits<COMB>::GRUEN) {
-        // g = (x_out << in_bits) | x_in  (src/zkvm/spartan/product_remainder.zig:293-296)
-        const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
-        w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+    } else {
+      // evaluation only: per warp two buffers of K boxes (32 rows x 64 B, 64-byte swizzle), filled one iteration ahead
+      constexpr int kTab = 32 * 64, kBuf = K * kTab, kWarpBytes = 2 * kBuf;
+      unsigned char* const wbase = smem + warp * kWarpBytes;
+      unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem + (kRoundThreads / 32) * kWarpBytes) + 2 * warp;
+      if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
-      accumulate_pair<COMB, P1>(wacc, facc, scr, w);
+      __syncwarp();
+      auto issue = [&](size_t gi, int buf) {
+        if (lane == 0) {
+          if (gi < pairs) {
+            mbar_expect_tx(bars + buf, kBuf);
+#pragma unroll
+            for (int k = 0; k < K; k++) tma_rows_g2s(wbase + buf * kBuf + k * kTab, &tm.m[k], (int)gi, bars + buf);  // row g = (lo, hi) of pair g
+          } else {
+            mbar_expect_tx(bars + buf, 0);
+          }
+        }
+      };
+      issue(g0, 0);
+      unsigned parity[2] = {0u, 0u};
+      int buf = 0;
+      const int sw = ((lane >> 1) & 3) << 4;  // 64-byte swizzle: chunk c of row `lane` sits at byte (16 c) ^ sw
+      for (size_t it = 0; it < iters; it++, g += stride, g0 += stride) {
+        issue(g0 + stride, buf ^ 1);
+        mbar_wait(bars + buf, parity[buf]);
+        parity[buf] ^= 1u;
+        if (g < pairs) {
+          Fr w;
+          if constexpr (CombTraits<COMB>::GRUEN) {
+            const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
+            w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+          }
+          const SwizzledRows64 st{wbase + buf * kBuf + lane * 64, sw, kTab};
+          accumulate_pair<COMB, P1>(wacc, facc, st, w);
+        }
+        __syncwarp();  // every lane is done with this buffer before the next iteration re-arms it
+        buf ^= 1;
+      }
     }
   } else {
-    // no bind: the (lo, hi) values of every table are copied straight into the stash layout, double
-    // buffered (units 0..15 and 16..31) one pair ahead.
-    auto prefetch_pair = [&](size_t gi, int buf) {
-      const size_t i_lo = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * gi : gi;
-      const size_t i_hi = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * gi + 1 : gi + half_cur;
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        scr_prefetch(scr, 16 * buf + 4 * k, t.src[k] + i_lo);
-        scr_prefetch(scr, 16 * buf + 4 * k + 2, t.src[k] + i_hi);
-      }
-    };
-    if (g < pairs) prefetch_pair(g, 0);
-    cp_async_commit();
-    int buf = 0;
-    for (; g < pairs; g += stride) {
-      if (g + stride < pairs) prefetch_pair(g + stride, buf ^ 1);
+    // ============ half-split pairs (HighToLow): cp.async into [unit][thread] slots =====================================
+    // (degree-1 provers; their sources are four / two separate runs per table, copied cooperatively 512 contiguous bytes per
+    // warp instruction, lane L the 16-byte piece L, each piece dropped into the slot of the thread that owns it)
+    uint4* const scr = scratch + threadIdx.x;
+    uint4* const warp_scr = scratch + (threadIdx.x & ~31);  // slot of lane 0 of this warp
+    size_t g = g0 + lane;
+    if constexpr (FUSED) {
+      // units 0..15: stash of the bound values (unit 4k lo, 4k+2 hi of table k); units 16..23: the four source elements
+      // of one table's two binds
+      const int kt = K + n_extra;
+      auto prefetch_table = [&](size_t gi, int k) {
+        if (gi >= pairs) return;
+        const Fr* s = t.src[k];
+        const int vp = pairs - gi < 32 ? (int)(pairs - gi) : 32;  // valid pairs of this warp's chunk
+        // outputs g, g + half_cur <- sources (g, g + half_old), (g + half_cur, g + half_cur + half_old): four runs
+        warp_copy_run<2>(warp_scr, 16, s + gi, 2 * vp, lane);
+        warp_copy_run<2>(warp_scr, 18, s + gi + half_old, 2 * vp, lane);
+        warp_copy_run<2>(warp_scr, 20, s + gi + half_cur, 2 * vp, lane);
+        warp_copy_run<2>(warp_scr, 22, s + gi + half_cur + half_old, 2 * vp, lane);
+      };
+      prefetch_table(g0, 0);
       cp_async_commit();
-      cp_async_wait<1>();
-      Fr w;
-      if constexpr (CombTraits<COMB>::GRUEN) {
-        const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
-        w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+      for (size_t it = 0; it < iters; it++, g += stride, g0 += stride) {
+        const bool act = g < pairs;
+#pragma unroll 1
+        for (int k = 0; k < kt; k++) {
+          cp_async_wait<0>();  // this table's sources have landed (every lane waits for the pieces IT copied) ...
+          __syncwarp();        // ... and the pieces the other lanes copied into this thread's slots are visible
+          const Fr a0 = scr_ld(scr, 16), a1 = scr_ld(scr, 18), b0 = scr_ld(scr, 20), b1 = scr_ld(scr, 22);
+          __syncwarp();        // every lane has read its slots before any lane re-arms them
+          {
+            const bool wrap = k + 1 == kt;
+            prefetch_table(wrap ? g0 + stride : g0, wrap ? 0 : k + 1);
+            cp_async_commit();
+          }
+          const Fr v0 = fp_bind_fixed<FrParams>(a0, a1, rt.i32), v1 = fp_bind_fixed<FrParams>(b0, b1, rt.i32);
+          if (act) {
+            st_fr(t.dst[k] + g, v0);
+            st_fr(t.dst[k] + g + half_cur, v1);
+          }
+          if (k < K) {
+            scr_st(scr, 4 * k, v0);
+            scr_st(scr, 4 * k + 2, v1);
+          }
+        }
+        if (act) accumulate_pair<COMB, P1>(wacc, facc, UnitStash<kScrStride>{scr}, Fr::zero());
       }
-      accumulate_pair<COMB, P1>(wacc, facc, scr + 16 * buf * kRoundThreads, w);
-      buf ^= 1;
+    } else {
+      auto prefetch_pairs = [&](size_t gi, int buf) {
+        if (gi >= pairs) return;
+        const int vp = pairs - gi < 32 ? (int)(pairs - gi) : 32;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          warp_copy_run<2>(warp_scr, 16 * buf + 4 * k, t.src[k] + gi, 2 * vp, lane);
+          warp_copy_run<2>(warp_scr, 16 * buf + 4 * k + 2, t.src[k] + gi + half_cur, 2 * vp, lane);
+        }
+      };
+      prefetch_pairs(g0, 0);
+      cp_async_commit();
+      int buf = 0;
+      for (size_t it = 0; it < iters; it++, g += stride, g0 += stride) {
+        prefetch_pairs(g0 + stride, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();  // the other lanes' pieces of this buffer are visible
+        if (g < pairs) accumulate_pair<COMB, P1>(wacc, facc, UnitStash<kScrStride>{scr + 16 * buf * kScrStride}, Fr::zero());
+        __syncwarp();  // every lane is done with this buffer before the next iteration re-arms it
+        buf ^= 1;
+      }
     }
+    cp_async_wait<0>();
   }
-  cp_async_wait<0>();
   Fr raw[kRaw];
   collapse<COMB, P1>(wacc, facc, raw);
   round_finish(raw, reinterpret_cast<Fr*>(scratch), out);
@@ -1031,8 +1263,68 @@ FixedMulTable fixed_mul_table_host(const Fr& r) {
   return t;
 }
 
+// FP64 form of the same table (fp_bind_fixed_f64): row l = limbs of r_std * 2^(16 l) mod p as doubles.  Rows 2i are the
+// rows of the integer table; rows 2i+1 are 16 modular doublings further.
+void fixed_mul_table_f64_host(const Fr& r, FixedMulTableF64* out) {
+  static const uint64_t P[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+  Fr one_raw = Fr::zero();
+  one_raw.v[0] = 1;
+  const Fr r_std = fp_mul<FrParams>(r, one_raw);
+  uint64_t c[4];
+  for (int j = 0; j < 4; j++) c[j] = (uint64_t)r_std.v[2 * j] | ((uint64_t)r_std.v[2 * j + 1] << 32);
+  for (int l = 0; l < 16; l++) {
+    for (int j = 0; j < 4; j++) {
+      out->c[l][j] = F64Pair{(double)(uint32_t)c[j], (double)(uint32_t)(c[j] >> 32)};
+    }
+    for (int d = 0; d < 16; d++) {
+      c[3] = (c[3] << 1) | (c[2] >> 63);
+      c[2] = (c[2] << 1) | (c[1] >> 63);
+      c[1] = (c[1] << 1) | (c[0] >> 63);
+      c[0] <<= 1;
+      uint64_t s[4];
+      unsigned __int128 bw = 0;
+      for (int j = 0; j < 4; j++) {
+        const unsigned __int128 x = (unsigned __int128)c[j] - P[j] - (uint64_t)bw;
+        s[j] = (uint64_t)x;
+        bw = (x >> 64) & 1;
+      }
+      if (!bw)
+        for (int j = 0; j < 4; j++) c[j] = s[j];
+    }
+  }
+}
+
+// 2-D tensor map over a table viewed as rows of `row_bytes` (64 or 128): box = 32 rows, swizzle = the row width.
+// The encoder is a driver entry point; it is fetched through the runtime so the library links against cudart only.
+int encode_rows_tmap(CUtensorMap* out, const void* base, size_t rows, unsigned row_bytes) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ZOLT_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) {
+      fprintf(stderr, "[zolt_gpu] cuTensorMapEncodeTiled is not available from this driver\n");
+      return ZOLT_ERR_CUDA;
+    }
+    enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const cuuint64_t gdim[2] = {row_bytes / 4, rows ? rows : 1};
+  const cuuint64_t gstride[1] = {row_bytes};
+  const cuuint32_t box[2] = {row_bytes / 4, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    fprintf(stderr, "[zolt_gpu] cuTensorMapEncodeTiled failed (%d) for %zu rows of %u bytes at %p\n", (int)rc, rows, row_bytes, base);
+    return ZOLT_ERR_CUDA;
+  }
+  return ZOLT_OK;
+}
+
 template <int COMB, int PAIR>
-void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
+int launch_round(zolt_sc* sc, bool fused, const Fr& r) {
+  constexpr int COMBK = CombTraits<COMB>::K;
   ScPtrs t{};
   const int total = sc->k + sc->n_extra;
   for (int i = 0; i < total; i++) {
@@ -1060,14 +1352,39 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   const int mode = fused ? 2 : (sc->have_claim && sc->cur < 0 && out.deg != 0 ? 1 : 0);
   out.claim_src = mode == 2 ? CLAIM_PREV : (mode == 1 ? CLAIM_HOST : CLAIM_NONE);
   sc->pending_claim_src = out.claim_src;
-  const size_t kDynSmem = (size_t)(fused ? kFusedScratchUnits : kEvalScratchUnits) * kRoundThreads * sizeof(uint4);
-  static bool attr_set[3] = {false, false, false};  // per (COMB, PAIR) instantiation of this function
-  if (!attr_set[mode]) {
-    if (mode == 2) cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
-    else if (mode == 1) cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
-    else cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
-    attr_set[mode] = true;
+  // shared memory: the layout of this pairing (see the kernel) + the per-warp mbarriers + slack for 1024-byte alignment
+  const size_t kWarps = kRoundThreads / 32;
+  const size_t smem_unit = (size_t)(fused ? kFusedScratchUnits : kEvalScratchUnits) * kScrStride * sizeof(uint4);
+  const size_t smem_tma = (fused ? kWarps * (32 * 128 + 16 * 32 * 16) + kWarps * 8 : kWarps * 2 * (size_t)COMBK * 32 * 64 + kWarps * 16) + 1024;
+  const size_t kDynSmem = PAIR == ZOLT_PAIR_ADJACENT ? smem_tma : smem_unit;
+  TmapArray tm{};
+  if (PAIR == ZOLT_PAIR_ADJACENT && !(n_cur / 2 <= (size_t)sc->ctx->sc_small_pairs)) {
+    // one row = what one pair reads from a table: 4 source elements (fused) or 2 (evaluation only)
+    const unsigned row_bytes = fused ? 128u : 64u;
+    for (int i = 0; i < (fused ? total : sc->k); i++) ZOLT_TRY(encode_rows_tmap(&tm.m[i], t.src[i], sc->n * sizeof(Fr) / row_bytes, row_bytes));
   }
+  const bool f64 = mode == 2 && PAIR == ZOLT_PAIR_ADJACENT && (sc->ctx->sc_bind_f64 & 0xff) != 0;  // sc_bind_f64: mask of the tables whose binds take the FP64 pipe
+  {
+    // cudaFuncSetAttribute applies to the CURRENT device only: remember it per (instantiation, device), so a process
+    // that drives several GPUs (zolt_gpu_init_multi) opts every one of them in to the 64 KB of dynamic shared memory
+    static std::atomic<unsigned long long> attr_devs[4];  // per (COMB, PAIR) instantiation of this function; bit = device
+    const int slot = mode == 2 ? (f64 ? 3 : 2) : mode;
+    const unsigned long long bit = 1ull << (sc->ctx->device & 63);
+    if (!(attr_devs[slot].load(std::memory_order_acquire) & bit)) {
+      cudaError_t e;
+      if (slot == 3) e = cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+      else if (slot == 2) e = cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+      else if (slot == 1) e = cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+      else e = cudaFuncSetAttribute(sc_round_kernel<COMB, PAIR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+      if (e != cudaSuccess) {
+        fprintf(stderr, "[zolt_gpu] cudaFuncSetAttribute(dynamic shared memory) failed on device %d: %s\n", sc->ctx->device,
+                cudaGetErrorString(e));
+        return ZOLT_ERR_CUDA;
+      }
+      attr_devs[slot].fetch_or(bit, std::memory_order_release);
+    }
+  }
+  const BindTables rt0{};
   const int ps = prof_begin(sc->ctx, fused ? PROF_SC_FUSED : PROF_SC_EVAL);
   if (n_cur / 2 <= (size_t)sc->ctx->sc_small_pairs) {
     // latency-bound sizes: one element / one term per thread (sc_small_kernel)
@@ -1077,33 +1394,43 @@ void launch_round(zolt_sc* sc, bool fused, const Fr& r) {
     if (chunks == 0) chunks = 1;
     sc_small_kernel<PAIR><<<(unsigned)chunks, kSmallThreads, 0, sc->ctx->stream>>>(t, a, sc->n, r, sq, out);
   } else if (mode == 2) {
-    const FixedMulTable rt = fixed_mul_table_host(r);  // O(1) host glue per launch
-    sc_round_kernel<COMB, PAIR, 2><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, rt);
+    BindTables rt{};  // O(1) host glue per launch
+    if (f64) {
+      fixed_mul_table_f64_host(r, &rt.f64[0]);
+      rt.f64[1] = rt.f64[0];
+      rt.i32 = fixed_mul_table_host(r);
+      rt.f64_mask = (unsigned)sc->ctx->sc_bind_f64 & 0xffu;
+      sc_round_kernel<COMB, PAIR, 2, 1><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, rt, tm);
+    } else {
+      rt.i32 = fixed_mul_table_host(r);
+      sc_round_kernel<COMB, PAIR, 2, 0><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, rt, tm);
+    }
   } else if (mode == 1) {
-    sc_round_kernel<COMB, PAIR, 1><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, FixedMulTable{});
+    sc_round_kernel<COMB, PAIR, 1><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, rt0, tm);
   } else {
-    sc_round_kernel<COMB, PAIR, 0><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, FixedMulTable{});
+    sc_round_kernel<COMB, PAIR, 0><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, rt0, tm);
   }
   prof_end(sc->ctx, ps);
   sc->ctx->launches++;
   sc->evals_final = !sc->sharded;
+  return ZOLT_OK;
 }
 
 template <int COMB>
-void launch_round_p(zolt_sc* sc, bool fused, const Fr& r) {
-  if (sc->pairing == ZOLT_PAIR_ADJACENT) launch_round<COMB, ZOLT_PAIR_ADJACENT>(sc, fused, r);
-  else launch_round<COMB, ZOLT_PAIR_HALF>(sc, fused, r);
+int launch_round_p(zolt_sc* sc, bool fused, const Fr& r) {
+  if (sc->pairing == ZOLT_PAIR_ADJACENT) return launch_round<COMB, ZOLT_PAIR_ADJACENT>(sc, fused, r);
+  return launch_round<COMB, ZOLT_PAIR_HALF>(sc, fused, r);
 }
 
-void launch_round_any(zolt_sc* sc, bool fused, const Fr& r) {
+int launch_round_any(zolt_sc* sc, bool fused, const Fr& r) {
   switch (sc->combiner) {
-    case ZOLT_SC_SUM: launch_round_p<ZOLT_SC_SUM>(sc, fused, r); break;
-    case ZOLT_SC_PROD2: launch_round_p<ZOLT_SC_PROD2>(sc, fused, r); break;
-    case ZOLT_SC_PROD3: launch_round_p<ZOLT_SC_PROD3>(sc, fused, r); break;
-    case ZOLT_SC_EQ_A_BMC: launch_round_p<ZOLT_SC_EQ_A_BMC>(sc, fused, r); break;
-    case ZOLT_SC_EQ_AB_MINUS_C: launch_round_p<ZOLT_SC_EQ_AB_MINUS_C>(sc, fused, r); break;
-    case ZOLT_SC_GRUEN_AB: launch_round_p<ZOLT_SC_GRUEN_AB>(sc, fused, r); break;
-    default: launch_round_p<ZOLT_SC_GRUEN_AB_MINUS_C>(sc, fused, r); break;
+    case ZOLT_SC_SUM: return launch_round_p<ZOLT_SC_SUM>(sc, fused, r);
+    case ZOLT_SC_PROD2: return launch_round_p<ZOLT_SC_PROD2>(sc, fused, r);
+    case ZOLT_SC_PROD3: return launch_round_p<ZOLT_SC_PROD3>(sc, fused, r);
+    case ZOLT_SC_EQ_A_BMC: return launch_round_p<ZOLT_SC_EQ_A_BMC>(sc, fused, r);
+    case ZOLT_SC_EQ_AB_MINUS_C: return launch_round_p<ZOLT_SC_EQ_AB_MINUS_C>(sc, fused, r);
+    case ZOLT_SC_GRUEN_AB: return launch_round_p<ZOLT_SC_GRUEN_AB>(sc, fused, r);
+    default: return launch_round_p<ZOLT_SC_GRUEN_AB_MINUS_C>(sc, fused, r);
   }
 }
 
@@ -1212,7 +1539,7 @@ static int sc_ensure_evals(zolt_sc* sc) {
   if (sc->n < 2) return ZOLT_ERR_STATE;  // all variables bound: no round polynomial left
   if (combiner_gruen(sc->combiner) && !sc->d_e_out) return ZOLT_ERR_STATE;
   ZOLT_CUDA_TRY(cudaSetDevice(sc->ctx->device));
-  launch_round_any(sc, false, Fr::zero());
+  ZOLT_TRY(launch_round_any(sc, false, Fr::zero()));
   ZOLT_CUDA_TRY(cudaGetLastError());
   sc->evals_valid = true;
   return ZOLT_OK;
@@ -1339,7 +1666,7 @@ extern "C" int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]) {
     }
     if (!sc->evals_final) return ZOLT_ERR_STATE;  // sharded: zolt_sc_finish_partials has not run
     sc->last_r = r;
-    launch_round_any(sc, true, r);
+    ZOLT_TRY(launch_round_any(sc, true, r));
     sc->evals_valid = true;
   } else {
     // last variable: bind only, nothing left to evaluate (both pairings pair elements 0 and 1)

@@ -40,6 +40,17 @@ def load_host() -> C.CDLL:
                                                          C.c_void_p, C.c_void_p]
         _host.zolt_host_sumcheck_prove_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                                            C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _host.zolt_host_sumcheck_prove_dev_claim.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                                             C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _host.zolt_host_sumcheck_prove_sharded_claim.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                                                 C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                                 C.c_void_p]
+        _host.zolt_host_sumcheck_prove_gruen_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                                             C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p,
+                                                             C.c_void_p, C.c_void_p]
+        _host.zolt_host_eq_mle.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        _host.zolt_host_horner_eval.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        _host.zolt_host_dense_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
         _host.zolt_host_batched_sumcheck.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                                      C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_hyperkzg_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -110,20 +121,59 @@ def sumcheck_prove(ctx: Context, combiner: int, pairing: int, tables, n_extra: i
 
 
 def sumcheck_prove_dev(ctx: Context, combiner: int, pairing: int, d_tables, log_n: int, n_extra: int = 0,
-                       domain: bytes = b"bench", label: bytes = b"round"):
-    """Same as sumcheck_prove for tables already resident on the device (list of device pointers)."""
+                       domain: bytes = b"bench", label: bytes = b"round", claim=None):
+    """Same as sumcheck_prove for tables already resident on the device (list of device pointers).  `claim`: the
+    instance's input claim (SumcheckInstance.input_claim); round 0 then takes p(1) from it."""
     arr = (C.c_void_p * len(d_tables))(*d_tables)
     evals = np.zeros((log_n, 4, 4), dtype=np.uint64)
     chal = np.zeros((log_n, 4), dtype=np.uint64)
     final = np.zeros((len(d_tables), 4), dtype=np.uint64)
-    st = load_host().zolt_host_sumcheck_prove_dev(ctx.handle, combiner, pairing, log_n, len(d_tables), n_extra, arr, domain,
-                                                  len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
-    _lib.check(st, "zolt_host_sumcheck_prove_dev")
+    cl = _as_u64(claim, 4) if claim is not None else None
+    st = load_host().zolt_host_sumcheck_prove_dev_claim(ctx.handle, combiner, pairing, log_n, len(d_tables), n_extra, arr, _ptr(cl), domain,
+                                                        len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
+    _lib.check(st, "zolt_host_sumcheck_prove_dev_claim")
     return evals, chal, final
 
 
+def sumcheck_prove_gruen_dev(ctx: Context, d_tables, log_n: int, tau, claim, with_c: bool = False, domain: bytes = b"bench",
+                             label: bytes = b"round"):
+    """Gruen split-eq sumcheck (GruenProductProver) over device-resident tables."""
+    arr = (C.c_void_p * len(d_tables))(*d_tables)
+    t, cl = _as_u64(tau, 4), _as_u64(claim, 4)
+    evals = np.zeros((log_n, 4, 4), dtype=np.uint64)
+    chal = np.zeros((log_n, 4), dtype=np.uint64)
+    final_claim = np.zeros(4, dtype=np.uint64)
+    st = load_host().zolt_host_sumcheck_prove_gruen_dev(ctx.handle, int(with_c), log_n, len(d_tables), arr, _ptr(t), _ptr(cl), domain,
+                                                        len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final_claim))
+    _lib.check(st, "zolt_host_sumcheck_prove_gruen_dev")
+    return evals, chal, final_claim
+
+
+def eq_mle(r, x) -> np.ndarray:
+    rr, xx = _as_u64(r, 4), _as_u64(x, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    load_host().zolt_host_eq_mle(_ptr(rr), _ptr(xx), rr.shape[0], _ptr(out))
+    return out
+
+
+def horner_eval(coeffs, x) -> np.ndarray:
+    cc, xx = _as_u64(coeffs, 4), _as_u64(x, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    load_host().zolt_host_horner_eval(_ptr(cc), cc.shape[0], _ptr(xx), _ptr(out))
+    return out
+
+
+def dense_evaluate(ctx: Context, evals, point) -> np.ndarray:
+    """DensePolynomial.evaluate (src/poly/mod.zig:73-92) through the C++ mirror (device folds)."""
+    ee = _as_u64(evals, 4)
+    pp = _as_u64(point, 4) if len(point) else np.empty((0, 4), dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    _lib.check(load_host().zolt_host_dense_evaluate(ctx.handle, _ptr(ee), ee.shape[0], _ptr(pp), pp.shape[0], _ptr(out)), "zolt_host_dense_evaluate")
+    return out
+
+
 def sumcheck_prove_sharded(ctx: Context, box, combiner: int, d_tables, local_log: int, domain: bytes = b"bench",
-                           label: bytes = b"round"):
+                           label: bytes = b"round", claim=None):
     """One rank of the dense LowToHigh sumcheck over contiguous hypercube blocks (zolt_host.hpp proveSumcheckSharded):
     the round kernels exchange their sums through the NVLink mailboxes, every rank returns the whole proof."""
     world = box.world
@@ -132,9 +182,10 @@ def sumcheck_prove_sharded(ctx: Context, box, combiner: int, d_tables, local_log
     evals = np.zeros((rounds, 4, 4), dtype=np.uint64)
     chal = np.zeros((rounds, 4), dtype=np.uint64)
     final = np.zeros((len(d_tables), 4), dtype=np.uint64)
-    st = load_host().zolt_host_sumcheck_prove_sharded(ctx.handle, box.handle, world, combiner, local_log, len(d_tables), arr, domain,
-                                                      len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
-    _lib.check(st, "zolt_host_sumcheck_prove_sharded")
+    cl = _as_u64(claim, 4) if claim is not None else None
+    st = load_host().zolt_host_sumcheck_prove_sharded_claim(ctx.handle, box.handle, world, combiner, local_log, len(d_tables), arr, _ptr(cl),
+                                                            domain, len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
+    _lib.check(st, "zolt_host_sumcheck_prove_sharded_claim")
     return evals, chal, final
 
 

@@ -81,8 +81,80 @@ int zolt_host_sumcheck_prove_dev(zolt_ctx* ctx, int combiner, int pairing, int l
   return ZOLT_OK;
 }
 
+// zolt_host_sumcheck_prove_dev with the instance's input claim (may be NULL): round 0 then derives p(1) from it
+int zolt_host_sumcheck_prove_dev_claim(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
+                                       const void* const* d_tables, const uint64_t* claim, const char* domain, size_t dn,
+                                       const char* label, size_t ln, uint64_t* evals_out, uint64_t* challenges_out,
+                                       uint64_t* final_out) {
+  Context c(ctx);
+  std::vector<const void*> tabs(d_tables, d_tables + n_tables);
+  DenseSumcheckProver prover(c, DenseSumcheckProver::DeviceTables{}, combiner, pairing, tabs, log_n, n_extra);
+  if (claim) prover.setInputClaim(Fr::fromRaw(claim));
+  Transcript tr(std::string_view(domain, dn));
+  SumcheckProof proof = proveSumcheck(prover, tr, std::string_view(label, ln));
+  store_proof(proof, evals_out, challenges_out);
+  if (final_out)
+    for (int t = 0; t < n_tables; t++) prover.table(t)[0].store(final_out + 4 * t);
+  return ZOLT_OK;
+}
+
+// Gruen split-eq sumcheck over tables resident on the device
+int zolt_host_sumcheck_prove_gruen_dev(zolt_ctx* ctx, int with_c, int log_n, int n_tables, const void* const* d_tables,
+                                       const uint64_t* tau, const uint64_t* claim, const char* domain, size_t dn,
+                                       const char* label, size_t ln, uint64_t* evals_out, uint64_t* challenges_out,
+                                       uint64_t* final_claim_out) {
+  Context c(ctx);
+  std::vector<const void*> tabs(d_tables, d_tables + n_tables);
+  std::vector<Fr> tv(log_n);
+  for (int i = 0; i < log_n; i++) tv[i] = Fr::fromRaw(tau + 4 * i);
+  GruenProductProver prover(c, DenseSumcheckProver::DeviceTables{}, tabs, log_n, tv, Fr::fromRaw(claim), with_c != 0);
+  Transcript tr(std::string_view(domain, dn));
+  SumcheckProof proof = proveSumcheck(prover, tr, std::string_view(label, ln));
+  store_proof(proof, evals_out, challenges_out);
+  if (final_claim_out) prover.current_claim.store(final_claim_out);
+  return ZOLT_OK;
+}
+
+// host glue parity hooks: EqPolynomial.mle, BatchOps.hornerEval, DensePolynomial.evaluate
+void zolt_host_eq_mle(const uint64_t* r, const uint64_t* x, size_t n, uint64_t* out) {
+  std::vector<Fr> rv(n), xv(n);
+  for (size_t i = 0; i < n; i++) { rv[i] = Fr::fromRaw(r + 4 * i); xv[i] = Fr::fromRaw(x + 4 * i); }
+  EqPolynomial::mle(rv, xv).store(out);
+}
+void zolt_host_horner_eval(const uint64_t* coeffs, size_t n, const uint64_t* x, uint64_t* out) {
+  std::vector<Fr> cv(n);
+  for (size_t i = 0; i < n; i++) cv[i] = Fr::fromRaw(coeffs + 4 * i);
+  BatchOps::hornerEval(cv, Fr::fromRaw(x)).store(out);
+}
+int zolt_host_dense_evaluate(zolt_ctx* ctx, const uint64_t* evals, size_t n, const uint64_t* point, size_t n_vars, uint64_t* out) {
+  Context c(ctx);
+  std::vector<Fr> ev(n), pt(n_vars);
+  for (size_t i = 0; i < n; i++) ev[i] = Fr::fromRaw(evals + 4 * i);
+  for (size_t i = 0; i < n_vars; i++) pt[i] = Fr::fromRaw(point + 4 * i);
+  DensePolynomial poly(c, ev);
+  poly.evaluate(pt).store(out);
+  return ZOLT_OK;
+}
+
 // One rank of the sharded dense sumcheck (contiguous hypercube blocks, NVLink mailbox exchange inside the round
 // kernels).  evals_out / challenges_out hold local_log + log2(world) rounds.
+int zolt_host_sumcheck_prove_sharded_claim(zolt_ctx* ctx, zolt_peer_box* box, int world, int combiner, int local_log, int n_tables,
+                                           const void* const* d_tables, const uint64_t* claim, const char* domain, size_t dn,
+                                           const char* label, size_t ln, uint64_t* evals_out, uint64_t* challenges_out,
+                                           uint64_t* final_out) {
+  Context c(ctx);
+  std::vector<const void*> tabs(d_tables, d_tables + n_tables);
+  Transcript tr(std::string_view(domain, dn));
+  std::vector<Fr> fin;
+  Fr cl;
+  if (claim) cl = Fr::fromRaw(claim);
+  SumcheckProof proof = proveSumcheckSharded(c, box, world, combiner, tabs, local_log, tr, std::string_view(label, ln), &fin, claim ? &cl : nullptr);
+  store_proof(proof, evals_out, challenges_out);
+  if (final_out)
+    for (int t = 0; t < n_tables; t++) fin[t].store(final_out + 4 * t);
+  return ZOLT_OK;
+}
+
 int zolt_host_sumcheck_prove_sharded(zolt_ctx* ctx, zolt_peer_box* box, int world, int combiner, int local_log, int n_tables,
                                      const void* const* d_tables, const char* domain, size_t dn, const char* label, size_t ln,
                                      uint64_t* evals_out, uint64_t* challenges_out, uint64_t* final_out) {

@@ -233,6 +233,22 @@ class DensePolynomial {
     return out;
   }
   const void* devicePtr() const { return d_; }
+  // evaluate(point) (src/poly/mod.zig:73-92): the multilinear extension at `point`, point[j] <-> variable j (index bit j).
+  // The reference folds one variable at a time on a copy; here the same folds run on the device (bindLow per variable on
+  // a scratch copy), the table itself is left untouched.
+  Fr evaluate(const std::vector<Fr>& point) const {
+    if (point.size() != numVars()) panic("DensePolynomial.evaluate: point length != num_vars", ZOLT_ERR_ARG);
+    if (len_ == 1) return evaluations()[0];
+    void* tmp = nullptr;
+    must(zolt_dev_alloc(ctx_.raw(), len_ * 32, &tmp), "zolt_dev_alloc");
+    must(zolt_dev_copy(ctx_.raw(), tmp, d_, len_ * 32), "zolt_dev_copy");
+    size_t n = len_;
+    for (size_t j = 0; j < point.size(); j++, n /= 2) must(zolt_poly_bind_low(ctx_.raw(), tmp, tmp, n, point[j].limbs.data()), "zolt_poly_bind_low");
+    Fr out;
+    must(zolt_dev_download(ctx_.raw(), out.limbs.data(), tmp, 32), "zolt_dev_download");
+    zolt_dev_free(ctx_.raw(), tmp);
+    return out;
+  }
 
  private:
   Context& ctx_;
@@ -240,7 +256,23 @@ class DensePolynomial {
   void* d_ = nullptr;
 };
 
+// BatchOps.hornerEval (src/field/mod.zig:1164-1280): sum_i coeffs[i] x^i, O(n) host glue (Horner from the top coefficient)
+struct BatchOps {
+  static Fr hornerEval(const std::vector<Fr>& coeffs, const Fr& x) {
+    Fr acc = Fr::zero();
+    for (size_t i = coeffs.size(); i-- > 0;) acc = acc.mul(x).add(coeffs[i]);
+    return acc;
+  }
+};
+
 struct EqPolynomial {
+  // mle(r, x) (src/poly/mod.zig:311-321): prod_i (r_i x_i + (1 - r_i)(1 - x_i)); O(n) host glue
+  static Fr mle(const std::vector<Fr>& r, const std::vector<Fr>& x) {
+    if (r.size() != x.size()) panic("EqPolynomial.mle: length mismatch", ZOLT_ERR_ARG);
+    Fr acc = Fr::one();
+    for (size_t i = 0; i < r.size(); i++) acc = acc.mul(r[i].mul(x[i]).add(Fr::one().sub(r[i]).mul(Fr::one().sub(x[i]))));
+    return acc;
+  }
   // evals(): big-endian table eq(r, .) (src/poly/mod.zig:240-290), computed on the device
   static std::vector<Fr> evals(Context& ctx, const std::vector<Fr>& r, const Fr* scale = nullptr) {
     const size_t n = size_t(1) << r.size();
@@ -338,6 +370,9 @@ class DenseSumcheckProver : public SumcheckInstance {
     return e;
   }
   void bindChallenge(const Fr& r) override { must(zolt_sc_bind(sc_, r.limbs.data()), "zolt_sc_bind"); }
+  // SumcheckInstance.input_claim (src/zkvm/batched_sumcheck.zig:34-74): with it the first round also takes p(1) from
+  // p(0) + p(1) = claim instead of summing it (one accumulator less in the round-0 kernel); same evaluations
+  void setInputClaim(const Fr& claim) { must(zolt_sc_set_claim(sc_, claim.limbs.data()), "zolt_sc_set_claim"); }
   std::vector<Fr> table(int t) {
     size_t n = 0;
     must(zolt_sc_len(sc_, &n), "zolt_sc_len");
@@ -362,6 +397,15 @@ class GruenProductProver : public SumcheckInstance {
     must(zolt_sc_create(ctx.raw(), with_c ? ZOLT_SC_GRUEN_AB_MINUS_C : ZOLT_SC_GRUEN_AB, ZOLT_PAIR_ADJACENT, log_n,
                         (int)tables.size(), 0, tables.data(), &sc_),
          "zolt_sc_create");
+    must(zolt_sc_set_split_eq(sc_, reinterpret_cast<const uint64_t*>(tau.data()), (int)tau.size()), "zolt_sc_set_split_eq");
+  }
+  // tables already resident on the device (borrowed read-only by the instance)
+  GruenProductProver(Context& ctx, DenseSumcheckProver::DeviceTables, const std::vector<const void*>& d_tables, int log_n,
+                     const std::vector<Fr>& tau, const Fr& initial_claim, bool with_c = false)
+      : log_n_(log_n), split_eq_(tau), current_claim(initial_claim) {
+    must(zolt_sc_create_dev(ctx.raw(), with_c ? ZOLT_SC_GRUEN_AB_MINUS_C : ZOLT_SC_GRUEN_AB, ZOLT_PAIR_ADJACENT, log_n,
+                            (int)d_tables.size(), 0, d_tables.data(), &sc_),
+         "zolt_sc_create_dev");
     must(zolt_sc_set_split_eq(sc_, reinterpret_cast<const uint64_t*>(tau.data()), (int)tau.size()), "zolt_sc_set_split_eq");
   }
   ~GruenProductProver() override { zolt_sc_free(sc_); }
@@ -477,10 +521,12 @@ class BatchedSumcheckProver {
 // receives the k fully bound table values.
 inline SumcheckProof proveSumcheckSharded(Context& ctx, zolt_peer_box* box, int world, int combiner,
                                           const std::vector<const void*>& d_tables, int local_log, Transcript& transcript,
-                                          std::string_view challenge_label, std::vector<Fr>* final_out) {
+                                          std::string_view challenge_label, std::vector<Fr>* final_out,
+                                          const Fr* input_claim = nullptr) {
   SumcheckProof proof;
   const int k = (int)d_tables.size();
   DenseSumcheckProver local(ctx, DenseSumcheckProver::DeviceTables{}, combiner, ZOLT_PAIR_ADJACENT, d_tables, local_log);
+  if (input_claim) local.setInputClaim(*input_claim);  // the GLOBAL claim: every rank's round kernel folds all ranks' sums
   if (world == 1) {
     proveSumcheckInto(proof, local, transcript, challenge_label);
     if (final_out)
