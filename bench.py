@@ -175,6 +175,57 @@ def ncu_traffic(key: str):
 
 
 # ------------------------------------------------------------------------------------------------------
+# synthetic inputs: functions of the GLOBAL index, independent of the number of GPUs
+# ------------------------------------------------------------------------------------------------------
+CHUNK_LOG = 16
+STREAM_BASE_LOGS, STREAM_SCALARS, STREAM_EQ, STREAM_AZ, STREAM_BZ, STREAM_CZ_RANDOM, STREAM_CZ_MASK, STREAM_M20, STREAM_TRACE = range(1, 10)
+
+
+def rows_global(stream: int, start: int, count: int, out: np.ndarray | None = None) -> np.ndarray:
+    """Rows [start, start + count) of synthetic stream `stream` (canonical Montgomery limbs, uniform below 2^252 < r).
+    Chunk c of 2^16 rows is seeded by (stream, c) alone, so every world size sees the SAME global data and a rank
+    generates only its own range: the MSM and the sumcheck of the 1-, 2-, 4- and 8-GPU runs are the same problem."""
+    res = out if out is not None else np.empty((count, 4), dtype=np.uint64)
+    c_rows = 1 << CHUNK_LOG
+    pos = 0
+    c = start // c_rows
+    while pos < count:
+        lo = c * c_rows
+        chunk = rand_mont(np.random.default_rng([0x5A17, stream, c]), c_rows)
+        a = max(start, lo) - lo
+        b = min(start + count, lo + c_rows) - lo
+        res[pos:pos + (b - a)] = chunk[a:b]
+        pos += b - a
+        c += 1
+    return res
+
+
+def bytes_global(stream: int, start: int, count: int) -> np.ndarray:
+    out = np.empty(count, dtype=np.uint8)
+    c_rows = 1 << CHUNK_LOG
+    pos, c = 0, start // c_rows
+    while pos < count:
+        lo = c * c_rows
+        chunk = np.random.default_rng([0x5A17, stream, c]).integers(0, 256, size=c_rows, dtype=np.uint8)
+        a = max(start, lo) - lo
+        b = min(start + count, lo + c_rows) - lo
+        out[pos:pos + (b - a)] = chunk[a:b]
+        pos += b - a
+        c += 1
+    return out
+
+
+def workload_config(log_n: int, sc_log_n: int) -> dict:
+    """The `config` both arms print (identical in the GPU arm and the reference arm)."""
+    return {
+        "workload": (f"BN254 G1 MSM 2^{log_n} points (HyperKZG commit shape, BASELINE config 4) + degree-3 Spartan-style sumcheck "
+                     f"sum eq*(Az*Bz-Cz) over 2^{sc_log_n} entries with the host Keccak transcript in the loop (BASELINE config 3)"),
+        "inputs": ("synthetic, seeded by GLOBAL index (numpy default_rng([0x5A17, stream, chunk]), 2^16-row chunks): scalars, bases k_i*G, "
+                   "tables Eq/Az/Bz uniform, Cz = Az o Bz on ~90 % of the rows; identical at every GPU count"),
+    }
+
+
+# ------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU algorithms (C++ restatement, oracle/cpu_ref.cpp) on the host cores
 # ------------------------------------------------------------------------------------------------------
 def cpu_msm_sample(log_sample: int, threads: int, seed: int = 7):
@@ -235,8 +286,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall / max(1, args.steps), "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
-        "config": {"workload": f"BN254 G1 MSM 2^{log_n} points + degree-3 sumcheck eq*(Az*Bz-Cz) 2^{args.sc_log_n} entries (BASELINE configs 4 and 3)",
-                   "cpu_sample": sample},
+        "config": workload_config(log_n, args.sc_log_n),
         "cpu_baseline": {"value": value, "unit": "ms", "cores": threads, "kind": "port", "sample": sample,
                          "sumcheck_ms_extrapolated": sc_ms * sc_scale, "host_cores_available": cores},
         "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -248,9 +298,50 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+# checks (untimed; the oracle is allowed here)
+# ------------------------------------------------------------------------------------------------------
+def _fr_ints(a) -> list[int]:
+    from oracle import bn254 as B
+
+    return B.mont_array_to_ints(np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4), B.FR_MOD)
+
+
+def check_msm_closed_form(result, dot_mont_parts) -> bool:
+    """result == (sum_i s_i k_i) * G for bases k_i * G; dot_mont_parts: per-rank Montgomery-form partial dot products."""
+    from oracle import bn254 as B
+
+    total = sum(_fr_ints(p)[0] for p in dot_mont_parts) % B.FR_MOD
+    want = B.g1_mul(B.G1_GEN, total)
+    got = B.arrays_to_points(np.asarray(result[0], dtype=np.uint64).reshape(1, 8), [int(result[1])])[0]
+    return got == want
+
+
+def check_sumcheck_chain(evals, chal, final, claim0: int | None, combine) -> bool:
+    """The verifier's own chain: p_j(0) + p_j(1) = claim_j, claim_{j+1} = p_j(r_j), claim_final = combine(final values)."""
+    from oracle import bn254 as B
+    from oracle import poly as OP
+
+    P = B.FR_MOD
+    rounds = evals.shape[0]
+    e0 = _fr_ints(evals[0])
+    claim = (e0[0] + e0[1]) % P
+    if claim0 is not None and claim != claim0 % P:
+        return False
+    for j in range(rounds):
+        e = _fr_ints(evals[j])
+        if (e[0] + e[1]) % P != claim:
+            return False
+        claim = OP.evaluate_cubic_at_point(e, _fr_ints(chal[j])[0])
+    f = [_fr_ints(final[t])[0] for t in range(final.shape[0])]
+    return claim == combine(f) % P
+
+
+# ------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
 def run_b200(args):
+    import hashlib
+
     import torch
     import torch.distributed as dist
 
@@ -278,25 +369,82 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_rows(row: np.ndarray) -> list[np.ndarray]:
+        """one (4,) uint64 row per rank, rank-ordered (setup/check plumbing, never inside a timed region)"""
+        if world == 1:
+            return [np.asarray(row, dtype=np.uint64)]
+        t = torch.from_numpy(np.asarray(row, dtype=np.uint64).view(np.int64).copy()).cuda()
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.cpu().numpy().view(np.uint64) for o in out]
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    def time_ms(fn, reps: int, warm: int = 1) -> float:
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            a = ev()
+            fn()
+            b = ev()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.mean(ts)
+
     log_n, sc_log_n = args.log_n, args.sc_log_n
     shift = (world - 1).bit_length()
     if (1 << shift) != world:
         raise SystemExit("world size must be a power of two")
     n_local = 1 << (log_n - shift)
     sc_local_log = sc_log_n - shift
+    sc_local = 1 << sc_local_log
     K_TABLES = 4
-    rng = np.random.default_rng(0x5A170000 + rank)
+    pt0, sc0 = rank * n_local, rank * sc_local  # this rank's global ranges (MSM: point range; sumcheck: hypercube block)
 
     # ---- setup (untimed): bases k_i*G generated on the device, host inputs in pinned memory -------------
-    bases = Z.Bases.fixed_base_mul(ctx, rand_mont(rng, n_local))
-    if not args.no_table:
-        bases.precompute(0)  # once per SRS (long-lived SetupParams): window-level table, 13 additions per point
-    msm_windows = 16 if args.no_table or n_local < (1 << 15) else (13 if n_local >= (1 << 20) else 16)
-    h_scalars = rand_mont(rng, n_local, pinned_u64(n_local))
+    h_logs = rows_global(STREAM_BASE_LOGS, pt0, n_local)
+    bases = Z.Bases.fixed_base_mul(ctx, h_logs)
+    h_scalars = rows_global(STREAM_SCALARS, pt0, n_local, pinned_u64(n_local))
     d_scalars = Z.DeviceBuffer.from_host(ctx, h_scalars)
-    h_tabs = [rand_mont(rng, 1 << sc_local_log, pinned_u64(1 << sc_local_log)) for _ in range(K_TABLES)]
+    extras = {}
+    # plain bases first (MSM.compute(bases, scalars) on arbitrary bases), then the per-SRS table
+    if not args.no_table:
+        extras["msm_no_table_ms"] = time_ms(lambda: Z.MSM.compute_dev(bases, d_scalars.ptr, n_local), 3)
+        ctx.sync()
+        t0 = time.perf_counter()
+        bases.precompute(0)  # once per SRS (long-lived SetupParams): window-level table, 13 additions per point
+        ctx.sync()
+        extras["precompute_ms"] = (time.perf_counter() - t0) * 1e3
+    msm_windows = 16 if args.no_table or n_local < (1 << 15) else (13 if n_local >= (1 << 20) else 16)
+
+    h_tabs = [rows_global(s, sc0, sc_local, pinned_u64(sc_local)) for s in (STREAM_EQ, STREAM_AZ, STREAM_BZ)]
     d_tabs = [Z.DeviceBuffer.from_host(ctx, t) for t in h_tabs]
+    # Cz = Az o Bz on ~90 % of the rows (a mostly satisfied R1CS), uniform elsewhere: the product runs on the device (input
+    # generation, untimed), the patch on the host
+    d_cz = Z.DeviceBuffer(ctx, sc_local * 32)
+    ctx.fr_vec_dev(Z.VEC_MUL, d_cz.ptr, d_tabs[1].ptr, d_tabs[2].ptr, n=sc_local)
+    h_cz = pinned_u64(sc_local)
+    h_cz[:] = d_cz.download((sc_local, 4))
+    bad = bytes_global(STREAM_CZ_MASK, sc0, sc_local) < 26
+    h_cz[bad] = rows_global(STREAM_CZ_RANDOM, sc0, sc_local)[bad]
+    d_cz.upload(h_cz)
+    h_tabs.append(h_cz)
+    d_tabs.append(d_cz)
     d_tab_ptrs = [b.ptr for b in d_tabs]
+    # the instance's input claim sum eq*(az*bz - cz) (SumcheckInstance.input_claim: the protocol hands it to the prover)
+    d_tmp = Z.DeviceBuffer(ctx, sc_local * 32)
+    ctx.fr_vec_dev(Z.VEC_EQ_AB_MINUS_C, d_tmp.ptr, d_tabs[1].ptr, d_tabs[2].ptr, d_tabs[3].ptr, d_tabs[0].ptr, n=sc_local)
+    part_sum = np.zeros(4, dtype=np.uint64)
+    Z._lib.check(ctx.lib.zolt_poly_sum(ctx.handle, __import__("ctypes").c_void_p(d_tmp.ptr), sc_local, part_sum.ctypes.data_as(__import__("ctypes").c_void_p)), "zolt_poly_sum")
+    d_tmp.free()
+    claim = np.zeros(4, dtype=np.uint64)
+    for row in gather_rows(part_sum):
+        claim = H.fr_op(1, claim.reshape(1, 4), row.reshape(1, 4))[0]
+
     part = torch.zeros(128, dtype=torch.uint8, device="cuda")
     gathered = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
     ev_part = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -327,40 +475,35 @@ def run_b200(args):
 
     def sumcheck_resident():
         if world == 1:
-            return H.sumcheck_prove_dev(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, d_tab_ptrs, sc_local_log)
+            return H.sumcheck_prove_dev(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, d_tab_ptrs, sc_local_log, claim=claim)
         if box is not None:
-            return H.sumcheck_prove_sharded(ctx, box, Z.SC_EQ_AB_MINUS_C, d_tab_ptrs, sc_local_log)
+            return H.sumcheck_prove_sharded(ctx, box, Z.SC_EQ_AB_MINUS_C, d_tab_ptrs, sc_local_log, claim=claim)
         from zolt_b200 import dist as ZD
 
         return ZD.sharded_sumcheck_gpu(ctx, stream, Z.SC_EQ_AB_MINUS_C, d_tab_ptrs, sc_local_log, world, ev_part, ev_gath)
 
-    def msm_e2e():
+    def msm_e2e(scalars=h_scalars):
         if world == 1:
-            return Z.MSM.compute(bases, h_scalars)
+            return Z.MSM.compute(bases, scalars)
         if box is not None:
-            return Z.MSM.compute_sharded(bases, h_scalars, box)
+            return Z.MSM.compute_sharded(bases, scalars, box)
         with torch.cuda.stream(stream):
-            d_scalars.upload(h_scalars)
+            d_scalars.upload(scalars)
             Z.MSM.partial_dev(bases, d_scalars.ptr, n_local, part.data_ptr())
             dist.all_gather_into_tensor(gathered, part)
             return Z.MSM.sum_partials(ctx, gathered.data_ptr(), world)
 
-    def sumcheck_e2e():
+    def sumcheck_e2e(tabs=h_tabs):
         if world == 1:
-            return H.sumcheck_prove(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, h_tabs)
-        for b, t in zip(d_tabs, h_tabs):
+            return H.sumcheck_prove(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, tabs, claim=claim)
+        for b, t in zip(d_tabs, tabs):
             b.upload(t)
         return sumcheck_resident()
-
-    def ev():
-        e = torch.cuda.Event(enable_timing=True)
-        e.record(stream)
-        return e
 
     # ---- warm-up -----------------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 1)):
         r_msm = msm_resident()
-        sumcheck_resident()
+        r_sc = sumcheck_resident()
     if args.warmup:
         msm_e2e()
         sumcheck_e2e()
@@ -381,7 +524,7 @@ def run_b200(args):
         a = ev()
         r_msm = msm_resident()
         b = ev()
-        sumcheck_resident()
+        r_sc = sumcheck_resident()
         c = ev()
         c.synchronize()
         msm_ms.append(a.elapsed_time(b))
@@ -393,7 +536,7 @@ def run_b200(args):
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- timed loop 2: end to end through the C ABI with host buffers -------------------------------------------
+    # ---- timed loop 2: end to end through the C ABI with host buffers (pinned) ----------------------------------
     barrier()
     e2e_msm, e2e_sc = [], []
     for _ in range(args.steps):
@@ -408,6 +551,23 @@ def run_b200(args):
         e2e_msm.append(a.elapsed_time(b))
         e2e_sc.append(b.elapsed_time(c))
     barrier()
+    # ... and once more from PAGEABLE host memory, which is what a Zig caller's []const F is (2 steps)
+    pg_scalars = np.array(h_scalars, copy=True)
+    pg_tabs = [np.array(t, copy=True) for t in h_tabs]
+    pg_msm, pg_sc = [], []
+    for _ in range(2):
+        if box is not None:
+            box.barrier()
+        a = ev()
+        msm_e2e(pg_scalars)
+        b = ev()
+        sumcheck_e2e(pg_tabs)
+        c = ev()
+        c.synchronize()
+        pg_msm.append(a.elapsed_time(b))
+        pg_sc.append(b.elapsed_time(c))
+    del pg_tabs
+    barrier()
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
@@ -421,8 +581,32 @@ def run_b200(args):
     v_wall = max_over_ranks(wall_ms)
     v_e2e_msm = max_over_ranks(statistics.mean(e2e_msm))
     v_e2e_sc = max_over_ranks(statistics.mean(e2e_sc))
+    v_pg_msm = max_over_ranks(statistics.mean(pg_msm))
+    v_pg_sc = max_over_ranks(statistics.mean(pg_sc))
+
+    # ---- checks (untimed): every rank contributes its part of the closed form, rank 0 decides ---------------------
+    from oracle import cpu_ref as R  # checker only
+
+    cores = os.cpu_count() or 1
+    dot_parts = gather_rows(R.fr_dot(h_logs, h_scalars, threads=max(1, min(8, cores // max(1, world)))))
+    sc_evals, sc_chal, sc_final = r_sc
+    digest_src = hashlib.sha256()
+    for arr in (np.asarray(r_msm[0], dtype=np.uint64), np.asarray([r_msm[1]], dtype=np.uint64), sc_evals, sc_chal, sc_final):
+        digest_src.update(np.ascontiguousarray(arr).tobytes())
+    digests = [digest_src.hexdigest()]
+    if world > 1:
+        all_d = [None] * world
+        dist.all_gather_object(all_d, digests[0])
+        digests = all_d
 
     if rank == 0:
+        checks = {
+            "msm_equals_closed_form": check_msm_closed_form(r_msm, dot_parts),
+            "sumcheck_verifier_chain": check_sumcheck_chain(sc_evals, sc_chal, sc_final, _fr_ints(claim)[0], lambda f: f[0] * (f[1] * f[2] - f[3])),
+            "all_ranks_same_digest": len(set(digests)) == 1,
+            "digest": digests[0],
+            "digest_of": "sha256(MSM affine x|y limbs, infinity flag, all round evaluations, all challenges, final bound values); identical at every GPU count",
+        }
         # per-kernel device times (CUDA events inside the library, on the launching stream)
         acc = {}
         for log in phase_log:
@@ -437,21 +621,23 @@ def run_b200(args):
         # windows actually accumulated x multiply-adds of one mixed addition: 8 products x 128 + 2 squarings x 72 + 9 reductions
         # x 136 (y3 shares one reduction between its two products)
         executed_imad = msm_windows * 2392 * n_local / (accum_ms * 1e-3) / 1e12
-        sc_bytes = 128 * K_TABLES * (1 << sc_local_log)
+        sc_bytes = 128 * K_TABLES * sc_local
         sc_gbs = sc_bytes / (sc_kernel_ms * 1e-3) / 1e9 if sc_kernel_ms else float("nan")
         n_sc = 1 << sc_log_n
+        cfg = workload_config(log_n, sc_log_n)
+        cfg.update({
+            "sharding": ("MSM by point range, sumcheck by contiguous hypercube blocks; exchange: "
+                         + ("NVLink peer mailboxes written by the kernels (no collective library on the data path)" if box is not None
+                            else "NCCL all-gather per round")) if world > 1 else "single GPU",
+            "l2": "inputs (1.5 GiB MSM, 2 GiB sumcheck) exceed the 126 MB L2; no flush needed",
+            "msm_bases": "window-level table built once per SRS in setup (zolt_msm_bases_precompute, c=20, 13 windows); plain-bases time and table build time in `extras`" if not args.no_table else "plain bases (16 windows)",
+            "sumcheck_claim": "input claim supplied (SumcheckInstance.input_claim): round 0 takes p(1) from p(0) + p(1) = claim",
+        })
         line = {
             "metric": METRIC, "value": v_msm, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": v_wall / args.steps, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
-            "config": {
-                "workload": f"BN254 G1 MSM 2^{log_n} points (HyperKZG commit shape) + degree-3 sumcheck eq*(Az*Bz-Cz) over 2^{sc_log_n} entries with host Keccak transcript (BASELINE configs 4 and 3)",
-                "sharding": ("MSM by point range, sumcheck by contiguous hypercube blocks; exchange: "
-                             + ("NVLink peer mailboxes written by the kernels (no collective library on the data path)" if box is not None
-                                else "NCCL all-gather per round")) if world > 1 else "single GPU",
-                "l2": "inputs (1.5 GiB MSM, 2 GiB sumcheck) exceed the 126 MB L2; no flush needed",
-                "msm_bases": "window-level table built once per SRS in setup (zolt_msm_bases_precompute, c=20, 13 windows)" if not args.no_table else "plain bases (16 windows)",
-            },
+            "config": cfg,
             "roofline": {
                 "kernel": "msm_accum_points_kernel (bucket accumulation, mixed additions)", "bound": "int32",
                 "achieved": achieved_imad, "peak": int_peak / 1e12, "unit": "TIMAD/s", "frac": achieved_imad / (int_peak / 1e12) if int_peak else None,
@@ -459,13 +645,13 @@ def run_b200(args):
                 "work_per_launch": f"{IMAD_PER_POINT} IMAD/point x {n_local} points (SURVEY 8d convention: 16 windows x 10 modmul x 264)",
                 "achieved_executed": executed_imad, "frac_executed": executed_imad / (int_peak / 1e12) if int_peak else None,
                 "note": f"the kernel accumulates {msm_windows} windows per point, not the convention's 16, and spends 2392 multiply-adds per mixed addition (dedicated squarings, one shared reduction), not 2640: frac > 1 means fewer operations than the convention's algorithm, frac_executed is the pipe utilisation of the operations actually issued",
-                "kernel_ms": accum_ms, "traffic": ncu_traffic("msm_accum_points_kernel"),
+                "kernel_ms": accum_ms, "traffic": ncu_traffic("msm_accum_points_kernel") if world == 1 else None,
             },
             "roofline_sumcheck": {
                 "kernel": "sc_round_kernel (round-0 eval + fused bind/eval rounds, all launches of one sumcheck)", "bound": "hbm",
                 "achieved": sc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sc_gbs / hbm_peak, "peak_source": peak_src,
                 "frac_of_8000_spec": sc_gbs / 8000.0, "bytes_per_sumcheck": sc_bytes, "kernel_ms": sc_kernel_ms,
-                "traffic": ncu_traffic("sc_round_kernel"),
+                "traffic": ncu_traffic("sc_round_kernel") if world == 1 else None,
             },
             "sumcheck": {
                 "ms": v_sc, "kernel_ms": sc_kernel_ms, "fr_elems_per_s": K_TABLES * n_sc / (v_sc * 1e-3), "hbm_gbs_wall": 128 * K_TABLES * n_sc / (v_sc * 1e-3) / 1e9,
@@ -473,14 +659,20 @@ def run_b200(args):
             },
             "msm_phases_ms": {k: round(v, 4) for k, v in phase_ms.items() if not k.startswith("sc_")},
             "sc_round_kernel_ms": [round(ms, 4) for tag, ms in phase_log[-1] if tag in (16, 17)] if phase_log else [],
-            "e2e": {"value": v_e2e_msm, "unit": "ms", "h2d_bytes_per_step": int(n_local * 32 + K_TABLES * (1 << sc_local_log) * 32),
-                    "d2h_bytes_per_step": int(65 + sc_log_n * (128 + 32) + K_TABLES * 32), "sumcheck_ms": v_e2e_sc},
+            "e2e": {"value": v_e2e_msm, "unit": "ms", "h2d_bytes_per_step": int(n_local * 32 + K_TABLES * sc_local * 32),
+                    "d2h_bytes_per_step": int(65 + sc_log_n * (128 + 32) + K_TABLES * 32), "sumcheck_ms": v_e2e_sc,
+                    "host_buffers": "pinned", "pageable_ms": v_pg_msm, "pageable_sumcheck_ms": v_pg_sc},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "result_check": {"msm_infinity_flag": int(r_msm[1]), "msm_x_limb0": int(r_msm[0][0])},
+            "checks": checks,
+            "extras": {k: round(v, 4) for k, v in extras.items()},
         }
+        if not all(v for k, v in checks.items() if isinstance(v, bool)):
+            line["error"] = "a result check failed: see `checks`"
+    if world == 1 and not args.no_extras:
+        line["extras"].update(extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, time_ms, args))
+    if rank == 0:
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
             threads = min(8, cores)
             s, ms = pick_cpu_sample(threads, budget_s=10.0)
             scale = float(1 << (log_n - s))
@@ -501,6 +693,106 @@ def run_b200(args):
     ctx.close()
 
 
+def extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, time_ms, args) -> dict:
+    """Single-GPU only: the other BASELINE configs and workload variants, each timed on the device (CUDA events on the
+    launching stream, 1 warm-up + 3-5 runs) and checked: MSM 2^16 (config 1), the trace-like scalar distribution of config 4,
+    the degree-2 Eq*MLE sumcheck over 2^20 entries (config 2, the latency-bound case) and the Gruen form of config 3."""
+    from oracle import bn254 as B
+
+    out = {}
+    hbm_peak, _ = measured_peaks()
+    n = h_scalars.shape[0]
+    # config 1: MSM 2^16 over the first 2^16 bases
+    n16 = min(1 << 16, n)
+    d16 = Z.DeviceBuffer.from_host(ctx, h_scalars[:n16])
+    res = [None]
+
+    def run16():
+        res[0] = Z.MSM.compute_dev(bases, d16.ptr, n16)
+
+    ms = time_ms(run16, 5)
+    out["msm_2^16_ms"] = ms
+    out["msm_2^16_frac_int32_convention"] = IMAD_PER_POINT * n16 / (ms * 1e-3) / int_peak if int_peak else None
+    out["msm_2^16_ok"] = check_msm_closed_form(res[0], [R.fr_dot(h_logs[:n16], h_scalars[:n16])])
+    d16.free()
+    # config 4, trace-like scalars: half of the entries byte-sized (a third of those zero), a quarter 64-bit, a quarter zero
+    rng = np.random.default_rng([0x5A17, STREAM_TRACE])
+    small = rng.integers(0, 256, size=n, dtype=np.uint64)
+    small[::3] = 0
+    kind = rng.integers(0, 4, size=n)
+    vals = np.where(kind < 2, small, np.where(kind == 2, rng.integers(0, 1 << 63, size=n, dtype=np.uint64), 0)).astype(np.uint64)
+    raw = np.zeros((n, 4), dtype=np.uint64)
+    raw[:, 0] = vals
+    step = 1 << 20
+    trace = np.empty_like(raw)
+    for lo in range(0, n, step):  # into Montgomery form on the device (zolt_field_batch_op TO_MONT): input generation
+        trace[lo:lo + step] = ctx.field_op(Z.FIELD_FR, Z.OP_TO_MONT, raw[lo:lo + step])
+    d_tr = Z.DeviceBuffer.from_host(ctx, trace)
+
+    def run_tr():
+        res[0] = Z.MSM.compute_dev(bases, d_tr.ptr, n)
+
+    out["msm_trace_like_ms"] = time_ms(run_tr, 3)
+    out["msm_trace_like_ok"] = check_msm_closed_form(res[0], [R.fr_dot(h_logs, trace, threads=min(8, os.cpu_count() or 1))])
+    d_tr.free()
+    # config 2: degree-2 Eq*M over 2^20 entries, host Keccak in the loop (latency-bound: report kernels and wall)
+    l2 = min(20, args.sc_log_n)
+    tau = rows_global(STREAM_EQ, 0, l2)
+    d_eq = Z.DeviceBuffer(ctx, 32 << l2)
+    import ctypes as C
+
+    Z._lib.check(ctx.lib.zolt_eq_evals(ctx.handle, tau.ctypes.data_as(C.c_void_p), l2, None, C.c_void_p(d_eq.ptr)), "zolt_eq_evals")
+    d_m = Z.DeviceBuffer.from_host(ctx, rows_global(STREAM_M20, 0, 1 << l2))
+
+    def run_c2():
+        res[0] = H.sumcheck_prove_dev(ctx, Z.SC_PROD2, Z.PAIR_ADJACENT, [d_eq.ptr, d_m.ptr], l2)
+
+    run_c2()
+    ctx.prof_enable(True)
+    wall = time_ms(run_c2, 5, warm=0)
+    kms = sum(ms for tag, ms in ctx.prof_read() if tag in (16, 17)) / 5
+    ctx.prof_enable(False)
+    out[f"sumcheck_deg2_2^{l2}_ms"] = wall
+    out[f"sumcheck_deg2_2^{l2}_kernel_ms"] = kms
+    out[f"sumcheck_deg2_2^{l2}_frac_hbm_kernels"] = 128 * 2 * (1 << l2) / (kms * 1e-3) / 1e9 / hbm_peak if kms else None
+    out[f"sumcheck_deg2_2^{l2}_ok"] = check_sumcheck_chain(*res[0], None, lambda f: f[0] * f[1])
+    d_eq.free()
+    d_m.free()
+    # config 3, Gruen form: eq(tau, .) never materialised (GRUEN_AB_MINUS_C over Az, Bz, Cz + split-eq weights)
+    lg = args.sc_log_n
+    tau_g = rows_global(STREAM_EQ, 1 << 16, lg)
+    d_eqg = Z.DeviceBuffer(ctx, 32 << lg)  # only to compute the input claim sum eq(tau, x)(az bz - cz)(x), untimed
+    Z._lib.check(ctx.lib.zolt_eq_evals(ctx.handle, tau_g.ctypes.data_as(C.c_void_p), lg, None, C.c_void_p(d_eqg.ptr)), "zolt_eq_evals")
+    ctx.fr_vec_dev(Z.VEC_EQ_AB_MINUS_C, d_eqg.ptr, d_tab_ptrs[1], d_tab_ptrs[2], d_tab_ptrs[3], d_eqg.ptr, n=1 << lg)
+    claim_g = np.zeros(4, dtype=np.uint64)
+    Z._lib.check(ctx.lib.zolt_poly_sum(ctx.handle, C.c_void_p(d_eqg.ptr), 1 << lg, claim_g.ctypes.data_as(C.c_void_p)), "zolt_poly_sum")
+    d_eqg.free()
+
+    def run_g():
+        res[0] = H.sumcheck_prove_gruen_dev(ctx, d_tab_ptrs[1:4], lg, tau_g, claim_g, with_c=True)
+
+    run_g()
+    ctx.prof_enable(True)
+    wall = time_ms(run_g, 3, warm=0)
+    kms = sum(ms for tag, ms in ctx.prof_read() if tag in (16, 17)) / 3
+    ctx.prof_enable(False)
+    out[f"sumcheck_gruen_2^{lg}_ms"] = wall
+    out[f"sumcheck_gruen_2^{lg}_kernel_ms"] = kms
+    out[f"sumcheck_gruen_2^{lg}_frac_hbm_kernels"] = 128 * 3 * (1 << lg) / (kms * 1e-3) / 1e9 / hbm_peak if kms else None
+    # verifier chain of the Gruen proof: p_j(0) + p_j(1) = claim_j, claim_{j+1} = p_j(r_j), first claim = the input claim
+    g_evals, g_chal, g_final_claim = res[0]
+    from oracle import poly as OP
+
+    cl = _fr_ints(claim_g)[0]
+    ok = True
+    for j in range(lg):
+        e = _fr_ints(g_evals[j])
+        ok = ok and (e[0] + e[1]) % B.FR_MOD == cl
+        cl = OP.evaluate_cubic_at_point(e, _fr_ints(g_chal[j])[0])
+    out[f"sumcheck_gruen_2^{lg}_ok"] = bool(ok and cl == _fr_ints(g_final_claim)[0])
+    return {k: (round(v, 5) if isinstance(v, float) else v) for k, v in out.items()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -510,6 +802,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=24, help="MSM size (log2 points)")
     ap.add_argument("--sc-log-n", type=int, default=24, help="sumcheck table size (log2 entries)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-GPU extra legs (configs 1, 2, Gruen, trace-like)")
     ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: host-driven NCCL all-gathers instead of the NVLink mailboxes")
     ap.add_argument("--no-table", action="store_true", help="MSM without the precomputed window-level table")
     args = ap.parse_args()

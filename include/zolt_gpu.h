@@ -54,9 +54,14 @@ const char* zolt_gpu_version(void);
  *   ZOLT_TUNE_SC_BIND_F64     bit k set: the fused adjacent-pair passes bind table k on the FP64 pipe (exact 16 x 32-bit
  *                             limb products in doubles, csrc/field.cuh fp_bind2_fixed_f64) instead of the integer
  *                             multiplier.  Same values; default 0 (measured on B200: the passes are bound by instruction
- *                             issue, the idle FP64 pipe buys nothing -- kept as a parity-tested alternative) */
+ *                             issue, the idle FP64 pipe buys nothing -- kept as a parity-tested alternative)
+ *   ZOLT_TUNE_PEER_TIMEOUT_MS how long a kernel waits for its peers' part of an exchange before the call fails with
+ *                             ZOLT_ERR_PEER (default 4000).  Measured from the waiting kernel's own start, so ranks should be
+ *                             aligned (zolt_peer_barrier) after anything slow and rank-local: a first multi-GiB workspace
+ *                             allocation, zolt_msm_bases_precompute, a debugger */
 #define ZOLT_TUNE_SC_SMALL_PAIRS 1
 #define ZOLT_TUNE_SC_BIND_F64 2
+#define ZOLT_TUNE_PEER_TIMEOUT_MS 3
 int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value);
 
 /* raw device buffers, so a host without CUDA bindings can keep tables resident */

@@ -418,6 +418,31 @@ void ref_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint6
   }
 }
 
+// sum_i a_i * b_i (Montgomery form in, Montgomery form out): BatchOps.innerProduct (src/field/mod.zig:1164-1280), split
+// over `threads` contiguous chunks.  bench.py uses it, untimed, for the closed-form check (sum s_i k_i) * G of the MSM.
+void ref_fr_dot(const uint64_t* a, const uint64_t* b, size_t n, int threads, uint64_t* out) {
+  if (threads < 1) threads = 1;
+  std::vector<Fr> part((size_t)threads, Fr::zero());
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) {
+    pool.emplace_back([&, t]() {
+      const size_t lo = n * (size_t)t / (size_t)threads, hi = n * (size_t)(t + 1) / (size_t)threads;
+      Fr acc = Fr::zero();
+      for (size_t i = lo; i < hi; i++) {
+        Fr x, y;
+        memcpy(x.l, a + 4 * i, 32);
+        memcpy(y.l, b + 4 * i, 32);
+        acc = acc.add(x.mul(y));
+      }
+      part[(size_t)t] = acc;
+    });
+  }
+  for (auto& th : pool) th.join();
+  Fr acc = Fr::zero();
+  for (auto& p : part) acc = acc.add(p);
+  memcpy(out, acc.l, 32);
+}
+
 static std::vector<Affine> load_points(const uint64_t* xy, const uint8_t* inf, size_t n) {
   std::vector<Affine> pts(n);
   for (size_t i = 0; i < n; i++) {

@@ -46,6 +46,14 @@ def field_op(field: int, op: int, a, b=None) -> np.ndarray:
     return out
 
 
+def fr_dot(a, b, threads: int = 1) -> np.ndarray:
+    """sum_i a_i * b_i over Fr (Montgomery limbs in and out)."""
+    a, b = _u64(a, 4), _u64(b, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().ref_fr_dot(_p(a), _p(b), C.c_size_t(a.shape[0]), threads, _p(out))
+    return out
+
+
 def msm(xy, inf, scalars, threads: int = 1):
     xy = _u64(xy, 8)
     s = _u64(scalars, 4)

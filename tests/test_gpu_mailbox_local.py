@@ -1,4 +1,4 @@
-"""The NVLink mailbox protocol (csrc/peer.cuh) on ONE GPU: two ranks = two contexts with their own streams in one process,
+"""The NVLink mailbox protocol (csrc/peer.cuh) on ONE GPU: 2, 4 and 8 ranks = that many contexts with their own streams in one process,
 mailboxes addressed directly (zolt_peer_box_connect_local), each rank driven by its own host thread.  Exercises exactly the
 kernels and the C++ round loop the multi-GPU runs use (publish / flag / wait inside the round kernels, the MSM partial
 sum, the table gather of the tail), so the exchange code is covered on a single-GPU box as well; tests/test_gpu_multi.py
@@ -16,10 +16,9 @@ from zolt_b200 import dist as ZD
 from zolt_b200 import host as H
 
 pytestmark = pytest.mark.gpu
-WORLD = 2
 
 
-def _run_ranks(fn):
+def _run_ranks(fn, WORLD):
     """fn(rank, barrier) on one thread per rank; re-raises the first failure.
 
     Two ranks on ONE device share its allocator: cudaMalloc / cudaFree synchronise the whole device, so a rank that allocates
@@ -47,8 +46,9 @@ def _run_ranks(fn):
     return out
 
 
-@pytest.fixture(scope="module")
-def ranks(built_lib):
+@pytest.fixture(scope="module", params=[2, 4, 8], ids=lambda w: f"world{w}")
+def ranks(built_lib, request):
+    WORLD = request.param
     ctxs = [Z.Context(0) for _ in range(WORLD)]  # private non-blocking streams: the ranks' kernels overlap on the GPU
     boxes = Z.PeerBox.local_group(ctxs)
     yield ctxs, boxes
@@ -60,8 +60,10 @@ def ranks(built_lib):
 
 @pytest.mark.parametrize("kind,comb,k,log_n", [("eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4, 13), ("prod2", Z.SC_PROD2, 2, 16),
                                                ("eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4, 5)])
-def test_sharded_sumcheck_two_ranks_one_gpu(ranks, kind, comb, k, log_n):
+def test_sharded_sumcheck_ranks_one_gpu(ranks, kind, comb, k, log_n):
     ctxs, boxes = ranks
+    WORLD = len(ctxs)
+    local_log = log_n - (WORLD.bit_length() - 1)
     full = [fr_arr(rand_fr(700 + 10 * log_n + t, 1 << log_n)) for t in range(k)]
     r_evals, r_chal, r_final = R.sc_prove(kind, 0, full)
     ne = 3 if comb == Z.SC_PROD2 else 4
@@ -70,23 +72,24 @@ def test_sharded_sumcheck_two_ranks_one_gpu(ranks, kind, comb, k, log_n):
         lo, hi = ZD.shard_range(1 << log_n, rank, WORLD)
         ctx = ctxs[rank]
         bufs = [Z.DeviceBuffer.from_host(ctx, t[lo:hi]) for t in full]
-        H.sumcheck_prove_dev(ctx, comb, Z.PAIR_ADJACENT, [b.ptr for b in bufs], log_n - 1)  # warm-up: fills the buffer pool
+        H.sumcheck_prove_dev(ctx, comb, Z.PAIR_ADJACENT, [b.ptr for b in bufs], local_log)  # warm-up: fills the buffer pool
         ctx.sync()
         barrier.wait()
-        res = H.sumcheck_prove_sharded(ctx, boxes[rank], comb, [b.ptr for b in bufs], log_n - 1)
+        res = H.sumcheck_prove_sharded(ctx, boxes[rank], comb, [b.ptr for b in bufs], local_log)
         ctx.sync()
         barrier.wait()
         for b in bufs:
             b.free()
         return res
 
-    for evals, chal, final in _run_ranks(rank_fn):
+    for evals, chal, final in _run_ranks(rank_fn, WORLD):
         assert (chal == r_chal).all() and (evals[:, :ne] == r_evals[:, :ne]).all()
         assert all((final[t] == r_final[t][0]).all() for t in range(k))
 
 
-def test_sharded_msm_and_primitives_two_ranks_one_gpu(ranks):
+def test_sharded_msm_and_primitives_ranks_one_gpu(ranks):
     ctxs, boxes = ranks
+    WORLD = len(ctxs)
     n = 1 << 12
     logs, scalars = rand_fr(811, n), rand_fr(812, n)
     want = B.msm_closed_form(logs, scalars)
@@ -119,7 +122,7 @@ def test_sharded_msm_and_primitives_two_ranks_one_gpu(ranks):
         bases.free()
         return xy, inf, flat, tr
 
-    for xy, inf, flat, tr in _run_ranks(rank_fn):
+    for xy, inf, flat, tr in _run_ranks(rank_fn, WORLD):
         assert B.arrays_to_points(xy.reshape(1, 8), [inf])[0] == want
         assert flat == list(range(16 * WORLD))
         assert tr == [g * 16 + i * 4 + j for i in range(4) for g in range(WORLD) for j in range(4)]

@@ -1,4 +1,4 @@
-"""GPU parity, 2 ranks over NCCL (skipped unless >= 2 GPUs are visible): the sharded MSM and sharded
+"""GPU parity, 2 / 4 / 8 ranks, one process per GPU (each case skipped unless that many GPUs are visible): the sharded MSM and sharded
 sumcheck of zolt_b200/dist.py must reproduce the single-process results bit for bit."""
 import os
 import subprocess
@@ -93,17 +93,18 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_rank_nccl_parity(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_parity(tmp_path, world):
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run under `gpurun --gpus {world}`)")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, ZOLT_ROOT=str(ROOT))
     res = subprocess.run(
-        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-         "--master-port", "29533", str(script)],
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+         "--master-port", str(29533 + world), str(script)],
         capture_output=True, text=True, env=env, timeout=600,
     )
     assert res.returncode == 0 and "MULTI_GPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]

@@ -108,3 +108,20 @@ def test_batched_sumcheck_prover_rlc(ctx):
                                     fr_arr(challenges))
     assert [fr_ints(g) for g in got] == want
     assert fr_ints(final) == [want_final]
+
+
+def test_dense_polynomial_evaluate_mirror(ctx):
+    """DensePolynomial.evaluate (src/poly/mod.zig:73-92) through the C++ mirror: point[j] <-> variable j (index bit j)."""
+    from oracle import bn254 as B
+    from tests.util import P, fr_arr, fr_ints, rand_fr
+    from zolt_b200 import host as H
+
+    for nv in (0, 1, 5, 10):
+        ev, pt = rand_fr(300 + nv, 1 << nv), rand_fr(400 + nv, nv)
+        want = 0
+        for i, v in enumerate(ev):
+            w = v
+            for j in range(nv):
+                w = w * (pt[j] if (i >> j) & 1 else (1 - pt[j])) % P
+            want = (want + w) % P
+        assert fr_ints(H.dense_evaluate(ctx, fr_arr(ev), fr_arr(pt) if nv else [])) == [want]

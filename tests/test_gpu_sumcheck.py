@@ -54,6 +54,38 @@ def test_dense_rounds_and_tables(ctx, kind, comb, k, pairing, log_n):
     _run_and_compare(ctx, kind, comb, k, pairing, log_n, seed=log_n + 17 * comb + pairing)
 
 
+def test_fp64_pipe_bind_is_bit_identical(ctx):
+    """ZOLT_TUNE_SC_BIND_F64: the fused passes multiply by the challenge on the FP64 pipe (16-bit x 32-bit limb products summed
+    exactly in doubles) for the selected tables -- every round polynomial and every bound table must be unchanged."""
+    try:
+        for mask in (0xF, 0x5, 0x8):
+            ctx.set_tuning(Z.TUNE_SC_BIND_F64, mask)
+            _run_and_compare(ctx, "eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4, Z.PAIR_ADJACENT, 12, seed=41 + mask)
+        ctx.set_tuning(Z.TUNE_SC_BIND_F64, 0x7)
+        _run_and_compare(ctx, "prod3", Z.SC_PROD3, 3, Z.PAIR_ADJACENT, 16, seed=43)
+        _run_and_compare(ctx, "eq_a_bmc", Z.SC_EQ_A_BMC, 4, Z.PAIR_ADJACENT, 9, seed=44, n_extra=1)
+    finally:
+        ctx.set_tuning(Z.TUNE_SC_BIND_F64, 0)
+
+
+def test_shard_protocols_refuse_half_split_and_gruen(ctx):
+    """Blocked hypercube shards are only meaningful for adjacent pairs and dense combiners: the C ABI must say
+    so instead of returning plausible but wrong polynomials."""
+    tabs = [fr_arr(rand_fr(70 + t, 16)) for t in range(2)]
+    inst = Z.SumcheckInstance(ctx, Z.SC_PROD2, Z.PAIR_HALF, tabs)
+    try:
+        with pytest.raises(Exception):
+            inst.set_sharded(True)
+    finally:
+        inst.free()
+    inst = Z.SumcheckInstance(ctx, Z.SC_GRUEN_AB, Z.PAIR_ADJACENT, tabs, tau=fr_arr(rand_fr(72, 4)))
+    try:
+        with pytest.raises(Exception):
+            inst.set_sharded(True)
+    finally:
+        inst.free()
+
+
 def test_dispatch_crossover(ctx):
     # 2^16 entries: rounds 0-1 stream, the rest run on the small-round kernel (several chunks per block)
     _run_and_compare(ctx, "eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4, Z.PAIR_ADJACENT, 16, seed=31)

@@ -49,3 +49,22 @@ def test_unipoly_glue(built_lib):
     x = rand_fr(6, 1)
     assert fr_ints(H.evals_to_compressed(fr_arr(e))) == OP.evals_to_compressed(e)
     assert fr_ints(H.cubic_eval(fr_arr(e), fr_arr(x))) == [OP.evaluate_cubic_at_point(e, x[0])]
+
+
+def test_eq_mle_and_horner_glue(built_lib):
+    """EqPolynomial.mle (src/poly/mod.zig:311-321) and BatchOps.hornerEval (src/field/mod.zig:1164-1280) of the C++ mirror;
+    the reference's own example: 1 + 2x + 3x^2 at x = 4 -> 57 ... and 49 for [1, 2, 3] at 4 is 1 + 8 + 48 = 57."""
+    from zolt_b200 import host as H
+
+    r, x = rand_fr(7, 9), rand_fr(8, 9)
+    want = 1
+    for a, b in zip(r, x):
+        want = want * (a * b + (1 - a) * (1 - b)) % P
+    assert fr_ints(H.eq_mle(fr_arr(r), fr_arr(x))) == [want]
+    # eq on the boolean cube is the indicator
+    bits = [0, 1, 1, 0, 1]
+    assert fr_ints(H.eq_mle(fr_arr(bits), fr_arr(bits))) == [1]
+    assert fr_ints(H.eq_mle(fr_arr(bits), fr_arr([1, 1, 1, 0, 1]))) == [0]
+    coeffs, pt = rand_fr(9, 13), rand_fr(10, 1)[0]
+    assert fr_ints(H.horner_eval(fr_arr(coeffs), fr_arr([pt]))) == [sum(c * pow(pt, i, P) for i, c in enumerate(coeffs)) % P]
+    assert fr_ints(H.horner_eval(fr_arr([1, 2, 3]), fr_arr([4]))) == [57]

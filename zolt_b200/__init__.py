@@ -29,6 +29,8 @@ from ._lib import (  # noqa: F401
     SC_PROD2,
     SC_PROD3,
     SC_SUM,
+    TUNE_PEER_TIMEOUT_MS,
+    TUNE_SC_BIND_F64,
     TUNE_SC_SMALL_PAIRS,
     VEC_AFFINE_INDEX,
     VEC_AXPY,

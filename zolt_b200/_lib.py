@@ -21,6 +21,8 @@ OP_MUL, OP_ADD, OP_SUB, OP_INV, OP_FROM_MONT, OP_TO_MONT, OP_NEG = range(7)
 PAIR_ADJACENT, PAIR_HALF = 0, 1
 SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN_AB_MINUS_C = range(7)
 TUNE_SC_SMALL_PAIRS = 1
+TUNE_SC_BIND_F64 = 2
+TUNE_PEER_TIMEOUT_MS = 3
 VEC_MUL, VEC_EQ_AB_MINUS_C, VEC_AXPY, VEC_AFFINE_INDEX = range(4)
 
 

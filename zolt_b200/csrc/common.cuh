@@ -56,6 +56,7 @@ struct zolt_ctx {
   unsigned long long launches = 0;
   // tuning (zolt_gpu_set_tuning)
   long long sc_small_pairs = 1 << 14;
+  long long peer_timeout_ms = 0;  // 0: default (4 s); ZOLT_TUNE_PEER_TIMEOUT_MS
   int sc_bind_f64 = 0;  // mask of the tables whose binds run on the FP64 pipe in a fused sumcheck pass (ZOLT_TUNE_SC_BIND_F64; measured: no gain)
   // second stream + events for the host-scalar MSM: the second half of the scalars crosses PCIe during the first half's MSM
   cudaStream_t copy_stream = nullptr;

@@ -31,13 +31,15 @@ constexpr size_t kPeerTailTableStride = (size_t)kPeerMaxWorld * kPeerTailEntries
 constexpr size_t kPeerTailBufBytes = (size_t)kPeerTailTables * kPeerTailTableStride * 32;   // 2 MiB
 constexpr size_t kPeerBoxBytes = kPeerHeaderBytes + 2 * kPeerTailBufBytes;
 static_assert(kPeerDataBytes + 2ull * kPeerMaxWorld * sizeof(unsigned) <= kPeerHeaderBytes, "mailbox header");
-constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;
+constexpr unsigned long long kPeerTimeoutNsDefault = 4000000000ull;  // ZOLT_TUNE_PEER_TIMEOUT_MS overrides it per context
 
 struct PeerDev {
   unsigned char* box[kPeerMaxWorld];  // every rank's mailbox in this process's address space (box[rank] is local)
   int rank, world;                    // world <= 1: no exchange
   unsigned seq;                       // this exchange's number (> 0)
   int* err;                           // mapped host flag, set when a peer never showed up
+  unsigned long long timeout_ns;      // how long a kernel waits for its peers, measured from ITS OWN start: ranks must be
+                                      // roughly aligned (zolt_peer_barrier after set-up) or the knob raised
 };
 
 #ifdef __CUDACC__
@@ -84,7 +86,7 @@ static __device__ __noinline__ bool peer_wait(const PeerDev& p) {
       if ((++spins & 1023u) == 0) {
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > kPeerTimeoutNs) {
+        if (t1 - t0 > p.timeout_ns) {
           *p.err = 1 + g;
           __threadfence_system();
           return false;
@@ -135,6 +137,7 @@ inline PeerDev peer_next(zolt_peer_box* box) {
   p.seq = ++box->seq;
   if (p.seq == 0) p.seq = box->seq = 2;  // wrap: keep the slot parity alternating and the number non-zero
   p.err = box->d_err;
+  p.timeout_ns = box->ctx && box->ctx->peer_timeout_ms > 0 ? (unsigned long long)box->ctx->peer_timeout_ms * 1000000ull : kPeerTimeoutNsDefault;
   return p;
 }
 // peer.cu

@@ -1582,8 +1582,14 @@ extern "C" int zolt_sc_set_claim(zolt_sc* sc, const uint64_t claim[4]) {
   return ZOLT_OK;
 }
 
+// The shard protocols (blocked hypercube ranges) are only correct for adjacent pairs and dense combiners: a
+// half-split bind pairs an element with one in another rank's block, and the Gruen weights are indexed by the LOCAL pair
+// index with tau covering the local variables only.  Refuse instead of returning plausible but wrong polynomials.
+static bool sc_shardable(const zolt_sc* sc) { return sc->pairing == ZOLT_PAIR_ADJACENT && !combiner_gruen(sc->combiner); }
+
 extern "C" int zolt_sc_set_sharded(zolt_sc* sc, int on) {
   if (!sc) return ZOLT_ERR_ARG;
+  if (on && !sc_shardable(sc)) return ZOLT_ERR_ARG;
   if (sc->evals_valid && !sc->evals_final) return ZOLT_ERR_STATE;
   sc->sharded = on != 0;
   return ZOLT_OK;
@@ -1600,6 +1606,7 @@ extern "C" int zolt_sc_round_evals(zolt_sc* sc, uint64_t* evals_out) {
 
 extern "C" int zolt_sc_set_peers(zolt_sc* sc, zolt_peer_box* box) {
   if (!sc || !box || !box->connected || box->ctx != sc->ctx) return ZOLT_ERR_ARG;
+  if (!sc_shardable(sc)) return ZOLT_ERR_ARG;
   if (sc->evals_valid || sc->cur >= 0 || sc->sharded) return ZOLT_ERR_STATE;  // before the first round
   sc->box = box;
   return ZOLT_OK;

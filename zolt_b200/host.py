@@ -40,6 +40,8 @@ def load_host() -> C.CDLL:
                                                          C.c_void_p, C.c_void_p]
         _host.zolt_host_sumcheck_prove_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                                            C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _host.zolt_host_sumcheck_prove_claim.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                                         C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_sumcheck_prove_dev_claim.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
                                                              C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_sumcheck_prove_sharded_claim.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
@@ -104,7 +106,7 @@ def cubic_eval(evals, x) -> np.ndarray:
 
 
 def sumcheck_prove(ctx: Context, combiner: int, pairing: int, tables, n_extra: int = 0, domain: bytes = b"bench",
-                   label: bytes = b"round"):
+                   label: bytes = b"round", claim=None):
     """Whole dense sumcheck from HOST tables: upload, then per round GPU evals -> Keccak -> GPU fused
     bind+evals.  Returns (evals (rounds,4,4), challenges (rounds,4), final table values (k,4))."""
     tabs = [_as_u64(t, 4) for t in tables]
@@ -114,9 +116,10 @@ def sumcheck_prove(ctx: Context, combiner: int, pairing: int, tables, n_extra: i
     evals = np.zeros((log_n, 4, 4), dtype=np.uint64)
     chal = np.zeros((log_n, 4), dtype=np.uint64)
     final = np.zeros((len(tabs), 4), dtype=np.uint64)
-    st = load_host().zolt_host_sumcheck_prove(ctx.handle, combiner, pairing, log_n, len(tabs), n_extra, arr, domain, len(domain),
-                                              label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
-    _lib.check(st, "zolt_host_sumcheck_prove")
+    cl = _as_u64(claim, 4) if claim is not None else None
+    st = load_host().zolt_host_sumcheck_prove_claim(ctx.handle, combiner, pairing, log_n, len(tabs), n_extra, arr, _ptr(cl), domain, len(domain),
+                                                    label, len(label), _ptr(evals), _ptr(chal), _ptr(final))
+    _lib.check(st, "zolt_host_sumcheck_prove_claim")
     return evals, chal, final
 
 

@@ -66,6 +66,22 @@ int zolt_host_sumcheck_prove(zolt_ctx* ctx, int combiner, int pairing, int log_n
   return ZOLT_OK;
 }
 
+// zolt_host_sumcheck_prove with the instance's input claim (may be NULL)
+int zolt_host_sumcheck_prove_claim(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
+                                   const uint64_t* const* tables, const uint64_t* claim, const char* domain, size_t dn,
+                                   const char* label, size_t ln, uint64_t* evals_out, uint64_t* challenges_out, uint64_t* final_out) {
+  Context c(ctx);
+  std::vector<const uint64_t*> tabs(tables, tables + n_tables);
+  DenseSumcheckProver prover(c, combiner, pairing, tabs, log_n, n_extra);
+  if (claim) prover.setInputClaim(Fr::fromRaw(claim));
+  Transcript tr(std::string_view(domain, dn));
+  SumcheckProof proof = proveSumcheck(prover, tr, std::string_view(label, ln));
+  store_proof(proof, evals_out, challenges_out);
+  if (final_out)
+    for (int t = 0; t < n_tables; t++) prover.table(t)[0].store(final_out + 4 * t);
+  return ZOLT_OK;
+}
+
 // Same round loop over tables that are already resident on the device.
 int zolt_host_sumcheck_prove_dev(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
                                  const void* const* d_tables, const char* domain, size_t dn, const char* label, size_t ln,
