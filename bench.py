@@ -35,7 +35,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "bn254_g1_msm_ms_at_2^24_points"
 IMAD_PER_POINT = 42240  # SURVEY 8d convention: 16 windows x 10 modmul x 264 int32 multiply-adds
-TAGS = {1: "digits", 2: "scan", 3: "scatter", 4: "accum0", 5: "edges", 6: "reduce", 7: "affine", 16: "sc_eval", 17: "sc_fused"}
+TAGS = {1: "digits", 2: "scan", 3: "scatter", 4: "accum0", 5: "edges", 6: "reduce", 7: "affine", 16: "sc_eval", 17: "sc_fused", 18: "sc_tail"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -615,7 +615,7 @@ def run_b200(args):
         steps = max(1, len(phase_log))
         phase_ms = {k: sum(v) / steps for k, v in acc.items()}
         accum_ms = phase_ms.get("accum0", float("nan"))
-        sc_kernel_ms = phase_ms.get("sc_eval", 0.0) + phase_ms.get("sc_fused", 0.0)
+        sc_kernel_ms = phase_ms.get("sc_eval", 0.0) + phase_ms.get("sc_fused", 0.0) + phase_ms.get("sc_tail", 0.0)
         hbm_peak, peak_src = measured_peaks()
         achieved_imad = IMAD_PER_POINT * n_local / (accum_ms * 1e-3) / 1e12
         # windows actually accumulated x multiply-adds of one mixed addition: 8 products x 128 + 2 squarings x 72 + 9 reductions
@@ -648,7 +648,7 @@ def run_b200(args):
                 "kernel_ms": accum_ms, "traffic": ncu_traffic("msm_accum_points_kernel") if world == 1 else None,
             },
             "roofline_sumcheck": {
-                "kernel": "sc_round_kernel (round-0 eval + fused bind/eval rounds, all launches of one sumcheck)", "bound": "hbm",
+                "kernel": "sc_round_kernel + sc_tail_kernel (round-0 eval, fused bind/eval rounds, resident tail: all launches of one sumcheck)", "bound": "hbm",
                 "achieved": sc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sc_gbs / hbm_peak, "peak_source": peak_src,
                 "frac_of_8000_spec": sc_gbs / 8000.0, "bytes_per_sumcheck": sc_bytes, "kernel_ms": sc_kernel_ms,
                 "traffic": ncu_traffic("sc_round_kernel") if world == 1 else None,
@@ -658,7 +658,8 @@ def run_b200(args):
                 "e2e_ms": v_e2e_sc, "e2e_fr_elems_per_s": K_TABLES * n_sc / (v_e2e_sc * 1e-3),
             },
             "msm_phases_ms": {k: round(v, 4) for k, v in phase_ms.items() if not k.startswith("sc_")},
-            "sc_round_kernel_ms": [round(ms, 4) for tag, ms in phase_log[-1] if tag in (16, 17)] if phase_log else [],
+            "sc_round_kernel_ms": [round(ms, 4) for tag, ms in phase_log[-1] if tag in (16, 17, 18)] if phase_log else [],
+            "sc_round_kernel_note": "one entry per launch: round 0, the fused rounds, and last the resident tail kernel (all rounds of at most 2^12 pairs, host round trips included)",
             "e2e": {"value": v_e2e_msm, "unit": "ms", "h2d_bytes_per_step": int(n_local * 32 + K_TABLES * sc_local * 32),
                     "d2h_bytes_per_step": int(65 + sc_log_n * (128 + 32) + K_TABLES * 32), "sumcheck_ms": v_e2e_sc,
                     "host_buffers": "pinned", "pageable_ms": v_pg_msm, "pageable_sumcheck_ms": v_pg_sc},
@@ -750,7 +751,7 @@ def extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, tim
     run_c2()
     ctx.prof_enable(True)
     wall = time_ms(run_c2, 5, warm=0)
-    kms = sum(ms for tag, ms in ctx.prof_read() if tag in (16, 17)) / 5
+    kms = sum(ms for tag, ms in ctx.prof_read() if tag in (16, 17, 18)) / 5
     ctx.prof_enable(False)
     out[f"sumcheck_deg2_2^{l2}_ms"] = wall
     out[f"sumcheck_deg2_2^{l2}_kernel_ms"] = kms
@@ -774,7 +775,7 @@ def extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, tim
     run_g()
     ctx.prof_enable(True)
     wall = time_ms(run_g, 3, warm=0)
-    kms = sum(ms for tag, ms in ctx.prof_read() if tag in (16, 17)) / 3
+    kms = sum(ms for tag, ms in ctx.prof_read() if tag in (16, 17, 18)) / 3
     ctx.prof_enable(False)
     out[f"sumcheck_gruen_2^{lg}_ms"] = wall
     out[f"sumcheck_gruen_2^{lg}_kernel_ms"] = kms

@@ -62,6 +62,14 @@ const char* zolt_gpu_version(void);
 #define ZOLT_TUNE_SC_SMALL_PAIRS 1
 #define ZOLT_TUNE_SC_BIND_F64 2
 #define ZOLT_TUNE_PEER_TIMEOUT_MS 3
+/*   ZOLT_TUNE_SC_TAIL_PAIRS   rounds whose table has at most this many pairs run inside ONE resident kernel (a cluster of 8
+ *                             CTAs) that takes each challenge from mapped host memory and writes each round polynomial back,
+ *                             instead of one launch per round (default 2^12; 0 = one launch per round).  zolt_sc_bind posts the
+ *                             challenge, zolt_sc_round_evals reads the answer: the call pattern does not change.
+ *   ZOLT_TUNE_SC_TAIL_TIMEOUT_MS  how long that kernel waits for the next challenge before it retires by itself (default
+ *                             10000); a challenge that arrives later is served by a regular launch, transparently */
+#define ZOLT_TUNE_SC_TAIL_PAIRS 4
+#define ZOLT_TUNE_SC_TAIL_TIMEOUT_MS 5
 int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value);
 
 /* raw device buffers, so a host without CUDA bindings can keep tables resident */

@@ -86,6 +86,76 @@ def test_shard_protocols_refuse_half_split_and_gruen(ctx):
         inst.free()
 
 
+def test_resident_tail_kernel(ctx):
+    """The rounds of at most ZOLT_TUNE_SC_TAIL_PAIRS pairs run inside one resident cluster kernel that is fed challenges
+    through mapped memory.  Same round polynomials and tables (a) when nothing interrupts it (whole proofs through the C++
+    round loop), (b) when every round reads the tables back (each read joins the kernel, the next bind restarts it),
+    (c) for two instances driven alternately on one context (a batched sumcheck), (d) when the host pauses longer than
+    the kernel's patience (the command is then served by a regular launch), and (e) with the tail switched off."""
+    import time
+
+    from oracle import cpu_ref as R
+    from zolt_b200 import host as H
+
+    def prove(kind, comb, k, log_n, pairing=Z.PAIR_ADJACENT, seed=0):
+        tabs = [fr_arr(rand_fr(9000 + seed + t, 1 << log_n)) for t in range(k)]
+        bufs = [Z.DeviceBuffer.from_host(ctx, t) for t in tabs]
+        try:
+            got = H.sumcheck_prove_dev(ctx, comb, pairing, [b.ptr for b in bufs], log_n)
+        finally:
+            for b in bufs:
+                b.free()
+        want = R.sc_prove(kind, pairing, tabs)
+        ne = {Z.SC_SUM: 2, Z.SC_PROD2: 3}.get(comb, 4)
+        assert (got[1] == want[1]).all() and (got[0][:, :ne] == want[0][:, :ne]).all(), (kind, log_n)
+        assert all((got[2][t] == want[2][t][0]).all() for t in range(k)), (kind, log_n)
+
+    try:
+        for pairs in (1 << 12, 1 << 14, 64, 0):
+            ctx.set_tuning(Z.TUNE_SC_TAIL_PAIRS, pairs)
+            prove("eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4, 15, seed=pairs)
+            prove("prod2", Z.SC_PROD2, 2, 13, pairing=Z.PAIR_HALF, seed=pairs + 1)
+            prove("sum", Z.SC_SUM, 1, 9, seed=pairs + 2)
+            prove("prod3", Z.SC_PROD3, 3, 3, seed=pairs + 3)
+        ctx.set_tuning(Z.TUNE_SC_TAIL_PAIRS, 1 << 12)
+        # (b) tables read back every round, (with an extra bound-only table)
+        _run_and_compare(ctx, "eq_a_bmc", Z.SC_EQ_A_BMC, 4, Z.PAIR_ADJACENT, 10, seed=61, n_extra=1)
+        # (c) two instances on one context, rounds interleaved
+        log_n = 11
+        ta = [rand_fr(9100 + t, 1 << log_n) for t in range(3)]
+        tb = [rand_fr(9200 + t, 1 << log_n) for t in range(2)]
+        ch = rand_fr(9300, log_n)
+        ea, _ = OS.run_dense("prod3", ta, Z.PAIR_ADJACENT, ch)
+        eb, _ = OS.run_dense("prod2", tb, Z.PAIR_ADJACENT, ch)
+        ia = Z.SumcheckInstance(ctx, Z.SC_PROD3, Z.PAIR_ADJACENT, [fr_arr(t) for t in ta])
+        ib = Z.SumcheckInstance(ctx, Z.SC_PROD2, Z.PAIR_ADJACENT, [fr_arr(t) for t in tb])
+        try:
+            for rnd, r in enumerate(ch):
+                assert fr_ints(ia.compute_round_poly()) == ea[rnd] and fr_ints(ib.compute_round_poly()) == eb[rnd], rnd
+                ia.bind_challenge(fr_arr([r]))
+                ib.bind_challenge(fr_arr([r]))
+        finally:
+            ia.free()
+            ib.free()
+        # (d) a host slower than the kernel's patience
+        ctx.set_tuning(Z.TUNE_SC_TAIL_TIMEOUT_MS, 50)
+        tabs = [rand_fr(9400 + t, 1 << 8) for t in range(4)]
+        ch = rand_fr(9500, 8)
+        exp, _ = OS.run_dense("eq_ab_minus_c", tabs, Z.PAIR_ADJACENT, ch)
+        inst = Z.SumcheckInstance(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, [fr_arr(t) for t in tabs])
+        try:
+            for rnd, r in enumerate(ch):
+                assert fr_ints(inst.compute_round_poly()) == exp[rnd], rnd
+                if rnd in (2, 5):
+                    time.sleep(0.25)
+                inst.bind_challenge(fr_arr([r]))
+        finally:
+            inst.free()
+    finally:
+        ctx.set_tuning(Z.TUNE_SC_TAIL_TIMEOUT_MS, 0)
+        ctx.set_tuning(Z.TUNE_SC_TAIL_PAIRS, 1 << 12)
+
+
 def test_dispatch_crossover(ctx):
     # 2^16 entries: rounds 0-1 stream, the rest run on the small-round kernel (several chunks per block)
     _run_and_compare(ctx, "eq_ab_minus_c", Z.SC_EQ_AB_MINUS_C, 4, Z.PAIR_ADJACENT, 16, seed=31)

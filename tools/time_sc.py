@@ -40,7 +40,9 @@ def main():
     if os.environ.get("SC_CLAIM"):
         ev0, _, _ = H.sumcheck_prove_dev(ctx, comb, Z.PAIR_ADJACENT, ptrs, log_n)
         claim = H.fr_op(1, ev0[0][0:1], ev0[0][1:2])[0]  # p(0) + p(1) of round 0 = the input claim
-    masks = [int(x, 0) for x in os.environ.get('SC_MASKS', '0,0xffff,0,0xffff').split(',')]
+    masks = [int(x, 0) for x in os.environ.get('SC_MASKS', '0').split(',')]
+    if os.environ.get("SC_TAIL") is not None:
+        ctx.set_tuning(4, int(os.environ["SC_TAIL"]))
     for setting in masks:
         ctx.set_tuning(TUNE_BIND_F64, setting)
         H.sumcheck_prove_dev(ctx, comb, Z.PAIR_ADJACENT, ptrs, log_n, claim=claim)  # warm
@@ -52,7 +54,7 @@ def main():
             wall = ctx.timer_stop_ms()
             log = ctx.prof_read()
             ctx.prof_enable(False)
-            ks = [ms for tag, ms in log if tag in (16, 17)]
+            ks = [ms for tag, ms in log if tag in (16, 17, 18)]
             if best is None or sum(ks) < sum(best[1]):
                 best = (wall, ks)
         if ref is None:
@@ -61,8 +63,22 @@ def main():
         gb = 128 * k * n / 1e9
         key = f"bind_f64={setting:#x}"
         out.setdefault(key, []).append({"wall_ms": best[0], "kernel_ms": sum(best[1]), "GBps_kernel": gb / (sum(best[1]) * 1e-3),
-                                        "rounds_ms": [round(x, 4) for x in best[1][:8]], "same_as_first": same})
-        print(key, f"wall {best[0]:.3f} ms kernels {sum(best[1]):.3f} ms -> {gb / (sum(best[1]) * 1e-3):.0f} GB/s", [round(x, 3) for x in best[1][:6]], "same:", same, flush=True)
+                                        "rounds_ms": [round(x, 4) for x in best[1]], "same_as_first": same})
+        print(key, f"wall {best[0]:.3f} ms kernels {sum(best[1]):.3f} ms -> {gb / (sum(best[1]) * 1e-3):.0f} GB/s", [round(x, 3) for x in best[1]], "same:", same, flush=True)
+    if os.environ.get("SC_TAIL_DBG"):
+        dbg = Z.DeviceBuffer(ctx, 8 * 4 * 64)
+        dbg.upload(np.zeros(4 * 64, dtype=np.uint64))
+        ctx.set_tuning(6, dbg.ptr)
+        H.sumcheck_prove_dev(ctx, comb, Z.PAIR_ADJACENT, ptrs, log_n, claim=claim)
+        ctx.sync()
+        t = dbg.download((64, 4)).astype(np.int64)
+        ctx.set_tuning(6, 0)
+        base = t[0, 0]
+        for i in range(64):
+            if t[i, 0] == 0:
+                break
+            prev_pub = t[i - 1, 3] if i else t[i, 0]
+            print(f"tail round {i}: cmd seen +{(t[i,0]-prev_pub)/1e3:.1f} us after prev publish | work {(t[i,1]-t[i,0])/1e3:.1f} | fold+sync {(t[i,2]-t[i,1])/1e3:.1f} | finalize+publish {(t[i,3]-t[i,2])/1e3:.1f}")
     os.makedirs(ROOT / "gpurun_out", exist_ok=True)
     (ROOT / "gpurun_out" / "time_sc.json").write_text(json.dumps(out, indent=1))
     for b in bufs:

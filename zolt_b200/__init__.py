@@ -32,6 +32,8 @@ from ._lib import (  # noqa: F401
     TUNE_PEER_TIMEOUT_MS,
     TUNE_SC_BIND_F64,
     TUNE_SC_SMALL_PAIRS,
+    TUNE_SC_TAIL_PAIRS,
+    TUNE_SC_TAIL_TIMEOUT_MS,
     VEC_AFFINE_INDEX,
     VEC_AXPY,
     VEC_EQ_AB_MINUS_C,

@@ -23,6 +23,8 @@ SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN
 TUNE_SC_SMALL_PAIRS = 1
 TUNE_SC_BIND_F64 = 2
 TUNE_PEER_TIMEOUT_MS = 3
+TUNE_SC_TAIL_PAIRS = 4
+TUNE_SC_TAIL_TIMEOUT_MS = 5
 VEC_MUL, VEC_EQ_AB_MINUS_C, VEC_AXPY, VEC_AFFINE_INDEX = range(4)
 
 

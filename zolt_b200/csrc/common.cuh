@@ -56,6 +56,10 @@ struct zolt_ctx {
   unsigned long long launches = 0;
   // tuning (zolt_gpu_set_tuning)
   long long sc_small_pairs = 1 << 14;
+  long long sc_tail_pairs = 1 << 12;   // rounds with at most this many pairs run inside the resident tail kernel (0: never)
+  unsigned long long* sc_tail_dbg = nullptr;  // diagnostics: device buffer for the tail kernel's per-round time stamps (tuning key 6)
+  long long sc_tail_timeout_ms = 0;    // how long the tail kernel waits for the host's next challenge (0: 10 s)
+  std::vector<cudaStream_t> tail_streams_free;  // recycled private streams of tail kernels
   long long peer_timeout_ms = 0;  // 0: default (4 s); ZOLT_TUNE_PEER_TIMEOUT_MS
   int sc_bind_f64 = 0;  // mask of the tables whose binds run on the FP64 pipe in a fused sumcheck pass (ZOLT_TUNE_SC_BIND_F64; measured: no gain)
   // second stream + events for the host-scalar MSM: the second half of the scalars crosses PCIe during the first half's MSM
@@ -81,7 +85,8 @@ enum ProfTag {
   PROF_MSM_REDUCE = 6,
   PROF_MSM_AFFINE = 7,
   PROF_SC_EVAL = 16,     // round-0 evaluation kernel
-  PROF_SC_FUSED = 17     // fused bind + next-round evaluation kernel
+  PROF_SC_FUSED = 17,    // fused bind + next-round evaluation kernel
+  PROF_SC_TAIL = 18      // resident tail kernel: all rounds below the tail threshold, host round trips included
 };
 // Stream-ordered reuse: buffers are only handed out again to work queued on the same stream.
 inline cudaError_t pool_alloc(zolt_ctx* ctx, size_t bytes, void** out) {
@@ -105,6 +110,8 @@ inline void pool_release(zolt_ctx* ctx, void* p, size_t bytes) {
   if (p) ctx->pool_free.emplace_back(p, pool_capacity_of(bytes));
 }
 inline void pool_destroy(zolt_ctx* ctx) {
+  for (cudaStream_t st : ctx->tail_streams_free) cudaStreamDestroy(st);
+  ctx->tail_streams_free.clear();
   for (auto& b : ctx->pool_free) cudaFree(b.first);
   ctx->pool_free.clear();
   for (void* p : ctx->pinned_free) cudaFreeHost(p);
@@ -137,5 +144,20 @@ inline int prof_begin(zolt_ctx* ctx, int tag) {
 }
 inline void prof_end(zolt_ctx* ctx, int slot) {
   if (slot >= 0) cudaEventRecord(ctx->prof_ev[2 * slot + 1], ctx->stream);
+}
+// the same on another stream of the context (the tail kernel's private stream)
+inline int prof_begin_on(zolt_ctx* ctx, int tag, cudaStream_t stream) {
+  if (!ctx->prof_on || ctx->prof_used >= zolt_ctx::kMaxProf) return -1;
+  const int slot = ctx->prof_used++;
+  ctx->prof_tag[slot] = tag;
+  if (!ctx->prof_ev[2 * slot]) {
+    cudaEventCreate(&ctx->prof_ev[2 * slot]);
+    cudaEventCreate(&ctx->prof_ev[2 * slot + 1]);
+  }
+  cudaEventRecord(ctx->prof_ev[2 * slot], stream);
+  return slot;
+}
+inline void prof_end_on(zolt_ctx* ctx, int slot, cudaStream_t stream) {
+  if (slot >= 0) cudaEventRecord(ctx->prof_ev[2 * slot + 1], stream);
 }
 }  // namespace zolt

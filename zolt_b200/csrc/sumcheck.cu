@@ -17,7 +17,10 @@
 #include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cudaTypedefs.h>
 
+#include <emmintrin.h>
+
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <new>
 
@@ -895,7 +898,8 @@ __device__ __noinline__ Fr bind_pair_cold(Fr lo, Fr hi, Fr r) { return fr_add(lo
 enum { PT_NONE = 0, PT_0, PT_1, PT_2, PT_LEAD };
 
 // the term of pair p of this chunk that belongs to raw sum e (layout of the raw sums: see the combiners above)
-__device__ __noinline__ Fr small_term(const SmallArgs& a, int e, const Fr (*stash)[2][kSmallPairs], int p, const SplitEqDev& sq,
+template <int NP>
+__device__ __noinline__ Fr small_term(const SmallArgs& a, int e, const Fr (*stash)[2][NP], int p, const SplitEqDev& sq,
                                       size_t g) {
   const bool gruen = a.comb == ZOLT_SC_GRUEN_AB || a.comb == ZOLT_SC_GRUEN_AB_MINUS_C;
   int pt = PT_NONE;
@@ -984,6 +988,272 @@ sc_small_kernel(const __grid_constant__ ScPtrs t, const SmallArgs a, size_t n, c
   }
   if (warp < kSmallWorkWarps) x = warp_sum_cold(x);
   grid_fold_publish(x, out);
+}
+
+// ---- persistent tail ------------------------------------------------------------------------------------------------
+// Below ~2^12 pairs a round is all fixed cost: ~25 us of kernel (launch, one pair per thread, grid fold, finalize) plus
+// ~13 us of host (Keccak, launch, mailbox round trip), 12 times per sumcheck (r2 v9 launch list) -- more than the
+// streaming rounds 3..23 together.  The tail therefore runs as ONE kernel that stays resident for all remaining
+// rounds: a thread-block CLUSTER (8 CTAs, co-scheduled by the hardware, so its barrier cannot dead-lock on residency the
+// way a hand-made grid barrier can) that, per round,
+//   waits for the host's command (the challenge) in mapped pinned memory -> binds every table -> evaluates the next round
+//   polynomial -> cluster barrier -> CTA 0 folds the 8 partials, completes the polynomial and writes it, then the
+//   command's sequence number, into the mapped result mailbox the host is already spinning on.
+// The call pattern of the reference (SumcheckInstance.computeRoundPolyFn / bindChallengeFn, prover.zig:405-428) is
+// unchanged: zolt_sc_bind posts the command, zolt_sc_round_evals reads the mailbox.  The kernel runs on a private
+// stream of the instance, so other work on the context's stream (another instance of a batched sumcheck, an MSM) is
+// not queued behind it; anything that needs the tables (download, table_dev, free) first tells it to exit.
+constexpr int kTailCluster = 8;
+constexpr int kTailThreads = 512;
+constexpr int kTailChunk = 128;  // pairs per CTA step (stash: 4 tables x 2 halves x 128 x 32 B = 32 KB)
+enum { TAIL_OP_BIND = 1, TAIL_OP_EXIT = 2 };
+enum { TAIL_ST_RUNNING = 1, TAIL_ST_DONE = 2, TAIL_ST_TIMEOUT = 3 };
+// layout of the instance's 256-byte mapped mailbox: [0,128) evaluations, 128 result sequence number, 132 tail status,
+// 136 number of the last command the kernel has taken (the single command slot may be rewritten after that) (device -> host); 160 command sequence number, 164 op, 168 result sequence number to report, [192, 224) challenge
+// (host -> device)
+constexpr int kMbResultSeq = 128, kMbTailStatus = 132, kMbCmdAck = 136, kMbCmd = 144, kCmdChunks = 6;  // command: 6 chunks of 16 bytes
+
+struct TailArgs {
+  const Fr* in[kMaxTables];  // tables of the instance: inputs, and the two ping-pong sets
+  Fr* b0[kMaxTables];
+  Fr* b1[kMaxTables];
+  int cur;                   // -1 / 0 / 1 as in zolt_sc
+  size_t n;                  // current table length when the kernel starts
+  SmallArgs a;
+  const Fr* e_out;           // split-eq prefix tables (Gruen combiners), level L at offset 2^L - 1
+  const Fr* e_in;
+  int n_tau;
+  Fr* partials;              // kTailCluster * kRaw
+  Fr* d_evals;               // previous round's evaluations in, latest evaluations out
+  Fr* d_raw;
+  unsigned char* mailbox;    // device address of the mapped mailbox
+  unsigned long long timeout_ns;
+  unsigned long long* dbg;   // optional: per round 4 globaltimer stamps of CTA 0 (command seen, work done, folded, published)
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+// sc_finalize with the claim, arithmetic inlined (the tail kernel's one serial step per round)
+__device__ __forceinline__ void sc_finalize_inl(int deg, const Fr* raw, const Fr& claim, Fr* out) {
+  if (deg == 0) {
+#pragma unroll
+    for (int i = 0; i < kRaw; i++) out[i] = raw[i];
+    return;
+  }
+  const Fr p0 = raw[0];
+  const Fr p1 = fr_sub(claim, p0);
+  Fr p2, p3;
+  if (deg == 3) {
+    p2 = raw[2];
+    const Fr lead = raw[3];
+    Fr t = fr_add(fr_add(lead, lead), lead);
+    t = fr_add(t, t);
+    const Fr d = fr_sub(p2, p1);
+    p3 = fr_add(fr_add(t, fr_add(fr_add(d, d), d)), p0);
+  } else {
+    const Fr lead = raw[2];
+    const Fr l2 = fr_add(lead, lead);
+    const Fr s = fr_sub(p1, p0);
+    const Fr p1s = fr_add(p1, s);
+    p2 = fr_add(p1s, l2);
+    p3 = fr_add(fr_add(p1s, s), fr_add(fr_add(l2, l2), l2));
+  }
+  out[0] = p0;
+  out[1] = p1;
+  out[2] = p2;
+  out[3] = p3;
+}
+
+// store a 32-bit word into the same shared-memory variable of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ void dsmem_st_u32(const void* local_var, unsigned rank, unsigned v) {
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_var)), "r"(rank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+}
+
+template <int PAIR>
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThreads)
+sc_tail_kernel(const __grid_constant__ TailArgs ta) {
+  __shared__ Fr stash[4][2][kTailChunk];
+  __shared__ Fr red[kTailThreads / 32];
+  __shared__ unsigned cmd_sh[2 + 8];  // op, result seq, challenge: written by CTA 0 into every CTA's copy
+  __shared__ unsigned claim_w[8];     // CTA 0: the host-supplied claim of the round being evaluated
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned cta = cluster_ctarank();
+  const SmallArgs& a = ta.a;
+  const int kt = a.k + a.n_extra;
+  int cur = ta.cur;
+  size_t n = ta.n;
+  unsigned expect = 1;
+  volatile unsigned* const mb32 = reinterpret_cast<volatile unsigned*>(ta.mailbox);
+  unsigned status = TAIL_ST_DONE;
+  __syncthreads();
+  while (n >= 2) {
+    // ---- the host's next command: ONE thread of the cluster polls the mapped word (a PCIe read per poll) and hands the
+    // command to every CTA through distributed shared memory; everybody else waits at the cluster barrier ----
+    if (cta == 0 && tid == 0) {
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      unsigned w[18];
+      const volatile uint4* const cmd = reinterpret_cast<const volatile uint4*>(ta.mailbox + kMbCmd);
+      for (unsigned spins = 1;; spins++) {
+        uint4 c[kCmdChunks];  // independent system-memory loads, in flight together
+#pragma unroll
+        for (int i = 0; i < kCmdChunks; i++)
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c[i].x), "=r"(c[i].y), "=r"(c[i].z), "=r"(c[i].w) : "l"(cmd + i));
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < kCmdChunks; i++) ok = ok && c[i].x == expect;
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < kCmdChunks; i++) {
+            w[3 * i] = c[i].y;
+            w[3 * i + 1] = c[i].z;
+            w[3 * i + 2] = c[i].w;
+          }
+          break;
+        }
+        if ((spins & 63u) == 0) {
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > ta.timeout_ns) {
+            w[0] = 0xffffffffu;
+#pragma unroll
+            for (int i = 1; i < 18; i++) w[i] = 0;
+            break;
+          }
+        }
+      }
+      // CTA 0 alone needs the claim; every CTA needs op, result seq and the challenge
+#pragma unroll
+      for (int i = 0; i < 8; i++) claim_w[i] = w[10 + i];
+#pragma unroll 1
+      for (unsigned b = 0; b < kTailCluster; b++) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) dsmem_st_u32(&cmd_sh[i], b, w[i]);
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();  // the command sits in every CTA's shared memory
+    const unsigned op = cmd_sh[0];
+    if (cta == 0 && tid == 0) mb32[kMbCmdAck / 4] = expect;  // the host may rewrite the command slot
+    if (ta.dbg && cta == 0 && tid == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); ta.dbg[(expect - 1) * 4 + 0] = tt; }
+    if (op != TAIL_OP_BIND) {  // uniform over the cluster
+      status = op == TAIL_OP_EXIT ? TAIL_ST_DONE : TAIL_ST_TIMEOUT;
+      break;
+    }
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = cmd_sh[2 + i];
+    const Fr* src[kMaxTables];
+    Fr* dst[kMaxTables];
+#pragma unroll
+    for (int k = 0; k < kMaxTables; k++) {
+      src[k] = cur < 0 ? ta.in[k] : (cur == 0 ? ta.b0[k] : ta.b1[k]);
+      dst[k] = cur < 0 ? ta.b0[k] : (cur == 0 ? ta.b1[k] : ta.b0[k]);
+    }
+    Fr x = Fr::zero();
+    if (n >= 4) {
+      // fused round: bind src (n) into dst (n/2), evaluate the next round over dst (n/4 pairs)
+      const size_t n_cur = n / 2, pairs = n_cur / 2, half_old = n / 2, half_cur = n_cur / 2;
+      SplitEqDev sq{nullptr, nullptr, 0};
+      if (ta.e_out) {  // split_eq_for(n_cur)
+        int u = 0;
+        while ((size_t(1) << u) < n_cur) u++;
+        const int head_len = u > 0 ? u - 1 : 0, m = ta.n_tau / 2;
+        const int out_bits = head_len < m ? head_len : m, in_bits = head_len - out_bits;
+        sq.e_out = ta.e_out + ((size_t(1) << out_bits) - 1);
+        sq.e_in = ta.e_in + ((size_t(1) << in_bits) - 1);
+        sq.in_bits = in_bits;
+      }
+      const size_t n_chunks = (pairs + kTailChunk - 1) / kTailChunk;
+      for (size_t c = cta; c < n_chunks; c += kTailCluster) {
+#pragma unroll 1
+        for (int it = tid; it < kTailChunk * 2 * kt; it += kTailThreads) {
+          const int p = it % kTailChunk, h = (it / kTailChunk) & 1, k = it / (2 * kTailChunk);
+          const size_t g = c * kTailChunk + p;
+          if (g >= pairs) continue;
+          const size_t idx = (PAIR == ZOLT_PAIR_ADJACENT) ? 2 * g + h : g + (h ? half_cur : 0);
+          const Fr* s = src[k];
+          const Fr lo = (PAIR == ZOLT_PAIR_ADJACENT) ? ldcg_fr(s + 2 * idx) : ldcg_fr(s + idx);
+          const Fr hi = (PAIR == ZOLT_PAIR_ADJACENT) ? ldcg_fr(s + 2 * idx + 1) : ldcg_fr(s + idx + half_old);
+          const Fr v = bind_pair_cold(lo, hi, r);
+          st_fr(dst[k] + idx, v);
+          if (k < a.k) stash[k][h][p] = v;
+        }
+        __syncthreads();
+        {
+          // warp w: raw sum (w & 3) of pairs (w >> 2) * 32 + lane of this chunk
+          const int e = warp & 3, p = (warp >> 2) * 32 + lane;
+          const size_t g = c * kTailChunk + p;
+          if (g < pairs) x = fr_add_cold(x, small_term(a, e, stash, p, sq, g));
+        }
+        __syncthreads();
+      }
+    } else {
+      // last variable: bind only
+      if (cta == 0 && tid < kt) st_fr(dst[tid], bind_pair_cold(ldcg_fr(src[tid]), ldcg_fr(src[tid] + 1), r));
+    }
+    if (ta.dbg && cta == 0 && tid == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); ta.dbg[(expect - 1) * 4 + 1] = tt; }
+    // ---- fold: warp -> CTA -> cluster ----
+    x = warp_sum_cold(x);
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    if (tid < kRaw) {
+      Fr s = red[tid];
+#pragma unroll 1
+      for (int w = tid + 4; w < kTailThreads / 32; w += 4) s = fr_add_cold(s, red[w]);
+      st_fr(&ta.partials[cta * kRaw + tid], s);
+    }
+    cluster_sync_all();  // every CTA's partials and bound tables are written (release) and visible (acquire)
+    if (ta.dbg && cta == 0 && tid == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); ta.dbg[(expect - 1) * 4 + 2] = tt; }
+    if (cta == 0 && n >= 4) {
+      // thread e folds raw sum e over the CTAs; thread 0 completes the polynomial and publishes it
+      if (tid < kRaw) {
+        Fr s = Fr::zero();
+#pragma unroll 1
+        for (int b = 0; b < kTailCluster; b++) s = fr_add(s, ldcg_fr(&ta.partials[b * kRaw + tid]));
+        red[tid] = s;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        Fr tot[kRaw], ev[4], claim;
+#pragma unroll 1
+        for (int e = 0; e < kRaw; e++) tot[e] = red[e];
+#pragma unroll
+        for (int i = 0; i < 8; i++) claim.v[i] = claim_w[i];
+        sc_finalize_inl(a.deg, tot, claim, ev);
+        Fr* h_evals = reinterpret_cast<Fr*>(ta.mailbox);
+#pragma unroll 1
+        for (int e = 0; e < 4; e++) st_fr(&h_evals[e], ev[e]);
+        __threadfence_system();
+        mb32[kMbResultSeq / 4] = cmd_sh[1];
+#pragma unroll 1
+        for (int e = 0; e < 4; e++) {
+          st_fr(&ta.d_evals[e], ev[e]);
+          st_fr(&ta.d_raw[e], tot[e]);
+        }
+      }
+    }
+    if (ta.dbg && cta == 0 && tid == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); ta.dbg[(expect - 1) * 4 + 3] = tt; }
+    cluster_sync_all();  // partials may be overwritten, the next round may read dst and d_evals, cmd_sh may be rewritten
+    cur = cur < 0 ? 0 : (cur ^ 1);
+    n /= 2;
+    expect++;
+  }
+  if (cta == 0 && tid == 0) {
+    __threadfence_system();
+    mb32[kMbTailStatus / 4] = status;
+    __threadfence_system();
+  }
+  cluster_sync_all();  // no CTA leaves while another may still address its shared memory
 }
 
 // last variable (n == 2): bind every table's single pair, nothing left to evaluate
@@ -1179,6 +1449,15 @@ struct zolt_sc {
   unsigned max_grid = 0;
   unsigned wait_seq = 0;         // mailbox word that marks the evaluations of the latest launch as delivered
   zolt_peer_box* box = nullptr;  // zolt_sc_set_peers: rounds exchange their sums through the NVLink mailboxes
+  // persistent tail kernel (sc_tail_kernel): resident from the first small round to the last bind
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t tail_ev = nullptr;
+  bool tail_active = false;     // the kernel has been launched and not yet joined
+  unsigned tail_cmds = 0;       // commands posted to the running kernel
+  int tail_prof = -1;
+  bool tail_pending = false;    // a bind command has been posted whose evaluations have not been read yet
+  int tail_prev_cur = 0;        // state before that command (to redo it through a regular launch if the kernel timed out)
+  size_t tail_prev_n = 0;
 };
 
 namespace {
@@ -1475,6 +1754,114 @@ int sc_alloc(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, 
 
 }  // namespace
 
+namespace {
+
+inline volatile unsigned* mb_word(zolt_sc* sc, int byte_off) {
+  return reinterpret_cast<volatile unsigned*>(reinterpret_cast<unsigned char*>(sc->h_evals) + byte_off);
+}
+
+bool tail_eligible(const zolt_sc* sc) {
+  return sc->ctx->sc_tail_pairs > 0 && !sc->sharded && !sc->box && sc->k <= 4 && sc->k + sc->n_extra <= kMaxTables;
+}
+
+int tail_launch(zolt_sc* sc) {
+  zolt_ctx* ctx = sc->ctx;
+  if (!sc->tail_stream) {
+    if (!ctx->tail_streams_free.empty()) {
+      sc->tail_stream = ctx->tail_streams_free.back();
+      ctx->tail_streams_free.pop_back();
+    } else {
+      ZOLT_CUDA_TRY(cudaStreamCreateWithFlags(&sc->tail_stream, cudaStreamNonBlocking));
+    }
+    ZOLT_CUDA_TRY(cudaEventCreateWithFlags(&sc->tail_ev, cudaEventDisableTiming));
+  }
+  TailArgs ta{};
+  const int total = sc->k + sc->n_extra;
+  for (int i = 0; i < total; i++) {
+    ta.in[i] = sc->tab_in[i];
+    ta.b0[i] = sc->buf[0][i];
+    ta.b1[i] = sc->buf[1][i];
+  }
+  ta.cur = sc->cur;
+  ta.n = sc->n;
+  ta.a = SmallArgs{sc->combiner, sc->k, sc->n_extra, combiner_deg(sc->combiner), 1, 0};
+  ta.e_out = combiner_gruen(sc->combiner) ? sc->d_e_out : nullptr;
+  ta.e_in = sc->d_e_in;
+  ta.n_tau = sc->n_tau;
+  ta.partials = sc->d_partials;
+  ta.d_evals = sc->d_evals;
+  ta.d_raw = sc->d_raw;
+  ta.mailbox = reinterpret_cast<unsigned char*>(sc->h_evals_dev);
+  ta.timeout_ns = (unsigned long long)(ctx->sc_tail_timeout_ms > 0 ? ctx->sc_tail_timeout_ms : 10000) * 1000000ull;
+  ta.dbg = ctx->sc_tail_dbg;
+  memset(reinterpret_cast<unsigned char*>(sc->h_evals) + kMbCmd, 0, 16 * kCmdChunks);
+  *mb_word(sc, kMbCmdAck) = 0;
+  *mb_word(sc, kMbTailStatus) = TAIL_ST_RUNNING;
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+  // the kernel continues from what the context's stream has produced so far (the tables, d_evals)
+  ZOLT_CUDA_TRY(cudaEventRecord(sc->tail_ev, ctx->stream));
+  ZOLT_CUDA_TRY(cudaStreamWaitEvent(sc->tail_stream, sc->tail_ev, 0));
+  sc->tail_prof = prof_begin_on(ctx, PROF_SC_TAIL, sc->tail_stream);
+  if (sc->pairing == ZOLT_PAIR_ADJACENT) sc_tail_kernel<ZOLT_PAIR_ADJACENT><<<kTailCluster, kTailThreads, 0, sc->tail_stream>>>(ta);
+  else sc_tail_kernel<ZOLT_PAIR_HALF><<<kTailCluster, kTailThreads, 0, sc->tail_stream>>>(ta);
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  prof_end_on(ctx, sc->tail_prof, sc->tail_stream);
+  ctx->launches++;
+  sc->tail_active = true;
+  sc->tail_cmds = 0;
+  return ZOLT_OK;
+}
+
+void tail_post(zolt_sc* sc, unsigned op, const Fr* r, unsigned result_seq, const Fr* claim = nullptr) {
+  // one command slot: the previous command must have been taken (acknowledged) before it is rewritten
+  for (unsigned spins = 1; *mb_word(sc, kMbCmdAck) != sc->tail_cmds; spins++) {
+    if ((spins & 0xfffu) == 0 && cudaStreamQuery(sc->tail_stream) != cudaErrorNotReady) break;  // the kernel is gone (timed out)
+  }
+  const unsigned seq = ++sc->tail_cmds;
+  unsigned w[18] = {op, result_seq};
+  if (r)
+    for (int i = 0; i < 8; i++) w[2 + i] = r->v[i];
+  if (claim)
+    for (int i = 0; i < 8; i++) w[10 + i] = claim->v[i];
+  unsigned char* const base = reinterpret_cast<unsigned char*>(sc->h_evals) + kMbCmd;
+  for (int c = 0; c < kCmdChunks; c++) {  // one aligned 16-byte store per chunk: a chunk is never seen half written
+    alignas(16) const unsigned chunk[4] = {seq, w[3 * c], w[3 * c + 1], w[3 * c + 2]};
+    _mm_store_si128(reinterpret_cast<__m128i*>(base + 16 * c), _mm_load_si128(reinterpret_cast<const __m128i*>(chunk)));
+  }
+  _mm_sfence();
+}
+
+// p(r) for the cubic through (0, e0) .. (3, e3), on the host (Newton forward differences; exact field arithmetic, so the
+// same canonical value as any other evaluation formula -- evaluateCubicAtPointGeneric, batched_sumcheck.zig:437-457)
+Fr host_cubic_at(const Fr* e, const Fr& r) {
+  using P = FrParams;
+  const Fr d1 = fp_sub<P>(e[1], e[0]), d1b = fp_sub<P>(e[2], e[1]), d1c = fp_sub<P>(e[3], e[2]);
+  const Fr d2 = fp_sub<P>(d1b, d1), d2b = fp_sub<P>(d1c, d1b), d3 = fp_sub<P>(d2b, d2);
+  Fr inv2, inv6;
+  for (int i = 0; i < 8; i++) {
+    inv2.v[i] = P::inv2(i);
+    inv6.v[i] = P::inv6(i);
+  }
+  const Fr rm1 = fp_sub<P>(r, Fr::one()), rm2 = fp_sub<P>(rm1, Fr::one());
+  const Fr rr1 = fp_mul<P>(r, rm1);
+  const Fr c2 = fp_mul<P>(rr1, inv2), c3 = fp_mul<P>(fp_mul<P>(rr1, rm2), inv6);
+  Fr acc = fp_add<P>(e[0], fp_mul<P>(r, d1));
+  acc = fp_add<P>(acc, fp_mul<P>(c2, d2));
+  return fp_add<P>(acc, fp_mul<P>(c3, d3));
+}
+
+// Join the tail kernel (telling it to exit if it is still waiting for commands).  Afterwards the instance's tables and
+// d_evals are exactly what the host-side bookkeeping (cur, n, evals_valid) says, and regular launches can continue.
+int tail_stop(zolt_sc* sc) {
+  if (!sc->tail_active) return ZOLT_OK;
+  if (sc->n >= 2) tail_post(sc, TAIL_OP_EXIT, nullptr, 0);  // after the last bind the kernel has left its loop by itself
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->tail_stream));
+  sc->tail_active = false;
+  return ZOLT_OK;
+}
+
+}  // namespace
+
 extern "C" int zolt_sc_create(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
                               const uint64_t* const* tables, zolt_sc** out) {
   if (!tables) return ZOLT_ERR_ARG;
@@ -1549,18 +1936,35 @@ static int sc_ensure_evals(zolt_sc* sc) {
 // sequence number next to them.  Spinning on that word hands the result to the transcript a kernel-retirement
 // and a driver round trip earlier than cudaStreamSynchronize (per round, 24 rounds per sumcheck); the stream is
 // still queried now and then so that a failed launch or a peer time-out ends the wait.
+static int sc_bind_launch(zolt_sc* sc, const Fr& r);
 static int sc_wait_evals(zolt_sc* sc) {
   if (!sc->wait_seq) {
     ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
     return peer_check(sc->box);
   }
   volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(sc->h_evals + 4);
+  const cudaStream_t stream = sc->tail_active ? sc->tail_stream : sc->ctx->stream;
+  // cudaStreamQuery is a driver call of several microseconds that delays the very flag it guards: look at the stream
+  // only every ~100 us of spinning (r2 v10: queried every 1024 spins, the host noticed a published round 30 us late)
+  auto t_last = std::chrono::steady_clock::now();
   for (unsigned spins = 1;; spins++) {
     if (*flag == sc->wait_seq) break;
-    if ((spins & 0x3ffu) == 0) {
-      const cudaError_t q = cudaStreamQuery(sc->ctx->stream);
+    if ((spins & 0xffu) == 0 && std::chrono::steady_clock::now() - t_last > std::chrono::microseconds(100)) {
+      t_last = std::chrono::steady_clock::now();
+      const cudaError_t q = cudaStreamQuery(stream);
       if (q == cudaSuccess) {
         if (*flag == sc->wait_seq) break;
+        if (sc->tail_active && sc->tail_pending && *mb_word(sc, kMbTailStatus) == TAIL_ST_TIMEOUT) {
+          // the tail kernel gave up waiting before this command was posted (a host that paused for seconds between
+          // two rounds): nothing of the command was executed -- take it back and run it as a regular launch
+          sc->tail_active = false;
+          sc->tail_pending = false;
+          sc->cur = sc->tail_prev_cur;
+          sc->n = sc->tail_prev_n;
+          sc->evals_valid = true;
+          ZOLT_TRY(sc_bind_launch(sc, sc->last_r));
+          return sc_wait_evals(sc);
+        }
         ZOLT_TRY(peer_check(sc->box));
         fprintf(stderr, "[zolt_gpu] round kernel retired without delivering its evaluations\n");
         return ZOLT_ERR_CUDA;
@@ -1569,6 +1973,7 @@ static int sc_wait_evals(zolt_sc* sc) {
     }
   }
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  sc->tail_pending = false;
   return ZOLT_OK;
 }
 
@@ -1590,6 +1995,7 @@ static bool sc_shardable(const zolt_sc* sc) { return sc->pairing == ZOLT_PAIR_AD
 extern "C" int zolt_sc_set_sharded(zolt_sc* sc, int on) {
   if (!sc) return ZOLT_ERR_ARG;
   if (on && !sc_shardable(sc)) return ZOLT_ERR_ARG;
+  ZOLT_TRY(tail_stop(sc));
   if (sc->evals_valid && !sc->evals_final) return ZOLT_ERR_STATE;
   sc->sharded = on != 0;
   return ZOLT_OK;
@@ -1614,6 +2020,7 @@ extern "C" int zolt_sc_set_peers(zolt_sc* sc, zolt_peer_box* box) {
 
 extern "C" int zolt_sc_gather_tail(zolt_sc* sc, const void** d_tables_out, size_t* n_out) {
   if (!sc || !d_tables_out || !n_out || !sc->box) return ZOLT_ERR_ARG;
+  ZOLT_TRY(tail_stop(sc));
   if (sc->n < 1 || sc->n > kPeerTailEntries) return ZOLT_ERR_STATE;  // bind further first
   const Fr* ptrs[kMaxTables];
   const Fr* outs[kMaxTables];
@@ -1658,13 +2065,9 @@ extern "C" int zolt_sc_finish_partials(zolt_sc* sc, const void* d_rows, size_t r
   return ZOLT_OK;
 }
 
-extern "C" int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]) {
-  if (!sc || !challenge) return ZOLT_ERR_ARG;
-  if (sc->n < 2) return ZOLT_ERR_STATE;
-  if (combiner_gruen(sc->combiner) && !sc->d_e_out) return ZOLT_ERR_STATE;
+// one bind through a regular launch (fused bind + next evaluation, or the final bind)
+static int sc_bind_launch(zolt_sc* sc, const Fr& r) {
   zolt_ctx* ctx = sc->ctx;
-  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
-  const Fr r = fr_from_host(challenge);
   if (sc->n >= 4) {
     // the fused pass derives p(1) of the next round from this round's polynomial at r
     if (!sc->evals_valid) {
@@ -1693,6 +2096,46 @@ extern "C" int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]) {
   return ZOLT_OK;
 }
 
+extern "C" int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]) {
+  if (!sc || !challenge) return ZOLT_ERR_ARG;
+  if (sc->n < 2) return ZOLT_ERR_STATE;
+  if (combiner_gruen(sc->combiner) && !sc->d_e_out) return ZOLT_ERR_STATE;
+  zolt_ctx* ctx = sc->ctx;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  const Fr r = fr_from_host(challenge);
+  // small rounds: post the challenge to the resident tail kernel instead of launching (see sc_tail_kernel)
+  if (tail_eligible(sc) && sc->n / 4 <= (size_t)ctx->sc_tail_pairs) {
+    if (!sc->tail_active && !sc->evals_valid) ZOLT_TRY(sc_ensure_evals(sc));  // the kernel starts from the current round's evaluations
+    Fr claim = Fr::zero();
+    if (sc->n >= 4 && combiner_deg(sc->combiner) != 0) {
+      // the next round's claim is this round's polynomial at r: O(1) host glue on the evaluations in the result mailbox
+      // (waited for here if the caller has not fetched them; this also notices a tail kernel that timed out)
+      ZOLT_TRY(sc_wait_evals(sc));
+      claim = host_cubic_at(sc->h_evals, r);
+    } else if (sc->tail_pending) {
+      ZOLT_TRY(sc_wait_evals(sc));
+    }
+    if (!sc->tail_active) ZOLT_TRY(tail_launch(sc));
+    sc->last_r = r;
+    sc->tail_prev_cur = sc->cur;
+    sc->tail_prev_n = sc->n;
+    unsigned seq = 0;
+    if (sc->n >= 4) {
+      if (++ctx->mail_seq == 0) ++ctx->mail_seq;
+      seq = sc->wait_seq = ctx->mail_seq;
+    }
+    tail_post(sc, TAIL_OP_BIND, &r, seq, &claim);
+    sc->tail_pending = sc->n >= 4;
+    sc->evals_valid = sc->n >= 4;
+    sc->evals_final = true;
+    sc->cur = sc->cur < 0 ? 0 : (sc->cur ^ 1);
+    sc->n /= 2;
+    return ZOLT_OK;
+  }
+  ZOLT_TRY(tail_stop(sc));
+  return sc_bind_launch(sc, r);
+}
+
 extern "C" int zolt_sc_len(const zolt_sc* sc, size_t* n) {
   if (!sc || !n) return ZOLT_ERR_ARG;
   *n = sc->n;
@@ -1702,6 +2145,7 @@ extern "C" int zolt_sc_len(const zolt_sc* sc, size_t* n) {
 extern "C" int zolt_sc_download(zolt_sc* sc, int table, uint64_t* dst) {
   if (!sc || !dst || table < 0 || table >= sc->k + sc->n_extra) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(sc->ctx->device));
+  ZOLT_TRY(tail_stop(sc));  // the resident tail kernel owns the tables until it is joined
   const Fr* src = sc->cur < 0 ? sc->tab_in[table] : sc->buf[sc->cur][table];
   ZOLT_CUDA_TRY(cudaMemcpyAsync(dst, src, sc->n * sizeof(Fr), cudaMemcpyDeviceToHost, sc->ctx->stream));
   ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
@@ -1710,6 +2154,7 @@ extern "C" int zolt_sc_download(zolt_sc* sc, int table, uint64_t* dst) {
 
 extern "C" int zolt_sc_table_dev(zolt_sc* sc, int table, const void** d_ptr) {
   if (!sc || !d_ptr || table < 0 || table >= sc->k + sc->n_extra) return ZOLT_ERR_ARG;
+  ZOLT_TRY(tail_stop(sc));
   *d_ptr = sc->cur < 0 ? sc->tab_in[table] : sc->buf[sc->cur][table];
   return ZOLT_OK;
 }
@@ -1717,8 +2162,11 @@ extern "C" int zolt_sc_table_dev(zolt_sc* sc, int table, const void** d_ptr) {
 extern "C" int zolt_sc_free(zolt_sc* sc) {
   if (!sc) return ZOLT_ERR_ARG;
   cudaSetDevice(sc->ctx->device);
+  tail_stop(sc);
   cudaStreamSynchronize(sc->ctx->stream);
   zolt_ctx* ctx = sc->ctx;
+  if (sc->tail_stream) ctx->tail_streams_free.push_back(sc->tail_stream);
+  if (sc->tail_ev) cudaEventDestroy(sc->tail_ev);
   for (int i = 0; i < kMaxTables; i++) {
     if (sc->owns_in && sc->tab_in[i]) pool_release(ctx, const_cast<Fr*>(sc->tab_in[i]), sc->in_bytes);
     if (sc->buf[0][i]) pool_release(ctx, sc->buf[0][i], sc->buf_bytes[0]);

@@ -174,7 +174,7 @@ struct UniPoly {
     return acc;
   }
   static std::array<Fr, 4> interpolateDegree3(const std::array<Fr, 4>& e) {
-    const Fr inv6 = Fr::fromU64(6).inverse(), inv2 = Fr::fromU64(2).inverse();
+    static const Fr inv6 = Fr::fromU64(6).inverse(), inv2 = Fr::fromU64(2).inverse();  // once, not per call as the reference does
     auto k = [](uint64_t v) { return Fr::fromU64(v); };
     Fr c1 = Fr::zero().sub(k(11).mul(e[0])).add(k(18).mul(e[1])).sub(k(9).mul(e[2])).add(k(2).mul(e[3])).mul(inv6);
     Fr c2 = k(2).mul(e[0]).sub(k(5).mul(e[1])).add(k(4).mul(e[2])).sub(e[3]).mul(inv2);
@@ -189,12 +189,15 @@ struct UniPoly {
 
 // evaluateCubicAtPointGeneric (src/zkvm/batched_sumcheck.zig:437-457)
 inline Fr evaluateCubicAtPoint(const std::array<Fr, 4>& e, const Fr& x) {
-  const Fr one = Fr::one(), two = Fr::fromU64(2), three = Fr::fromU64(3), six = Fr::fromU64(6);
+  // the reference inverts 6, 2, -2, -6 on every call (four Fermat inversions per round); same values, computed once
+  static const Fr one = Fr::one(), two = Fr::fromU64(2), three = Fr::fromU64(3);
+  static const Fr inv_m6 = Fr::fromU64(6).neg().inverse(), inv_2 = Fr::fromU64(2).inverse(), inv_m2 = Fr::fromU64(2).neg().inverse(),
+                  inv_6 = Fr::fromU64(6).inverse();
   const Fr x1 = x.sub(one), x2 = x.sub(two), x3 = x.sub(three);
-  const Fr L0 = x1.mul(x2).mul(x3).mul(six.neg().inverse());
-  const Fr L1 = x.mul(x2).mul(x3).mul(two.inverse());
-  const Fr L2 = x.mul(x1).mul(x3).mul(two.neg().inverse());
-  const Fr L3 = x.mul(x1).mul(x2).mul(six.inverse());
+  const Fr L0 = x1.mul(x2).mul(x3).mul(inv_m6);
+  const Fr L1 = x.mul(x2).mul(x3).mul(inv_2);
+  const Fr L2 = x.mul(x1).mul(x3).mul(inv_m2);
+  const Fr L3 = x.mul(x1).mul(x2).mul(inv_6);
   return e[0].mul(L0).add(e[1].mul(L1)).add(e[2].mul(L2)).add(e[3].mul(L3));
 }
 
