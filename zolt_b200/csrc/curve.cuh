@@ -175,8 +175,11 @@ ZOLT_HD AffineG1 affine_neg(const AffineG1& p) {
 
 // k * P for a small unsigned k (double-and-add, MSB first)
 ZOLT_HD XYZZ xyzz_mul_small(const XYZZ& p, uint32_t k) {
-  XYZZ acc = XYZZ::identity();
-  for (int bit = 31; bit >= 0; bit--) {
+  if (k == 0) return XYZZ::identity();
+  int top = 31;
+  while (!((k >> top) & 1u)) top--;  // start at the leading one: no doublings of the identity
+  XYZZ acc = p;
+  for (int bit = top - 1; bit >= 0; bit--) {
     acc = xyzz_dbl(acc);
     if ((k >> bit) & 1u) xyzz_add(acc, p);
   }

@@ -634,7 +634,18 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   if (num_keys >= 0xfffffff0ull || max_entries >= 0xfffffff0ull || n >= 0x7fffffffull) return ZOLT_ERR_ARG;
   if (pre && (size_t)g.windows * bases->n >= 0x7fffffffull) return ZOLT_ERR_ARG;
 
-  const uint32_t slice_len = max_entries >= (size_t(1) << 26) ? kSlice0Big : kSlice0;
+  // Level-0 slice length: about 128 (256 for very long lists), adjusted so that the blocks of the accumulation kernel fill
+  // a whole number of waves (4 blocks of 128 threads per SM): a trailing partial wave costs a full wave of time -- at 2^21
+  // points per GPU (the 8-GPU shard of 2^24) 2.81 waves of 128-entry slices became 3 waves of 120-entry ones.
+  uint32_t slice_len = max_entries >= (size_t(1) << 26) ? kSlice0Big : kSlice0;
+  {
+    const size_t wave = (size_t)ctx->num_sms * 4 * 128;  // threads resident at once
+    const size_t waves = (max_entries + (size_t)slice_len * wave - 1) / ((size_t)slice_len * wave);
+    if (waves >= 1 && waves <= 64) {
+      const size_t even = (max_entries + waves * wave - 1) / (waves * wave);
+      if (even >= 32 && even <= slice_len) slice_len = (uint32_t)even;
+    }
+  }
   const size_t slices0 = (max_entries + slice_len - 1) / slice_len;
   const size_t L0 = 2 * slices0;
   const size_t edge_total = L0 + edge_levels_total(L0);
