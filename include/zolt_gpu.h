@@ -155,6 +155,56 @@ int zolt_hyperkzg_open_dev(zolt_ctx* ctx, const zolt_bases* params, const void* 
                            int num_vars, uint64_t* quotients_xy, uint8_t* quotients_inf, int* n_quotients,
                            uint64_t final_eval[4]);
 
+/* ---- Dory, G1 side, and the wire formats that feed the MSM (pairings / G2 / GT stay on the CPU) ---------------------------
+ * zolt_msm_bases_upload_wire: n G1 points of 64 bytes each straight from a file into resident bases; the conversion to
+ * Montgomery form, the identity detection and the curve check run on the device.
+ *   ZOLT_G1_WIRE_BE      x || y big-endian standard integers: the raw-binary SRS (srs.zig:65-99, :256-306); all-zero =
+ *                        identity; a point off y^2 = x^3 + 3 fails the call (ZOLT_ERR_ARG, *bad_index = first offender:
+ *                        SRSError.PointNotOnCurve)
+ *   ZOLT_G1_WIRE_LE      little-endian: a snarkjs PTAU tauG1 section as the reference reads it (srs.zig:616-660, :733-900)
+ *   ZOLT_G1_WIRE_ARK_LE  little-endian, arkworks flag bits in the top of y cleared, no curve check: the Jolt Dory SRS
+ *                        file (dory.zig:740-751, :828-880)
+ * The container parsers (headers, section tables) are host glue: host/zolt_host.hpp srs::. */
+#define ZOLT_G1_WIRE_BE 0
+#define ZOLT_G1_WIRE_LE 1
+#define ZOLT_G1_WIRE_ARK_LE 2
+int zolt_msm_bases_upload_wire(zolt_ctx* ctx, const uint8_t* bytes /* n*64 */, size_t n, int format, zolt_bases** out,
+                               size_t* bad_index /* may be NULL */);
+/* A bases handle over device-resident points the caller owns (not copied, not freed): lets every MSM entry point run on a
+ * vector that was produced on the device, e.g. Dory's folded row commitments v1 (dory.zig:1298-1299 E1+ / E1-). */
+int zolt_msm_bases_wrap_dev(zolt_ctx* ctx, const void* d_xy /* n*64 */, const uint8_t* d_inf /* n or NULL */, size_t n,
+                            zolt_bases** out);
+int zolt_msm_bases_dev_ptrs(const zolt_bases* bases, const void** d_xy, const uint8_t** d_inf);
+/* compressG1 (dory.zig:51-76, yIsPositive :162-175): 32 bytes per point, x little-endian standard form, flags 0x40 infinity /
+ * 0x80 "y negative" in the top bits of the last byte. */
+int zolt_g1_compress(zolt_ctx* ctx, const zolt_bases* pts, size_t offset, size_t n, uint8_t* out32 /* n*32 */);
+/* v[i] += scalar * g[i] for i < n: the first-challenge update of a Dory reduce round (dory.zig:1277-1281) on resident vectors */
+int zolt_g1_scale_add(zolt_ctx* ctx, zolt_bases* v, const zolt_bases* g, size_t n, const uint64_t scalar[4]);
+/* The G1 half of DoryCommitmentScheme.commit (dory.zig:989-1042, computeRowCommitments :646-670): sigma = (num_vars + 1) / 2,
+ * nu = num_vars - sigma with num_vars = floor(log2 len) (1 for a single entry); row r is the MSM of evals[r 2^sigma ..] over
+ * g1_vec[0 .. 2^sigma): 2^nu MSMs over shared bases, run as ONE batched MSM.  Entries beyond 2^num_vars are ignored, as in
+ * the reference.  rows_xy / rows_inf hold up to 2^nu results; *num_rows, *num_cols report the split. */
+int zolt_dory_row_commitments(zolt_ctx* ctx, const zolt_bases* g1, const uint64_t* evals /* len*4, host */, size_t len,
+                              uint64_t* rows_xy, uint8_t* rows_inf, size_t* num_rows, size_t* num_cols);
+int zolt_dory_row_commitments_dev(zolt_ctx* ctx, const zolt_bases* g1, const void* d_evals, size_t len, uint64_t* rows_xy,
+                                  uint8_t* rows_inf, size_t* num_rows, size_t* num_cols);
+
+/* HyperKZG.batchOpen (commitment/mod.zig:607-732): evaluations[i] = evaluateMultilinear(polys[i], point) exactly as the
+ * reference writes it (:788-817: index bit j <-> point[j]; the direct sum for at most 1024 entries and 10 variables, and
+ * polys[i][0] for anything larger -- that fallback is reproduced, not corrected, so proofs stay byte-identical); the
+ * batching challenge gamma = 0x9a8b7c6d * prod_i (point[i] + 11) (1 if zero, :631-638); the combined table
+ * sum_i gamma^i polys[i] over the first table's length, built on the device; then the fold-and-commit loop of open().
+ * With num_vars == 0 final_eval = sum_i gamma^i evaluations[i] and there are no quotients.  k == 0: final_eval 0, gamma 1.
+ * Outputs: evaluations k*4, quotient commitments as in zolt_hyperkzg_open, final_eval, batching_challenge. */
+int zolt_hyperkzg_batch_open(zolt_ctx* ctx, const zolt_bases* params, const uint64_t* const* polys /* k host tables */,
+                             const size_t* lens /* k */, size_t k, const uint64_t* point, int num_vars, uint64_t* evaluations,
+                             uint64_t* quotients_xy, uint8_t* quotients_inf, int* n_quotients, uint64_t final_eval[4],
+                             uint64_t batching_challenge[4]);
+int zolt_hyperkzg_batch_open_dev(zolt_ctx* ctx, const zolt_bases* params, const void* const* d_polys /* k device tables */,
+                                 const size_t* lens, size_t k, const uint64_t* point, int num_vars, uint64_t* evaluations,
+                                 uint64_t* quotients_xy, uint8_t* quotients_inf, int* n_quotients, uint64_t final_eval[4],
+                                 uint64_t batching_challenge[4]);
+
 /* ---- dense multilinear tables ------------------------------------------------------------------
  * Device-resident tables of 2^v Fr elements (32 B each, same layout as []F). */
 /* DensePolynomial.bindLow (src/poly/mod.zig:160-175): dst[i] = src[2i] + r*(src[2i+1]-src[2i]).

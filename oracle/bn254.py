@@ -359,6 +359,53 @@ def hyperkzg_open(powers, evals, point, value):
     return quotients, (cur[0] if cur else 0)
 
 
+def evaluate_multilinear_as_written(evals, point):
+    """HyperKZG.evaluateMultilinear (src/poly/commitment/mod.zig:788-817) AS WRITTEN: index bit j <-> point[j]; the direct
+    sum only when there are at most 10 variables and 1024 entries, otherwise the "fallback" returns evals[0]."""
+    if not evals:
+        return 0
+    if not point:
+        return evals[0] % FR_MOD
+    if len(point) <= 10 and len(evals) <= 1024:
+        total = 0
+        for idx, e in enumerate(evals):
+            term, bits = e, idx
+            for r in point:
+                term = term * (r if bits & 1 else (1 - r)) % FR_MOD
+                bits >>= 1
+            total = (total + term) % FR_MOD
+        return total
+    return evals[0] % FR_MOD
+
+
+def hyperkzg_batch_open(powers, polys, point):
+    """HyperKZG.batchOpen (src/poly/commitment/mod.zig:607-732).  Returns (quotient commitments, evaluations, final_eval,
+    batching challenge).  `powers` may be None (closed-form commitments of the mock SRS)."""
+    if not polys:
+        return [], [], 0, 1
+    evaluations = [evaluate_multilinear_as_written(p, point) for p in polys]
+    gamma = 0x9A8B7C6D
+    for r in point:
+        gamma = gamma * ((r + 11) % FR_MOD) % FR_MOD
+    if gamma == 0:
+        gamma = 1
+    size = len(polys[0])
+    combined = [0] * size
+    gp = 1
+    for p in polys:
+        for j in range(min(size, len(p))):
+            combined[j] = (combined[j] + gp * p[j]) % FR_MOD
+        gp = gp * gamma % FR_MOD
+    if not point:
+        acc, gp = 0, 1
+        for e in evaluations:
+            acc = (acc + gp * e) % FR_MOD
+            gp = gp * gamma % FR_MOD
+        return [], evaluations, acc, gamma
+    quotients, final = hyperkzg_open(powers, combined, point, 0)
+    return quotients, evaluations, final, gamma
+
+
 # --- affine point <-> C-ABI layout --------------------------------------------------
 def points_to_arrays(points):
     """Affine tuples/None -> (xy (n,8) uint64 Montgomery Fq limbs, inf (n,) uint8).

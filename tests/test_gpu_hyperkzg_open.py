@@ -73,3 +73,58 @@ def test_open_edge_cases(ctx):
     _check(ctx, short, B.hyperkzg_setup(2), rand_fr(10, 8), rand_fr(11, 3))
     short.free()
     params.free()
+
+
+def _check_batch(ctx, params, powers, polys, point, device=False):
+    if device:
+        bufs = [Z.DeviceBuffer.from_host(ctx, fr_arr(p)) for p in polys]
+        got = Z.HyperKZG.batch_open(params, [b.ptr for b in bufs], fr_arr(point) if point else [], device_lens=[len(p) for p in polys])
+        for b, p in zip(bufs, polys):
+            assert (b.download((len(p), 4)) == fr_arr(p)).all()  # borrowed tables are not modified
+            b.free()
+    else:
+        got = Z.HyperKZG.batch_open(params, [fr_arr(p) if p else np.empty((0, 4), np.uint64) for p in polys], fr_arr(point) if point else [])
+    ev, qxy, qinf, final, gamma = got
+    want_q, want_ev, want_final, want_gamma = B.hyperkzg_batch_open(powers, polys, point)
+    assert fr_ints(gamma) == [want_gamma]
+    assert fr_ints(ev) == want_ev if polys else len(ev) == 0
+    assert (B.arrays_to_points(qxy, qinf) if len(qxy) else []) == want_q
+    assert fr_ints(final) == [want_final]
+
+
+def test_batch_open_vs_oracle(ctx):
+    """HyperKZG.batchOpen (src/poly/commitment/mod.zig:607-732) incl. evaluateMultilinear as written (:788-817)."""
+    params = Z.HyperKZG.setup(ctx, 64)
+    powers = B.hyperkzg_setup(64)
+    nv = 4
+    polys = [rand_fr(500 + i, 1 << nv) for i in range(3)]
+    point = rand_fr(510, nv)
+    _check_batch(ctx, params, powers, polys, point)
+    _check_batch(ctx, params, powers, polys, point, device=True)
+    # evaluations are the multilinear extensions with point[j] <-> index bit j
+    ev = Z.HyperKZG.batch_open(params, [fr_arr(p) for p in polys], fr_arr(point))[0]
+    for p, e in zip(polys, fr_ints(ev)):
+        cur = p
+        for r in point:
+            cur = OP.bind_low(cur, r)
+        assert e == cur[0]
+    # one polynomial; later polynomials shorter / longer than the first; an empty one
+    _check_batch(ctx, params, powers, polys[:1], point)
+    _check_batch(ctx, params, powers, [polys[0], polys[1][:8], polys[2] + rand_fr(511, 16), []], point)
+    # no variables: no quotients, final_eval = sum gamma^i evaluation_i; and no polynomials at all
+    _check_batch(ctx, params, powers, [[7], [9], [11]], [])
+    _check_batch(ctx, params, powers, [], rand_fr(512, 3))
+    params.free()
+
+
+def test_batch_open_large_uses_the_reference_fallback(ctx):
+    """Above 1024 entries (or 10 variables) evaluateMultilinear returns evals[0] in the reference: reproduced as written;
+    the combined table and the proof are unaffected.  2^12 entries, closed-form commitments."""
+    nv = 12
+    params = Z.HyperKZG.setup(ctx, 1 << nv)
+    polys = [rand_fr(520 + i, 1 << nv) for i in range(2)]
+    point = rand_fr(530, nv)
+    ev = Z.HyperKZG.batch_open(params, [fr_arr(p) for p in polys], fr_arr(point))[0]
+    assert fr_ints(ev) == [p[0] for p in polys]
+    _check_batch(ctx, params, None, polys, point)
+    params.free()

@@ -29,6 +29,9 @@ from ._lib import (  # noqa: F401
     SC_PROD2,
     SC_PROD3,
     SC_SUM,
+    G1_WIRE_ARK_LE,
+    G1_WIRE_BE,
+    G1_WIRE_LE,
     TUNE_PEER_TIMEOUT_MS,
     TUNE_SC_BIND_F64,
     TUNE_SC_SMALL_PAIRS,
@@ -47,6 +50,7 @@ from .api import (  # noqa: F401
     Context,
     DensePolynomial,
     DeviceBuffer,
+    Dory,
     EqPolynomial,
     HyperKZG,
     PeerBox,

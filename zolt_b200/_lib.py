@@ -21,6 +21,7 @@ OP_MUL, OP_ADD, OP_SUB, OP_INV, OP_FROM_MONT, OP_TO_MONT, OP_NEG = range(7)
 PAIR_ADJACENT, PAIR_HALF = 0, 1
 SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN_AB_MINUS_C = range(7)
 TUNE_SC_SMALL_PAIRS = 1
+G1_WIRE_BE, G1_WIRE_LE, G1_WIRE_ARK_LE = 0, 1, 2
 TUNE_SC_BIND_F64 = 2
 TUNE_PEER_TIMEOUT_MS = 3
 TUNE_SC_TAIL_PAIRS = 4
@@ -63,6 +64,15 @@ SIGNATURES = {
     "zolt_msm_batch": [_vp, _vp, _vp, _sz, _sz, _vp, _vp],
     "zolt_hyperkzg_open": [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, C.POINTER(_i), _vp],
     "zolt_hyperkzg_open_dev": [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, C.POINTER(_i), _vp],
+    "zolt_msm_bases_upload_wire": [_vp, _vp, _sz, _i, C.POINTER(_vp), C.POINTER(_sz)],
+    "zolt_msm_bases_wrap_dev": [_vp, _vp, _vp, _sz, C.POINTER(_vp)],
+    "zolt_msm_bases_dev_ptrs": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
+    "zolt_g1_compress": [_vp, _vp, _sz, _sz, _vp],
+    "zolt_g1_scale_add": [_vp, _vp, _vp, _sz, _vp],
+    "zolt_dory_row_commitments": [_vp, _vp, _vp, _sz, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz)],
+    "zolt_dory_row_commitments_dev": [_vp, _vp, _vp, _sz, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz)],
+    "zolt_hyperkzg_batch_open": [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp],
+    "zolt_hyperkzg_batch_open_dev": [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp],
     "zolt_fr_inner_product_dev": [_vp, _vp, _vp, _sz, _vp],
     "zolt_fr_vec_dev": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
     "zolt_msm_partial_dev": [_vp, _vp, _sz, _vp, _sz, _vp],

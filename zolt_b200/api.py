@@ -181,6 +181,41 @@ class Bases:
         check(ctx.lib.zolt_g1_fixed_base_mul(ctx.handle, _ptr(s), s.shape[0], C.byref(h)), "zolt_g1_fixed_base_mul")
         return cls(ctx, h)
 
+    @classmethod
+    def from_wire(cls, ctx: Context, data: bytes, n: int, fmt: int) -> "Bases":
+        """n G1 points of 64 bytes straight off a file (zolt_msm_bases_upload_wire): fmt = G1_WIRE_BE (raw-binary SRS),
+        G1_WIRE_LE (PTAU tauG1) or G1_WIRE_ARK_LE (Jolt Dory SRS).  Raises ZoltGpuError if a point is off the curve."""
+        buf = np.frombuffer(data, dtype=np.uint8, count=64 * n) if n else np.zeros(0, dtype=np.uint8)
+        h = C.c_void_p()
+        bad = C.c_size_t()
+        check(ctx.lib.zolt_msm_bases_upload_wire(ctx.handle, _ptr(np.ascontiguousarray(buf)), n, fmt, C.byref(h), C.byref(bad)),
+              f"zolt_msm_bases_upload_wire (first point off the curve: {bad.value})")
+        return cls(ctx, h)
+
+    @classmethod
+    def wrap_dev(cls, ctx: Context, d_xy: int, d_inf: int | None, n: int) -> "Bases":
+        """A handle over device-resident points the caller owns (zolt_msm_bases_wrap_dev)."""
+        h = C.c_void_p()
+        check(ctx.lib.zolt_msm_bases_wrap_dev(ctx.handle, C.c_void_p(d_xy), C.c_void_p(d_inf or None), n, C.byref(h)), "zolt_msm_bases_wrap_dev")
+        return cls(ctx, h)
+
+    def dev_ptrs(self):
+        xy, inf = C.c_void_p(), C.c_void_p()
+        check(self.ctx.lib.zolt_msm_bases_dev_ptrs(self.handle, C.byref(xy), C.byref(inf)), "zolt_msm_bases_dev_ptrs")
+        return xy.value, inf.value
+
+    def compress(self, offset: int = 0, n: int | None = None) -> np.ndarray:
+        """compressG1 (src/poly/commitment/dory.zig:51-76) -> (n, 32) uint8."""
+        n = len(self) - offset if n is None else n
+        out = np.zeros((n, 32), dtype=np.uint8)
+        check(self.ctx.lib.zolt_g1_compress(self.ctx.handle, self.handle, offset, n, _ptr(out)), "zolt_g1_compress")
+        return out
+
+    def scale_add(self, g: "Bases", n: int, scalar):
+        """self[i] += scalar * g[i] for i < n (Dory's v1 += beta * g1_vec, dory.zig:1277-1281)."""
+        s = _as_u64(scalar, 4)
+        check(self.ctx.lib.zolt_g1_scale_add(self.ctx.handle, self.handle, g.handle, n, _ptr(s)), "zolt_g1_scale_add")
+
     def precompute(self, window_bits: int = 0) -> "Bases":
         """zolt_msm_bases_precompute: build the window-level table (once per SRS); MSM results are unchanged."""
         check(self.ctx.lib.zolt_msm_bases_precompute(self.handle, window_bits), "zolt_msm_bases_precompute")
@@ -323,6 +358,26 @@ class PeerBox:
             self.handle = None
 
 
+class Dory:
+    """DoryCommitmentScheme, G1 side (src/poly/commitment/dory.zig)."""
+
+    @staticmethod
+    def row_commitments(g1: Bases, evals, device_len: int | None = None):
+        """The row MSMs of commit (dory.zig:989-1042) -> (xy (rows, 8), inf (rows,), num_rows, num_cols)."""
+        ctx = g1.ctx
+        if device_len is None:
+            e = _as_u64(evals, 4) if len(evals) else np.empty((0, 4), dtype=np.uint64)
+            n, arg, fn = e.shape[0], _ptr(e), "zolt_dory_row_commitments"
+        else:
+            n, arg, fn = device_len, C.c_void_p(evals), "zolt_dory_row_commitments_dev"
+        cap = max(1, 1 << max(0, (max(n, 1).bit_length() - 1) // 2))
+        xy = np.zeros((cap, 8), dtype=np.uint64)
+        inf = np.zeros(cap, dtype=np.uint8)
+        rows, cols = C.c_size_t(), C.c_size_t()
+        check(getattr(ctx.lib, fn)(ctx.handle, g1.handle, arg, n, _ptr(xy), _ptr(inf), C.byref(rows), C.byref(cols)), fn)
+        return xy[: rows.value], inf[: rows.value], rows.value, cols.value
+
+
 class HyperKZG:
     """HyperKZG(F) commit path (src/poly/commitment/mod.zig:108-255)."""
 
@@ -364,7 +419,36 @@ def hyperkzg_open_dev(params: Bases, d_evals: int, n: int, point):
     return _hyperkzg_open(params, "zolt_hyperkzg_open_dev", C.c_void_p(d_evals), n, point)
 
 
+def hyperkzg_batch_open(params: Bases, polys, point, device_lens=None):
+    """HyperKZG.batchOpen (src/poly/commitment/mod.zig:607-732).  polys: list of host tables ((n_i, 4) uint64), or device
+    pointers when `device_lens` gives their lengths.  -> (evaluations (k,4), quotient xy (q,8), infinity flags (q,), final_eval
+    (4,), batching challenge gamma (4,))."""
+    ctx = params.ctx
+    pt = _as_u64(point, 4) if len(point) else np.empty((0, 4), dtype=np.uint64)
+    nv = pt.shape[0]
+    k = len(polys)
+    if device_lens is None:
+        tabs = [_as_u64(t, 4) if len(t) else np.empty((0, 4), dtype=np.uint64) for t in polys]
+        ptrs = (C.c_void_p * max(k, 1))(*[t.ctypes.data for t in tabs])
+        lens = (C.c_size_t * max(k, 1))(*[t.shape[0] for t in tabs])
+        fn = "zolt_hyperkzg_batch_open"
+    else:
+        ptrs = (C.c_void_p * max(k, 1))(*polys)
+        lens = (C.c_size_t * max(k, 1))(*device_lens)
+        fn = "zolt_hyperkzg_batch_open_dev"
+    ev = np.zeros((max(k, 1), 4), dtype=np.uint64)
+    qxy = np.zeros((max(nv, 1), 8), dtype=np.uint64)
+    qinf = np.zeros(max(nv, 1), dtype=np.uint8)
+    nq = C.c_int()
+    final = np.zeros(4, dtype=np.uint64)
+    gamma = np.zeros(4, dtype=np.uint64)
+    check(getattr(ctx.lib, fn)(ctx.handle, params.handle, ptrs, lens, k, _ptr(pt), nv, _ptr(ev), _ptr(qxy), _ptr(qinf), C.byref(nq),
+                               _ptr(final), _ptr(gamma)), fn)
+    return ev[:k], qxy[: nq.value], qinf[: nq.value], final, gamma
+
+
 HyperKZG.open = staticmethod(hyperkzg_open)
+HyperKZG.batch_open = staticmethod(hyperkzg_batch_open)
 HyperKZG.open_dev = staticmethod(hyperkzg_open_dev)
 
 

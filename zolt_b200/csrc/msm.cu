@@ -40,6 +40,7 @@ struct zolt_bases {
   // instead of 16).  12.9 GB at n = 2^24: HBM3e capacity is what buys the 25 % of integer work.
   AffineG1* d_pre = nullptr;
   int pre_c = 0, pre_w = 0;
+  bool borrowed = false;  // zolt_msm_bases_wrap_dev: d_xy / d_inf belong to the caller
 };
 
 namespace {
@@ -854,8 +855,8 @@ extern "C" int zolt_msm_bases_free(zolt_bases* b) {
   if (!b) return ZOLT_ERR_ARG;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
-  if (b->d_xy) cudaFree(b->d_xy);
-  if (b->d_inf) cudaFree(b->d_inf);
+  if (b->d_xy && !b->borrowed) cudaFree(b->d_xy);
+  if (b->d_inf && !b->borrowed) cudaFree(b->d_inf);
   if (b->d_pre) cudaFree(b->d_pre);
   delete b;
   return ZOLT_OK;
@@ -1187,6 +1188,403 @@ extern "C" int zolt_hyperkzg_open(zolt_ctx* ctx, const zolt_bases* params, const
   const int s = hyperkzg_open_core(ctx, params, d_cur, n, point, num_vars, quotients_xy, quotients_inf, n_quotients, final_eval);
   pool_release(ctx, d_cur, (n ? n : 1) * sizeof(Fr));
   return s;
+}
+
+// ---- Dory, G1 side, and the wire formats either side of the MSM -------------------------------------------
+// (pairings, G2 and GT stay on the CPU: out of scope)
+
+// G1 points as they come off the wire -> resident bases (affine, Montgomery) + infinity flags + validity.
+//   ZOLT_G1_WIRE_BE      x || y, 32-byte big-endian standard integers: raw-binary SRS (src/poly/commitment/srs.zig:65-99, :256-306);
+//                        all-zero = identity; the point must satisfy y^2 = x^3 + 3 (PointNotOnCurve otherwise)
+//   ZOLT_G1_WIRE_LE      the same, little-endian: the tauG1 section of a snarkjs PTAU file as the reference reads it (:616-660, :733-900)
+//   ZOLT_G1_WIRE_ARK_LE  little-endian with arkworks' two flag bits in the top of y cleared, no curve check: the Jolt Dory SRS
+//                        file (src/poly/commitment/dory.zig:740-751, :828-880)
+__global__ void __launch_bounds__(256)
+g1_from_wire_kernel(const uint8_t* __restrict__ bytes, size_t n, int format, AffineG1* __restrict__ out_xy, uint8_t* __restrict__ out_inf,
+                    unsigned long long* __restrict__ first_bad) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint8_t* p = bytes + 64 * i;
+    Fq raw[2];
+    bool all_zero = true;
+    for (int c = 0; c < 2; c++) {
+      for (int w = 0; w < 8; w++) {
+        uint32_t v = 0;
+        for (int b = 0; b < 4; b++) {
+          const int k = 4 * w + b;  // byte k of the little-endian value
+          const uint8_t byte = format == ZOLT_G1_WIRE_BE ? p[32 * c + 31 - k] : p[32 * c + k];
+          v |= (uint32_t)byte << (8 * b);
+        }
+        if (format == ZOLT_G1_WIRE_ARK_LE && c == 1 && w == 7) v &= 0x3fffffffu;
+        raw[c].v[w] = v;
+        all_zero = all_zero && v == 0;
+      }
+    }
+    AffineG1 a;
+    a.x = Fq::zero();
+    a.y = Fq::zero();
+    bool inf = all_zero;
+    if (!inf) {
+      a.x = fp_to_mont<FqParams>(raw[0]);  // fromBytesBE / toMontgomery: value * R mod q (values >= q reduce, as in the reference)
+      a.y = fp_to_mont<FqParams>(raw[1]);
+      if (format != ZOLT_G1_WIRE_ARK_LE) {
+        const Fq three = fp_from_u32<FqParams>(3u);
+        const Fq lhs = fq_sqr(a.y), rhs = fp_add<FqParams>(fq_mul(fq_sqr(a.x), a.x), three);
+        if (lhs != rhs) atomicMin(first_bad, (unsigned long long)i);
+      }
+    }
+    st_fq(&out_xy[i].x, a.x);
+    st_fq(&out_xy[i].y, a.y);
+    out_inf[i] = inf ? 1 : 0;
+  }
+}
+
+// compressG1 (src/poly/commitment/dory.zig:51-76): 32 bytes = x as a little-endian standard integer with the flags in the top
+// two bits of the last byte: 0x40 point at infinity (everything else zero), 0x80 when y > -y as standard integers (:162-175)
+__global__ void __launch_bounds__(256)
+g1_compress_kernel(const AffineG1* __restrict__ xy, const uint8_t* __restrict__ inf, size_t n, uint8_t* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint8_t* o = out + 32 * i;
+    if (inf && inf[i]) {
+      for (int k = 0; k < 32; k++) o[k] = 0;
+      o[31] = 0x40;
+      continue;
+    }
+    const AffineG1 p = ld_affine(xy + i);
+    const Fq xs = fp_from_mont<FqParams>(p.x);
+    const Fq ys = fp_from_mont<FqParams>(p.y), nys = fp_from_mont<FqParams>(fp_neg<FqParams>(p.y));
+    bool positive = true;  // equal counts as positive
+    for (int w = 7; w >= 0; w--) {
+      if (ys.v[w] != nys.v[w]) {
+        positive = ys.v[w] < nys.v[w];
+        break;
+      }
+    }
+    for (int k = 0; k < 32; k++) o[k] = (uint8_t)(xs.v[k >> 2] >> (8 * (k & 3)));
+    o[31] = (uint8_t)((o[31] & 0x3f) | (positive ? 0x00 : 0x80));
+  }
+}
+
+// v[i] += s * g[i]  (the first-challenge update of Dory's reduce round, dory.zig:1277-1281: scalarMul + affine add + toAffine
+// per element as written; here one thread per element, double-and-add over the canonical scalar, one inversion)
+__global__ void __launch_bounds__(128)
+g1_scale_add_kernel(AffineG1* __restrict__ v_xy, uint8_t* __restrict__ v_inf, const AffineG1* __restrict__ g_xy,
+                    const uint8_t* __restrict__ g_inf, const __grid_constant__ Fr s_std, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ acc = XYZZ::identity();
+  if (!(g_inf && g_inf[i])) {
+    const AffineG1 g = ld_affine(g_xy + i);
+    bool started = false;
+    for (int w = 7; w >= 0; w--) {
+      for (int b = 31; b >= 0; b--) {
+        if (started) acc = xyzz_dbl(acc);
+        if ((s_std.v[w] >> b) & 1u) {
+          xyzz_madd(acc, g);
+          started = true;
+        }
+      }
+    }
+  }
+  if (!v_inf[i]) xyzz_madd(acc, ld_affine(v_xy + i));
+  AffineG1 a;
+  const bool finite = xyzz_to_affine(acc, a);
+  st_fq(&v_xy[i].x, a.x);
+  st_fq(&v_xy[i].y, a.y);
+  v_inf[i] = finite ? 0 : 1;
+}
+
+// ---- HyperKZG.batchOpen (src/poly/commitment/mod.zig:607-732) ------------------------------------------------------------
+// evaluateMultilinear (:788-817) as written: index bit j <-> point[j]; the direct sum only for at most 1024 entries and 10
+// variables -- one block, one term per thread.
+__global__ void __launch_bounds__(1024) hk_mle_small_kernel(const Fr* __restrict__ evals, size_t n, const Fr* __restrict__ point,
+                                                            int nv, Fr* __restrict__ out) {
+  __shared__ Fr red[1024];
+  const unsigned tid = threadIdx.x;
+  Fr term = Fr::zero();
+  if (tid < n) {
+    term = evals[tid];
+    unsigned bits = tid;
+    for (int j = 0; j < nv; j++, bits >>= 1) {
+      const Fr r = point[j];
+      term = fp_mul<FrParams>(term, (bits & 1u) ? r : fp_sub<FrParams>(Fr::one(), r));
+    }
+  }
+  red[tid] = term;
+  __syncthreads();
+  for (unsigned s = 512; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = fp_add<FrParams>(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  if (tid == 0) *out = red[0];
+}
+
+// polys: k tables (host pointers when `on_host`, device pointers otherwise), lens[i] entries each.
+static int hyperkzg_batch_open_impl(zolt_ctx* ctx, const zolt_bases* params, const void* const* polys, const size_t* lens, size_t k,
+                                    bool on_host, const uint64_t* point, int num_vars, uint64_t* evaluations, uint64_t* quotients_xy,
+                                    uint8_t* quotients_inf, int* n_quotients, uint64_t final_eval[4], uint64_t batching_challenge[4]) {
+  if (!ctx || !params || !final_eval || !batching_challenge || num_vars < 0 || (num_vars && !point)) return ZOLT_ERR_ARG;
+  if (k && (!polys || !lens || !evaluations)) return ZOLT_ERR_ARG;
+  if (num_vars && k && (!quotients_xy || !quotients_inf)) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (n_quotients) *n_quotients = 0;
+  const Fr one = Fr::one();
+  auto store = [](uint64_t* dst, const Fr& x) {
+    for (int j = 0; j < 4; j++) dst[j] = (uint64_t)x.v[2 * j] | ((uint64_t)x.v[2 * j + 1] << 32);
+  };
+  auto load = [](const uint64_t* src) {
+    Fr x;
+    for (int j = 0; j < 4; j++) {
+      x.v[2 * j] = (uint32_t)src[j];
+      x.v[2 * j + 1] = (uint32_t)(src[j] >> 32);
+    }
+    return x;
+  };
+  if (k == 0) {  // :613-621
+    memset(final_eval, 0, 32);
+    store(batching_challenge, one);
+    return ZOLT_OK;
+  }
+  cudaStream_t st = ctx->stream;
+  const size_t poly_size = lens[0];
+  size_t max_len = 0;
+  for (size_t i = 0; i < k; i++) max_len = lens[i] > max_len ? lens[i] : max_len;
+  // device copies of the tables (host input) and of the point
+  Fr *d_stage = nullptr, *d_point = nullptr, *d_eval = nullptr, *d_comb = nullptr;
+  const size_t stage_bytes = (max_len ? max_len : 1) * sizeof(Fr), comb_bytes = (poly_size ? poly_size : 1) * sizeof(Fr);
+  if (on_host) ZOLT_CUDA_TRY(pool_alloc(ctx, stage_bytes, (void**)&d_stage));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, (size_t)(num_vars ? num_vars : 1) * sizeof(Fr), (void**)&d_point));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, k * sizeof(Fr), (void**)&d_eval));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, comb_bytes, (void**)&d_comb));
+  int status = ZOLT_OK;
+  auto cuda_ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && status == ZOLT_OK) {
+      fprintf(stderr, "[zolt_gpu] hyperkzg batch open: %s\n", cudaGetErrorString(e));
+      status = ZOLT_ERR_CUDA;
+    }
+    return e == cudaSuccess;
+  };
+  if (num_vars) cuda_ok(cudaMemcpyAsync(d_point, point, (size_t)num_vars * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  cuda_ok(cudaMemsetAsync(d_comb, 0, comb_bytes, st));
+  // Step 2 (:631-638): gamma = 0x9a8b7c6d * prod_i (r_i + 11), 1 if that is zero -- O(num_vars) host glue
+  Fr gamma = fp_from_u32<FrParams>(0x9a8b7c6du);
+  const Fr eleven = fp_from_u32<FrParams>(11u);
+  for (int i = 0; i < num_vars; i++) gamma = fp_mul<FrParams>(gamma, fp_add<FrParams>(load(point + 4 * i), eleven));
+  if (gamma.is_zero()) gamma = one;
+  store(batching_challenge, gamma);
+  // Steps 1 and 3 (:625-656): evaluations and combined = sum_i gamma^i poly_i over the first polynomial's length
+  Fr gamma_power = one;
+  for (size_t i = 0; i < k && status == ZOLT_OK; i++) {
+    const Fr* d_poly = static_cast<const Fr*>(polys[i]);
+    if (on_host) {
+      if (lens[i]) cuda_ok(cudaMemcpyAsync(d_stage, polys[i], lens[i] * sizeof(Fr), cudaMemcpyHostToDevice, st));
+      d_poly = d_stage;
+    }
+    if (lens[i] == 0) {
+      cuda_ok(cudaMemsetAsync(d_eval + i, 0, sizeof(Fr), st));  // evaluateMultilinear of an empty table is zero
+    } else if (num_vars == 0 || !(num_vars <= 10 && lens[i] <= 1024)) {
+      // no variables, or the reference's fallback for larger tables: evals[0] as written (:815-816)
+      cuda_ok(cudaMemcpyAsync(d_eval + i, d_poly, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    } else {
+      hk_mle_small_kernel<<<1, 1024, 0, st>>>(d_poly, lens[i], d_point, num_vars, d_eval + i);
+      ctx->launches++;
+    }
+    const size_t m = lens[i] < poly_size ? lens[i] : poly_size;
+    if (m && status == ZOLT_OK) {
+      uint64_t s64[4];
+      store(s64, gamma_power);
+      status = zolt_fr_vec_dev(ctx, ZOLT_VEC_AXPY, d_comb, d_poly, nullptr, nullptr, nullptr, s64, m);
+    }
+    gamma_power = fp_mul<FrParams>(gamma_power, gamma);
+    if (on_host) cuda_ok(cudaStreamSynchronize(st));  // the staging buffer is reused by the next table
+  }
+  if (status == ZOLT_OK) {
+    cuda_ok(cudaMemcpyAsync(evaluations, d_eval, k * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    cuda_ok(cudaStreamSynchronize(st));
+  }
+  if (status == ZOLT_OK) {
+    if (num_vars == 0) {
+      // Step 4/5 (:658-673): nothing to fold, final_eval = sum_i gamma^i * evaluation_i
+      Fr acc = Fr::zero(), gp = one;
+      for (size_t i = 0; i < k; i++) {
+        acc = fp_add<FrParams>(acc, fp_mul<FrParams>(gp, load(evaluations + 4 * i)));
+        gp = fp_mul<FrParams>(gp, gamma);
+      }
+      store(final_eval, acc);
+    } else {
+      // Step 5 (:675-718): the same fold-and-commit loop as open(), on the combined table (consumed in place)
+      status = hyperkzg_open_core(ctx, params, d_comb, poly_size, point, num_vars, quotients_xy, quotients_inf, n_quotients, final_eval);
+    }
+  }
+  if (d_stage) pool_release(ctx, d_stage, stage_bytes);
+  pool_release(ctx, d_point, (size_t)(num_vars ? num_vars : 1) * sizeof(Fr));
+  pool_release(ctx, d_eval, k * sizeof(Fr));
+  pool_release(ctx, d_comb, comb_bytes);
+  return status;
+}
+
+extern "C" int zolt_msm_bases_upload_wire(zolt_ctx* ctx, const uint8_t* bytes, size_t n, int format, zolt_bases** out, size_t* bad_index) {
+  if (!ctx || !out || (n && !bytes) || format < ZOLT_G1_WIRE_BE || format > ZOLT_G1_WIRE_ARK_LE) return ZOLT_ERR_ARG;
+  *out = nullptr;
+  if (bad_index) *bad_index = (size_t)-1;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  zolt_bases* b = new (std::nothrow) zolt_bases();
+  if (!b) return ZOLT_ERR_ARG;
+  b->ctx = ctx;
+  b->n = n;
+  uint8_t* d_bytes = nullptr;
+  unsigned long long* d_bad = nullptr;
+  int status = ZOLT_OK;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && status == ZOLT_OK) {
+      fprintf(stderr, "[zolt_gpu] bases from wire format: %s\n", cudaGetErrorString(e));
+      status = ZOLT_ERR_CUDA;
+    }
+    return e == cudaSuccess;
+  };
+  unsigned long long bad = ~0ull;
+  if (ok(cudaMalloc((void**)&b->d_xy, (n ? n : 1) * sizeof(AffineG1))) && ok(cudaMalloc((void**)&b->d_inf, n ? n : 1)) &&
+      ok(cudaMalloc((void**)&d_bytes, n ? 64 * n : 1)) && ok(cudaMalloc((void**)&d_bad, 8))) {
+    ok(cudaMemcpyAsync(d_bad, &bad, 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+      ok(cudaMemcpyAsync(d_bytes, bytes, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
+      size_t blocks = (n + 255) / 256;
+      if (blocks > (size_t)ctx->num_sms * 8) blocks = (size_t)ctx->num_sms * 8;
+      g1_from_wire_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_bytes, n, format, b->d_xy, b->d_inf, d_bad);
+      ctx->launches++;
+      ok(cudaGetLastError());
+    }
+    ok(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ok(cudaStreamSynchronize(ctx->stream));
+  }
+  if (d_bytes) cudaFree(d_bytes);
+  if (d_bad) cudaFree(d_bad);
+  if (status == ZOLT_OK && bad != ~0ull) {  // SRSError.PointNotOnCurve
+    if (bad_index) *bad_index = (size_t)bad;
+    status = ZOLT_ERR_ARG;
+  }
+  if (status != ZOLT_OK) {
+    zolt_msm_bases_free(b);
+    return status;
+  }
+  *out = b;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_msm_bases_wrap_dev(zolt_ctx* ctx, const void* d_xy, const uint8_t* d_inf, size_t n, zolt_bases** out) {
+  if (!ctx || !out || (n && !d_xy)) return ZOLT_ERR_ARG;
+  zolt_bases* b = new (std::nothrow) zolt_bases();
+  if (!b) return ZOLT_ERR_ARG;
+  b->ctx = ctx;
+  b->n = n;
+  b->d_xy = const_cast<AffineG1*>(static_cast<const AffineG1*>(d_xy));
+  b->d_inf = const_cast<uint8_t*>(d_inf);
+  b->borrowed = true;
+  *out = b;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_msm_bases_dev_ptrs(const zolt_bases* b, const void** d_xy, const uint8_t** d_inf) {
+  if (!b || !d_xy || !d_inf) return ZOLT_ERR_ARG;
+  *d_xy = b->d_xy;
+  *d_inf = b->d_inf;
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_g1_compress(zolt_ctx* ctx, const zolt_bases* pts, size_t offset, size_t n, uint8_t* out32) {
+  if (!ctx || !pts || (n && !out32) || offset > pts->n || n > pts->n - offset) return ZOLT_ERR_ARG;
+  if (n == 0) return ZOLT_OK;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  uint8_t* d_out = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 32 * n, (void**)&d_out));
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)ctx->num_sms * 8) blocks = (size_t)ctx->num_sms * 8;
+  g1_compress_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(pts->d_xy + offset, pts->d_inf ? pts->d_inf + offset : nullptr, n, d_out);
+  ctx->launches++;
+  int status = ZOLT_OK;
+  if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(out32, d_out, 32 * n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    status = ZOLT_ERR_CUDA;
+  pool_release(ctx, d_out, 32 * n);
+  return status;
+}
+
+extern "C" int zolt_g1_scale_add(zolt_ctx* ctx, zolt_bases* v, const zolt_bases* g, size_t n, const uint64_t scalar[4]) {
+  if (!ctx || !v || !g || !scalar || n > v->n || n > g->n) return ZOLT_ERR_ARG;
+  if (n == 0) return ZOLT_OK;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!v->d_inf) {  // the sums may hit the identity: the vector needs flags from now on
+    if (v->borrowed) return ZOLT_ERR_ARG;
+    ZOLT_CUDA_TRY(cudaMalloc((void**)&v->d_inf, v->n ? v->n : 1));
+    ZOLT_CUDA_TRY(cudaMemsetAsync(v->d_inf, 0, v->n ? v->n : 1, ctx->stream));
+  }
+  Fr s;
+  for (int j = 0; j < 4; j++) {
+    s.v[2 * j] = (uint32_t)scalar[j];
+    s.v[2 * j + 1] = (uint32_t)(scalar[j] >> 32);
+  }
+  const Fr s_std = fp_from_mont<FrParams>(s);
+  g1_scale_add_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(v->d_xy, v->d_inf, g->d_xy, g->d_inf, s_std, n);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  if (v->d_pre) {  // a window-level table of the old points is stale
+    ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(v->d_pre);
+    v->d_pre = nullptr;
+  }
+  return ZOLT_OK;
+}
+
+// DoryCommitmentScheme.commit's G1 half (dory.zig:989-1042): sigma = (num_vars + 1) / 2, nu = num_vars - sigma, row r =
+// MSM(g1_vec[0 .. 2^sigma], evals[r 2^sigma ..]) for the 2^nu rows -- one batched MSM over the shared bases.
+static int dory_rows_impl(zolt_ctx* ctx, const zolt_bases* g1, const void* evals, bool on_host, size_t len, uint64_t* rows_xy,
+                          uint8_t* rows_inf, size_t* num_rows, size_t* num_cols) {
+  if (!ctx || !g1 || !num_rows || !num_cols || (len && (!evals || !rows_xy || !rows_inf))) return ZOLT_ERR_ARG;
+  *num_rows = *num_cols = 0;
+  if (len == 0) return ZOLT_OK;  // commit() returns GT.one(): no rows
+  size_t num_vars = 0;
+  while ((size_t(2) << num_vars) <= len) num_vars++;  // log2_int(len)
+  if (len <= 1) num_vars = 1;
+  const size_t sigma = (num_vars + 1) / 2, nu = num_vars - sigma;
+  size_t cols = size_t(1) << sigma, rows = size_t(1) << nu;
+  if (len < cols) {  // a single entry: one row with what there is (row_evals = evals[0 .. min(cols, len)])
+    cols = len;
+    rows = 1;
+  }
+  if (cols > g1->n) return ZOLT_ERR_ARG;
+  *num_rows = rows;
+  *num_cols = cols;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (on_host) return zolt_msm_batch(ctx, g1, static_cast<const uint64_t*>(evals), rows, cols, rows_xy, rows_inf);
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, rows * sizeof(XYZZ), (void**)&d_res));
+  int status = msm_core(ctx, g1, 0, static_cast<const Fr*>(evals), rows, cols, d_res);
+  if (status == ZOLT_OK) status = finish_affine(ctx, d_res, rows, rows_xy, rows_inf);
+  pool_release(ctx, d_res, rows * sizeof(XYZZ));
+  return status;
+}
+
+extern "C" int zolt_dory_row_commitments(zolt_ctx* ctx, const zolt_bases* g1, const uint64_t* evals, size_t len, uint64_t* rows_xy,
+                                         uint8_t* rows_inf, size_t* num_rows, size_t* num_cols) {
+  return dory_rows_impl(ctx, g1, evals, true, len, rows_xy, rows_inf, num_rows, num_cols);
+}
+extern "C" int zolt_dory_row_commitments_dev(zolt_ctx* ctx, const zolt_bases* g1, const void* d_evals, size_t len, uint64_t* rows_xy,
+                                             uint8_t* rows_inf, size_t* num_rows, size_t* num_cols) {
+  return dory_rows_impl(ctx, g1, d_evals, false, len, rows_xy, rows_inf, num_rows, num_cols);
+}
+
+extern "C" int zolt_hyperkzg_batch_open(zolt_ctx* ctx, const zolt_bases* params, const uint64_t* const* polys, const size_t* lens, size_t k,
+                                        const uint64_t* point, int num_vars, uint64_t* evaluations, uint64_t* quotients_xy,
+                                        uint8_t* quotients_inf, int* n_quotients, uint64_t final_eval[4], uint64_t batching_challenge[4]) {
+  return hyperkzg_batch_open_impl(ctx, params, reinterpret_cast<const void* const*>(polys), lens, k, true, point, num_vars, evaluations,
+                                  quotients_xy, quotients_inf, n_quotients, final_eval, batching_challenge);
+}
+
+extern "C" int zolt_hyperkzg_batch_open_dev(zolt_ctx* ctx, const zolt_bases* params, const void* const* d_polys, const size_t* lens, size_t k,
+                                            const uint64_t* point, int num_vars, uint64_t* evaluations, uint64_t* quotients_xy,
+                                            uint8_t* quotients_inf, int* n_quotients, uint64_t final_eval[4],
+                                            uint64_t batching_challenge[4]) {
+  return hyperkzg_batch_open_impl(ctx, params, d_polys, lens, k, false, point, num_vars, evaluations, quotients_xy, quotients_inf,
+                                  n_quotients, final_eval, batching_challenge);
 }
 
 extern "C" int zolt_hyperkzg_setup(zolt_ctx* ctx, size_t max_degree, zolt_bases** out) {

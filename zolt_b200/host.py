@@ -50,6 +50,8 @@ def load_host() -> C.CDLL:
         _host.zolt_host_sumcheck_prove_gruen_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
                                                              C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p,
                                                              C.c_void_p, C.c_void_p]
+        _host.zolt_host_srs_load.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                             C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]
         _host.zolt_host_eq_mle.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         _host.zolt_host_horner_eval.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _host.zolt_host_dense_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -224,3 +226,21 @@ def sumcheck_prove_gruen(ctx: Context, tables, tau, claim, with_c: bool = False,
                                                     len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final_claim))
     _lib.check(st, "zolt_host_sumcheck_prove_gruen")
     return evals, chal, final_claim
+
+
+SRS_RAW_BINARY, SRS_PTAU, SRS_DORY = 0, 1, 2
+SRS_ERRORS = {0: "Ok", 1: "TruncatedData", 2: "InvalidFileFormat", 3: "UnsupportedFormat", 4: "PointNotOnCurve", 5: "Device"}
+
+
+def srs_load(ctx: Context, kind: int, data: bytes):
+    """srs.loadFromRawBinary / loadFromPtau / DoryCommitmentScheme.loadFromFile through the C++ mirror: the container is
+    parsed on the host, the G1 array converted and checked on the device.  -> (Bases or None, error name, count,
+    max_num_vars, index of the first point off the curve or None)."""
+    from .api import Bases
+
+    h = C.c_void_p()
+    count, bad = C.c_size_t(), C.c_size_t()
+    nv = C.c_uint64()
+    err = load_host().zolt_host_srs_load(ctx.handle, kind, data, len(data), C.byref(h), C.byref(count), C.byref(nv), C.byref(bad))
+    bases = Bases(ctx, h) if err == 0 and h.value else None
+    return bases, SRS_ERRORS.get(err, str(err)), count.value, nv.value, (None if bad.value == (1 << 64) - 1 else bad.value)

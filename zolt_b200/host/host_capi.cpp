@@ -131,6 +131,21 @@ int zolt_host_sumcheck_prove_gruen_dev(zolt_ctx* ctx, int with_c, int log_n, int
   return ZOLT_OK;
 }
 
+// SRS container parsers: kind 0 raw binary (srs.zig:256-306), 1 snarkjs PTAU (:733-900), 2 Jolt Dory SRS (dory.zig:740-826).
+// Returns the srs::Error code (0 = ok); *bases_out is a zolt_bases handle the caller frees.
+int zolt_host_srs_load(zolt_ctx* ctx, int kind, const uint8_t* data, size_t len, zolt_bases** bases_out, size_t* count,
+                       uint64_t* max_num_vars, size_t* bad_index) {
+  Context c(ctx);
+  srs::G1Srs s;
+  const srs::Error e = kind == 0 ? srs::loadFromRawBinary(c, data, len, &s) : kind == 1 ? srs::loadFromPtau(c, data, len, &s)
+                                                                                        : srs::loadDorySrs(c, data, len, &s);
+  *bases_out = s.powers;
+  *count = s.count;
+  *max_num_vars = s.max_num_vars;
+  *bad_index = s.bad_index;
+  return (int)e;
+}
+
 // host glue parity hooks: EqPolynomial.mle, BatchOps.hornerEval, DensePolynomial.evaluate
 void zolt_host_eq_mle(const uint64_t* r, const uint64_t* x, size_t n, uint64_t* out) {
   std::vector<Fr> rv(n), xv(n);

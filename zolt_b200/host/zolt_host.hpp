@@ -166,6 +166,76 @@ struct HyperKZG {
   }
 };
 
+// SRS containers (src/poly/commitment/srs.zig, dory.zig): host glue that walks the headers and hands the G1 array to the
+// device, where the points are converted, checked and kept resident (zolt_msm_bases_upload_wire).  G2 / pairing data is
+// located and skipped: it belongs to the CPU side of the verifier.
+namespace srs {
+enum class Error { Ok = 0, TruncatedData, InvalidFileFormat, UnsupportedFormat, PointNotOnCurve, Device };
+struct G1Srs {
+  zolt_bases* powers = nullptr;  // caller frees with zolt_msm_bases_free
+  size_t count = 0;
+  uint64_t max_num_vars = 0;     // Dory SRS only
+  size_t bad_index = (size_t)-1;
+};
+inline uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | (uint64_t)rd32(p + 4) << 32; }
+inline Error upload(Context& ctx, const uint8_t* pts, size_t n, int fmt, G1Srs* out) {
+  const int st = zolt_msm_bases_upload_wire(ctx.raw(), pts, n, fmt, &out->powers, &out->bad_index);
+  out->count = n;
+  if (st == ZOLT_OK) return Error::Ok;
+  return out->bad_index != (size_t)-1 ? Error::PointNotOnCurve : Error::Device;
+}
+// loadFromRawBinary (srs.zig:256-306): u32 count, count * 64-byte big-endian points, then tau*G2 (128), G1 generator (64),
+// G2 generator (128)
+inline Error loadFromRawBinary(Context& ctx, const uint8_t* data, size_t len, G1Srs* out) {
+  if (len < 4) return Error::TruncatedData;
+  const size_t n = rd32(data);
+  if (len < 4 + n * 64 + 128 + 64 + 128) return Error::TruncatedData;
+  return upload(ctx, data + 4, n, ZOLT_G1_WIRE_BE, out);
+}
+// loadFromPtau (srs.zig:733-900): "ptau", version 1, section table; header section: field size 32, prime, power; the tauG1
+// section holds min(2^(power+1) - 1, size / 64) little-endian points
+inline Error loadFromPtau(Context& ctx, const uint8_t* data, size_t len, G1Srs* out) {
+  if (len < 12) return Error::TruncatedData;
+  if (std::memcmp(data, "ptau", 4) != 0) return Error::InvalidFileFormat;
+  if (rd32(data + 4) != 1) return Error::UnsupportedFormat;
+  const uint32_t sections = rd32(data + 8);
+  size_t off = 12, hdr_off = 0, hdr_size = 0, g1_off = 0, g1_size = 0;
+  bool have_hdr = false, have_g1 = false;
+  for (uint32_t i = 0; i < sections; i++) {
+    if (off + 12 > len) return Error::TruncatedData;
+    const uint32_t type = rd32(data + off);
+    const uint64_t size = rd64(data + off + 4);
+    off += 12;
+    if (type == 1) { hdr_off = off; hdr_size = (size_t)size; have_hdr = true; }
+    if (type == 2) { g1_off = off; g1_size = (size_t)size; have_g1 = true; }
+    off += (size_t)size;
+  }
+  if (!have_hdr) return Error::InvalidFileFormat;
+  if (hdr_off + hdr_size > len || hdr_size < 8) return Error::TruncatedData;
+  if (rd32(data + hdr_off) != 32) return Error::UnsupportedFormat;
+  if (hdr_size < 4 + 32 + 4 + 4) return Error::TruncatedData;
+  const uint32_t power = rd32(data + hdr_off + 36);
+  size_t n = 0;
+  if (have_g1) {
+    if (g1_off + g1_size > len) return Error::TruncatedData;
+    const size_t want = (size_t(1) << power) * 2 - 1;
+    n = want < g1_size / 64 ? want : g1_size / 64;
+  }
+  return upload(ctx, data + g1_off, n, ZOLT_G1_WIRE_LE, out);
+}
+// DoryCommitmentScheme.loadFromFile (dory.zig:740-826): "JOLT_DORY_SRS_V1", u64 max_num_vars, u64 g1_count, the G1 vector
+// (arkworks uncompressed), u64 g2_count, the G2 vector, the blinding generators
+inline Error loadDorySrs(Context& ctx, const uint8_t* data, size_t len, G1Srs* out) {
+  if (len < 32) return Error::TruncatedData;
+  if (std::memcmp(data, "JOLT_DORY_SRS_V1", 16) != 0) return Error::InvalidFileFormat;
+  out->max_num_vars = rd64(data + 16);
+  const size_t n = (size_t)rd64(data + 24);
+  if (len < 32 + n * 64) return Error::TruncatedData;
+  return upload(ctx, data + 32, n, ZOLT_G1_WIRE_ARK_LE, out);
+}
+}  // namespace srs
+
 // UniPoly(F) helpers used around the round loop (src/poly/mod.zig:608-685)
 struct UniPoly {
   static Fr evaluate(const std::vector<Fr>& coeffs, const Fr& x) {
