@@ -348,6 +348,24 @@ int zolt_msm_sharded_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, 
 int zolt_msm_sharded(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars /* n*4, host */, size_t n,
                      zolt_peer_box* box, uint64_t out_xy[8], uint8_t* out_inf);
 
+/* ---- one process, several devices --------------------------------------------------------------------
+ * `zolt prove` is ONE process (src/zkvm/mod.zig:366-462).  zolt_gpu_init_multi (SURVEY 8b's proposal) creates a context and
+ * a mailbox per entry of device_ids, connects the mailboxes directly (peer access between distinct devices, no IPC) and
+ * hands out the per-rank handles, which are ordinary zolt_ctx / zolt_peer_box: one host thread per device then drives
+ * zolt_msm_sharded*, zolt_sc_set_peers or the C++ round loop exactly as a rank of the one-process-per-GPU deployment does.
+ * A device may be listed more than once (ranks share it): that is how a one-GPU box exercises this path.
+ * zolt_multi_msm: MSM.compute over all bases = ParallelMSM.compute's point-range split (src/msm/mod.zig:588-653) with one GPU
+ * and one host thread per chunk; bases[r] is rank r's contiguous range (resident on its device), scalars the whole vector. */
+typedef struct zolt_multi zolt_multi;
+int zolt_gpu_init_multi(const int* device_ids, int n_devices, zolt_multi** out);
+int zolt_multi_shutdown(zolt_multi* m);
+int zolt_multi_size(const zolt_multi* m, int* n_devices);
+int zolt_multi_rank(zolt_multi* m, int rank, zolt_ctx** ctx, zolt_peer_box** box);
+int zolt_multi_msm(zolt_multi* m, zolt_bases* const* bases /* n_devices */, const uint64_t* scalars /* n_total*4, host */,
+                   size_t n_total, uint64_t out_xy[8], uint8_t* out_inf);
+/* zolt_msm_partial_dev from HOST scalars (upload overlapped with the multiplication as in zolt_msm) */
+int zolt_msm_partial(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n, void* d_out /* 16 u64 */);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------
  * Integer-pipe micro-benchmarks (the MSM roofline denominator).  `kind`: 0 = IMAD (3-reg),
  * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery products, 3 = Fq Montgomery products, 4 = IMAD immediate form,

@@ -53,6 +53,7 @@ from .api import (  # noqa: F401
     Dory,
     EqPolynomial,
     HyperKZG,
+    MultiContext,
     PeerBox,
     SumcheckInstance,
 )

@@ -71,6 +71,12 @@ SIGNATURES = {
     "zolt_g1_scale_add": [_vp, _vp, _vp, _sz, _vp],
     "zolt_dory_row_commitments": [_vp, _vp, _vp, _sz, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz)],
     "zolt_dory_row_commitments_dev": [_vp, _vp, _vp, _sz, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz)],
+    "zolt_gpu_init_multi": [C.POINTER(_i), _i, C.POINTER(_vp)],
+    "zolt_multi_shutdown": [_vp],
+    "zolt_multi_size": [_vp, C.POINTER(_i)],
+    "zolt_multi_rank": [_vp, _i, C.POINTER(_vp), C.POINTER(_vp)],
+    "zolt_multi_msm": [_vp, C.POINTER(_vp), _vp, _sz, _vp, _vp],
+    "zolt_msm_partial": [_vp, _vp, _sz, _vp, _sz, _vp],
     "zolt_hyperkzg_batch_open": [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp],
     "zolt_hyperkzg_batch_open_dev": [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp],
     "zolt_fr_inner_product_dev": [_vp, _vp, _vp, _sz, _vp],

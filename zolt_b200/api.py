@@ -358,6 +358,41 @@ class PeerBox:
             self.handle = None
 
 
+class MultiContext:
+    """One process, several devices (zolt_gpu_init_multi): per-rank Context / PeerBox views + the packaged sharded MSM."""
+
+    def __init__(self, device_ids):
+        self.lib = _lib.load_library()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        h = C.c_void_p()
+        check(self.lib.zolt_gpu_init_multi(ids, len(device_ids), C.byref(h)), "zolt_gpu_init_multi")
+        self.handle = h
+        self.world = len(device_ids)
+
+    def rank(self, r: int):
+        """-> (Context, PeerBox) views of rank r (owned by this object: do not close / free them)."""
+        ch, bh = C.c_void_p(), C.c_void_p()
+        check(self.lib.zolt_multi_rank(self.handle, r, C.byref(ch), C.byref(bh)), "zolt_multi_rank")
+        ctx = Context.__new__(Context)
+        ctx.lib, ctx.handle, ctx.device = self.lib, ch, -1
+        box = PeerBox.__new__(PeerBox)
+        box.ctx, box.rank, box.world, box.handle = ctx, r, self.world, bh
+        return ctx, box
+
+    def msm(self, bases_per_rank, scalars):
+        s = _as_u64(scalars, 4)
+        arr = (C.c_void_p * self.world)(*[b.handle for b in bases_per_rank])
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_uint8()
+        check(self.lib.zolt_multi_msm(self.handle, arr, _ptr(s), s.shape[0], _ptr(out), C.byref(inf)), "zolt_multi_msm")
+        return out, int(inf.value)
+
+    def close(self):
+        if self.handle:
+            self.lib.zolt_multi_shutdown(self.handle)
+            self.handle = None
+
+
 class Dory:
     """DoryCommitmentScheme, G1 side (src/poly/commitment/dory.zig)."""
 

@@ -1014,6 +1014,19 @@ extern "C" int zolt_msm(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, c
   return s;
 }
 
+// The un-normalised partial sum from HOST scalars, left on the device (128 bytes at d_out): zolt_msm_partial_dev with the
+// upload overlapped as in zolt_msm.  Used by the one-process multi-device MSM (multi.cu).
+extern "C" int zolt_msm_partial(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n, void* d_out) {
+  if (!ctx || !bases || !d_out || (n && !scalars) || offset + n > bases->n) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  XYZZ* d_res = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(XYZZ), (void**)&d_res));
+  int s = msm_host_partial(ctx, bases, offset, scalars, n, d_res);
+  if (s == ZOLT_OK && cudaMemcpyAsync(d_out, d_res, sizeof(XYZZ), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) s = ZOLT_ERR_CUDA;
+  pool_release(ctx, d_res, 4 * sizeof(XYZZ));
+  return s;
+}
+
 // zolt_msm_sharded_dev for HOST scalars (this rank's range): upload overlapped as in zolt_msm, then the mailbox exchange.
 extern "C" int zolt_msm_sharded(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n,
                                 zolt_peer_box* box, uint64_t out_xy[8], uint8_t* out_inf) {

@@ -50,6 +50,8 @@ def load_host() -> C.CDLL:
         _host.zolt_host_sumcheck_prove_gruen_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
                                                              C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p,
                                                              C.c_void_p, C.c_void_p]
+        _host.zolt_host_sumcheck_prove_multi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_char_p,
+                                                         C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_srs_load.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]
         _host.zolt_host_eq_mle.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -244,3 +246,18 @@ def srs_load(ctx: Context, kind: int, data: bytes):
     err = load_host().zolt_host_srs_load(ctx.handle, kind, data, len(data), C.byref(h), C.byref(count), C.byref(nv), C.byref(bad))
     bases = Bases(ctx, h) if err == 0 and h.value else None
     return bases, SRS_ERRORS.get(err, str(err)), count.value, nv.value, (None if bad.value == (1 << 64) - 1 else bad.value)
+
+
+def sumcheck_prove_multi(multi, combiner: int, tables, claim=None, domain: bytes = b"bench", label: bytes = b"round"):
+    """Dense LowToHigh sumcheck of ONE process over the devices of a MultiContext (zolt_host.hpp proveSumcheckMultiDevice)."""
+    tabs = [_as_u64(t, 4) for t in tables]
+    log_n = tabs[0].shape[0].bit_length() - 1
+    arr = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+    evals = np.zeros((log_n, 4, 4), dtype=np.uint64)
+    chal = np.zeros((log_n, 4), dtype=np.uint64)
+    final = np.zeros((len(tabs), 4), dtype=np.uint64)
+    cl = _as_u64(claim, 4) if claim is not None else None
+    st = load_host().zolt_host_sumcheck_prove_multi(multi.handle, combiner, log_n, len(tabs), arr, _ptr(cl), domain, len(domain), label,
+                                                    len(label), _ptr(evals), _ptr(chal), _ptr(final))
+    _lib.check(st, "zolt_host_sumcheck_prove_multi")
+    return evals, chal, final

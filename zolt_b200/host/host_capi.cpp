@@ -131,6 +131,22 @@ int zolt_host_sumcheck_prove_gruen_dev(zolt_ctx* ctx, int with_c, int log_n, int
   return ZOLT_OK;
 }
 
+// One process, several devices: dense sumcheck over the devices of a zolt_multi (one host thread per device)
+int zolt_host_sumcheck_prove_multi(zolt_multi* multi, int combiner, int log_n, int n_tables, const uint64_t* const* tables,
+                                   const uint64_t* claim, const char* domain, size_t dn, const char* label, size_t ln,
+                                   uint64_t* evals_out, uint64_t* challenges_out, uint64_t* final_out) {
+  std::vector<const uint64_t*> tabs(tables, tables + n_tables);
+  std::vector<Fr> fin;
+  Fr cl;
+  if (claim) cl = Fr::fromRaw(claim);
+  SumcheckProof proof = proveSumcheckMultiDevice(multi, combiner, tabs, log_n, std::string_view(domain, dn), std::string_view(label, ln), &fin,
+                                                 claim ? &cl : nullptr);
+  store_proof(proof, evals_out, challenges_out);
+  if (final_out)
+    for (int t = 0; t < n_tables; t++) fin[t].store(final_out + 4 * t);
+  return ZOLT_OK;
+}
+
 // SRS container parsers: kind 0 raw binary (srs.zig:256-306), 1 snarkjs PTAU (:733-900), 2 Jolt Dory SRS (dory.zig:740-826).
 // Returns the srs::Error code (0 = ok); *bases_out is a zolt_bases handle the caller frees.
 int zolt_host_srs_load(zolt_ctx* ctx, int kind, const uint8_t* data, size_t len, zolt_bases** bases_out, size_t* count,

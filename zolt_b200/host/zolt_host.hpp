@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zolt_gpu.h"
@@ -622,6 +623,63 @@ inline SumcheckProof proveSumcheckSharded(Context& ctx, zolt_peer_box* box, int 
   if (final_out)
     for (int t = 0; t < k; t++) final_out->push_back(tail.table(t)[0]);
   return proof;
+}
+
+// The dense LowToHigh sumcheck of a single-process prover over the devices of a zolt_multi: host tables are split into
+// contiguous hypercube blocks, block r is uploaded to device r, and one host thread per device runs proveSumcheckSharded
+// (every thread keeps its own copy of the transcript, they all derive the same challenges).  Returns rank 0's proof.
+inline SumcheckProof proveSumcheckMultiDevice(zolt_multi* multi, int combiner, const std::vector<const uint64_t*>& tables, int log_n,
+                                              std::string_view domain, std::string_view challenge_label, std::vector<Fr>* final_out,
+                                              const Fr* input_claim = nullptr) {
+  int world = 0;
+  must(zolt_multi_size(multi, &world), "zolt_multi_size");
+  int shift = 0;
+  while ((1 << shift) < world) shift++;
+  if ((1 << shift) != world || shift > log_n) panic("proveSumcheckMultiDevice: device count must be a power of two <= the table length", ZOLT_ERR_ARG);
+  const int local_log = log_n - shift;
+  const size_t local = size_t(1) << local_log;
+  const int k = (int)tables.size();
+  std::vector<SumcheckProof> proofs((size_t)world);
+  std::vector<std::vector<Fr>> finals((size_t)world);
+  std::vector<std::vector<void*>> bufs((size_t)world, std::vector<void*>((size_t)k, nullptr));
+  // stage 1 (no exchange yet): upload the blocks and warm the pools; ranks sharing a device must not allocate while a peer's
+  // kernel is already waiting for them
+  for (int r = 0; r < world; r++) {
+    zolt_ctx* c = nullptr;
+    must(zolt_multi_rank(multi, r, &c, nullptr), "zolt_multi_rank");
+    for (int t = 0; t < k; t++) {
+      must(zolt_dev_alloc(c, local * 32, &bufs[(size_t)r][(size_t)t]), "zolt_dev_alloc");
+      must(zolt_dev_upload(c, bufs[(size_t)r][(size_t)t], tables[(size_t)t] + 4 * local * (size_t)r, local * 32), "zolt_dev_upload");
+    }
+    Context ctx(c);
+    std::vector<const void*> d(bufs[(size_t)r].begin(), bufs[(size_t)r].end());
+    DenseSumcheckProver warm(ctx, DenseSumcheckProver::DeviceTables{}, combiner, ZOLT_PAIR_ADJACENT, d, local_log);
+    Transcript tr(domain);
+    SumcheckProof p;
+    proveSumcheckInto(p, warm, tr, challenge_label);
+    must(zolt_gpu_sync(c), "zolt_gpu_sync");
+  }
+  std::vector<std::thread> pool;
+  for (int r = 0; r < world; r++) {
+    pool.emplace_back([&, r]() {
+      zolt_ctx* c = nullptr;
+      zolt_peer_box* b = nullptr;
+      must(zolt_multi_rank(multi, r, &c, &b), "zolt_multi_rank");
+      Context ctx(c);
+      std::vector<const void*> d(bufs[(size_t)r].begin(), bufs[(size_t)r].end());
+      Transcript tr(domain);
+      proofs[(size_t)r] = proveSumcheckSharded(ctx, b, world, combiner, d, local_log, tr, challenge_label, &finals[(size_t)r], input_claim);
+      must(zolt_gpu_sync(c), "zolt_gpu_sync");
+    });
+  }
+  for (auto& t : pool) t.join();
+  for (int r = 0; r < world; r++) {
+    zolt_ctx* c = nullptr;
+    must(zolt_multi_rank(multi, r, &c, nullptr), "zolt_multi_rank");
+    for (void* p : bufs[(size_t)r]) zolt_dev_free(c, p);
+  }
+  if (final_out) *final_out = finals[0];
+  return proofs[0];
 }
 
 inline SumcheckProof proveSumcheck(SumcheckInstance& inst, Transcript& transcript, std::string_view challenge_label) {
