@@ -141,14 +141,16 @@ def test_resident_tail_kernel(ctx):
         ctx.set_tuning(Z.TUNE_SC_TAIL_TIMEOUT_MS, 50)
         tabs = [rand_fr(9400 + t, 1 << 8) for t in range(4)]
         ch = rand_fr(9500, 8)
-        exp, _ = OS.run_dense("eq_ab_minus_c", tabs, Z.PAIR_ADJACENT, ch)
+        exp, bound = OS.run_dense("eq_ab_minus_c", tabs, Z.PAIR_ADJACENT, ch)
         inst = Z.SumcheckInstance(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, [fr_arr(t) for t in tabs])
         try:
             for rnd, r in enumerate(ch):
                 assert fr_ints(inst.compute_round_poly()) == exp[rnd], rnd
-                if rnd in (2, 5):
+                if rnd in (2, 5, len(ch) - 1):  # ... including before the LAST bind, which nobody waits for
                     time.sleep(0.25)
                 inst.bind_challenge(fr_arr([r]))
+            for t in range(4):
+                assert fr_ints(inst.table(t)) == bound[-1][t]
         finally:
             inst.free()
     finally:
@@ -297,3 +299,39 @@ def test_raf_evaluation_prover_shape(ctx, log_k):
     inst.free()
     d_ra.free()
     d_unmap.free()
+
+
+def test_serialised_launches_disable_the_resident_tail(built_lib, tmp_path):
+    """Under a profiler (ncu) or CUDA_LAUNCH_BLOCKING=1 a launch returns only when the kernel has retired, so a kernel that
+    waits for the host can only time out: the library must notice (first launch), fall back to one launch per round for the
+    context, and still produce the same proof."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    script = tmp_path / "blocking.py"
+    script.write_text(f"""
+import sys, time
+sys.path.insert(0, {str(root)!r})
+import numpy as np
+import zolt_b200 as Z
+from zolt_b200 import host as H
+from oracle import cpu_ref as R
+from tests.util import fr_arr, rand_fr
+ctx = Z.Context(0)
+tabs = [fr_arr(rand_fr(9600 + t, 1 << 13)) for t in range(4)]
+bufs = [Z.DeviceBuffer.from_host(ctx, t) for t in tabs]
+t0 = time.time()
+for _ in range(2):
+    got = H.sumcheck_prove_dev(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, [b.ptr for b in bufs], 13)
+want = R.sc_prove("eq_ab_minus_c", 0, tabs)
+assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+assert all((got[2][t] == want[2][t][0]).all() for t in range(4))
+assert time.time() - t0 < 5.0, "every round paid a time-out"
+print("BLOCKING_OK")
+""")
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, env=dict(os.environ, CUDA_LAUNCH_BLOCKING="1"))
+    assert res.returncode == 0 and "BLOCKING_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "resident sumcheck tail disabled" in res.stderr

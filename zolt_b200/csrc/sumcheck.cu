@@ -1027,7 +1027,8 @@ struct TailArgs {
   Fr* d_evals;               // previous round's evaluations in, latest evaluations out
   Fr* d_raw;
   unsigned char* mailbox;    // device address of the mapped mailbox
-  unsigned long long timeout_ns;
+  unsigned long long timeout_ns;        // patience for every command but the first
+  unsigned long long first_timeout_ns;  // ... and for the first, which the launching call posts at once
   unsigned long long* dbg;   // optional: per round 4 globaltimer stamps of CTA 0 (command seen, work done, folded, published)
 };
 
@@ -1123,7 +1124,7 @@ sc_tail_kernel(const __grid_constant__ TailArgs ta) {
         if ((spins & 63u) == 0) {
           unsigned long long t1;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          if (t1 - t0 > ta.timeout_ns) {
+          if (t1 - t0 > (expect == 1 ? ta.first_timeout_ns : ta.timeout_ns)) {
             w[0] = 0xffffffffu;
 #pragma unroll
             for (int i = 1; i < 18; i++) w[i] = 0;
@@ -1143,7 +1144,7 @@ sc_tail_kernel(const __grid_constant__ TailArgs ta) {
     __syncwarp();
     cluster_sync_all();  // the command sits in every CTA's shared memory
     const unsigned op = cmd_sh[0];
-    if (cta == 0 && tid == 0) mb32[kMbCmdAck / 4] = expect;  // the host may rewrite the command slot
+    if (cta == 0 && tid == 0 && op != 0xffffffffu) mb32[kMbCmdAck / 4] = expect;  // taken: the host may rewrite the command slot (a time-out acknowledges nothing)
     if (ta.dbg && cta == 0 && tid == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); ta.dbg[(expect - 1) * 4 + 0] = tt; }
     if (op != TAIL_OP_BIND) {  // uniform over the cluster
       status = op == TAIL_OP_EXIT ? TAIL_ST_DONE : TAIL_ST_TIMEOUT;
@@ -1455,6 +1456,7 @@ struct zolt_sc {
   bool tail_active = false;     // the kernel has been launched and not yet joined
   unsigned tail_cmds = 0;       // commands posted to the running kernel
   int tail_prof = -1;
+  unsigned tail_bind_seq = 0;   // number of the last BIND command posted (0: none) -- compared with the kernel's acknowledgement
   bool tail_pending = false;    // a bind command has been posted whose evaluations have not been read yet
   int tail_prev_cur = 0;        // state before that command (to redo it through a regular launch if the kernel timed out)
   size_t tail_prev_n = 0;
@@ -1793,6 +1795,7 @@ int tail_launch(zolt_sc* sc) {
   ta.d_raw = sc->d_raw;
   ta.mailbox = reinterpret_cast<unsigned char*>(sc->h_evals_dev);
   ta.timeout_ns = (unsigned long long)(ctx->sc_tail_timeout_ms > 0 ? ctx->sc_tail_timeout_ms : 10000) * 1000000ull;
+  ta.first_timeout_ns = ta.timeout_ns < 250000000ull ? ta.timeout_ns : 250000000ull;
   ta.dbg = ctx->sc_tail_dbg;
   memset(reinterpret_cast<unsigned char*>(sc->h_evals) + kMbCmd, 0, 16 * kCmdChunks);
   *mb_word(sc, kMbCmdAck) = 0;
@@ -1809,6 +1812,16 @@ int tail_launch(zolt_sc* sc) {
   ctx->launches++;
   sc->tail_active = true;
   sc->tail_cmds = 0;
+  sc->tail_bind_seq = 0;
+  if (cudaStreamQuery(sc->tail_stream) == cudaSuccess) {
+    // The kernel is over before its first command could be posted: kernel launches are being serialised (a profiler such
+    // as ncu, CUDA_LAUNCH_BLOCKING), so a kernel that waits for the host can only time out.  Use one launch per round on
+    // this context from now on.
+    fprintf(stderr, "[zolt_gpu] kernel launches are serialised on device %d: resident sumcheck tail disabled for this context\n", ctx->device);
+    ctx->sc_tail_pairs = 0;
+    sc->tail_active = false;
+    return ZOLT_ERR_STATE;
+  }
   return ZOLT_OK;
 }
 
@@ -1818,6 +1831,7 @@ void tail_post(zolt_sc* sc, unsigned op, const Fr* r, unsigned result_seq, const
     if ((spins & 0xfffu) == 0 && cudaStreamQuery(sc->tail_stream) != cudaErrorNotReady) break;  // the kernel is gone (timed out)
   }
   const unsigned seq = ++sc->tail_cmds;
+  if (op == TAIL_OP_BIND) sc->tail_bind_seq = seq;
   unsigned w[18] = {op, result_seq};
   if (r)
     for (int i = 0; i < 8; i++) w[2 + i] = r->v[i];
@@ -1852,11 +1866,26 @@ Fr host_cubic_at(const Fr* e, const Fr& r) {
 
 // Join the tail kernel (telling it to exit if it is still waiting for commands).  Afterwards the instance's tables and
 // d_evals are exactly what the host-side bookkeeping (cur, n, evals_valid) says, and regular launches can continue.
+int tail_stop(zolt_sc* sc);
+}  // namespace
+static int sc_bind_launch(zolt_sc* sc, const Fr& r);
+namespace {
 int tail_stop(zolt_sc* sc) {
   if (!sc->tail_active) return ZOLT_OK;
   if (sc->n >= 2) tail_post(sc, TAIL_OP_EXIT, nullptr, 0);  // after the last bind the kernel has left its loop by itself
   ZOLT_CUDA_TRY(cudaStreamSynchronize(sc->tail_stream));
   sc->tail_active = false;
+  sc->tail_pending = false;
+  if (sc->tail_bind_seq && *mb_word(sc, kMbCmdAck) < sc->tail_bind_seq) {
+    // the kernel retired (it ran out of patience) before it took the last bind: nothing of that command was executed --
+    // take it back and run it as a regular launch
+    sc->tail_bind_seq = 0;
+    sc->cur = sc->tail_prev_cur;
+    sc->n = sc->tail_prev_n;
+    sc->evals_valid = true;
+    return sc_bind_launch(sc, sc->last_r);
+  }
+  sc->tail_bind_seq = 0;
   return ZOLT_OK;
 }
 
@@ -1959,6 +1988,7 @@ static int sc_wait_evals(zolt_sc* sc) {
           // two rounds): nothing of the command was executed -- take it back and run it as a regular launch
           sc->tail_active = false;
           sc->tail_pending = false;
+          sc->tail_bind_seq = 0;
           sc->cur = sc->tail_prev_cur;
           sc->n = sc->tail_prev_n;
           sc->evals_valid = true;
@@ -2115,7 +2145,11 @@ extern "C" int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]) {
     } else if (sc->tail_pending) {
       ZOLT_TRY(sc_wait_evals(sc));
     }
-    if (!sc->tail_active) ZOLT_TRY(tail_launch(sc));
+    if (!sc->tail_active) {
+      const int st = tail_launch(sc);
+      if (st == ZOLT_ERR_STATE) return sc_bind_launch(sc, r);  // launches are serialised: one launch per round
+      ZOLT_TRY(st);
+    }
     sc->last_r = r;
     sc->tail_prev_cur = sc->cur;
     sc->tail_prev_n = sc->n;
