@@ -5,7 +5,7 @@
 //!   msm.MSM(F, Fp).compute                 src/msm/mod.zig:355-372          -> msmCompute
 //!   HyperKZG.commit / batchCommit / open   src/poly/commitment/mod.zig:239-324, :558-570 -> commit / openProof
 //!   HyperKZG.batchOpen                     src/poly/commitment/mod.zig:607-732 -> batchOpen
-//!   DoryCommitmentScheme row commitments   src/poly/commitment/dory.zig:989-1042 -> doryRowCommitments
+//!   DoryCommitmentScheme row commitments   src/poly/commitment/dory.zig:646-670, :989-1042 -> doryRowCommitments
 //!   batched_sumcheck.SumcheckInstance      src/zkvm/batched_sumcheck.zig:34-74 -> GpuSumcheck.instance()
 //!   DensePolynomial.bindLow / bindFirst    src/poly/mod.zig:128-175         -> bindLow / bindFirst
 //!   EqPolynomial.evals                     src/poly/mod.zig:240-290         -> eqEvals
