@@ -86,6 +86,8 @@ extern "C" int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value) {
     case ZOLT_TUNE_SC_SMALL_PAIRS: ctx->sc_small_pairs = value > (1 << 14) ? (1 << 14) : value; return ZOLT_OK;
     case ZOLT_TUNE_SC_TAIL_PAIRS: ctx->sc_tail_pairs = value > (1 << 14) ? (1 << 14) : value; return ZOLT_OK;
     case ZOLT_TUNE_SC_TAIL_TIMEOUT_MS: ctx->sc_tail_timeout_ms = value; return ZOLT_OK;
+    case 8: ctx->msm_dbg = reinterpret_cast<unsigned long long*>(value); return ZOLT_OK;          // diagnostics: device pointer or 0
+    case 7: ctx->sc_round_dbg = reinterpret_cast<unsigned long long*>(value); return ZOLT_OK;     // diagnostics: device pointer or 0
     case 6: ctx->sc_tail_dbg = reinterpret_cast<unsigned long long*>(value); return ZOLT_OK;  // diagnostics: device pointer or 0
     case ZOLT_TUNE_PEER_TIMEOUT_MS: ctx->peer_timeout_ms = value; return ZOLT_OK;
     case ZOLT_TUNE_SC_BIND_F64: ctx->sc_bind_f64 = (int)(value & 0xff); return ZOLT_OK;

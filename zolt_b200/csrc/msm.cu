@@ -276,8 +276,14 @@ msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, M
 __global__ void __launch_bounds__(128, 4)
 msm_accum_points_kernel(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets, uint32_t num_keys,
                         const AffineG1* __restrict__ bases, XYZZ* __restrict__ buckets,
-                        uint32_t* __restrict__ edge_keys, XYZZ* __restrict__ edge_pts, size_t num_slices, uint32_t slice_len) {
+                        uint32_t* __restrict__ edge_keys, XYZZ* __restrict__ edge_pts, size_t num_slices, uint32_t slice_len,
+                        unsigned long long* __restrict__ dbg) {
   const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (dbg && (threadIdx.x & 31) == 0) {  // diagnostics (tuning key 8): per warp start, end, SM
+    unsigned long long tt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+    dbg[3 * (t >> 5)] = tt;
+  }
   if (t >= num_slices) return;
   const uint32_t total = offsets[num_keys];
   const uint64_t p0 = (uint64_t)t * slice_len;
@@ -336,6 +342,17 @@ msm_accum_points_kernel(const uint32_t* __restrict__ sorted, const uint32_t* __r
   }
   if (ek0 == kInvalidKey) edge_keys[2 * t] = kInvalidKey;
   if (ek1 == kInvalidKey) edge_keys[2 * t + 1] = kInvalidKey;
+  if (dbg) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long tt;
+      unsigned sm;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      dbg[3 * (t >> 5) + 1] = tt;
+      dbg[3 * (t >> 5) + 2] = sm;
+    }
+  }
 }
 
 // ---- 5. accumulate, edge levels --------------------------------------------------------------------------
@@ -740,7 +757,7 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
     // level 0
     ps = prof_begin(ctx, PROF_MSM_ACCUM0);
     msm_accum_points_kernel<<<(unsigned)((slices0 + 127) / 128), 128, 0, st>>>(
-        sorted, offsets, (uint32_t)num_keys, d_pts, buckets, edge_keys, edge_pts, slices0, slice_len);
+        sorted, offsets, (uint32_t)num_keys, d_pts, buckets, edge_keys, edge_pts, slices0, slice_len, ctx->msm_dbg);
     prof_end(ctx, ps);
     ctx->launches++;
     // edge levels

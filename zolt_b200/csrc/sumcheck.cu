@@ -458,6 +458,7 @@ __device__ __forceinline__ void block_reduce(Fr* acc, Fr* smem) {
 struct ScOut {
   Fr* partials;       // gridDim.x * kRaw
   unsigned* ticket;
+  unsigned* next_chunk;  // streaming kernels (adjacent pairs): work counter of the 32-pair chunks handed out dynamically
   Fr* d_raw;          // kRaw raw sums of this launch (what a sharded run all-gathers)
   Fr* d_evals;        // 4 evaluations: read as "previous round" (CLAIM_PREV), then overwritten
   Fr* h_evals;        // mapped pinned host copy of d_evals
@@ -467,8 +468,17 @@ struct ScOut {
   int claim_src;
   int finalize;       // 0: sharded run (host-driven exchange), stop at the raw sums
   unsigned seq;       // finalize: written to the host mailbox (byte 128) after the evaluations, the host polls it
+  unsigned long long* dbg;  // diagnostics (tuning key 7): 8 globaltimer stamps per launch at dbg + 8 * (seq & 63), or null
   PeerDev peer;       // world > 1: the raw sums of all ranks are exchanged through the NVLink mailboxes right here
 };
+
+__device__ __forceinline__ void sc_stamp(const ScOut& o, int i) {
+  if (o.dbg) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    o.dbg[8 * (o.seq & 63u) + i] = t;
+  }
+}
 
 __device__ __forceinline__ Fr ldcg_fr(const Fr* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -512,6 +522,7 @@ __device__ __noinline__ void sc_publish(const ScOut& o, const Fr* tot_local) {
     else if (o.claim_src == CLAIM_HOST) claim = ld_fr(o.d_claim);
     Fr ev[4];
     sc_finalize(o.deg, o.claim_src != CLAIM_NONE, tot, claim, ev);
+    sc_stamp(o, 4);
 #pragma unroll 1
     for (int e = 0; e < 4; e++) {
       st_fr(&o.d_evals[e], ev[e]);
@@ -522,6 +533,7 @@ __device__ __noinline__ void sc_publish(const ScOut& o, const Fr* tot_local) {
     *reinterpret_cast<volatile unsigned*>(o.h_evals + 4) = o.seq;
   }
   __threadfence_system();
+  sc_stamp(o, 5);
 }
 
 // Each block publishes its partial; the last block to arrive folds all partials, turns the raw sums into
@@ -578,6 +590,7 @@ __device__ __noinline__ void grid_fold_publish(Fr x, const ScOut& o) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    if (tid == 0) sc_stamp(o, 2);
     if (warp < kRaw) {
       Fr tot = Fr::zero();
 #pragma unroll 1
@@ -589,6 +602,8 @@ __device__ __noinline__ void grid_fold_publish(Fr x, const ScOut& o) {
   __syncthreads();
   if (tid == 0) {
     if (gridDim.x > 1) *o.ticket = 0;
+    if (o.next_chunk) *o.next_chunk = 0;  // every block took its last chunk before it took its ticket
+    sc_stamp(o, 3);
     sc_publish(o, fin);
   }
 }
@@ -597,6 +612,15 @@ __device__ __noinline__ void grid_fold_publish(Fr x, const ScOut& o) {
 // block's dynamic scratch, re-used as [kRaw][kRoundThreads] field elements once every thread has left its loop.
 __device__ __noinline__ void round_finish(const Fr* raw, Fr* vals, const ScOut& o) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (blockIdx.x == 0 && tid == 0) sc_stamp(o, 1);
+  if (o.dbg && tid == 0) {  // per block: when it left its loop, and on which SM (words 512 + 2 b, overwritten by every launch)
+    unsigned long long tt;
+    unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    o.dbg[512 + 2 * blockIdx.x] = tt;
+    o.dbg[512 + 2 * blockIdx.x + 1] = sm;
+  }
   __syncthreads();
 #pragma unroll 1
   for (int e = 0; e < kRaw; e++) st_fr(&vals[e * kRoundThreads + tid], raw[e]);
@@ -649,6 +673,7 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
       __threadfence();
     }
   }
+  if (out.dbg && blockIdx.x == 0 && threadIdx.x == 0) sc_stamp(out, 0);
   uint32_t wacc[NACC > 0 ? NACC : 1][16];
   Fr facc[2] = {Fr::zero(), Fr::zero()};
 #pragma unroll
@@ -661,10 +686,9 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   size_t g0 = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31);  // first pair of this warp's 32
-  // The trip count is the same for every thread of the grid (a ragged last iteration is predicated), so the loops below
-  // are warp-convergent code: warp-cooperative copies, __syncwarp, and -- for the FP64 bind -- multiplier-table constants
-  // as uniform-register operands loaded by LDCU next to their DFMAs.  (Inside a loop whose trip count depends on the
-  // thread ptxas may not touch the uniform datapath: one indexed LDC per DFMA, measured slower than the integer bind.)
+  // Half-split pairing: the trip count is the same for every thread of the grid (a ragged last iteration is predicated), so
+  // the loops are warp-convergent code: warp-cooperative copies and __syncwarp are safe.  (The adjacent-pair loops below take
+  // their chunks from a counter instead; a warp's lanes still share every chunk index.)
   const size_t iters = (pairs + stride - 1) / stride;
 
   if constexpr (PAIR == ZOLT_PAIR_ADJACENT) {
@@ -672,7 +696,21 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
     // 1024-byte aligned start (the swizzle pattern is a function of the shared-memory address); plain pointer arithmetic on
     // `scratch` so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     unsigned char* const smem = reinterpret_cast<unsigned char*>(scratch) + ((1024u - (smem_u32(scratch) & 1023u)) & 1023u);
-    size_t g = g0 + lane;
+    // Work is handed out in chunks of 32 pairs (one TMA box row range per warp) from a grid-wide counter, not by a fixed
+    // stride: the SM's warp arbiter is not fair (r2 v14 per-block stamps: of the 3-4 co-resident blocks of an SM two finished
+    // a statically assigned share at 60-70 % of the kernel's duration and the starved one ran the rest alone, one warp per
+    // scheduler, with the multiplier half idle).  Every warp now stays busy until the table runs out.  A warp's first chunk
+    // is static; the next two are always known one iteration ahead so the copy of chunk i+1 overlaps the arithmetic of chunk i
+    // and the counter's round trip is never waited for.  (Field sums are exact: the order of the terms does not matter.)
+    const unsigned nchunks = (unsigned)((pairs + 31) / 32);
+    const unsigned grid_warps = gridDim.x * (kRoundThreads / 32);
+    auto grab = [&]() -> unsigned {  // valid in lane 0; broadcast where it is consumed
+      unsigned v = 0;
+      if (lane == 0) v = grid_warps + atomicAdd(out.next_chunk, 1u);
+      return v;
+    };
+    unsigned cur = blockIdx.x * (kRoundThreads / 32) + warp;
+    unsigned nxt = __shfl_sync(0xffffffffu, grab(), 0);
     if constexpr (FUSED) {
       // per warp: one 4 KB slot for a table's sources (32 rows x 128 B, 128-byte swizzle), then the stash of the bound
       // values ([unit][lane] 16-byte slots, unit 4k = lo, 4k+2 = hi of table k); mbarriers after the last warp
@@ -690,14 +728,10 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
       const int kt = K + n_extra;
       // `dep` is always zero but computed from the words just read out of the slot: the copy that overwrites the slot cannot
       // issue before those shared loads have returned (the TMA unit is not ordered behind the LSU queue the way cp.async is)
-      auto issue = [&](size_t gi, int k, unsigned dep) {
-        if (lane == 0) {
-          if (gi < pairs) {
-            mbar_expect_tx(bar, kSlot);
-            tma_rows_g2s(slot, &tm.m[k], (int)gi + (int)dep, bar);  // row g = sources 4g .. 4g+3 of pair g
-          } else {
-            mbar_expect_tx(bar, 0);
-          }
+      auto issue = [&](unsigned chunk, int k, unsigned dep) {
+        if (lane == 0 && chunk < nchunks) {
+          mbar_expect_tx(bar, kSlot);
+          tma_rows_g2s(slot, &tm.m[k], (int)(chunk * 32u + dep), bar);  // row g = sources 4g .. 4g+3 of pair g
         }
       };
       auto ld_chunks = [&](int c) {  // the element made of chunks c, c+1 of this lane's row
@@ -708,10 +742,12 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
         x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
         return x;
       };
-      issue(g0, 0, 0u);
+      issue(cur, 0, 0u);
       unsigned parity = 0;
-      for (size_t it = 0; it < iters; it++, g += stride, g0 += stride) {
+      while (cur < nchunks) {
+        const size_t g = (size_t)cur * 32 + lane;
         const bool act = g < pairs;
+        const unsigned after = grab();  // in flight while this chunk is processed
 #pragma unroll 1
         for (int k = 0; k < kt; k++) {
           mbar_wait(bar, parity);  // this table's sources have landed
@@ -722,7 +758,7 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
             // canonical limbs: the top word of every element is below 2^30, so this is 0
             const unsigned dep = (a0.v[7] | a1.v[7] | b0.v[7] | b1.v[7] | (a0.v[3] & a1.v[3] & b0.v[3] & b1.v[3] & a0.v[7])) >> 31;
             const bool wrap = k + 1 == kt;
-            issue(wrap ? g0 + stride : g0, wrap ? 0 : k + 1, dep);
+            issue(wrap ? nxt : cur, wrap ? 0 : k + 1, dep);
           }
           Fr v0, v1;  // lo + r (hi - lo): multiplier table in the constant bank
           if constexpr (BIND == 1) {
@@ -757,6 +793,8 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
           }
           accumulate_pair<COMB, P1>(wacc, facc, UnitStash<32>{stash}, w);
         }
+        cur = nxt;
+        nxt = __shfl_sync(0xffffffffu, after, 0);
       }
     } else {
       // evaluation only: per warp two buffers of K boxes (32 rows x 64 B, 64-byte swizzle), filled one iteration ahead
@@ -769,23 +807,21 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
       __syncwarp();
-      auto issue = [&](size_t gi, int buf) {
-        if (lane == 0) {
-          if (gi < pairs) {
-            mbar_expect_tx(bars + buf, kBuf);
+      auto issue = [&](unsigned chunk, int buf) {
+        if (lane == 0 && chunk < nchunks) {
+          mbar_expect_tx(bars + buf, kBuf);
 #pragma unroll
-            for (int k = 0; k < K; k++) tma_rows_g2s(wbase + buf * kBuf + k * kTab, &tm.m[k], (int)gi, bars + buf);  // row g = (lo, hi) of pair g
-          } else {
-            mbar_expect_tx(bars + buf, 0);
-          }
+          for (int k = 0; k < K; k++) tma_rows_g2s(wbase + buf * kBuf + k * kTab, &tm.m[k], (int)(chunk * 32u), bars + buf);  // row g = (lo, hi) of pair g
         }
       };
-      issue(g0, 0);
+      issue(cur, 0);
       unsigned parity[2] = {0u, 0u};
       int buf = 0;
       const int sw = ((lane >> 1) & 3) << 4;  // 64-byte swizzle: chunk c of row `lane` sits at byte (16 c) ^ sw
-      for (size_t it = 0; it < iters; it++, g += stride, g0 += stride) {
-        issue(g0 + stride, buf ^ 1);
+      while (cur < nchunks) {
+        const size_t g = (size_t)cur * 32 + lane;
+        const unsigned after = grab();  // in flight while this chunk is processed
+        issue(nxt, buf ^ 1);
         mbar_wait(bars + buf, parity[buf]);
         parity[buf] ^= 1u;
         if (g < pairs) {
@@ -799,6 +835,8 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
         }
         __syncwarp();  // every lane is done with this buffer before the next iteration re-arms it
         buf ^= 1;
+        cur = nxt;
+        nxt = __shfl_sync(0xffffffffu, after, 0);
       }
     }
   } else {
@@ -1618,6 +1656,7 @@ int launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   ScOut out{};
   out.partials = sc->d_partials;
   out.ticket = sc->d_ticket;
+  out.next_chunk = sc->d_ticket + 32;  // its own 128-byte line
   out.d_raw = sc->d_raw;
   out.d_evals = sc->d_evals;
   out.h_evals = sc->h_evals_dev;
@@ -1630,6 +1669,7 @@ int launch_round(zolt_sc* sc, bool fused, const Fr& r) {
     if (++sc->ctx->mail_seq == 0) ++sc->ctx->mail_seq;
     out.seq = sc->wait_seq = sc->ctx->mail_seq;
   }
+  out.dbg = sc->ctx->sc_round_dbg;
   const int mode = fused ? 2 : (sc->have_claim && sc->cur < 0 && out.deg != 0 ? 1 : 0);
   out.claim_src = mode == 2 ? CLAIM_PREV : (mode == 1 ? CLAIM_HOST : CLAIM_NONE);
   sc->pending_claim_src = out.claim_src;
@@ -1747,7 +1787,7 @@ int sc_alloc(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, 
   ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(Fr), (void**)&sc->d_raw));
   ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(Fr), (void**)&sc->d_claim));
   ZOLT_CUDA_TRY(pool_alloc(ctx, 256, (void**)&sc->d_ticket));
-  ZOLT_CUDA_TRY(cudaMemsetAsync(sc->d_ticket, 0, sizeof(unsigned), ctx->stream));
+  ZOLT_CUDA_TRY(cudaMemsetAsync(sc->d_ticket, 0, 256, ctx->stream));
   ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(Fr), (void**)&sc->d_evals));
   ZOLT_CUDA_TRY(pinned_mailbox_alloc(ctx, (void**)&sc->h_evals, (void**)&sc->h_evals_dev));
   *out = sc;
