@@ -231,8 +231,19 @@ int zolt_fr_inner_product_dev(zolt_ctx* ctx, const void* d_a, const void* d_b, s
 #define ZOLT_VEC_EQ_AB_MINUS_C 1
 #define ZOLT_VEC_AXPY 2
 #define ZOLT_VEC_AFFINE_INDEX 3
+/*   ZOLT_VEC_LIN2           out = s[0] * a + s[1] * b   ra = gamma rs1_ra + gamma^2 rs2_ra (stage4_gruen_prover.zig:211, :224)
+ *   ZOLT_VEC_STAGE4_TERM    out = e * (a * b + c * (b + out))   one term of computeInputClaim (:385-430): e = eq, a = ra,
+ *                           b = val, c = wa, out holds inc on entry */
+#define ZOLT_VEC_LIN2 4
+#define ZOLT_VEC_STAGE4_TERM 5
 int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d_a, const void* d_b, const void* d_c, const void* d_e,
                     const uint64_t* s /* 4, AXPY only */, size_t n);
+
+/* dst[i] = src[((i / d1) % m1) * s1 + ((i / d2) % m2) * s2] for i < n: re-layouts between the phases of a prover --
+ * transpose [k][j] -> [j][k] (d1 = 1, m1 = K, s1 = T, d2 = K, m2 = T, s2 = 1), a vector replicated over rows (d1 = 1,
+ * m1 = len, s1 = 1, s2 = 0), every element repeated (d1 = K, m1 = len, s1 = 1, s2 = 0).  m = 0 disables a term. */
+int zolt_fr_index_map_dev(zolt_ctx* ctx, void* d_dst, const void* d_src, size_t n, size_t d1, size_t m1, size_t s1, size_t d2,
+                          size_t m2, size_t s2);
 
 /* ---- sumcheck prover inner loop ----------------------------------------------------------------
  * One instance = k dense tables bound in lock-step.  The call pattern is the reference's:
@@ -268,7 +279,20 @@ enum {
    * The host finishes with GruenSplitEqPolynomial.computeCubicRoundPoly (src/poly/split_eq.zig:353). */
   ZOLT_SC_GRUEN_AB = 5,
   /* k=3 (az, bz, cz) + split-eq weights: t0 = sum w (az0 bz0 - cz0), t_inf = sum w daz dbz. */
-  ZOLT_SC_GRUEN_AB_MINUS_C = 6
+  ZOLT_SC_GRUEN_AB_MINUS_C = 6,
+  /* Stage4GruenProver (registers read/write checking, src/zkvm/spartan/stage4_gruen_prover.zig), body
+   * C(X) = ra(X) val(X) + wa(X) (val(X) + inc(X)) over K x T tables laid out [k][j] with the row stride equal to the
+   * CURRENT cycle length, so that the reference's per-row pairs (k*T + 2i, k*T + 2i + 1) are the adjacent pairs of the flat
+   * table.  Both return raw sums (no claim handling on the device; the O(1) completion is host glue).
+   * k=4 (ra, wa, val, inc replicated over k) + split-eq weights over the CYCLE bits only (zolt_sc_set_split_eq with
+   * n_tau = log_n - 7: the pair's row k is masked out of the weight index) -> [q(0), q_X2]
+   * = sum_i E_out E_in sum_k [C(0), leading coefficient of C]  (phase1ComputeMessage, :561-757). */
+  ZOLT_SC_STAGE4_GRUEN = 7,
+  /* k=5 (eq, ra, wa, val, inc), all of the same length -> [p(0), p(2), p(3)] of sum eq(X) C(X): phases 2 and 3
+   * (:764-1015) on tables transposed to [j][k] with eq and inc repeated over k -- an address round binds them to
+   * themselves (the round polynomial then has degree 2 and p(3) is not used), a cycle round (k exhausted) is the
+   * dense-eq cubic. */
+  ZOLT_SC_STAGE4_DENSE = 8
 };
 
 /* tables: k host pointers (n*4 u64 each), n = 2^log_n.  n_extra further tables are bound in
@@ -279,10 +303,12 @@ int zolt_sc_create(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_ta
  * until the first zolt_sc_bind has completed (or the instance is freed before that). */
 int zolt_sc_create_dev(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, int n_extra,
                        const void* const* d_tables, zolt_sc** out);
-/* Gruen combiners only: tau (n_tau*4, n_tau == log_n) -> builds the E_out / E_in prefix tables of
- * GruenSplitEqPolynomial.initWithScaling on the device (src/poly/split_eq.zig:63-183). */
+/* Gruen combiners only: tau (n_tau*4, n_tau == log_n; ZOLT_SC_STAGE4_GRUEN: n_tau <= log_n, the weights then depend on the
+ * low n_tau - 1 bits of the pair index only) -> builds the E_out / E_in prefix tables of
+ * GruenSplitEqPolynomial.initWithScaling on the device (src/poly/split_eq.zig:63-183; the same tables as
+ * src/zkvm/spartan/gruen_eq.zig:296-334). */
 int zolt_sc_set_split_eq(zolt_sc* sc, const uint64_t* tau, int n_tau);
-/* number of evaluations zolt_sc_round_evals writes (2 or 4) */
+/* number of evaluations zolt_sc_round_evals writes (2, 3 or 4) */
 int zolt_sc_num_evals(const zolt_sc* sc, int* out);
 int zolt_sc_round_evals(zolt_sc* sc, uint64_t* evals_out /* num_evals*4 */);
 int zolt_sc_bind(zolt_sc* sc, const uint64_t challenge[4]);

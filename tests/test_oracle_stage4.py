@@ -1,0 +1,52 @@
+"""The Stage 4 oracle (oracle/stage4.py) against the protocol's own invariants: every round polynomial satisfies
+p(0) + p(1) = claim, the last claim is eq(r_cycle, r) * C(bound values), and the merged eq equals the closed form; plus the
+reference's own unit expectations for the split eq (gruen_eq.zig:343-420)."""
+import random
+
+import pytest
+
+from oracle import stage4 as S
+from oracle.bn254 import FR_MOD as P
+from oracle.poly import eq_mle
+
+
+@pytest.mark.parametrize("log_T", [1, 2, 3, 4])
+def test_stage4_oracle_invariants(log_T):
+    rng = random.Random(log_T)
+    T = 1 << log_T
+    n = S.K * T
+    tabs = [[rng.randrange(P) for _ in range(n)] for _ in range(4)]
+    inc = [rng.randrange(P) for _ in range(T)]
+    rc = [rng.randrange(P) for _ in range(log_T)]
+    for p1 in range(1, log_T + 1):
+        pr = S.Stage4Prover(*tabs, inc, rng.randrange(P), rc, p1, S.LOG_K)
+        ch = [rng.randrange(P) for _ in range(pr.num_rounds)]
+        claim0 = pr.compute_input_claim()
+        evals, final = pr.run(ch, claim0)
+        c = claim0
+        for e, r in zip(evals, ch):
+            assert (e[0] + e[1]) % P == c
+            c = S.eval_coeffs(S.coeffs_from_evals(e), r)
+        fc = pr.final_claims()
+        ra = (pr.gamma * fc["rs1_ra"] + pr.gamma_sq * fc["rs2_ra"]) % P
+        body = (ra * fc["val"] + fc["rd_wa"] * (fc["val"] + fc["inc"])) % P
+        assert pr.merged_eq[0] * body % P == final
+        # cycle challenges: rounds 0..p1-1 and the last log_T - p1; round order is little-endian, r_cycle too
+        cyc = ch[:p1] + ch[p1 + S.LOG_K:]
+        assert pr.merged_eq[0] == eq_mle(rc, cyc)
+
+
+def test_gruen_eq_reference_unit_expectations():
+    # gruen_eq.zig "gruen eq polynomial initialization" (:337-356)
+    g = S.GruenEq([1, 2, 3, 4])
+    assert g.current_index == 4 and g.current_scalar == 1
+    assert len(g.E_out_current()) == 4 and len(g.E_in_current()) == 2  # m = 2 out bits, n - 1 - m = 1 in bit
+    # "gruen eq polynomial bind" (:358-385): w = [2, 3], r = 5 -> index 1, scalar = eq(3, 5) = 1 - 3 - 5 + 30
+    g = S.GruenEq([2, 3])
+    g.bind(5)
+    assert g.current_index == 1 and g.current_scalar == (1 - 3 - 5 + 30) % P
+    m = g.merge()  # eq(w[0..1], .) scaled (:172-203)
+    assert len(m) == 2 and sum(m) % P == g.current_scalar
+    # "gruen poly deg 3" (:387-414): p(0) + p(1) = claim
+    c = S.GruenEq([1, 2]).gruen_poly_deg3(10, 5, 100)
+    assert (c[0] + sum(c)) % P == 100

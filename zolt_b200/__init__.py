@@ -26,6 +26,8 @@ from ._lib import (  # noqa: F401
     SC_EQ_AB_MINUS_C,
     SC_GRUEN_AB,
     SC_GRUEN_AB_MINUS_C,
+    SC_STAGE4_DENSE,
+    SC_STAGE4_GRUEN,
     SC_PROD2,
     SC_PROD3,
     SC_SUM,
@@ -40,6 +42,8 @@ from ._lib import (  # noqa: F401
     VEC_AFFINE_INDEX,
     VEC_AXPY,
     VEC_EQ_AB_MINUS_C,
+    VEC_LIN2,
+    VEC_STAGE4_TERM,
     VEC_MUL,
     ZoltGpuError,
     load_library,

@@ -19,14 +19,14 @@ _ERR_NAMES = {1: "ZOLT_ERR_CUDA", 2: "ZOLT_ERR_ARG", 3: "ZOLT_ERR_STATE", 4: "ZO
 FIELD_FR, FIELD_FQ = 0, 1
 OP_MUL, OP_ADD, OP_SUB, OP_INV, OP_FROM_MONT, OP_TO_MONT, OP_NEG = range(7)
 PAIR_ADJACENT, PAIR_HALF = 0, 1
-SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN_AB_MINUS_C = range(7)
+SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN_AB_MINUS_C, SC_STAGE4_GRUEN, SC_STAGE4_DENSE = range(9)
 TUNE_SC_SMALL_PAIRS = 1
 G1_WIRE_BE, G1_WIRE_LE, G1_WIRE_ARK_LE = 0, 1, 2
 TUNE_SC_BIND_F64 = 2
 TUNE_PEER_TIMEOUT_MS = 3
 TUNE_SC_TAIL_PAIRS = 4
 TUNE_SC_TAIL_TIMEOUT_MS = 5
-VEC_MUL, VEC_EQ_AB_MINUS_C, VEC_AXPY, VEC_AFFINE_INDEX = range(4)
+VEC_MUL, VEC_EQ_AB_MINUS_C, VEC_AXPY, VEC_AFFINE_INDEX, VEC_LIN2, VEC_STAGE4_TERM = range(6)
 
 
 class ZoltGpuError(RuntimeError):
@@ -81,6 +81,7 @@ SIGNATURES = {
     "zolt_hyperkzg_batch_open_dev": [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp],
     "zolt_fr_inner_product_dev": [_vp, _vp, _vp, _sz, _vp],
     "zolt_fr_vec_dev": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
+    "zolt_fr_index_map_dev": [_vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _sz],
     "zolt_msm_partial_dev": [_vp, _vp, _sz, _vp, _sz, _vp],
     "zolt_g1_sum_partials": [_vp, _vp, _sz, _vp, _vp],
     "zolt_g1_fixed_base_mul": [_vp, _vp, _sz, C.POINTER(_vp)],

@@ -40,12 +40,6 @@ struct ScPtrs {
   Fr* dst[kMaxTables];
 };
 
-struct SplitEqDev {
-  const Fr* e_out;  // level `out_bits` table of E_out_vec
-  const Fr* e_in;   // level `in_bits` table of E_in_vec
-  int in_bits;
-};
-
 __device__ __forceinline__ Fr ld_fr(const Fr* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = __ldg(q), b = __ldg(q + 1);
@@ -67,6 +61,19 @@ __device__ __forceinline__ Fr fr_sub(const Fr& a, const Fr& b) { return fp_sub<F
 __device__ __forceinline__ Fr fr_add_lazy(const Fr& a, const Fr& b) { return fp_add_lazy<FrParams>(a, b); }
 __device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) { return fp_mul<FrParams>(a, b); }
 
+struct SplitEqDev {
+  const Fr* e_out;  // level `out_bits` table of E_out_vec
+  const Fr* e_in;   // level `in_bits` table of E_in_vec
+  int in_bits;
+  unsigned out_mask = 0xffffffffu;  // bits of (pair >> in_bits) that index e_out (Stage 4: the row k above them is masked out)
+  __device__ __forceinline__ Fr weight(size_t g) const {
+    // E_out[x_out] * E_in[x_in], pair g = (x_out << in_bits) | x_in  (src/zkvm/spartan/product_remainder.zig:293-296)
+    const size_t x_out = (g >> in_bits) & out_mask, x_in = g & ((size_t(1) << in_bits) - 1);
+    return fr_mul(ld_fr(e_out + x_out), ld_fr(e_in + x_in));
+  }
+};
+
+
 // lo + r*(hi - lo): DensePolynomial.bindLow's form (src/poly/mod.zig:171); equal, as a canonical
 // field element, to the (1-r)*lo + r*hi form used at val_evaluation.zig:626-631.
 __device__ __forceinline__ Fr bind_pair(const Fr& lo, const Fr& hi, const Fr& r) {
@@ -83,7 +90,7 @@ __device__ __forceinline__ Fr bind_pair(const Fr& lo, const Fr& hi, const Fr& r)
 //
 // Raw sums leave the kernel as 4 field elements:
 //   cubic      [p(0), p(1) or 0, p(2), lead]     quadratic [p(0), p(1) or 0, lead, 0]
-//   SUM/Gruen  [s0, s1, 0, 0]
+//   SUM/Gruen  [s0, s1, 0, 0]                    Stage-4 dense [p(0), p(2), p(3), 0]
 template <int COMB> struct CombTraits;
 template <> struct CombTraits<ZOLT_SC_SUM> { static constexpr int K = 1, NE = 2, NW = 0, DEG = 0; static constexpr bool GRUEN = false; };
 template <> struct CombTraits<ZOLT_SC_PROD2> { static constexpr int K = 2, NE = 4, NW = 2, DEG = 2; static constexpr bool GRUEN = false; };
@@ -92,6 +99,8 @@ template <> struct CombTraits<ZOLT_SC_EQ_A_BMC> { static constexpr int K = 4, NE
 template <> struct CombTraits<ZOLT_SC_EQ_AB_MINUS_C> { static constexpr int K = 4, NE = 4, NW = 3, DEG = 3; static constexpr bool GRUEN = false; };
 template <> struct CombTraits<ZOLT_SC_GRUEN_AB> { static constexpr int K = 2, NE = 2, NW = 2, DEG = 0; static constexpr bool GRUEN = true; };
 template <> struct CombTraits<ZOLT_SC_GRUEN_AB_MINUS_C> { static constexpr int K = 3, NE = 2, NW = 2, DEG = 0; static constexpr bool GRUEN = true; };
+template <> struct CombTraits<ZOLT_SC_STAGE4_GRUEN> { static constexpr int K = 4, NE = 2, NW = 2, DEG = 0; static constexpr bool GRUEN = true; };
+template <> struct CombTraits<ZOLT_SC_STAGE4_DENSE> { static constexpr int K = 5, NE = 3, NW = 3, DEG = 0; static constexpr bool GRUEN = false; };
 
 constexpr int kRaw = 4;  // field elements per partial result
 
@@ -313,6 +322,40 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
     if constexpr (COMB == ZOLT_SC_GRUEN_AB_MINUS_C) p0 = fr_sub(p0, LO(2));
     wide_acc(wacc[0], w, p0);
     wide_acc(wacc[1], w, fr_mul(fr_sub(l1, l0), fr_sub(r1, r0)));
+  } else if constexpr (COMB == ZOLT_SC_STAGE4_GRUEN) {
+    // C(X) = ra val + wa (val + inc): C(0) and its X^2 coefficient, weighted (stage4_gruen_prover.zig:629-700).  Each is two
+    // products under one Montgomery reduction.
+    Fr c0, cx;
+    {
+      const Fr ra0 = LO(0), wa0 = LO(1), v0 = LO(2), i0 = LO(3);
+      c0 = fp_mul2_add<FrParams>(ra0, v0, wa0, fr_add(v0, i0));
+      const Fr dv = fr_sub(HI(2), v0);
+      const Fr dvi = fr_add(dv, fr_sub(HI(3), i0));
+      cx = fp_mul2_add<FrParams>(fr_sub(HI(0), ra0), dv, fr_sub(HI(1), wa0), dvi);
+    }
+    wide_acc(wacc[0], w, c0);
+    wide_acc(wacc[1], w, cx);
+  } else if constexpr (COMB == ZOLT_SC_STAGE4_DENSE) {
+    // eq(X) * C(X) at X = 0, 2, 3, the reference's sample points (phase2ComputeMessage / phase3ComputeMessage, :764-1015).
+    // p(3) is summed like the reference does rather than derived from the leading coefficient: the caller's claim may be
+    // a batched one (prove, :433-536), and then only directly summed values match
+    Fr c0, c2, c3;
+    {
+      const Fr ra0 = LO(1), wa0 = LO(2), v0 = LO(3), i0 = LO(4);
+      const Fr ra1 = HI(1), wa1 = HI(2), v1 = HI(3), i1 = HI(4);
+      c0 = fp_mul2_add<FrParams>(ra0, v0, wa0, fr_add(v0, i0));
+      const Fr dra = fr_sub(ra1, ra0), dwa = fr_sub(wa1, wa0), dv = fr_sub(v1, v0), di = fr_sub(i1, i0);
+      const Fr ra2 = fr_add(ra1, dra), wa2 = fr_add(wa1, dwa), v2 = fr_add(v1, dv), i2 = fr_add(i1, di);
+      c2 = fp_mul2_add<FrParams>(ra2, v2, wa2, fr_add(v2, i2));
+      const Fr v3 = fr_add(v2, dv);
+      c3 = fp_mul2_add<FrParams>(fr_add(ra2, dra), v3, fr_add(wa2, dwa), fr_add(v3, fr_add(i2, di)));
+    }
+    const Fr e0 = LO(0), e1 = HI(0);
+    const Fr de = fr_sub(e1, e0);
+    const Fr e2 = fr_add(e1, de);
+    wide_acc(wacc[0], e0, c0);
+    wide_acc(wacc[1], e2, c2);
+    wide_acc(wacc[2], fr_add(e2, de), c3);
   }
 #undef LO
 #undef HI
@@ -358,6 +401,7 @@ __device__ __forceinline__ void collapse(uint32_t (*wacc)[16], const Fr* facc, F
   } else {
     raw[0] = wide_collapse(wacc[0]);
     raw[1] = wide_collapse(wacc[1]);
+    if constexpr (NW == 3) raw[2] = wide_collapse(wacc[2]);
   }
 }
 
@@ -714,7 +758,7 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
     if constexpr (FUSED) {
       // per warp: one 4 KB slot for a table's sources (32 rows x 128 B, 128-byte swizzle), then the stash of the bound
       // values ([unit][lane] 16-byte slots, unit 4k = lo, 4k+2 = hi of table k); mbarriers after the last warp
-      constexpr int kSlot = 32 * 128, kWarpBytes = kSlot + 16 * 32 * 16;
+      constexpr int kSlot = 32 * 128, kWarpBytes = kSlot + 4 * K * 32 * 16;
       unsigned char* const slot = smem + warp * kWarpBytes;
       uint4* const stash = reinterpret_cast<uint4*>(slot + kSlot) + lane;
       const unsigned char* const row = slot + lane * 128;
@@ -786,11 +830,7 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
         }
         if (act) {
           Fr w;
-          if constexpr (CombTraits<COMB>::GRUEN) {
-            // g = (x_out << in_bits) | x_in  (src/zkvm/spartan/product_remainder.zig:293-296)
-            const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
-            w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
-          }
+          if constexpr (CombTraits<COMB>::GRUEN) w = sq.weight(g);
           accumulate_pair<COMB, P1>(wacc, facc, UnitStash<32>{stash}, w);
         }
         cur = nxt;
@@ -826,10 +866,7 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
         parity[buf] ^= 1u;
         if (g < pairs) {
           Fr w;
-          if constexpr (CombTraits<COMB>::GRUEN) {
-            const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
-            w = fr_mul(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
-          }
+          if constexpr (CombTraits<COMB>::GRUEN) w = sq.weight(g);
           const SwizzledRows64 st{wbase + buf * kBuf + lane * 64, sw, kTab};
           accumulate_pair<COMB, P1>(wacc, facc, st, w);
         }
@@ -926,6 +963,7 @@ sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const _
 constexpr int kSmallWorkWarps = 4;                            // warp e evaluates raw sum e
 constexpr int kSmallThreads = 32 * (kSmallWorkWarps + 1);     // + one warp for the claim p_prev(r)
 constexpr int kSmallPairs = 16;                               // pairs of the current table per chunk
+constexpr int kSmallTables = 5;                               // most combiner tables of any combiner (Stage-4 dense)
 
 struct SmallArgs {
   int comb, k, n_extra, deg, fused, p1_direct;
@@ -933,20 +971,21 @@ struct SmallArgs {
 
 __device__ __noinline__ Fr bind_pair_cold(Fr lo, Fr hi, Fr r) { return fr_add(lo, fr_mul(r, fr_sub(hi, lo))); }
 
-enum { PT_NONE = 0, PT_0, PT_1, PT_2, PT_LEAD };
+enum { PT_NONE = 0, PT_0, PT_1, PT_2, PT_LEAD, PT_3 };
 
 // the term of pair p of this chunk that belongs to raw sum e (layout of the raw sums: see the combiners above)
 template <int NP>
 __device__ __noinline__ Fr small_term(const SmallArgs& a, int e, const Fr (*stash)[2][NP], int p, const SplitEqDev& sq,
                                       size_t g) {
-  const bool gruen = a.comb == ZOLT_SC_GRUEN_AB || a.comb == ZOLT_SC_GRUEN_AB_MINUS_C;
+  const bool gruen = a.comb == ZOLT_SC_GRUEN_AB || a.comb == ZOLT_SC_GRUEN_AB_MINUS_C || a.comb == ZOLT_SC_STAGE4_GRUEN;
   int pt = PT_NONE;
   if (a.deg == 3) pt = e == 0 ? PT_0 : (e == 1 ? (a.p1_direct ? PT_1 : PT_NONE) : (e == 2 ? PT_2 : PT_LEAD));
   else if (a.deg == 2) pt = e == 0 ? PT_0 : (e == 1 ? (a.p1_direct ? PT_1 : PT_NONE) : (e == 2 ? PT_LEAD : PT_NONE));
   else if (gruen) pt = e == 0 ? PT_0 : (e == 1 ? PT_LEAD : PT_NONE);
+  else if (a.comb == ZOLT_SC_STAGE4_DENSE) pt = e == 0 ? PT_0 : (e == 1 ? PT_2 : (e == 2 ? PT_3 : PT_NONE));
   else pt = e == 0 ? PT_0 : (e == 1 ? PT_1 : PT_NONE);
   if (pt == PT_NONE) return Fr::zero();
-  Fr v[4];
+  Fr v[kSmallTables];
 #pragma unroll 1
   for (int k = 0; k < a.k; k++) {
     const Fr lo = stash[k][0][p], hi = stash[k][1][p];
@@ -955,6 +994,7 @@ __device__ __noinline__ Fr small_term(const SmallArgs& a, int e, const Fr (*stas
     else {
       const Fr d = fr_sub_cold(hi, lo);
       v[k] = pt == PT_LEAD ? d : fr_add_cold(hi, d);
+      if (pt == PT_3) v[k] = fr_add_cold(v[k], d);
     }
   }
   const bool lead = pt == PT_LEAD;
@@ -968,8 +1008,15 @@ __device__ __noinline__ Fr small_term(const SmallArgs& a, int e, const Fr (*stas
       if (!lead) t = fr_sub_cold(t, v[3]);  // c(X) is linear: no cubic term
       return fr_mul_cold(v[0], t);
     }
+    case ZOLT_SC_STAGE4_DENSE:  // eq * (ra val + wa (val + inc)) at the sample point
+      return fr_mul_cold(v[0], fr_add_cold(fr_mul_cold(v[1], v[3]), fr_mul_cold(v[2], fr_add_cold(v[3], v[4]))));
+    case ZOLT_SC_STAGE4_GRUEN: {  // weight * (ra val + wa (val + inc))
+      const size_t x_out = (g >> sq.in_bits) & sq.out_mask, x_in = g & ((size_t(1) << sq.in_bits) - 1);
+      const Fr w = fr_mul_cold(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
+      return fr_mul_cold(w, fr_add_cold(fr_mul_cold(v[0], v[2]), fr_mul_cold(v[1], fr_add_cold(v[2], v[3]))));
+    }
     default: {  // Gruen: weight * (l r [- c])
-      const size_t x_out = g >> sq.in_bits, x_in = g & ((size_t(1) << sq.in_bits) - 1);
+      const size_t x_out = (g >> sq.in_bits) & sq.out_mask, x_in = g & ((size_t(1) << sq.in_bits) - 1);
       const Fr w = fr_mul_cold(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
       Fr t = fr_mul_cold(v[0], v[1]);
       if (a.comb == ZOLT_SC_GRUEN_AB_MINUS_C && !lead) t = fr_sub_cold(t, v[2]);
@@ -982,7 +1029,7 @@ template <int PAIR>
 __global__ void __launch_bounds__(kSmallThreads)
 sc_small_kernel(const __grid_constant__ ScPtrs t, const SmallArgs a, size_t n, const __grid_constant__ Fr r, const SplitEqDev sq,
                 const __grid_constant__ ScOut out) {
-  __shared__ Fr stash[4][2][kSmallPairs];  // [table][half][pair of the chunk]
+  __shared__ Fr stash[kSmallTables][2][kSmallPairs];  // [table][half][pair of the chunk]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (a.fused && warp == kSmallWorkWarps && blockIdx.x == 0 && lane == 0 && out.finalize) {
     Fr prev[4];
@@ -1061,6 +1108,7 @@ struct TailArgs {
   const Fr* e_out;           // split-eq prefix tables (Gruen combiners), level L at offset 2^L - 1
   const Fr* e_in;
   int n_tau;
+  int eq_skip;               // high bits of the table index the split-eq weights do not depend on (Stage 4: the row k)
   Fr* partials;              // kTailCluster * kRaw
   Fr* d_evals;               // previous round's evaluations in, latest evaluations out
   Fr* d_raw;
@@ -1206,11 +1254,13 @@ sc_tail_kernel(const __grid_constant__ TailArgs ta) {
       if (ta.e_out) {  // split_eq_for(n_cur)
         int u = 0;
         while ((size_t(1) << u) < n_cur) u++;
+        u = u > ta.eq_skip ? u - ta.eq_skip : 0;
         const int head_len = u > 0 ? u - 1 : 0, m = ta.n_tau / 2;
         const int out_bits = head_len < m ? head_len : m, in_bits = head_len - out_bits;
         sq.e_out = ta.e_out + ((size_t(1) << out_bits) - 1);
         sq.e_in = ta.e_in + ((size_t(1) << in_bits) - 1);
         sq.in_bits = in_bits;
+        sq.out_mask = (1u << out_bits) - 1u;
       }
       const size_t n_chunks = (pairs + kTailChunk - 1) / kTailChunk;
       for (size_t c = cta; c < n_chunks; c += kTailCluster) {
@@ -1404,6 +1454,13 @@ vec_kernel(Fr* __restrict__ out, const Fr* __restrict__ a, const Fr* __restrict_
       idx.v[0] = (uint32_t)i;
       idx.v[1] = (uint32_t)((unsigned long long)i >> 32);
       v = fr_add(a[0], fr_mul(a[1], fr_mul(Fr::r2(), idx)));
+    } else if constexpr (OP == ZOLT_VEC_LIN2) {
+      // s0 a + s1 b with the scalars in c[0], c[1]: ra = gamma rs1_ra + gamma^2 rs2_ra (stage4_gruen_prover.zig:211, :224)
+      v = fp_mul2_add<FrParams>(c[0], ld_fr(a + i), c[1], ld_fr(b + i));
+    } else if constexpr (OP == ZOLT_VEC_STAGE4_TERM) {
+      // eq (ra val + wa (val + inc)), inc in `out` (computeInputClaim, stage4_gruen_prover.zig:385-430)
+      const Fr val = ld_fr(b + i);
+      v = fr_mul(ld_fr(e + i), fp_mul2_add<FrParams>(ld_fr(a + i), val, ld_fr(c + i), fr_add(val, out[i])));
     } else {
       // out[i] += s * a[i]: the gamma-power combination of batchOpen (src/poly/commitment/mod.zig:648-656)
       const Fr x = ld_fr(a + i);
@@ -1511,13 +1568,17 @@ int combiner_k(int comb) {
     case ZOLT_SC_EQ_AB_MINUS_C: return 4;
     case ZOLT_SC_GRUEN_AB: return 2;
     case ZOLT_SC_GRUEN_AB_MINUS_C: return 3;
+    case ZOLT_SC_STAGE4_GRUEN: return 4;
+    case ZOLT_SC_STAGE4_DENSE: return 5;
     default: return -1;
   }
 }
 int combiner_ne(int comb) {
-  return (comb == ZOLT_SC_SUM || comb == ZOLT_SC_GRUEN_AB || comb == ZOLT_SC_GRUEN_AB_MINUS_C) ? 2 : 4;
+  if (comb == ZOLT_SC_STAGE4_DENSE) return 3;
+  return (comb == ZOLT_SC_SUM || comb == ZOLT_SC_GRUEN_AB || comb == ZOLT_SC_GRUEN_AB_MINUS_C || comb == ZOLT_SC_STAGE4_GRUEN) ? 2 : 4;
 }
-bool combiner_gruen(int comb) { return comb == ZOLT_SC_GRUEN_AB || comb == ZOLT_SC_GRUEN_AB_MINUS_C; }
+bool combiner_gruen(int comb) { return comb == ZOLT_SC_GRUEN_AB || comb == ZOLT_SC_GRUEN_AB_MINUS_C || comb == ZOLT_SC_STAGE4_GRUEN; }
+bool combiner_stage4(int comb) { return comb == ZOLT_SC_STAGE4_GRUEN || comb == ZOLT_SC_STAGE4_DENSE; }
 
 SplitEqDev split_eq_for(const zolt_sc* sc, size_t n_cur) {
   // getWindowEqTables with window_size 1 (src/poly/split_eq.zig:311-343); u = unbound variables.
@@ -1525,6 +1586,8 @@ SplitEqDev split_eq_for(const zolt_sc* sc, size_t n_cur) {
   if (!combiner_gruen(sc->combiner)) return s;
   int u = 0;
   while ((size_t(1) << u) < n_cur) u++;
+  const int skip = sc->log_n0 - sc->n_tau;  // Stage 4: the weights cover the cycle bits, not the row k above them
+  u = u > skip ? u - skip : 0;
   const int head_len = u > 0 ? u - 1 : 0;
   const int m = sc->n_tau / 2;
   const int out_bits = head_len < m ? head_len : m;
@@ -1532,6 +1595,7 @@ SplitEqDev split_eq_for(const zolt_sc* sc, size_t n_cur) {
   s.e_out = sc->d_e_out + ((size_t(1) << out_bits) - 1);
   s.e_in = sc->d_e_in + ((size_t(1) << in_bits) - 1);
   s.in_bits = in_bits;
+  s.out_mask = (1u << out_bits) - 1u;
   return s;
 }
 
@@ -1676,7 +1740,7 @@ int launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   // shared memory: the layout of this pairing (see the kernel) + the per-warp mbarriers + slack for 1024-byte alignment
   const size_t kWarps = kRoundThreads / 32;
   const size_t smem_unit = (size_t)(fused ? kFusedScratchUnits : kEvalScratchUnits) * kScrStride * sizeof(uint4);
-  const size_t smem_tma = (fused ? kWarps * (32 * 128 + 16 * 32 * 16) + kWarps * 8 : kWarps * 2 * (size_t)COMBK * 32 * 64 + kWarps * 16) + 1024;
+  const size_t smem_tma = (fused ? kWarps * (32 * 128 + 4 * (size_t)COMBK * 32 * 16) + kWarps * 8 : kWarps * 2 * (size_t)COMBK * 32 * 64 + kWarps * 16) + 1024;
   const size_t kDynSmem = PAIR == ZOLT_PAIR_ADJACENT ? smem_tma : smem_unit;
   TmapArray tm{};
   if (PAIR == ZOLT_PAIR_ADJACENT && !(n_cur / 2 <= (size_t)sc->ctx->sc_small_pairs)) {
@@ -1751,7 +1815,10 @@ int launch_round_any(zolt_sc* sc, bool fused, const Fr& r) {
     case ZOLT_SC_EQ_A_BMC: return launch_round_p<ZOLT_SC_EQ_A_BMC>(sc, fused, r);
     case ZOLT_SC_EQ_AB_MINUS_C: return launch_round_p<ZOLT_SC_EQ_AB_MINUS_C>(sc, fused, r);
     case ZOLT_SC_GRUEN_AB: return launch_round_p<ZOLT_SC_GRUEN_AB>(sc, fused, r);
-    default: return launch_round_p<ZOLT_SC_GRUEN_AB_MINUS_C>(sc, fused, r);
+    case ZOLT_SC_GRUEN_AB_MINUS_C: return launch_round_p<ZOLT_SC_GRUEN_AB_MINUS_C>(sc, fused, r);
+    // the Stage-4 combiners exist for adjacent pairs only (sc_alloc refuses the other pairing)
+    case ZOLT_SC_STAGE4_GRUEN: return launch_round<ZOLT_SC_STAGE4_GRUEN, ZOLT_PAIR_ADJACENT>(sc, fused, r);
+    default: return launch_round<ZOLT_SC_STAGE4_DENSE, ZOLT_PAIR_ADJACENT>(sc, fused, r);
   }
 }
 
@@ -1761,7 +1828,7 @@ int sc_alloc(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, 
   const int k = combiner_k(combiner);
   if (k < 0 || n_tables != k) return ZOLT_ERR_ARG;
   if (pairing != ZOLT_PAIR_ADJACENT && pairing != ZOLT_PAIR_HALF) return ZOLT_ERR_ARG;
-  if (combiner_gruen(combiner) && pairing != ZOLT_PAIR_ADJACENT) return ZOLT_ERR_ARG;  // Gruen provers bind low-to-high only
+  if ((combiner_gruen(combiner) || combiner_stage4(combiner)) && pairing != ZOLT_PAIR_ADJACENT) return ZOLT_ERR_ARG;  // Gruen provers bind low-to-high only
   if (log_n < 0 || log_n > 40 || n_extra < 0 || k + n_extra > kMaxTables) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   zolt_sc* sc = new (std::nothrow) zolt_sc();
@@ -1828,6 +1895,7 @@ int tail_launch(zolt_sc* sc) {
   ta.n = sc->n;
   ta.a = SmallArgs{sc->combiner, sc->k, sc->n_extra, combiner_deg(sc->combiner), 1, 0};
   ta.e_out = combiner_gruen(sc->combiner) ? sc->d_e_out : nullptr;
+  ta.eq_skip = sc->log_n0 - sc->n_tau;
   ta.e_in = sc->d_e_in;
   ta.n_tau = sc->n_tau;
   ta.partials = sc->d_partials;
@@ -1965,7 +2033,7 @@ extern "C" int zolt_sc_create_dev(zolt_ctx* ctx, int combiner, int pairing, int 
 
 extern "C" int zolt_sc_set_split_eq(zolt_sc* sc, const uint64_t* tau, int n_tau) {
   if (!sc || !tau || !combiner_gruen(sc->combiner)) return ZOLT_ERR_ARG;
-  if (n_tau != sc->log_n0 || n_tau < 1) return ZOLT_ERR_ARG;
+  if (n_tau < 1 || (sc->combiner == ZOLT_SC_STAGE4_GRUEN ? n_tau > sc->log_n0 : n_tau != sc->log_n0)) return ZOLT_ERR_ARG;
   zolt_ctx* ctx = sc->ctx;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   // w_out = tau[0..m], w_in = tau[m..n-1], w_last skipped (src/poly/split_eq.zig:63-110)
@@ -2060,7 +2128,9 @@ extern "C" int zolt_sc_set_claim(zolt_sc* sc, const uint64_t claim[4]) {
 // The shard protocols (blocked hypercube ranges) are only correct for adjacent pairs and dense combiners: a
 // half-split bind pairs an element with one in another rank's block, and the Gruen weights are indexed by the LOCAL pair
 // index with tau covering the local variables only.  Refuse instead of returning plausible but wrong polynomials.
-static bool sc_shardable(const zolt_sc* sc) { return sc->pairing == ZOLT_PAIR_ADJACENT && !combiner_gruen(sc->combiner); }
+static bool sc_shardable(const zolt_sc* sc) {
+  return sc->pairing == ZOLT_PAIR_ADJACENT && !combiner_gruen(sc->combiner) && !combiner_stage4(sc->combiner);
+}
 
 extern "C" int zolt_sc_set_sharded(zolt_sc* sc, int on) {
   if (!sc) return ZOLT_ERR_ARG;
@@ -2353,6 +2423,28 @@ extern "C" int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d
     pool_release(ctx, d_s, 2 * sizeof(Fr));
     return ZOLT_OK;
   }
+  if (op == ZOLT_VEC_LIN2 || op == ZOLT_VEC_STAGE4_TERM) {
+    if (!d_a || !d_b || (op == ZOLT_VEC_LIN2 ? !s : (!d_c || !d_e))) return ZOLT_ERR_ARG;
+    if (n == 0) return ZOLT_OK;
+    ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+    const unsigned grid = grid_for(ctx, n, 8);
+    if (op == ZOLT_VEC_STAGE4_TERM) {
+      vec_kernel<ZOLT_VEC_STAGE4_TERM><<<grid, kScThreads, 0, ctx->stream>>>((Fr*)d_out, (const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c,
+                                                                            (const Fr*)d_e, FixedMulTable{}, n);
+      ctx->launches++;
+      ZOLT_CUDA_TRY(cudaGetLastError());
+      return ZOLT_OK;
+    }
+    Fr* d_s = nullptr;
+    ZOLT_CUDA_TRY(pool_alloc(ctx, 2 * sizeof(Fr), (void**)&d_s));
+    ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, s, 2 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    vec_kernel<ZOLT_VEC_LIN2><<<grid, kScThreads, 0, ctx->stream>>>((Fr*)d_out, (const Fr*)d_a, (const Fr*)d_b, d_s, nullptr, FixedMulTable{}, n);
+    ctx->launches++;
+    ZOLT_CUDA_TRY(cudaGetLastError());
+    ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // s is a borrowed host buffer
+    pool_release(ctx, d_s, 2 * sizeof(Fr));
+    return ZOLT_OK;
+  }
   if (!d_a) return ZOLT_ERR_ARG;
   if (op == ZOLT_VEC_MUL && !d_b) return ZOLT_ERR_ARG;
   if (op == ZOLT_VEC_EQ_AB_MINUS_C && (!d_b || !d_c || !d_e)) return ZOLT_ERR_ARG;
@@ -2366,6 +2458,29 @@ extern "C" int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d
   if (op == ZOLT_VEC_MUL) vec_kernel<ZOLT_VEC_MUL><<<grid, kScThreads, 0, ctx->stream>>>(o, a, b, c, e, FixedMulTable{}, n);
   else if (op == ZOLT_VEC_EQ_AB_MINUS_C) vec_kernel<ZOLT_VEC_EQ_AB_MINUS_C><<<grid, kScThreads, 0, ctx->stream>>>(o, a, b, c, e, FixedMulTable{}, n);
   else vec_kernel<ZOLT_VEC_AXPY><<<grid, kScThreads, 0, ctx->stream>>>(o, a, b, c, e, fixed_mul_table_host(fr_from_host(s)), n);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  return ZOLT_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(kScThreads)
+index_map_kernel(Fr* __restrict__ dst, const Fr* __restrict__ src, size_t n, size_t d1, size_t m1, size_t s1, size_t d2, size_t m2, size_t s2) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t j = 0;
+    if (m1) j += ((i / d1) % m1) * s1;
+    if (m2) j += ((i / d2) % m2) * s2;
+    st_fr(dst + i, ld_fr(src + j));
+  }
+}
+}  // namespace
+
+extern "C" int zolt_fr_index_map_dev(zolt_ctx* ctx, void* d_dst, const void* d_src, size_t n, size_t d1, size_t m1, size_t s1, size_t d2,
+                                     size_t m2, size_t s2) {
+  if (!ctx || !d_dst || !d_src || d_dst == d_src || (m1 && !d1) || (m2 && !d2)) return ZOLT_ERR_ARG;
+  if (n == 0) return ZOLT_OK;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  index_map_kernel<<<grid_for(ctx, n, 8), kScThreads, 0, ctx->stream>>>((Fr*)d_dst, (const Fr*)d_src, n, d1, m1, s1, d2, m2, s2);
   ctx->launches++;
   ZOLT_CUDA_TRY(cudaGetLastError());
   return ZOLT_OK;

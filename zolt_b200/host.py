@@ -54,6 +54,8 @@ def load_host() -> C.CDLL:
                                                          C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_srs_load.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]
+        _host.zolt_host_stage4_run.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_eq_mle.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         _host.zolt_host_horner_eval.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _host.zolt_host_dense_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -154,6 +156,28 @@ def sumcheck_prove_gruen_dev(ctx: Context, d_tables, log_n: int, tau, claim, wit
                                                         len(domain), label, len(label), _ptr(evals), _ptr(chal), _ptr(final_claim))
     _lib.check(st, "zolt_host_sumcheck_prove_gruen_dev")
     return evals, chal, final_claim
+
+
+def stage4_run(ctx: Context, log_T: int, d_val, d_rd_wa, d_rs1_ra, d_rs2_ra, d_inc, gamma, r_cycle, phase1_rounds: int = -1,
+               input_claim=None, batching_coeff=None, challenges=None, domain: bytes = b"stage4"):
+    """Stage4GruenProver (src/zkvm/spartan/stage4_gruen_prover.zig) over device tables [k * T + j] (K = 128) and inc (T).
+    With `challenges`: the caller-driven loop, returns (evals (rounds,4,4), challenges, finals (6,4), (input claim, last claim));
+    without: `prove` against the Keccak transcript, returns the unbatched COEFFICIENTS per round and the squeezed challenges."""
+    rounds = 7 + log_T
+    g, rc = _as_u64(gamma, 4), _as_u64(r_cycle, 4)
+    ic = None if input_claim is None else _as_u64(input_claim, 4)
+    bc = None if batching_coeff is None else _as_u64(batching_coeff, 4)
+    ch = None if challenges is None else _as_u64(challenges, 4)
+    evals = np.zeros((rounds, 4, 4), dtype=np.uint64)
+    chal = np.zeros((rounds, 4), dtype=np.uint64) if ch is None else ch.copy()
+    finals = np.zeros((6, 4), dtype=np.uint64)
+    claims = np.zeros((2, 4), dtype=np.uint64)
+    st = load_host().zolt_host_stage4_run(ctx.handle, log_T, C.c_void_p(d_val), C.c_void_p(d_rd_wa), C.c_void_p(d_rs1_ra), C.c_void_p(d_rs2_ra),
+                                          C.c_void_p(d_inc), _ptr(g), _ptr(rc), phase1_rounds, _ptr(ic) if ic is not None else None,
+                                          _ptr(bc) if bc is not None else None, _ptr(ch) if ch is not None else None, domain, len(domain),
+                                          _ptr(evals), _ptr(chal), _ptr(finals), _ptr(claims))
+    _lib.check(st, "zolt_host_stage4_run")
+    return evals, chal, finals, claims
 
 
 def eq_mle(r, x) -> np.ndarray:

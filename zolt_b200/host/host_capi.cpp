@@ -147,6 +147,61 @@ int zolt_host_sumcheck_prove_multi(zolt_multi* multi, int combiner, int log_n, i
   return ZOLT_OK;
 }
 
+// Stage4GruenProver over device-resident tables.  challenges != NULL: the caller's round loop (proof_converter.zig:2112-2282 --
+// computeRoundEvals(round, claim) / claim = cubic at the challenge / bindChallenge), evals_out = rounds x 4 evaluations.
+// challenges == NULL: Stage4GruenProver.prove against the Keccak transcript of this repository (appendScalar ->
+// "stage4_coeff", challengeScalar -> "stage4_r"), evals_out = rounds x 4 UNBATCHED coefficients, challenges_out filled.
+// input_claim may be NULL (computeInputClaim over the tables).  finals_out: val, rs1_ra, rs2_ra, rd_wa, inc, eq (6 x 4).
+namespace {
+struct KeccakAdapter {
+  Transcript& t;
+  void appendScalar(const Fr& s) { t.appendScalar("stage4_coeff", s); }
+  Fr challengeScalar() { return t.challengeScalar("stage4_r"); }
+};
+}  // namespace
+int zolt_host_stage4_run(zolt_ctx* ctx, int log_T, const void* d_val, const void* d_rd_wa, const void* d_rs1_ra, const void* d_rs2_ra,
+                         const void* d_inc, const uint64_t* gamma, const uint64_t* r_cycle, int phase1_rounds,
+                         const uint64_t* input_claim, const uint64_t* batching_coeff, const uint64_t* challenges, const char* domain,
+                         size_t dn, uint64_t* evals_out, uint64_t* challenges_out, uint64_t* finals_out, uint64_t* claim_out) {
+  Context c(ctx);
+  std::vector<Fr> rc(log_T);
+  for (int i = 0; i < log_T; i++) rc[i] = Fr::fromRaw(r_cycle + 4 * i);
+  const Fr coeff = batching_coeff ? Fr::fromRaw(batching_coeff) : Fr::one();
+  Stage4GruenProver prover(c, log_T, d_val, d_rd_wa, d_rs1_ra, d_rs2_ra, d_inc, Fr::fromRaw(gamma), rc, nullptr, coeff, phase1_rounds);
+  const size_t rounds = prover.numRounds();
+  if (challenges) {
+    Fr claim = input_claim ? Fr::fromRaw(input_claim) : prover.computeInputClaim();
+    if (claim_out) claim.store(claim_out);
+    for (size_t r = 0; r < rounds; r++) {
+      const std::array<Fr, 4> e = prover.computeRoundEvals(r, claim);
+      for (int j = 0; j < 4; j++) e[j].store(evals_out + 16 * r + 4 * j);
+      const Fr ch = Fr::fromRaw(challenges + 4 * r);
+      claim = evaluateCubicAtPoint(e, ch);
+      prover.bindChallenge(r, ch);
+    }
+    if (claim_out) claim.store(claim_out + 4);
+  } else {
+    Transcript tr(std::string_view(domain, dn));
+    KeccakAdapter ad{tr};
+    if (claim_out) prover.computeInputClaim().store(claim_out);
+    Stage4GruenProver::Result res = prover.prove(ad);
+    for (size_t r = 0; r < rounds; r++) {
+      for (int j = 0; j < 4; j++) res.round_polys[r][j].store(evals_out + 16 * r + 4 * j);
+      if (challenges_out) res.challenges[r].store(challenges_out + 4 * r);
+    }
+  }
+  if (finals_out) {
+    const Stage4GruenProver::FinalClaims f = prover.getFinalClaims();
+    f.val_claim.store(finals_out);
+    f.rs1_ra_claim.store(finals_out + 4);
+    f.rs2_ra_claim.store(finals_out + 8);
+    f.rd_wa_claim.store(finals_out + 12);
+    f.inc_claim.store(finals_out + 16);
+    prover.finalEq().store(finals_out + 20);
+  }
+  return ZOLT_OK;
+}
+
 // SRS container parsers: kind 0 raw binary (srs.zig:256-306), 1 snarkjs PTAU (:733-900), 2 Jolt Dory SRS (dory.zig:740-826).
 // Returns the srs::Error code (0 = ok); *bases_out is a zolt_bases handle the caller frees.
 int zolt_host_srs_load(zolt_ctx* ctx, int kind, const uint8_t* data, size_t len, zolt_bases** bases_out, size_t* count,

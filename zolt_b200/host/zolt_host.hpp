@@ -506,6 +506,256 @@ class GruenProductProver : public SumcheckInstance {
   std::array<Fr, 4> last_{};
 };
 
+// Stage4GruenProver (src/zkvm/spartan/stage4_gruen_prover.zig): registers read/write checking,
+//   sum_{k,j} eq(r_cycle, j) * [ ra(k,j) val(k,j) + wa(k,j) (val(k,j) + inc(j)) ],   ra = gamma rs1_ra + gamma^2 rs2_ra,
+// over K = 128 registers x T cycles, LOG_K + log T rounds in three phases (:538-556): cycle variables through the Gruen
+// split eq, the 7 address variables with the eq not bound, the remaining cycle variables against the merged dense eq.
+// The prover is entered with the dense tables initWithPhaseConfig (:139-366) leaves (witness generation from the
+// ExecutionTrace is the caller's side of the boundary); everything O(K T) runs on the device:
+//   phase 1   ZOLT_SC_STAGE4_GRUEN over the flat [k][j] tables (rows compact, so the reference's pairs (k T + 2i, k T + 2i + 1)
+//             are the flat adjacent pairs), inc replicated over k, weights E_out E_in over the cycle bits; the cubic is
+//             gruenPolyDeg3 (gruen_eq.zig:214-262) on the host, O(1);
+//   phases 2, 3   ONE ZOLT_SC_STAGE4_DENSE instance over the tables transposed to [j][k], merged eq (gruen_eq.zig:172-203)
+//             and inc repeated over k: the k bit is now the lowest, address rounds bind eq and inc to themselves, and once
+//             k is exhausted the same flat pairs are the cycle pairs of phase 3.
+// Supported configurations are the ones the reference completes: 1 <= phase1 <= log T (merged_eq is only created inside a
+// phase-1 bind, :1083-1086) and phase2 == LOG_K (bindPolynomials' third branch never binds an address variable,
+// :1123-1158).  computeRoundEvals / bindChallenge / getFinalClaims keep the reference's signatures (:1165-1234).
+class Stage4GruenProver {
+ public:
+  static constexpr int LOG_K = 7;
+  static constexpr size_t K = size_t(1) << LOG_K;
+  struct Stage3Claims {
+    Fr rd_write_value, rs1_value, rs2_value;
+  };
+  struct FinalClaims {
+    Fr val_claim, rs1_ra_claim, rs2_ra_claim, rd_wa_claim, inc_claim;
+  };
+
+  // d_val, d_rd_wa, d_rs1_ra, d_rs2_ra: K * T elements each, [k * T + j]; d_inc: T elements; all device-resident and only
+  // read.  r_cycle in round order (little-endian), like the reference's argument.
+  Stage4GruenProver(Context& ctx, int log_T, const void* d_val, const void* d_rd_wa, const void* d_rs1_ra, const void* d_rs2_ra,
+                    const void* d_inc, const Fr& gamma, const std::vector<Fr>& r_cycle, const Stage3Claims* stage3_claims,
+                    const Fr& batching_coeff, int phase1_num_rounds = -1, int phase2_num_rounds = LOG_K)
+      : ctx_(ctx), log_T_(log_T), gamma_(gamma), batching_coeff_(batching_coeff),
+        p1_(phase1_num_rounds < 0 ? log_T / 2 : phase1_num_rounds), p2_(phase2_num_rounds) {
+    if (log_T < 1 || (int)r_cycle.size() != log_T || p1_ < 1 || p1_ > log_T || p2_ != LOG_K) panic("Stage4GruenProver: unsupported configuration", ZOLT_ERR_ARG);
+    if (stage3_claims) {
+      have_claims_ = true;
+      claims_ = *stage3_claims;
+    }
+    w_.assign(r_cycle.rbegin(), r_cycle.rend());  // big-endian copy for the split eq (:259-281)
+    current_index_ = w_.size();
+    current_scalar_ = Fr::one();
+    const size_t T = size_t(1) << log_T, n = K * T;
+    d_in_[0] = d_val;
+    d_in_[1] = d_rd_wa;
+    d_in_[2] = d_rs1_ra;
+    d_in_[3] = d_rs2_ra;
+    d_inc_in_ = d_inc;
+    // ra = gamma rs1_ra + gamma^2 rs2_ra (:211, :224); inc replicated over the rows
+    d_ra_ = alloc(n);
+    const Fr g2[2] = {gamma, gamma.mul(gamma)};
+    must(zolt_fr_vec_dev(ctx.raw(), ZOLT_VEC_LIN2, d_ra_, d_rs1_ra, d_rs2_ra, nullptr, nullptr, reinterpret_cast<const uint64_t*>(g2), n),
+         "zolt_fr_vec_dev");
+    d_inc_rep_ = alloc(n);
+    must(zolt_fr_index_map_dev(ctx.raw(), d_inc_rep_, d_inc, n, 1, T, 1, 0, 0, 0), "zolt_fr_index_map_dev");
+    const void* tabs[6] = {d_ra_, d_rd_wa, d_val, d_inc_rep_, d_rs1_ra, d_rs2_ra};
+    must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_STAGE4_GRUEN, ZOLT_PAIR_ADJACENT, LOG_K + log_T, 4, 2, tabs, &sc1_), "zolt_sc_create_dev");
+    must(zolt_sc_set_split_eq(sc1_, reinterpret_cast<const uint64_t*>(w_.data()), log_T), "zolt_sc_set_split_eq");
+  }
+  ~Stage4GruenProver() {
+    if (sc1_) zolt_sc_free(sc1_);
+    if (sc2_) zolt_sc_free(sc2_);
+    for (void* p : owned_) zolt_dev_free(ctx_.raw(), p);
+  }
+  Stage4GruenProver(const Stage4GruenProver&) = delete;
+  Stage4GruenProver& operator=(const Stage4GruenProver&) = delete;
+
+  size_t numRounds() const { return (size_t)(LOG_K + log_T_); }
+
+  // computeInputClaim (:385-430): from the Stage 3 claims when given, else summed over the tables
+  Fr computeInputClaim() {
+    if (have_claims_) return claims_.rd_write_value.add(gamma_.mul(claims_.rs1_value.add(gamma_.mul(claims_.rs2_value))));
+    const size_t T = size_t(1) << log_T_, n = K * T;
+    void* d_eq = alloc(T);
+    must(zolt_eq_evals(ctx_.raw(), reinterpret_cast<const uint64_t*>(w_.data()), log_T_, nullptr, d_eq), "zolt_eq_evals");
+    void* d_eq_rep = alloc(n);
+    must(zolt_fr_index_map_dev(ctx_.raw(), d_eq_rep, d_eq, n, 1, T, 1, 0, 0, 0), "zolt_fr_index_map_dev");
+    void* d_term = alloc(n);
+    must(zolt_dev_copy(ctx_.raw(), d_term, d_inc_rep_, n * sizeof(Fr)), "zolt_dev_copy");
+    must(zolt_fr_vec_dev(ctx_.raw(), ZOLT_VEC_STAGE4_TERM, d_term, d_ra_, d_in_[0], d_in_[1], d_eq_rep, nullptr, n), "zolt_fr_vec_dev");
+    Fr claim;
+    must(zolt_poly_sum(ctx_.raw(), d_term, n, claim.limbs.data()), "zolt_poly_sum");
+    release(d_term);
+    release(d_eq_rep);
+    release(d_eq);
+    return claim;
+  }
+
+  // computeRoundEvals (:1165-1190): the round polynomial's coefficients, handed back as evaluations at 0..3
+  std::array<Fr, 4> computeRoundEvals(size_t round, const Fr& current_claim) {
+    const std::array<Fr, 4> c = computeRoundPolynomialGruen(round, current_claim);
+    auto k = [](uint64_t v) { return Fr::fromU64(v); };
+    return {c[0], c[0].add(c[1]).add(c[2]).add(c[3]), c[0].add(c[1].mul(k(2))).add(c[2].mul(k(4))).add(c[3].mul(k(8))),
+            c[0].add(c[1].mul(k(3))).add(c[2].mul(k(9))).add(c[3].mul(k(27)))};
+  }
+  // computeRoundPolynomialGruen (:538-556): coefficients [c0, c1, c2, c3]
+  std::array<Fr, 4> computeRoundPolynomialGruen(size_t round, const Fr& previous_claim) {
+    uint64_t buf[16] = {0};
+    if ((int)round < p1_) {
+      must(zolt_sc_round_evals(sc1_, buf), "zolt_sc_round_evals");  // [q(0), q_X2]
+      return gruenPolyDeg3(Fr::fromRaw(buf), Fr::fromRaw(buf + 4), previous_claim);
+    }
+    must(zolt_sc_round_evals(sc2_, buf), "zolt_sc_round_evals");  // [p(0), p(2), p(3)], summed directly like the reference
+    const Fr e0 = Fr::fromRaw(buf), e2 = Fr::fromRaw(buf + 4), e3 = Fr::fromRaw(buf + 8);
+    const Fr e1 = previous_claim.sub(e0);
+    static const Fr two_inv = Fr::fromU64(2).inverse();
+    if ((int)round < p1_ + p2_) {
+      // phase 2 (:764-851): eq and inc do not depend on the address bit, the polynomial has degree 2
+      const Fr c2 = e0.sub(e1.mul(Fr::fromU64(2))).add(e2).mul(two_inv);
+      return {e0, e1.sub(e0).sub(c2), c2, Fr::zero()};
+    }
+    return coeffsFromEvals({e0, e1, e2, e3});  // phase 3 (:854-962)
+  }
+
+  // bindChallenge / bindPolynomials (:1047-1160, :1192-1217)
+  void bindChallenge(size_t round, const Fr& challenge) {
+    if ((int)round < p1_) {
+      must(zolt_sc_bind(sc1_, challenge.limbs.data()), "zolt_sc_bind");
+      // GruenSplitEqPolynomial.bind (gruen_eq.zig:120-160)
+      const Fr& w_i = w_[current_index_ - 1];
+      const Fr prod = w_i.mul(challenge);
+      current_scalar_ = current_scalar_.mul(Fr::one().sub(w_i).sub(challenge).add(prod).add(prod));
+      current_index_--;
+      if ((int)round == p1_ - 1) enterPhase2();
+      return;
+    }
+    must(zolt_sc_bind(sc2_, challenge.limbs.data()), "zolt_sc_bind");
+  }
+
+  // getFinalClaims (:1219-1234), after the last bind
+  FinalClaims getFinalClaims() {
+    FinalClaims f;
+    // sc2 tables: eq, ra, wa, val, inc, rs1_ra, rs2_ra
+    must(zolt_sc_download(sc2_, 3, f.val_claim.limbs.data()), "zolt_sc_download");
+    must(zolt_sc_download(sc2_, 5, f.rs1_ra_claim.limbs.data()), "zolt_sc_download");
+    must(zolt_sc_download(sc2_, 6, f.rs2_ra_claim.limbs.data()), "zolt_sc_download");
+    must(zolt_sc_download(sc2_, 2, f.rd_wa_claim.limbs.data()), "zolt_sc_download");
+    must(zolt_sc_download(sc2_, 4, f.inc_claim.limbs.data()), "zolt_sc_download");
+    return f;
+  }
+  // merged_eq[0] after the last bind: eq(r_cycle, challenges) (:1203-1215)
+  Fr finalEq() {
+    Fr e;
+    must(zolt_sc_download(sc2_, 0, e.limbs.data()), "zolt_sc_download");
+    return e;
+  }
+
+  struct Result {
+    std::vector<std::array<Fr, 4>> round_polys;  // UNBATCHED coefficients, like Stage4Result.round_polys
+    std::vector<Fr> challenges;
+    FinalClaims claims;
+  };
+  // prove (:433-536) against any transcript with the reference's two calls: appendScalar(F), challengeScalar() -> F
+  template <class TranscriptT>
+  Result prove(TranscriptT& transcript) {
+    Result res;
+    Fr current_claim = computeInputClaim().mul(batching_coeff_);
+    for (size_t round = 0; round < numRounds(); round++) {
+      const std::array<Fr, 4> c = computeRoundPolynomialGruen(round, current_claim);
+      transcript.appendScalar(c[0].mul(batching_coeff_));
+      transcript.appendScalar(c[2].mul(batching_coeff_));
+      transcript.appendScalar(c[3].mul(batching_coeff_));
+      const Fr r = transcript.challengeScalar();
+      res.challenges.push_back(r);
+      current_claim = c[0].add(r.mul(c[1].add(r.mul(c[2].add(r.mul(c[3])))))).mul(batching_coeff_);  // RoundPoly.evaluateAt (:20-27)
+      bindChallenge(round, r);
+      res.round_polys.push_back(c);
+    }
+    res.claims = getFinalClaims();
+    return res;
+  }
+
+  // gruenPolyDeg3 (gruen_eq.zig:214-262) on the host state of the split eq
+  std::array<Fr, 4> gruenPolyDeg3(const Fr& q_constant, const Fr& q_quadratic_coeff, const Fr& s_0_plus_s_1) const {
+    const Fr eq1 = current_scalar_.mul(w_[current_index_ - 1]);
+    const Fr eq0 = current_scalar_.sub(eq1);
+    const Fr m = eq1.sub(eq0);
+    const Fr eq2 = eq1.add(m), eq3 = eq2.add(m);
+    const Fr cubic0 = eq0.mul(q_constant);
+    const Fr cubic1 = s_0_plus_s_1.sub(cubic0);
+    if (eq1.isZero()) panic("Stage4GruenProver: eq_eval_1 is zero", ZOLT_ERR_ARG);  // the reference panics too (:241)
+    const Fr q1 = cubic1.mul(eq1.inverse());
+    const Fr e2 = q_quadratic_coeff.add(q_quadratic_coeff);
+    const Fr q2 = q1.add(q1).sub(q_constant).add(e2);
+    const Fr q3 = q2.add(q1).sub(q_constant).add(e2).add(e2);
+    return coeffsFromEvals({cubic0, cubic1, eq2.mul(q2), eq3.mul(q3)});
+  }
+  // fromEvals / coeffsFromEvals (gruen_eq.zig:265-291, stage4_gruen_prover.zig:1017-1039)
+  static std::array<Fr, 4> coeffsFromEvals(const std::array<Fr, 4>& e) {
+    static const Fr six_inv = Fr::fromU64(6).inverse(), two_inv = Fr::fromU64(2).inverse();
+    auto k = [](uint64_t v) { return Fr::fromU64(v); };
+    const Fr c3 = e[0].neg().add(e[1].mul(k(3))).sub(e[2].mul(k(3))).add(e[3]).mul(six_inv);
+    const Fr c2 = e[0].mul(k(2)).sub(e[1].mul(k(5))).add(e[2].mul(k(4))).sub(e[3]).mul(two_inv);
+    return {e[0], e[1].sub(e[0]).sub(c2).sub(c3), c2, c3};
+  }
+
+ private:
+  void* alloc(size_t elems) {
+    void* p = nullptr;
+    must(zolt_dev_alloc(ctx_.raw(), (elems ? elems : 1) * sizeof(Fr), &p), "zolt_dev_alloc");
+    owned_.push_back(p);
+    return p;
+  }
+  void release(void* p) {
+    for (size_t i = 0; i < owned_.size(); i++)
+      if (owned_[i] == p) {
+        owned_.erase(owned_.begin() + (long)i);
+        break;
+      }
+    zolt_dev_free(ctx_.raw(), p);
+  }
+  // After the last phase-1 bind: merge the split eq (gruen_eq.zig:172-203), transpose [k][j] -> [j][k], open the dense instance
+  void enterPhase2() {
+    const int log_Tc = log_T_ - p1_;
+    const size_t Tc = size_t(1) << log_Tc, n = K * Tc;
+    void* d_eq = alloc(Tc);
+    must(zolt_eq_evals(ctx_.raw(), reinterpret_cast<const uint64_t*>(w_.data()), (int)current_index_, current_scalar_.limbs.data(), d_eq),
+         "zolt_eq_evals");
+    void* t[7];
+    for (auto& p : t) p = alloc(n);
+    must(zolt_fr_index_map_dev(ctx_.raw(), t[0], d_eq, n, K, Tc, 1, 0, 0, 0), "zolt_fr_index_map_dev");  // eq[j] repeated over k
+    // sc1 tables: ra, wa, val, inc_rep, rs1_ra, rs2_ra  ->  sc2 tables: eq, ra, wa, val, inc, rs1_ra, rs2_ra
+    static const int from[6] = {0, 1, 2, 3, 4, 5};
+    for (int i = 0; i < 6; i++) {
+      const void* src = nullptr;
+      must(zolt_sc_table_dev(sc1_, from[i], &src), "zolt_sc_table_dev");
+      must(zolt_fr_index_map_dev(ctx_.raw(), t[1 + i], src, n, 1, K, Tc, K, Tc, 1), "zolt_fr_index_map_dev");  // dst[j K + k] = src[k Tc + j]
+    }
+    must(zolt_sc_create_dev(ctx_.raw(), ZOLT_SC_STAGE4_DENSE, ZOLT_PAIR_ADJACENT, LOG_K + log_Tc, 5, 2, t, &sc2_), "zolt_sc_create_dev");
+    zolt_sc_free(sc1_);  // joins its kernels first: the copies above are ordered behind them on the context's stream
+    sc1_ = nullptr;
+  }
+
+  Context& ctx_;
+  int log_T_;
+  Fr gamma_, batching_coeff_;
+  int p1_, p2_;
+  bool have_claims_ = false;
+  Stage3Claims claims_{};
+  std::vector<Fr> w_;
+  size_t current_index_ = 0;
+  Fr current_scalar_;
+  const void* d_in_[4] = {};
+  const void* d_inc_in_ = nullptr;
+  void* d_ra_ = nullptr;
+  void* d_inc_rep_ = nullptr;
+  zolt_sc* sc1_ = nullptr;
+  zolt_sc* sc2_ = nullptr;
+  std::vector<void*> owned_;
+};
+
 struct SumcheckProof {
   std::vector<std::array<Fr, 4>> round_polys;  // evaluations at 0..3
   std::vector<Fr> challenges;
