@@ -791,6 +791,45 @@ def extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, tim
         ok = ok and (e[0] + e[1]) % B.FR_MOD == cl
         cl = OP.evaluate_cubic_at_point(e, _fr_ints(g_chal[j])[0])
     out[f"sumcheck_gruen_2^{lg}_ok"] = bool(ok and cl == _fr_ints(g_final_claim)[0])
+    # Stage4GruenProver (registers read/write checking), K = 128 registers x T = 2^(sc_log_n - 8) cycles:
+    # val, rd_wa, rs1_ra, rs2_ra = the first halves of the four resident tables (2^(sc_log_n - 1) entries each), inc = T entries
+    # from the second half of the first.  Whole prover per run: ra, replicated inc, 7 + log T rounds with challenges from the
+    # host, re-layout between the phases, final claims.
+    if lg >= 12:
+        log_T = lg - 8
+        ptrs4 = d_tab_ptrs[:4] + [d_tab_ptrs[0] + (32 << (lg - 1))]
+        gamma, r_cyc = rows_global(STREAM_EQ, 1 << 17, 1), rows_global(STREAM_EQ, (1 << 17) + 64, log_T)
+        chal4 = rows_global(STREAM_EQ, (1 << 17) + 128, 7 + log_T)
+        first = H.stage4_run(ctx, log_T, *ptrs4, gamma, r_cyc, -1, challenges=chal4)  # computes the input claim (untimed)
+        claim4 = first[3][0].copy()
+
+        def run_s4():
+            res[0] = H.stage4_run(ctx, log_T, *ptrs4, gamma, r_cyc, -1, input_claim=claim4, challenges=chal4)
+
+        run_s4()
+        ctx.prof_enable(True)
+        wall = time_ms(run_s4, 3, warm=0)
+        ks = [ms for tag, ms in ctx.prof_read() if tag in (16, 17, 18)]
+        ctx.prof_enable(False)
+        per = len(ks) // 3
+        p1 = log_T // 2
+        k_p1 = sum(sum(ks[i * per: i * per + p1 + 1]) for i in range(3)) / 3
+        n4 = 128 << log_T
+        bytes_p1 = 32 * (4 * n4 + sum(6 * (n4 >> r) + 6 * (n4 >> (r + 1)) for r in range(p1)))
+        out[f"stage4_gruen_T2^{log_T}_ms"] = wall
+        out[f"stage4_gruen_T2^{log_T}_kernel_ms"] = sum(ks) / 3
+        out[f"stage4_gruen_T2^{log_T}_phase1_frac_hbm"] = bytes_p1 / (k_p1 * 1e-3) / 1e9 / hbm_peak if k_p1 else None
+        s_evals, s_chal, s_fin, s_claims = res[0]
+        cl = _fr_ints(claim4)[0]
+        ok = True
+        for j in range(7 + log_T):
+            e = _fr_ints(s_evals[j])
+            ok = ok and (e[0] + e[1]) % B.FR_MOD == cl
+            cl = OP.evaluate_cubic_at_point(e, _fr_ints(s_chal[j])[0])
+        f = _fr_ints(s_fin)
+        g1 = _fr_ints(gamma)[0]
+        body = ((g1 * f[1] + g1 * g1 * f[2]) * f[0] + f[3] * (f[0] + f[4])) % B.FR_MOD
+        out[f"stage4_gruen_T2^{log_T}_ok"] = bool(ok and cl == f[5] * body % B.FR_MOD and (s_evals == first[0]).all())
     return {k: (round(v, 5) if isinstance(v, float) else v) for k, v in out.items()}
 
 

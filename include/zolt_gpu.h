@@ -75,6 +75,12 @@ int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value);
 /* raw device buffers, so a host without CUDA bindings can keep tables resident */
 int zolt_dev_alloc(zolt_ctx* ctx, size_t bytes, void** dptr);
 int zolt_dev_free(zolt_ctx* ctx, void* dptr);
+/* The same from the context's buffer cache (what the library's own temporaries use): a released buffer serves the next
+ * request of a similar size without cudaMalloc / cudaFree -- milliseconds each for GiB-sized tables, and cudaFree
+ * synchronises the device.  Only for buffers whose work is issued on the context's stream; `bytes` on release must be the
+ * size asked for.  The cache is emptied by zolt_gpu_shutdown. */
+int zolt_dev_alloc_cached(zolt_ctx* ctx, size_t bytes, void** dptr);
+int zolt_dev_release_cached(zolt_ctx* ctx, void* dptr, size_t bytes);
 int zolt_dev_upload(zolt_ctx* ctx, void* dptr, const void* hptr, size_t bytes);
 int zolt_dev_download(zolt_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
 /* device-to-device copy, asynchronous on the context's stream */

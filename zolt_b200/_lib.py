@@ -50,6 +50,8 @@ SIGNATURES = {
     "zolt_gpu_set_tuning": [_vp, _i, C.c_longlong],
     "zolt_dev_alloc": [_vp, _sz, C.POINTER(_vp)],
     "zolt_dev_free": [_vp, _vp],
+    "zolt_dev_alloc_cached": [_vp, _sz, C.POINTER(C.c_void_p)],
+    "zolt_dev_release_cached": [_vp, _vp, _sz],
     "zolt_dev_upload": [_vp, _vp, _vp, _sz],
     "zolt_dev_download": [_vp, _vp, _vp, _sz],
     "zolt_dev_copy": [_vp, _vp, _vp, _sz],

@@ -102,6 +102,21 @@ extern "C" int zolt_dev_alloc(zolt_ctx* ctx, size_t bytes, void** dptr) {
   return ZOLT_OK;
 }
 
+// Scratch from the context's buffer cache: what the library's own calls use for their temporaries.  A released buffer is
+// handed to the next request of a similar size without cudaMalloc / cudaFree (each costs milliseconds for GiB-sized
+// tables and cudaFree synchronises the device); work on the buffer must have been issued on the context's stream.
+extern "C" int zolt_dev_alloc_cached(zolt_ctx* ctx, size_t bytes, void** dptr) {
+  if (!ctx || !dptr) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, bytes, dptr));
+  return ZOLT_OK;
+}
+extern "C" int zolt_dev_release_cached(zolt_ctx* ctx, void* dptr, size_t bytes) {
+  if (!ctx) return ZOLT_ERR_ARG;
+  pool_release(ctx, dptr, bytes);
+  return ZOLT_OK;
+}
+
 extern "C" int zolt_dev_free(zolt_ctx* ctx, void* dptr) {
   if (!ctx) return ZOLT_ERR_ARG;
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));

@@ -567,7 +567,7 @@ class Stage4GruenProver {
   ~Stage4GruenProver() {
     if (sc1_) zolt_sc_free(sc1_);
     if (sc2_) zolt_sc_free(sc2_);
-    for (void* p : owned_) zolt_dev_free(ctx_.raw(), p);
+    for (auto& b : owned_) zolt_dev_release_cached(ctx_.raw(), b.first, b.second);
   }
   Stage4GruenProver(const Stage4GruenProver&) = delete;
   Stage4GruenProver& operator=(const Stage4GruenProver&) = delete;
@@ -702,19 +702,21 @@ class Stage4GruenProver {
   }
 
  private:
+  // temporaries come from the context's buffer cache: a second proof of the same shape allocates nothing
   void* alloc(size_t elems) {
     void* p = nullptr;
-    must(zolt_dev_alloc(ctx_.raw(), (elems ? elems : 1) * sizeof(Fr), &p), "zolt_dev_alloc");
-    owned_.push_back(p);
+    const size_t bytes = (elems ? elems : 1) * sizeof(Fr);
+    must(zolt_dev_alloc_cached(ctx_.raw(), bytes, &p), "zolt_dev_alloc_cached");
+    owned_.emplace_back(p, bytes);
     return p;
   }
   void release(void* p) {
     for (size_t i = 0; i < owned_.size(); i++)
-      if (owned_[i] == p) {
+      if (owned_[i].first == p) {
+        zolt_dev_release_cached(ctx_.raw(), p, owned_[i].second);
         owned_.erase(owned_.begin() + (long)i);
-        break;
+        return;
       }
-    zolt_dev_free(ctx_.raw(), p);
   }
   // After the last phase-1 bind: merge the split eq (gruen_eq.zig:172-203), transpose [k][j] -> [j][k], open the dense instance
   void enterPhase2() {
@@ -753,7 +755,7 @@ class Stage4GruenProver {
   void* d_inc_rep_ = nullptr;
   zolt_sc* sc1_ = nullptr;
   zolt_sc* sc2_ = nullptr;
-  std::vector<void*> owned_;
+  std::vector<std::pair<void*, size_t>> owned_;
 };
 
 struct SumcheckProof {
