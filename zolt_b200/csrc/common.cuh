@@ -24,6 +24,21 @@ constexpr int kNumSMsB200 = 148;
     }                                                                                            \
   } while (0)
 
+// Runs `f` when the scope is left unless dismiss() was called: the C-ABI entry points return early through ZOLT_CUDA_TRY /
+// ZOLT_TRY, this releases what they had built so far.
+template <class F>
+struct OnFail {
+  F f;
+  bool armed = true;
+  explicit OnFail(F fn) : f(fn) {}
+  OnFail(const OnFail&) = delete;
+  OnFail& operator=(const OnFail&) = delete;
+  ~OnFail() {
+    if (armed) f();
+  }
+  void dismiss() { armed = false; }
+};
+
 #define ZOLT_TRY(expr)                 \
   do {                                 \
     int _s = (expr);                   \

@@ -853,6 +853,7 @@ extern "C" int zolt_msm_bases_upload(zolt_ctx* ctx, const uint64_t* xy, const ui
   if (!b) return ZOLT_ERR_ARG;
   b->ctx = ctx;
   b->n = n;
+  OnFail undo([&] { zolt_msm_bases_free(b); });
   ZOLT_CUDA_TRY(cudaMalloc((void**)&b->d_xy, (n ? n : 1) * sizeof(AffineG1)));
   ZOLT_CUDA_TRY(cudaMemcpyAsync(b->d_xy, xy, n * sizeof(AffineG1), cudaMemcpyHostToDevice, ctx->stream));
   bool any_inf = false;
@@ -864,6 +865,7 @@ extern "C" int zolt_msm_bases_upload(zolt_ctx* ctx, const uint64_t* xy, const ui
     ZOLT_CUDA_TRY(cudaMemcpyAsync(b->d_inf, inf, n, cudaMemcpyHostToDevice, ctx->stream));
   }
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  undo.dismiss();
   *out = b;
   return ZOLT_OK;
 }
@@ -896,11 +898,17 @@ extern "C" int zolt_msm_bases_precompute(zolt_bases* b, int window_bits) {
     b->d_pre = nullptr;
   }
   AffineG1* pre = nullptr;
+  XYZZ* tmp = nullptr;
+  Fq* prefix = nullptr;
+  OnFail undo([&] {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(pre);
+    cudaFree(tmp);
+    cudaFree(prefix);
+  });
   ZOLT_CUDA_TRY(cudaMalloc((void**)&pre, (size_t)W * b->n * sizeof(AffineG1)));
   const size_t chunk_max = size_t(1) << 20;
   const size_t chunk_alloc = b->n < chunk_max ? b->n : chunk_max;
-  XYZZ* tmp = nullptr;
-  Fq* prefix = nullptr;
   ZOLT_CUDA_TRY(cudaMalloc((void**)&tmp, (size_t)(W - 1) * chunk_alloc * sizeof(XYZZ)));
   ZOLT_CUDA_TRY(cudaMalloc((void**)&prefix, (size_t)(W - 1) * chunk_alloc * sizeof(Fq)));
   for (size_t first = 0; first < b->n; first += chunk_alloc) {
@@ -911,6 +919,7 @@ extern "C" int zolt_msm_bases_precompute(zolt_bases* b, int window_bits) {
   }
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  undo.dismiss();
   cudaFree(tmp);
   cudaFree(prefix);
   b->d_pre = pre;
@@ -1071,12 +1080,12 @@ extern "C" int zolt_msm_batch(zolt_ctx* ctx, const zolt_bases* bases, const uint
   Fr* d_s = nullptr;
   XYZZ* d_res = nullptr;
   ZOLT_TRY(staging_for(ctx, n * k * sizeof(Fr), &d_s));
-  ZOLT_CUDA_TRY(cudaMalloc((void**)&d_res, k * sizeof(XYZZ)));
+  ZOLT_CUDA_TRY(pool_alloc(ctx, k * sizeof(XYZZ), (void**)&d_res));  // from the context's buffer cache, like the workspace
+  OnFail undo([&] { pool_release(ctx, d_res, k * sizeof(XYZZ)); });
   ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n * k * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
   int s = msm_core(ctx, bases, 0, d_s, k, n, d_res);
-  if (s == ZOLT_OK) s = finish_affine(ctx, d_res, k, out_xy, out_inf);
-  cudaFree(d_res);
-  return s;
+  if (s == ZOLT_OK) s = finish_affine(ctx, d_res, k, out_xy, out_inf);  // synchronises the stream
+  return s;  // `undo` hands the result buffer back on every path
 }
 
 static int fixed_base_dev(zolt_ctx* ctx, const Fr* d_scalars, size_t n, zolt_bases** out) {
@@ -1085,6 +1094,11 @@ static int fixed_base_dev(zolt_ctx* ctx, const Fr* d_scalars, size_t n, zolt_bas
   b->ctx = ctx;
   b->n = n;
   AffineG1* d_table = nullptr;
+  OnFail undo([&] {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_table);
+    zolt_msm_bases_free(b);
+  });
   ZOLT_CUDA_TRY(cudaMalloc((void**)&b->d_xy, (n ? n : 1) * sizeof(AffineG1)));
   ZOLT_CUDA_TRY(cudaMalloc((void**)&b->d_inf, n ? n : 1));
   ZOLT_CUDA_TRY(cudaMalloc((void**)&d_table, 32 * 255 * sizeof(AffineG1)));
@@ -1098,6 +1112,7 @@ static int fixed_base_dev(zolt_ctx* ctx, const Fr* d_scalars, size_t n, zolt_bas
   }
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  undo.dismiss();
   cudaFree(d_table);
   *out = b;
   return ZOLT_OK;

@@ -1833,6 +1833,7 @@ int sc_alloc(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, 
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   zolt_sc* sc = new (std::nothrow) zolt_sc();
   if (!sc) return ZOLT_ERR_ARG;
+  OnFail undo([&] { zolt_sc_free(sc); });  // a half-built instance: zolt_sc_free skips what is still null
   sc->ctx = ctx;
   sc->combiner = combiner;
   sc->pairing = pairing;
@@ -1857,6 +1858,7 @@ int sc_alloc(zolt_ctx* ctx, int combiner, int pairing, int log_n, int n_tables, 
   ZOLT_CUDA_TRY(cudaMemsetAsync(sc->d_ticket, 0, 256, ctx->stream));
   ZOLT_CUDA_TRY(pool_alloc(ctx, 4 * sizeof(Fr), (void**)&sc->d_evals));
   ZOLT_CUDA_TRY(pinned_mailbox_alloc(ctx, (void**)&sc->h_evals, (void**)&sc->h_evals_dev));
+  undo.dismiss();
   *out = sc;
   return ZOLT_OK;
 }
@@ -2004,15 +2006,17 @@ extern "C" int zolt_sc_create(zolt_ctx* ctx, int combiner, int pairing, int log_
   if (!tables) return ZOLT_ERR_ARG;
   zolt_sc* sc = nullptr;
   ZOLT_TRY(sc_alloc(ctx, combiner, pairing, log_n, n_tables, n_extra, &sc));
+  OnFail undo([&] { zolt_sc_free(sc); });
   sc->owns_in = true;
   for (int i = 0; i < n_tables + n_extra; i++) {
-    if (!tables[i]) { zolt_sc_free(sc); return ZOLT_ERR_ARG; }
+    if (!tables[i]) return ZOLT_ERR_ARG;
     Fr* d = nullptr;
     ZOLT_CUDA_TRY(pool_alloc(ctx, sc->in_bytes, (void**)&d));
     sc->tab_in[i] = d;
     ZOLT_CUDA_TRY(cudaMemcpyAsync(d, tables[i], sc->n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
   }
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host buffers are only borrowed for the call
+  undo.dismiss();
   *out = sc;
   return ZOLT_OK;
 }
@@ -2361,14 +2365,15 @@ extern "C" int zolt_poly_bind_low(zolt_ctx* ctx, void* d_dst, const void* d_src,
   if (d_dst == d_src) {
     // in place (the reference's contract): thread i would overwrite element i while thread i/2 may
     // still need it, so bind into a scratch buffer and copy back on the same stream.
+    // The scratch comes from the context's buffer cache and goes back without a synchronisation: whoever gets it next
+    // works on the same stream, behind the copy.
     Fr* tmp = nullptr;
-    ZOLT_CUDA_TRY(cudaMalloc((void**)&tmp, (n / 2) * sizeof(Fr)));
+    ZOLT_CUDA_TRY(pool_alloc(ctx, (n / 2) * sizeof(Fr), (void**)&tmp));
+    OnFail give_back([&] { pool_release(ctx, tmp, (n / 2) * sizeof(Fr)); });
     bind_kernel<ZOLT_PAIR_ADJACENT><<<grid, kScThreads, 0, ctx->stream>>>(tmp, (const Fr*)d_src, n, rr);
     ctx->launches++;
     ZOLT_CUDA_TRY(cudaGetLastError());
     ZOLT_CUDA_TRY(cudaMemcpyAsync(d_dst, tmp, (n / 2) * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-    ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
   } else {
     bind_kernel<ZOLT_PAIR_ADJACENT><<<grid, kScThreads, 0, ctx->stream>>>((Fr*)d_dst, (const Fr*)d_src, n, rr);
     ctx->launches++;
