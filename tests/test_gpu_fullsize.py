@@ -96,3 +96,45 @@ def test_config3_spartan_sumcheck_2_24_vs_cpu_restatement(ctx):
         claim = OP.evaluate_cubic_at_point(e, fr_ints(chal[j])[0])
     f = [fr_ints(final[t])[0] for t in range(4)]
     assert claim == f[0] * (f[1] * f[2] - f[3]) % P
+
+
+def test_config3_bound_tables_at_2_24(ctx):
+    """BASELINE.md section 4's table checks at full size: after binds 0, 1, 2 a checksum of every bound table (its sum and its
+    inner product with a fixed random vector, both mod r, device reductions against the threaded C++ restatement), and the full
+    tables of the last 8 rounds element by element."""
+    n = 1 << LOG_N
+    tabs = [_rand_mont(0x5A170040 + t, n) for t in range(4)]
+    chal = _rand_mont(0x5A170048, LOG_N)
+    inst = Z.SumcheckInstance(ctx, Z.SC_EQ_AB_MINUS_C, Z.PAIR_ADJACENT, tabs)
+    weights = _rand_mont(0x5A170049, n // 2)
+    d_w = Z.DeviceBuffer.from_host(ctx, weights)
+    one = B.ints_to_mont_array([1], P)
+    ones = np.repeat(one, n // 2, axis=0)
+    ref, ref_round = list(tabs), 0
+
+    def advance(to):
+        nonlocal ref, ref_round
+        while ref_round < to:
+            ref = [R.bind_low(t, chal[ref_round]) for t in ref]
+            ref_round += 1
+
+    try:
+        for rnd in range(LOG_N):
+            inst.compute_round_poly()
+            inst.bind_challenge(chal[rnd:rnd + 1])
+            cur = n >> (rnd + 1)
+            if rnd < 3:
+                advance(rnd + 1)
+                for t in range(4):
+                    ptr = inst.table_dev(t)
+                    got_sum = ctx.poly_sum(ptr, cur)
+                    got_dot = ctx.fr_inner_product_dev(ptr, d_w.ptr, cur)
+                    assert (got_sum == R.fr_dot(ref[t], ones[:cur], threads=8)).all(), f"round {rnd} table {t}: sum"
+                    assert (got_dot == R.fr_dot(ref[t], weights[:cur], threads=8)).all(), f"round {rnd} table {t}: checksum"
+            elif cur <= 256:
+                advance(rnd + 1)
+                for t in range(4):
+                    assert (inst.table(t) == ref[t]).all(), f"round {rnd} table {t}"
+    finally:
+        d_w.free()
+        inst.free()

@@ -42,7 +42,7 @@ def main():
         log = ctx.prof_read()
         ctx.prof_enable(False)
         ks = [ms for tag, ms in log if tag in (16, 17, 18)]
-        if rep and (best is None or wall < best[0]):
+        if (rep or reps == 0) and (best is None or wall < best[0]):
             best = (wall, ks)
     wall, ks = best
     p1 = log_T // 2

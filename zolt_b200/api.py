@@ -115,6 +115,11 @@ class Context:
         check(self.lib.zolt_fr_vec_dev(self.handle, op, C.c_void_p(d_out), C.c_void_p(d_a or None), C.c_void_p(d_b or None), C.c_void_p(d_c or None),
                                        C.c_void_p(d_e or None), _ptr(sv), n), "zolt_fr_vec_dev")
 
+    def poly_sum(self, d_src: int, n: int) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        check(self.lib.zolt_poly_sum(self.handle, C.c_void_p(d_src), n, _ptr(out)), "zolt_poly_sum")
+        return out
+
     def fr_inner_product_dev(self, d_a: int, d_b: int, n: int) -> np.ndarray:
         out = np.zeros(4, dtype=np.uint64)
         check(self.lib.zolt_fr_inner_product_dev(self.handle, C.c_void_p(d_a), C.c_void_p(d_b), n, _ptr(out)), "zolt_fr_inner_product_dev")
@@ -612,6 +617,12 @@ class SumcheckInstance:
         out = np.empty((len(self), 4), dtype=np.uint64)
         check(self.ctx.lib.zolt_sc_download(self.handle, t, _ptr(out)), "zolt_sc_download")
         return out
+
+    def table_dev(self, t: int) -> int:
+        """Device pointer of table t's current buffer (valid until the next bind)."""
+        p = C.c_void_p()
+        check(self.ctx.lib.zolt_sc_table_dev(self.handle, t, C.byref(p)), "zolt_sc_table_dev")
+        return p.value
 
     def set_claim(self, claim):
         """SumcheckInstance.input_claim: lets the first round derive p(1) = claim - p(0) too."""
