@@ -696,10 +696,18 @@ struct BindTables {
   unsigned f64_mask;  // bit k: table k's binds take the FP64 pipe (BIND == 1 kernels)
 };
 
+// what a launch carries: the integer kernels only the 256-byte integer table (2 KB less to marshal per launch)
+struct BindTableI32 {
+  FixedMulTable i32;
+};
+template <int BIND> struct BindArg { using type = BindTableI32; };
+template <> struct BindArg<1> { using type = BindTables; };
+
 template <int COMB, int PAIR, int MODE, int BIND = 0>
 __global__ void __launch_bounds__(kRoundThreads, MODE == 2 ? kFusedBlocksPerSm : kEvalBlocksPerSm)
 sc_round_kernel(const __grid_constant__ ScPtrs t, int n_extra, size_t n, const __grid_constant__ Fr r, SplitEqDev sq,
-                const __grid_constant__ ScOut out, const __grid_constant__ BindTables rt, const __grid_constant__ TmapArray tm) {
+                const __grid_constant__ ScOut out, const __grid_constant__ typename BindArg<BIND>::type rt,
+                const __grid_constant__ TmapArray tm) {
   constexpr int K = CombTraits<COMB>::K;
   constexpr int NW = CombTraits<COMB>::NW;
   constexpr bool FUSED = MODE == 2;
@@ -1090,7 +1098,7 @@ sc_small_kernel(const __grid_constant__ ScPtrs t, const SmallArgs a, size_t n, c
 // not queued behind it; anything that needs the tables (download, table_dev, free) first tells it to exit.
 constexpr int kTailCluster = 8;
 constexpr int kTailThreads = 512;
-constexpr int kTailChunk = 128;  // pairs per CTA step (stash: 4 tables x 2 halves x 128 x 32 B = 32 KB)
+constexpr int kTailChunk = 128;  // pairs per CTA step (stash: up to 5 tables x 2 halves x 128 x 32 B = 40 KB)
 enum { TAIL_OP_BIND = 1, TAIL_OP_EXIT = 2 };
 enum { TAIL_ST_RUNNING = 1, TAIL_ST_DONE = 2, TAIL_ST_TIMEOUT = 3 };
 // layout of the instance's 256-byte mapped mailbox: [0,128) evaluations, 128 result sequence number, 132 tail status,
@@ -1168,7 +1176,7 @@ __device__ __forceinline__ void dsmem_st_u32(const void* local_var, unsigned ran
 template <int PAIR>
 __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThreads)
 sc_tail_kernel(const __grid_constant__ TailArgs ta) {
-  __shared__ Fr stash[4][2][kTailChunk];
+  __shared__ Fr stash[kSmallTables][2][kTailChunk];  // 5 x 2 x 128 x 32 B = 40 KB
   __shared__ Fr red[kTailThreads / 32];
   __shared__ unsigned cmd_sh[2 + 8];  // op, result seq, challenge: written by CTA 0 into every CTA's copy
   __shared__ unsigned claim_w[8];     // CTA 0: the host-supplied claim of the round being evaluated
@@ -1555,6 +1563,10 @@ struct zolt_sc {
   bool tail_pending = false;    // a bind command has been posted whose evaluations have not been read yet
   int tail_prev_cur = 0;        // state before that command (to redo it through a regular launch if the kernel timed out)
   size_t tail_prev_n = 0;
+  // tensor maps of the next fused launch, encoded ahead of time (launch_round)
+  TmapArray tm_next{};
+  size_t tm_next_n = 0;
+  const Fr* tm_next_src0 = nullptr;
 };
 
 namespace {
@@ -1746,7 +1758,11 @@ int launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   if (PAIR == ZOLT_PAIR_ADJACENT && !(n_cur / 2 <= (size_t)sc->ctx->sc_small_pairs)) {
     // one row = what one pair reads from a table: 4 source elements (fused) or 2 (evaluation only)
     const unsigned row_bytes = fused ? 128u : 64u;
-    for (int i = 0; i < (fused ? total : sc->k); i++) ZOLT_TRY(encode_rows_tmap(&tm.m[i], t.src[i], sc->n * sizeof(Fr) / row_bytes, row_bytes));
+    if (fused && sc->tm_next_n == sc->n && sc->tm_next_src0 == t.src[0]) {
+      tm = sc->tm_next;  // encoded while the previous round was running (below)
+    } else {
+      for (int i = 0; i < (fused ? total : sc->k); i++) ZOLT_TRY(encode_rows_tmap(&tm.m[i], t.src[i], sc->n * sizeof(Fr) / row_bytes, row_bytes));
+    }
   }
   const bool f64 = mode == 2 && PAIR == ZOLT_PAIR_ADJACENT && (sc->ctx->sc_bind_f64 & 0xff) != 0;  // sc_bind_f64: mask of the tables whose binds take the FP64 pipe
   {
@@ -1769,7 +1785,7 @@ int launch_round(zolt_sc* sc, bool fused, const Fr& r) {
       attr_devs[slot].fetch_or(bit, std::memory_order_release);
     }
   }
-  const BindTables rt0{};
+  const BindTableI32 rt0{};
   const int ps = prof_begin(sc->ctx, fused ? PROF_SC_FUSED : PROF_SC_EVAL);
   if (n_cur / 2 <= (size_t)sc->ctx->sc_small_pairs) {
     // latency-bound sizes: one element / one term per thread (sc_small_kernel)
@@ -1779,14 +1795,15 @@ int launch_round(zolt_sc* sc, bool fused, const Fr& r) {
     if (chunks == 0) chunks = 1;
     sc_small_kernel<PAIR><<<(unsigned)chunks, kSmallThreads, 0, sc->ctx->stream>>>(t, a, sc->n, r, sq, out);
   } else if (mode == 2) {
-    BindTables rt{};  // O(1) host glue per launch
     if (f64) {
+      BindTables rt{};  // O(1) host glue per launch
       fixed_mul_table_f64_host(r, &rt.f64[0]);
       rt.f64[1] = rt.f64[0];
       rt.i32 = fixed_mul_table_host(r);
       rt.f64_mask = (unsigned)sc->ctx->sc_bind_f64 & 0xffu;
       sc_round_kernel<COMB, PAIR, 2, 1><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, rt, tm);
     } else {
+      BindTableI32 rt{};
       rt.i32 = fixed_mul_table_host(r);
       sc_round_kernel<COMB, PAIR, 2, 0><<<grid, kRoundThreads, kDynSmem, sc->ctx->stream>>>(t, sc->n_extra, sc->n, r, sq, out, rt, tm);
     }
@@ -1798,6 +1815,18 @@ int launch_round(zolt_sc* sc, bool fused, const Fr& r) {
   prof_end(sc->ctx, ps);
   sc->ctx->launches++;
   sc->evals_final = !sc->sharded;
+  // The NEXT launch is a fused pass over the tables this one evaluates (n_cur entries, at t.src when this launch did not
+  // bind, else at t.dst): encode its tensor maps now, while the GPU works, instead of between the challenge and the launch.
+  sc->tm_next_n = 0;
+  if (PAIR == ZOLT_PAIR_ADJACENT && n_cur >= 4 && n_cur / 4 > (size_t)sc->ctx->sc_small_pairs) {
+    bool ok = true;
+    for (int i = 0; i < total && ok; i++)
+      ok = encode_rows_tmap(&sc->tm_next.m[i], fused ? t.dst[i] : t.src[i], n_cur * sizeof(Fr) / 128u, 128u) == ZOLT_OK;
+    if (ok) {
+      sc->tm_next_n = n_cur;
+      sc->tm_next_src0 = fused ? t.dst[0] : t.src[0];
+    }
+  }
   return ZOLT_OK;
 }
 
@@ -1872,7 +1901,7 @@ inline volatile unsigned* mb_word(zolt_sc* sc, int byte_off) {
 }
 
 bool tail_eligible(const zolt_sc* sc) {
-  return sc->ctx->sc_tail_pairs > 0 && !sc->sharded && !sc->box && sc->k <= 4 && sc->k + sc->n_extra <= kMaxTables;
+  return sc->ctx->sc_tail_pairs > 0 && !sc->sharded && !sc->box && sc->k <= kSmallTables && sc->k + sc->n_extra <= kMaxTables;
 }
 
 int tail_launch(zolt_sc* sc) {
