@@ -1098,7 +1098,7 @@ sc_small_kernel(const __grid_constant__ ScPtrs t, const SmallArgs a, size_t n, c
 // not queued behind it; anything that needs the tables (download, table_dev, free) first tells it to exit.
 constexpr int kTailCluster = 8;
 constexpr int kTailThreads = 512;
-constexpr int kTailChunk = 128;  // pairs per CTA step (stash: up to 5 tables x 2 halves x 128 x 32 B = 40 KB)
+constexpr int kTailChunk = 128;  // pairs per CTA step (stash: 4 tables x 2 halves x 128 x 32 B = 32 KB)
 enum { TAIL_OP_BIND = 1, TAIL_OP_EXIT = 2 };
 enum { TAIL_ST_RUNNING = 1, TAIL_ST_DONE = 2, TAIL_ST_TIMEOUT = 3 };
 // layout of the instance's 256-byte mapped mailbox: [0,128) evaluations, 128 result sequence number, 132 tail status,
@@ -1176,7 +1176,7 @@ __device__ __forceinline__ void dsmem_st_u32(const void* local_var, unsigned ran
 template <int PAIR>
 __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThreads)
 sc_tail_kernel(const __grid_constant__ TailArgs ta) {
-  __shared__ Fr stash[kSmallTables][2][kTailChunk];  // 5 x 2 x 128 x 32 B = 40 KB
+  __shared__ Fr stash[4][2][kTailChunk];
   __shared__ Fr red[kTailThreads / 32];
   __shared__ unsigned cmd_sh[2 + 8];  // op, result seq, challenge: written by CTA 0 into every CTA's copy
   __shared__ unsigned claim_w[8];     // CTA 0: the host-supplied claim of the round being evaluated
@@ -1901,7 +1901,7 @@ inline volatile unsigned* mb_word(zolt_sc* sc, int byte_off) {
 }
 
 bool tail_eligible(const zolt_sc* sc) {
-  return sc->ctx->sc_tail_pairs > 0 && !sc->sharded && !sc->box && sc->k <= kSmallTables && sc->k + sc->n_extra <= kMaxTables;
+  return sc->ctx->sc_tail_pairs > 0 && !sc->sharded && !sc->box && sc->k <= 4 && sc->k + sc->n_extra <= kMaxTables;  // 5-table combiners (Stage-4 dense): measured no faster in the tail than as small-round launches
 }
 
 int tail_launch(zolt_sc* sc) {
