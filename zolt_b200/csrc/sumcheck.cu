@@ -1189,7 +1189,9 @@ sc_tail_kernel(const __grid_constant__ TailArgs ta) {
   unsigned expect = 1;
   volatile unsigned* const mb32 = reinterpret_cast<volatile unsigned*>(ta.mailbox);
   unsigned status = TAIL_ST_DONE;
-  __syncthreads();
+  // every CTA of the cluster has started before anybody stores into a peer's shared memory (the hardware co-schedules a
+  // cluster, but only this barrier makes the peers' shared memory valid to address: compute-sanitizer flags the store otherwise)
+  cluster_sync_all();
   while (n >= 2) {
     // ---- the host's next command: ONE thread of the cluster polls the mapped word (a PCIe read per poll) and hands the
     // command to every CTA through distributed shared memory; everybody else waits at the cluster barrier ----
