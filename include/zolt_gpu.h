@@ -68,6 +68,9 @@ const char* zolt_gpu_version(void);
  *                             challenge, zolt_sc_round_evals reads the answer: the call pattern does not change.
  *   ZOLT_TUNE_SC_TAIL_TIMEOUT_MS  how long that kernel waits for the next challenge before it retires by itself (default
  *                             10000); a challenge that arrives later is served by a regular launch, transparently */
+/*   ZOLT_TUNE_MSM_SORT       0 (default): MSMs over a window-level table sort their bucket entries with the two-pass bin sort
+ *                             from 2^18 points up; 1: always the atomic counting-sort scatter (the A/B switch of tools/time_msm_sort.py) */
+#define ZOLT_TUNE_MSM_SORT 9
 #define ZOLT_TUNE_SC_TAIL_PAIRS 4
 #define ZOLT_TUNE_SC_TAIL_TIMEOUT_MS 5
 int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value);

@@ -73,6 +73,7 @@ struct zolt_ctx {
   long long sc_small_pairs = 1 << 14;
   long long sc_tail_pairs = 1 << 12;   // rounds with at most this many pairs run inside the resident tail kernel (0: never)
   unsigned long long* sc_round_dbg = nullptr;  // diagnostics: device buffer (64 x 8 words) for the round kernels' time stamps (tuning key 7)
+  int msm_sort = 0;  // tuning key 9: 0 = two-pass bucket sort where it applies, 1 = always the atomic scatter
   unsigned long long* msm_dbg = nullptr;       // diagnostics: per-warp (start, end, SM) of the level-0 accumulation kernel (tuning key 8)
   unsigned long long* sc_tail_dbg = nullptr;  // diagnostics: device buffer for the tail kernel's per-round time stamps (tuning key 6)
   long long sc_tail_timeout_ms = 0;    // how long the tail kernel waits for the host's next challenge (0: 10 s)

@@ -86,6 +86,7 @@ extern "C" int zolt_gpu_set_tuning(zolt_ctx* ctx, int key, long long value) {
     case ZOLT_TUNE_SC_SMALL_PAIRS: ctx->sc_small_pairs = value > (1 << 14) ? (1 << 14) : value; return ZOLT_OK;
     case ZOLT_TUNE_SC_TAIL_PAIRS: ctx->sc_tail_pairs = value > (1 << 14) ? (1 << 14) : value; return ZOLT_OK;
     case ZOLT_TUNE_SC_TAIL_TIMEOUT_MS: ctx->sc_tail_timeout_ms = value; return ZOLT_OK;
+    case 9: ctx->msm_sort = (int)value; return ZOLT_OK;
     case 8: ctx->msm_dbg = reinterpret_cast<unsigned long long*>(value); return ZOLT_OK;          // diagnostics: device pointer or 0
     case 7: ctx->sc_round_dbg = reinterpret_cast<unsigned long long*>(value); return ZOLT_OK;     // diagnostics: device pointer or 0
     case 6: ctx->sc_tail_dbg = reinterpret_cast<unsigned long long*>(value); return ZOLT_OK;  // diagnostics: device pointer or 0

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <new>
 
+#include <atomic>
 #include "common.cuh"
 #include "curve.cuh"
 #include "peer.cuh"
@@ -267,6 +268,328 @@ msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, M
       for (int j = 0; j < kScatterE; j++)
         if (d[j]) sorted[pos[j]] = (uint32_t)(pbase + i0 + (size_t)j * stride) | (d[j] & 0x80000000u);
     }
+  }
+}
+
+// ---- 3b. two-pass bucket sort (one shared bucket set: window-level table, k == 1) ---------------------------------
+// The scatter above pays one returning global atomic and one 4-byte store to a random address per entry: 2 x 218 M L2
+// round trips at 2^24 points (4.5 ms), with a write frontier (one open sector per bucket) far larger than L2.  Here the
+// entries are first partitioned into BINS of 512 consecutive buckets, then every bin is sorted in chunks that fit shared
+// memory, so that
+//   * all per-entry atomics are SHARED-memory atomics (a block owns its cursors: pass 1 reserved its runs with one exclusive
+//     scan over the [bin][block] histogram; pass 2 reserves one range per (bucket, chunk) -- 512 global atomics per 16384 entries);
+//   * pass 1 sorts a tile of 1024 scalars' entries by bin in shared memory and appends every bin's piece (13 records = 104 bytes
+//     on average) to the block's run of that bin;
+//   * pass 2 writes every bucket's share of a chunk as one contiguous run (32 entries = 128 bytes on average).
+// 2^24 points: 4.1 ms instead of 5.8 ms for digits + scatter (MSM 39.1 -> 37.3 ms); neutral from 2^18 to 2^21 points.
+// The digits are never materialised: both partition kernels re-derive them from the scalars (13 shifts per scalar).
+// Output is what the accumulation kernel expects: `sorted` (point index | sign) grouped by bucket, and `offsets`.
+constexpr int kBinSubBits = 9;                 // buckets per bin (the open 128-byte lines of pass 1, blocks x bins, must fit L2)
+constexpr int kBinSub = 1 << kBinSubBits;
+constexpr int kBinThreads = 1024;
+constexpr int kChunkRecs = 16384;              // records per pass-2 chunk: 32 per bucket on average, a full 128-byte line
+constexpr int kChunkThreads = 1024;
+constexpr int kChunkPer = kChunkRecs / kChunkThreads;
+
+// exclusive scan over the block (any multiple of 32 threads up to 1024); `sm` holds 33 words; total in sm[32] afterwards
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) sm[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t t = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0;
+    uint32_t ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, ti, d);
+      if (lane >= d) ti += y;
+    }
+    sm[lane] = ti - t;
+    if (lane == 31) sm[32] = ti;
+  }
+  __syncthreads();
+  return sm[warp] + incl - v;
+}
+
+// calls f(w, magnitude 1..B, negative) for every non-zero signed digit of the (standard-form) scalar s
+template <class F>
+__device__ __forceinline__ void for_each_digit(const Fr& s, const MsmGeom& g, F&& f) {
+  uint32_t carry = 0;
+  const uint32_t mask = (1u << g.c) - 1u;
+  for (int w = 0; w < g.windows; w++) {
+    const int pos = w * g.c;
+    const int word = pos >> 5, sh = pos & 31;
+    uint64_t two = (uint64_t)s.v[word < 8 ? word : 7];
+    if (word >= 8) two = 0;
+    if (word + 1 < 8) two |= (uint64_t)s.v[word + 1] << 32;
+    uint32_t d = ((uint32_t)(two >> sh) & mask) + carry;
+    uint32_t neg = 0;
+    if (d > g.B) {
+      d = (1u << g.c) - d;
+      neg = 1;
+      carry = 1;
+    } else {
+      carry = 0;
+    }
+    if (d) f(w, d, neg);
+  }
+}
+
+// pass 1a: histogram of this block's share of the scalars over the bins -> matrix[bin * gridDim.x + block]
+__global__ void __launch_bounds__(kBinThreads)
+msm_bin_hist_kernel(const Fr* __restrict__ scalars, const uint8_t* __restrict__ inf, size_t n, MsmGeom g, uint32_t nbins,
+                    uint32_t* __restrict__ matrix) {
+  extern __shared__ uint32_t bin_smem[];
+  for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) bin_smem[b] = 0;
+  __syncthreads();
+  const size_t per = (n + gridDim.x - 1) / gridDim.x;
+  const size_t lo = blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (inf != nullptr && inf[i] != 0) continue;  // identity bases are skipped (msm/mod.zig:407)
+    const Fr s = fp_from_mont<FrParams>(scalars[i]);
+    for_each_digit(s, g, [&](int, uint32_t d, uint32_t) { atomicAdd(&bin_smem[(d - 1) >> kBinSubBits], 1u); });
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) matrix[(size_t)b * gridDim.x + blockIdx.x] = bin_smem[b];
+}
+
+// pass 1b: the same walk in tiles of blockDim.x scalars.  A tile's entries are sorted by bin in shared memory and every
+// bin's share is appended to this block's run of that bin as ONE contiguous piece (the run cursors start at the exclusive
+// scan of the matrix and live in shared memory).  Writing each entry straight to its run -- 218 M scattered 8-byte stores --
+// ran at the DRAM's random-access rate, like the atomic scatter (ncu: 4.0 GB written and 1.7 GB read back for 1.75 GB of
+// records, 5.3 ms at 2^24): the open lines of (blocks x bins) runs do not survive in L2 between two touches.
+constexpr int kBinMaxWindows = 16;
+__global__ void __launch_bounds__(kBinThreads)
+msm_bin_partition_kernel(const Fr* __restrict__ scalars, const uint8_t* __restrict__ inf, size_t n, MsmGeom g, uint32_t nbins,
+                         const uint32_t* __restrict__ matrix_off, size_t pre_n, size_t pre_offset, uint2* __restrict__ recs) {
+  // dynamic shared memory: cursor[nbins] | cnt[nbins] | loff[nbins] | stage[blockDim * windows] (uint2) | stage_bin[...] (u16)
+  extern __shared__ uint32_t bin_smem[];
+  uint32_t* const cursor = bin_smem;
+  uint32_t* const cnt = cursor + nbins;
+  uint32_t* const loff = cnt + nbins;
+  uint2* const stage = reinterpret_cast<uint2*>(loff + nbins);
+  uint16_t* const stage_bin = reinterpret_cast<uint16_t*>(stage + (size_t)blockDim.x * g.windows);
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t pass_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t b = tid; b < nbins; b += blockDim.x) {
+    cursor[b] = matrix_off[(size_t)b * gridDim.x + blockIdx.x];
+    cnt[b] = 0;
+  }
+  __syncthreads();
+  const size_t per = (n + gridDim.x - 1) / gridDim.x;
+  const size_t lo = blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+  for (size_t base = lo; base < hi; base += blockDim.x) {
+    const size_t i = base + tid;
+    uint32_t dg[kBinMaxWindows];  // bucket | sign << 31, or 0xffffffff: no entry
+    uint16_t rank[kBinMaxWindows];
+#pragma unroll
+    for (int w = 0; w < kBinMaxWindows; w++) dg[w] = 0xffffffffu;
+    if (i < hi && !(inf != nullptr && inf[i] != 0)) {
+      const Fr s = fp_from_mont<FrParams>(scalars[i]);
+      uint32_t carry = 0;
+      const uint32_t mask = (1u << g.c) - 1u;
+#pragma unroll
+      for (int w = 0; w < kBinMaxWindows; w++) {
+        if (w < g.windows) {
+          const int pos = w * g.c;
+          const int word = pos >> 5, sh = pos & 31;
+          uint64_t two = word < 8 ? (uint64_t)s.v[word < 8 ? word : 7] : 0;
+          if (word + 1 < 8) two |= (uint64_t)s.v[word + 1 < 8 ? word + 1 : 7] << 32;
+          uint32_t d = ((uint32_t)(two >> sh) & mask) + carry;
+          uint32_t neg = 0;
+          if (d > g.B) {
+            d = (1u << g.c) - d;
+            neg = 1;
+            carry = 1;
+          } else {
+            carry = 0;
+          }
+          if (d) dg[w] = (d - 1) | (neg << 31);
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < kBinMaxWindows; w++)
+        if (dg[w] != 0xffffffffu) rank[w] = (uint16_t)atomicAdd(&cnt[(dg[w] & 0x7fffffffu) >> kBinSubBits], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..nbins) into loff, blockDim.x counters per pass
+    uint32_t running = 0;
+    for (uint32_t b0 = 0; b0 < nbins; b0 += blockDim.x) {
+      const uint32_t b = b0 + tid;
+      const uint32_t c = b < nbins ? cnt[b] : 0;
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t t = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
+        uint32_t ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, ti, d);
+          if (lane >= d) ti += y;
+        }
+        warp_tot[lane] = ti - t;  // exclusive prefix of every warp
+        if (lane == 31) pass_total = ti;
+      }
+      __syncthreads();
+      if (b < nbins) loff[b] = running + warp_tot[warp] + incl - c;
+      running += pass_total;
+      __syncthreads();  // warp_tot / pass_total are rewritten by the next pass
+    }
+    // stage the entries in bin order
+#pragma unroll
+    for (int w = 0; w < kBinMaxWindows; w++)
+      if (dg[w] != 0xffffffffu) {
+        const uint32_t bin = (dg[w] & 0x7fffffffu) >> kBinSubBits;
+        const uint32_t slot = loff[bin] + rank[w];
+        stage[slot] = make_uint2((uint32_t)((size_t)w * pre_n + pre_offset + i) | (dg[w] & 0x80000000u), dg[w] & 0x7fffffffu);
+        stage_bin[slot] = (uint16_t)bin;
+      }
+    __syncthreads();
+    // every bin's piece goes out contiguously behind what this block has already written for that bin
+    for (uint32_t j = tid; j < running; j += blockDim.x) {
+      const uint32_t bin = stage_bin[j];
+      recs[cursor[bin] + (j - loff[bin])] = stage[j];
+    }
+    __syncthreads();
+    for (uint32_t b = tid; b < nbins; b += blockDim.x) {
+      cursor[b] += cnt[b];
+      cnt[b] = 0;
+    }
+    __syncthreads();
+  }
+}
+
+// chunk_base[b] = number of pass-2 chunks before bin b (bin b has ceil(size / kChunkRecs) of them); one block
+__global__ void __launch_bounds__(kScanThreads)
+msm_chunk_index_kernel(const uint32_t* __restrict__ matrix_off, uint32_t nbins, uint32_t G, uint32_t* __restrict__ chunk_base) {
+  __shared__ uint32_t smem[kScanThreads];
+  const uint32_t per = (nbins + kScanThreads - 1) / kScanThreads;
+  const uint32_t b0 = threadIdx.x * per, b1 = b0 + per < nbins ? b0 + per : nbins;
+  uint32_t s = 0;
+  for (uint32_t b = b0; b < b1; b++) {
+    const uint32_t sz = matrix_off[(size_t)(b + 1) * G] - matrix_off[(size_t)b * G];  // matrix_off has nbins * G + 1 entries
+    s += (sz + kChunkRecs - 1) / kChunkRecs;
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, smem, &total);
+  for (uint32_t b = b0; b < b1; b++) {
+    chunk_base[b] = ex;
+    const uint32_t sz = matrix_off[(size_t)(b + 1) * G] - matrix_off[(size_t)b * G];
+    ex += (sz + kChunkRecs - 1) / kChunkRecs;
+  }
+  if (threadIdx.x == 0) chunk_base[nbins] = total;
+}
+
+// (bin, record range) of chunk `chunk`; false when there is no such chunk
+__device__ __forceinline__ bool chunk_range(const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ matrix_off,
+                                            uint32_t nbins, uint32_t G, uint32_t chunk, uint32_t* bin, uint32_t* start, uint32_t* end) {
+  if (chunk >= chunk_base[nbins]) return false;
+  uint32_t lo = 0, hi = nbins;  // invariant: chunk_base[lo] <= chunk < chunk_base[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (chunk_base[mid] <= chunk) lo = mid; else hi = mid;
+  }
+  const uint32_t b0 = matrix_off[(size_t)lo * G], b1 = matrix_off[(size_t)(lo + 1) * G];
+  *bin = lo;
+  *start = b0 + (chunk - chunk_base[lo]) * kChunkRecs;
+  *end = *start + kChunkRecs < b1 ? *start + kChunkRecs : b1;
+  return true;
+}
+
+// pass 2a: bucket histogram, one shared-memory count per chunk folded into `counts` with at most 128 global adds
+__global__ void __launch_bounds__(kChunkThreads)
+msm_chunk_count_kernel(const uint2* __restrict__ recs, const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ matrix_off,
+                       uint32_t nbins, uint32_t G, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t cnt[kBinSub];
+  __shared__ uint32_t rng[3];
+  if (threadIdx.x == 0) {
+    uint32_t bin = 0, start = 0, end = 0;
+    if (!chunk_range(chunk_base, matrix_off, nbins, G, blockIdx.x, &bin, &start, &end)) end = start = 0;
+    rng[0] = bin; rng[1] = start; rng[2] = end;
+  }
+  for (int q = threadIdx.x; q < kBinSub; q += kChunkThreads) cnt[q] = 0;
+  __syncthreads();
+  const uint32_t bin = rng[0], start = rng[1], end = rng[2];
+  if (start == end) return;
+  for (uint32_t p = start + threadIdx.x; p < end; p += kChunkThreads) atomicAdd(&cnt[__ldcs(&recs[p]).y & (kBinSub - 1)], 1u);
+  __syncthreads();
+  for (int q = threadIdx.x; q < kBinSub; q += kChunkThreads)
+    if (cnt[q]) atomicAdd(&counts[bin * kBinSub + q], cnt[q]);
+}
+
+// pass 2b: the chunk sorted by bucket in shared memory, every bucket's run copied to the range it reserves in `sorted`
+__global__ void __launch_bounds__(kChunkThreads)
+msm_chunk_place_kernel(const uint2* __restrict__ recs, const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ matrix_off,
+                       uint32_t nbins, uint32_t G, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  __shared__ uint32_t cnt[kBinSub], loff[kBinSub + 1], gpos[kBinSub];
+  extern __shared__ uint32_t place_smem[];  // kChunkRecs values, then kChunkRecs 16-bit bucket numbers (dynamic: > 48 KB)
+  uint32_t* const stage = place_smem;
+  uint16_t* const stage_b = reinterpret_cast<uint16_t*>(place_smem + kChunkRecs);
+  __shared__ uint32_t rng[3];
+  __shared__ uint32_t scan_sm[33];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    uint32_t bin = 0, start = 0, end = 0;
+    if (!chunk_range(chunk_base, matrix_off, nbins, G, blockIdx.x, &bin, &start, &end)) end = start = 0;
+    rng[0] = bin; rng[1] = start; rng[2] = end;
+  }
+  for (int q = tid; q < kBinSub; q += kChunkThreads) cnt[q] = 0;
+  __syncthreads();
+  const uint32_t bin = rng[0], start = rng[1], end = rng[2];
+  if (start == end) return;
+  uint32_t val[kChunkPer];
+  uint16_t rank[kChunkPer];
+  uint16_t bk[kChunkPer];
+#pragma unroll
+  for (int j = 0; j < kChunkPer; j++) {
+    const uint32_t p = start + j * kChunkThreads + tid;
+    if (p < end) {
+      const uint2 r = __ldcs(&recs[p]);
+      val[j] = r.x;
+      bk[j] = (uint16_t)(r.y & (kBinSub - 1));
+      rank[j] = (uint16_t)atomicAdd(&cnt[bk[j]], 1u);
+    }
+  }
+  __syncthreads();
+  {
+    // exclusive scan of the kBinSub counts (one per thread, the rest of the block scans zeros), then one global
+    // reservation per non-empty bucket
+    static_assert(kBinSub <= kChunkThreads, "one count per thread");
+    const uint32_t c = tid < kBinSub ? cnt[tid] : 0;
+    const uint32_t ex = block_scan_excl(c, scan_sm);
+    if (tid < kBinSub) {
+      loff[tid] = ex;
+      gpos[tid] = c ? atomicAdd(&cursor[bin * kBinSub + tid], c) : 0u;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kChunkPer; j++) {
+    const uint32_t p = start + j * kChunkThreads + tid;
+    if (p < end) {
+      const uint32_t slot = loff[bk[j]] + rank[j];
+      stage[slot] = val[j];
+      stage_b[slot] = bk[j];
+    }
+  }
+  __syncthreads();
+  const uint32_t count = end - start;
+  for (uint32_t j = tid; j < count; j += kChunkThreads) {
+    const uint32_t b = stage_b[j];
+    sorted[gpos[b] + (j - loff[b])] = stage[j];
   }
 }
 
@@ -671,8 +994,17 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   const uint32_t chunks_per_row = (g.B + Lc - 1) / Lc;
   const size_t num_tiles = (num_keys + kScanTile - 1) / kScanTile;
 
+  // Two-pass bucket sort (3b) when all windows share one bucket set and the bins are worth their set-up
+  const bool two_pass = pre && k == 1 && g.B >= 4096 && g.B <= (1u << 20) && g.windows <= kBinMaxWindows && n >= (size_t(1) << 18) && ctx->msm_sort != 1;
+  const uint32_t nbins = g.B >> kBinSubBits;
+  const uint32_t bin_grid = (uint32_t)ctx->num_sms;           // blocks of the two partition kernels (one per SM at 1024 threads)
+  const size_t matrix_n = two_pass ? (size_t)nbins * bin_grid : 0;
+  const size_t matrix_tiles = (matrix_n + kScanTile - 1) / kScanTile;
+  const size_t max_chunks = two_pass ? max_entries / kChunkRecs + nbins + 1 : 0;
+
   size_t bytes = 0;
-  bytes += align256(max_entries * 4) * 2;                     // digits, sorted
+  bytes += align256(max_entries * 4) * (two_pass ? 3 : 2);    // digits (or 8-byte records), sorted
+  bytes += align256((matrix_n + 1) * 4) * 2 + align256((matrix_tiles + 1) * 4) + align256(((size_t)nbins + 1) * 4);
   bytes += align256(num_keys * 4) + align256((num_keys + 1) * 4);  // counts/cursor, offsets
   bytes += align256((num_tiles + 1) * 4);
   bytes += align256(num_keys * sizeof(XYZZ));                 // buckets
@@ -694,8 +1026,12 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   Arena ar;
   ar.base = static_cast<char*>(ctx->ws);
   ar.size = bytes;
-  uint32_t* digits = ar.take<uint32_t>(max_entries);
+  uint32_t* digits = ar.take<uint32_t>(max_entries * (two_pass ? 2 : 1));
   uint32_t* sorted = ar.take<uint32_t>(max_entries);
+  uint32_t* matrix = ar.take<uint32_t>(matrix_n + 1);
+  uint32_t* matrix_off = ar.take<uint32_t>(matrix_n + 1);
+  uint32_t* matrix_tiles_buf = ar.take<uint32_t>(matrix_tiles + 1);
+  uint32_t* chunk_base = ar.take<uint32_t>((size_t)nbins + 1);
   uint32_t* counts = ar.take<uint32_t>(num_keys);
   uint32_t* offsets = ar.take<uint32_t>(num_keys + 1);
   uint32_t* tiles = ar.take<uint32_t>(num_tiles + 1);
@@ -724,6 +1060,39 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
 
     MSM_CHECK(cudaMemsetAsync(counts, 0, num_keys * 4, st));
     MSM_CHECK(cudaMemsetAsync(buckets, 0, num_keys * sizeof(XYZZ), st));  // identity everywhere
+    if (two_pass) {
+      uint2* recs = reinterpret_cast<uint2*>(digits);
+      const size_t bin_smem = (size_t)nbins * 4;
+      // partition kernel: cursor | cnt | loff | one tile of records (8 B) and their bins (2 B)
+      const size_t part_smem = 3 * bin_smem + (size_t)kBinThreads * g.windows * (8 + 2) + 16;
+      static std::atomic<unsigned long long> attr_devs{0};  // > 48 KB of dynamic shared memory needs an opt-in per device
+      if (!(attr_devs.load() & (1ull << (ctx->device & 63)))) {
+        MSM_CHECK(cudaFuncSetAttribute(msm_bin_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MSM_CHECK(cudaFuncSetAttribute(msm_bin_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MSM_CHECK(cudaFuncSetAttribute(msm_chunk_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChunkRecs * 6));
+        attr_devs.fetch_or(1ull << (ctx->device & 63));
+      }
+      int ps = prof_begin(ctx, PROF_MSM_DIGITS);
+      msm_bin_hist_kernel<<<bin_grid, kBinThreads, bin_smem, st>>>(d_scalars, d_inf, n, g, nbins, matrix);
+      scan_tile_sums_kernel<<<(unsigned)matrix_tiles, kScanThreads, 0, st>>>(matrix, matrix_n, matrix_tiles_buf);
+      scan_tile_offsets_kernel<<<1, kScanThreads, 0, st>>>(matrix_tiles_buf, matrix_tiles);
+      scan_apply_kernel<<<(unsigned)matrix_tiles, kScanThreads, 0, st>>>(matrix, matrix_n, matrix_tiles_buf, matrix_off);
+      msm_bin_partition_kernel<<<bin_grid, kBinThreads, part_smem, st>>>(d_scalars, d_inf, n, g, nbins, matrix_off, bases->n, offset, recs);
+      msm_chunk_index_kernel<<<1, kScanThreads, 0, st>>>(matrix_off, nbins, bin_grid, chunk_base);
+      prof_end(ctx, ps);
+      ps = prof_begin(ctx, PROF_MSM_SCAN);
+      msm_chunk_count_kernel<<<(unsigned)max_chunks, kChunkThreads, 0, st>>>(recs, chunk_base, matrix_off, nbins, bin_grid, counts);
+      scan_tile_sums_kernel<<<(unsigned)num_tiles, kScanThreads, 0, st>>>(counts, num_keys, tiles);
+      scan_tile_offsets_kernel<<<1, kScanThreads, 0, st>>>(tiles, num_tiles);
+      scan_apply_kernel<<<(unsigned)num_tiles, kScanThreads, 0, st>>>(counts, num_keys, tiles, offsets);
+      prof_end(ctx, ps);
+      MSM_CHECK(cudaMemcpyAsync(counts, offsets, num_keys * 4, cudaMemcpyDeviceToDevice, st));
+      ps = prof_begin(ctx, PROF_MSM_SCATTER);
+      msm_chunk_place_kernel<<<(unsigned)max_chunks, kChunkThreads, kChunkRecs * 6, st>>>(recs, chunk_base, matrix_off, nbins, bin_grid, counts, sorted);
+      prof_end(ctx, ps);
+      ctx->launches += 11;
+      MSM_CHECK(cudaGetLastError());
+    } else {
     {
       size_t blocks = (k * n + 255) / 256;
       if (blocks > (size_t)sm * 16) blocks = (size_t)sm * 16;
@@ -754,8 +1123,9 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
       prof_end(ctx, ps);
       ctx->launches++;
     }
+    }
     // level 0
-    ps = prof_begin(ctx, PROF_MSM_ACCUM0);
+    int ps = prof_begin(ctx, PROF_MSM_ACCUM0);
     msm_accum_points_kernel<<<(unsigned)((slices0 + 127) / 128), 128, 0, st>>>(
         sorted, offsets, (uint32_t)num_keys, d_pts, buckets, edge_keys, edge_pts, slices0, slice_len, ctx->msm_dbg);
     prof_end(ctx, ps);
