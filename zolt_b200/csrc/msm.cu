@@ -281,7 +281,8 @@ msm_scatter_kernel(const uint32_t* __restrict__ digits, size_t n, size_t rows, M
 //   * pass 1 sorts a tile of 1024 scalars' entries by bin in shared memory and appends every bin's piece (13 records = 104 bytes
 //     on average) to the block's run of that bin;
 //   * pass 2 writes every bucket's share of a chunk as one contiguous run (32 entries = 128 bytes on average).
-// 2^24 points: 4.1 ms instead of 5.8 ms for digits + scatter (MSM 39.1 -> 37.3 ms); neutral from 2^18 to 2^21 points.
+// 2^24 points: 3.4 ms instead of 5.8 ms for digits + scatter (MSM 39.1 -> 36.7 ms); neutral from 2^18 to 2^21 points, faster on
+// trace-like scalars at every size (many equal digits: the atomic scatter serialises on a few cursors).
 // The digits are never materialised: both partition kernels re-derive them from the scalars (13 shifts per scalar).
 // Output is what the accumulation kernel expects: `sorted` (point index | sign) grouped by bucket, and `offsets`.
 constexpr int kBinSubBits = 9;                 // buckets per bin (the open 128-byte lines of pass 1, blocks x bins, must fit L2)
@@ -385,14 +386,17 @@ msm_bin_partition_kernel(const Fr* __restrict__ scalars, const uint8_t* __restri
   __syncthreads();
   const size_t per = (n + gridDim.x - 1) / gridDim.x;
   const size_t lo = blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+  Fr next = lo + tid < hi ? scalars[lo + tid] : Fr::zero();
   for (size_t base = lo; base < hi; base += blockDim.x) {
     const size_t i = base + tid;
+    const Fr cur = next;
+    if (i + blockDim.x < hi) next = scalars[i + blockDim.x];  // the next tile's scalar travels while this tile is sorted
     uint32_t dg[kBinMaxWindows];  // bucket | sign << 31, or 0xffffffff: no entry
     uint16_t rank[kBinMaxWindows];
 #pragma unroll
     for (int w = 0; w < kBinMaxWindows; w++) dg[w] = 0xffffffffu;
     if (i < hi && !(inf != nullptr && inf[i] != 0)) {
-      const Fr s = fp_from_mont<FrParams>(scalars[i]);
+      const Fr s = fp_from_mont<FrParams>(cur);
       uint32_t carry = 0;
       const uint32_t mask = (1u << g.c) - 1u;
 #pragma unroll
@@ -554,14 +558,17 @@ msm_chunk_place_kernel(const uint2* __restrict__ recs, const uint32_t* __restric
   uint16_t rank[kChunkPer];
   uint16_t bk[kChunkPer];
 #pragma unroll
-  for (int j = 0; j < kChunkPer; j++) {
+  for (int j = 0; j < kChunkPer; j++) {  // all loads of the thread in flight together ...
     const uint32_t p = start + j * kChunkThreads + tid;
-    if (p < end) {
-      const uint2 r = __ldcs(&recs[p]);
-      val[j] = r.x;
-      bk[j] = (uint16_t)(r.y & (kBinSub - 1));
-      rank[j] = (uint16_t)atomicAdd(&cnt[bk[j]], 1u);
-    }
+    uint2 r = make_uint2(0u, 0u);
+    if (p < end) r = __ldcs(&recs[p]);
+    val[j] = r.x;
+    bk[j] = (uint16_t)(r.y & (kBinSub - 1));
+  }
+#pragma unroll
+  for (int j = 0; j < kChunkPer; j++) {  // ... then the ranks
+    const uint32_t p = start + j * kChunkThreads + tid;
+    if (p < end) rank[j] = (uint16_t)atomicAdd(&cnt[bk[j]], 1u);
   }
   __syncthreads();
   {
@@ -997,7 +1004,7 @@ int msm_core(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const Fr* d_
   // Two-pass bucket sort (3b) when all windows share one bucket set and the bins are worth their set-up
   const bool two_pass = pre && k == 1 && g.B >= 4096 && g.B <= (1u << 20) && g.windows <= kBinMaxWindows && n >= (size_t(1) << 18) && ctx->msm_sort != 1;
   const uint32_t nbins = g.B >> kBinSubBits;
-  const uint32_t bin_grid = (uint32_t)ctx->num_sms;           // blocks of the two partition kernels (one per SM at 1024 threads)
+  const uint32_t bin_grid = (uint32_t)ctx->num_sms;           // blocks of the two partition kernels: one per SM at 1024 threads (two of 512 measured slower)
   const size_t matrix_n = two_pass ? (size_t)nbins * bin_grid : 0;
   const size_t matrix_tiles = (matrix_n + kScanTile - 1) / kScanTile;
   const size_t max_chunks = two_pass ? max_entries / kChunkRecs + nbins + 1 : 0;
