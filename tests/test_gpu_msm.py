@@ -214,3 +214,54 @@ def test_msm_precomputed_special_points(ctx):
     out, oinf = Z.MSM.compute(b2, fr_arr(sc2))
     assert oinf == 1 and not out.any()
     b2.free()
+
+
+TUNE_MSM_SORT = 9
+
+
+@pytest.mark.parametrize("kind", ["uniform", "all_equal", "bytes_and_zeros", "offset_and_infinity"])
+def test_msm_two_pass_bucket_sort(ctx, kind):
+    """The two-pass shared-memory bucket sort of the window-level-table path (msm.cu 3b, from 2^18 points): the same point as
+    the closed form (sum s_i k_i) G and as the atomic counting-sort scatter -- for uniform scalars, for ONE scalar repeated
+    (every entry of a window in one bucket: the shared-memory cursors serialise, ranks reach the chunk size), for trace-like
+    values (bytes, many zeros: most digits vanish, bins of very different sizes) and over a sub-range of bases that contains
+    flagged identities."""
+    from oracle import cpu_ref as R
+
+    n = 1 << 18
+    rng = np.random.default_rng(77)
+
+    def mont_rows(count):
+        a = rng.integers(0, 1 << 64, size=(count, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 60) - 1)
+        return a
+
+    k = mont_rows(n)
+    if kind == "offset_and_infinity":
+        k[5000:5040] = 0  # k = 0: identity bases, flagged and skipped (msm/mod.zig:407)
+    bases = Z.Bases.fixed_base_mul(ctx, k)
+    bases.precompute(16)  # c = 16: 2^15 buckets = 64 bins of 512, 16 windows
+    if kind in ("uniform", "offset_and_infinity"):
+        s = mont_rows(n)
+    elif kind == "all_equal":
+        s = np.repeat(mont_rows(1), n, axis=0)
+    else:
+        raw = np.zeros((n, 4), dtype=np.uint64)
+        raw[:, 0] = rng.integers(0, 256, size=n, dtype=np.uint64)
+        raw[::3, 0] = 0
+        s = ctx.field_op(Z.FIELD_FR, Z.OP_TO_MONT, raw)
+    off, cnt = (1 << 10, n - (1 << 10)) if kind == "offset_and_infinity" else (0, n)
+    d_s = Z.DeviceBuffer.from_host(ctx, s[:cnt])
+    try:
+        ctx.set_tuning(TUNE_MSM_SORT, 1)
+        ref = Z.MSM.compute_dev(bases, d_s.ptr, cnt, offset=off)
+        ctx.set_tuning(TUNE_MSM_SORT, 0)
+        got = Z.MSM.compute_dev(bases, d_s.ptr, cnt, offset=off)
+        assert (got[0] == ref[0]).all() and got[1] == ref[1], "two-pass sort and atomic scatter disagree"
+        dot = R.fr_dot(k[off:off + cnt], s[:cnt], threads=8)  # Montgomery limbs of sum k_i s_i
+        want = B.g1_mul(B.G1_GEN, B.mont_array_to_ints(dot.reshape(1, 4), P)[0])
+        assert point_from_out(*got) == want
+    finally:
+        ctx.set_tuning(TUNE_MSM_SORT, 0)
+        d_s.free()
+        bases.free()
