@@ -82,7 +82,7 @@ struct zolt_ctx {
   int sc_bind_f64 = 0;  // mask of the tables whose binds run on the FP64 pipe in a fused sumcheck pass (ZOLT_TUNE_SC_BIND_F64; measured: no gain)
   // second stream + events for the host-scalar MSM: the second half of the scalars crosses PCIe during the first half's MSM
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_gate = nullptr, ev_copied = nullptr;
+  cudaEvent_t ev_gate = nullptr, ev_copied = nullptr, ev_copied2 = nullptr;
   unsigned mail_seq = 0;  // last sequence number handed to a kernel that reports through a mapped host mailbox
   // phase profiling (CUDA events on `stream`): begin/end pairs tagged by the caller
   static constexpr int kMaxProf = 96;

@@ -63,6 +63,7 @@ extern "C" int zolt_gpu_shutdown(zolt_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_gate) cudaEventDestroy(ctx->ev_gate);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->ev_copied2) cudaEventDestroy(ctx->ev_copied2);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ZOLT_OK;

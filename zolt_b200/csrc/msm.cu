@@ -1375,9 +1375,9 @@ extern "C" int zolt_msm_dev(zolt_ctx* ctx, const zolt_bases* bases, size_t offse
 }
 
 // sum_i scalars[i] * bases[offset + i] for HOST scalars, left on the device as one XYZZ point (d_out[0]; d_out needs room
-// for 3 points).  Large inputs: the scalars take ~10 ms per 2^24 over PCIe, so the points are split in two ranges
-// (ParallelMSM's split, src/msm/mod.zig:608-653, used here for overlap): the second half is copied on a second stream while
-// the first half is multiplied, then the two partial sums are added.  Same group element either way.
+// for 4 points).  Large inputs: the scalars take ~10 ms per 2^24 over PCIe, so the points are split in ranges
+// (ParallelMSM's split, src/msm/mod.zig:608-653, used here for overlap): every range but the first is copied on a second
+// stream while the range before it is multiplied, then the partial sums are added.  Same group element either way.
 static int msm_host_partial(zolt_ctx* ctx, const zolt_bases* bases, size_t offset, const uint64_t* scalars, size_t n, XYZZ* d_out) {
   Fr* d_s = nullptr;
   ZOLT_TRY(staging_for(ctx, n * sizeof(Fr), &d_s));
@@ -1389,17 +1389,39 @@ static int msm_host_partial(zolt_ctx* ctx, const zolt_bases* bases, size_t offse
     ZOLT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     ZOLT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_gate, cudaEventDisableTiming));
     ZOLT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+    ZOLT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied2, cudaEventDisableTiming));
   }
-  const size_t n0 = (n + 1) / 2, n1 = n - n0;
-  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, n0 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  ZOLT_CUDA_TRY(cudaEventRecord(ctx->ev_gate, ctx->stream));  // the second copy queues behind the first on the bus
-  ZOLT_TRY(msm_core(ctx, bases, offset, d_s, 1, n0, d_out + 1));
+  // Point ranges whose uploads hide behind the MSM of the range before: the bus moves a scalar ~4x faster than the GPU
+  // multiplies it, so a small first range (the only upload nobody hides) followed by growing ones -- 1/8, 3/8, 4/8 from 2^23
+  // points (e2e 2^24: 42.9 -> 40.9 ms), two halves below that (every extra range pays the per-call fixed costs once more).
+  size_t part[3];
+  int parts;
+  if (n >= (size_t(1) << 23)) {
+    parts = 3;
+    part[0] = n / 8;
+    part[1] = 3 * (n / 8);
+    part[2] = n - part[0] - part[1];
+  } else {
+    parts = 2;
+    part[0] = (n + 1) / 2;
+    part[1] = n - part[0];
+  }
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s, scalars, part[0] * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  ZOLT_CUDA_TRY(cudaEventRecord(ctx->ev_gate, ctx->stream));  // the later copies queue behind the first on the bus
   ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gate, 0));
-  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s + n0, scalars + 4 * n0, n1 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
-  ZOLT_CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
-  ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
-  ZOLT_TRY(msm_core(ctx, bases, offset + n0, d_s + n0, 1, n1, d_out + 2));
-  g1_sum_partials_kernel<<<1, 1, 0, ctx->stream>>>(d_out + 1, 2, d_out);
+  // Each range's MSM is launched BEFORE the next range's copy is issued: from pageable host memory cudaMemcpyAsync blocks
+  // the calling thread, and that time should pass while the GPU multiplies.
+  size_t done = 0;
+  for (int i = 0; i < parts; i++) {
+    if (i > 0) ZOLT_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, i == 1 ? ctx->ev_copied : ctx->ev_copied2, 0));
+    ZOLT_TRY(msm_core(ctx, bases, offset + done, d_s + done, 1, part[i], d_out + 1 + i));
+    done += part[i];
+    if (i + 1 < parts) {
+      ZOLT_CUDA_TRY(cudaMemcpyAsync(d_s + done, scalars + 4 * done, part[i + 1] * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+      ZOLT_CUDA_TRY(cudaEventRecord(i == 0 ? ctx->ev_copied : ctx->ev_copied2, ctx->copy_stream));
+    }
+  }
+  g1_sum_partials_kernel<<<1, 1, 0, ctx->stream>>>(d_out + 1, parts, d_out);
   ctx->launches++;
   ZOLT_CUDA_TRY(cudaGetLastError());
   return ZOLT_OK;
