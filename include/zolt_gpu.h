@@ -225,6 +225,10 @@ int zolt_poly_bind_first(zolt_ctx* ctx, void* d_dst, const void* d_src, size_t n
  * eq(r, x), r[0] <-> MSB of the index; scale may be NULL (= one).  d_out holds 2^n_vars elements. */
 int zolt_eq_evals(zolt_ctx* ctx, const uint64_t* r /* n_vars*4 */, int n_vars, const uint64_t* scale,
                   void* d_out);
+/* EqPlusOnePolynomial.mle(r, j) for every j in {0,1}^n_vars (src/poly/mod.zig:387-421; the table the Stage 3 provers build with
+ * one mle per entry, src/zkvm/spartan/stage3_prover.zig:1878-1895): eq+1(r, j) = 1 iff j = r + 1 on the hypercube; r[0] <-> MSB
+ * of the index like zolt_eq_evals.  d_out holds 2^n_vars elements. */
+int zolt_eq_plus_one_evals(zolt_ctx* ctx, const uint64_t* r /* n_vars*4 */, int n_vars, void* d_out);
 /* sum of all entries (initial sumcheck claim, src/subprotocols/mod.zig:306-309) */
 int zolt_poly_sum(zolt_ctx* ctx, const void* d_src, size_t n, uint64_t out[4]);
 /* BatchOps.innerProduct (src/field/mod.zig:1164-1280) over device tables: sum_i a[i] * b[i] */
@@ -247,6 +251,12 @@ int zolt_fr_inner_product_dev(zolt_ctx* ctx, const void* d_a, const void* d_b, s
 #define ZOLT_VEC_STAGE4_TERM 5
 int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d_a, const void* d_b, const void* d_c, const void* d_e,
                     const uint64_t* s /* 4, AXPY only */, size_t n);
+
+/* d_out[x_lo] = scale * sum_{x_hi < n_hi} d_in[x_lo + x_hi * n_lo] * d_w[x_hi] for x_lo < n_lo (scale NULL = one): the Q buffers of
+ * the prefix-suffix provers, a trace column folded over the high half of the cycle index against the suffix table
+ * (ShiftPrefixSuffixProver.init, src/zkvm/spartan/stage3_prover.zig:1053-1112; RegistersPrefixSuffixProver.init, :2262-2300). */
+int zolt_fr_fold_high_dev(zolt_ctx* ctx, void* d_out, const void* d_in, const void* d_w, size_t n_lo, size_t n_hi,
+                          const uint64_t* scale /* 4 or NULL */);
 
 /* dst[i] = src[((i / d1) % m1) * s1 + ((i / d2) % m2) * s2] for i < n: re-layouts between the phases of a prover --
  * transpose [k][j] -> [j][k] (d1 = 1, m1 = K, s1 = T, d2 = K, m2 = T, s2 = 1), a vector replicated over rows (d1 = 1,
@@ -301,7 +311,11 @@ enum {
    * (:764-1015) on tables transposed to [j][k] with eq and inc repeated over k -- an address round binds them to
    * themselves (the round polynomial then has degree 2 and p(3) is not used), a cycle round (k exhausted) is the
    * dense-eq cubic. */
-  ZOLT_SC_STAGE4_DENSE = 8
+  ZOLT_SC_STAGE4_DENSE = 8,
+  /* k=5 (w, a, b, c, d) -> [p(0), p(2), p(3)] of sum w(X) (a(X) b(X) + c(X) d(X)): one operand side of InstructionInputProver
+   * (src/zkvm/spartan/stage3_prover.zig:2029-2105; right = is_rs2 * rs2 + is_imm * imm, left = is_rs1 * rs1 + is_pc * pc under
+   * the weight eq_outer + gamma^2 eq_product -- the host adds right + gamma * left, exact in the field).  Adjacent pairs only. */
+  ZOLT_SC_EQ_DOT2 = 9
 };
 
 /* tables: k host pointers (n*4 u64 each), n = 2^log_n.  n_extra further tables are bound in

@@ -27,6 +27,7 @@ from ._lib import (  # noqa: F401
     SC_GRUEN_AB,
     SC_GRUEN_AB_MINUS_C,
     SC_STAGE4_DENSE,
+    SC_EQ_DOT2,
     SC_STAGE4_GRUEN,
     SC_PROD2,
     SC_PROD3,

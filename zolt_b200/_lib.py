@@ -19,7 +19,7 @@ _ERR_NAMES = {1: "ZOLT_ERR_CUDA", 2: "ZOLT_ERR_ARG", 3: "ZOLT_ERR_STATE", 4: "ZO
 FIELD_FR, FIELD_FQ = 0, 1
 OP_MUL, OP_ADD, OP_SUB, OP_INV, OP_FROM_MONT, OP_TO_MONT, OP_NEG = range(7)
 PAIR_ADJACENT, PAIR_HALF = 0, 1
-SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN_AB_MINUS_C, SC_STAGE4_GRUEN, SC_STAGE4_DENSE = range(9)
+SC_SUM, SC_PROD2, SC_PROD3, SC_EQ_A_BMC, SC_EQ_AB_MINUS_C, SC_GRUEN_AB, SC_GRUEN_AB_MINUS_C, SC_STAGE4_GRUEN, SC_STAGE4_DENSE, SC_EQ_DOT2 = range(10)
 TUNE_SC_SMALL_PAIRS = 1
 G1_WIRE_BE, G1_WIRE_LE, G1_WIRE_ARK_LE = 0, 1, 2
 TUNE_SC_BIND_F64 = 2
@@ -92,6 +92,8 @@ SIGNATURES = {
     "zolt_poly_bind_first": [_vp, _vp, _vp, _sz, _vp],
     "zolt_eq_evals": [_vp, _vp, _i, _vp, _vp],
     "zolt_poly_sum": [_vp, _vp, _sz, _vp],
+    "zolt_eq_plus_one_evals": [_vp, _vp, _i, _vp],
+    "zolt_fr_fold_high_dev": [_vp, _vp, _vp, _vp, _sz, _sz, _vp],
     "zolt_sc_create": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)],
     "zolt_sc_create_dev": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)],
     "zolt_sc_set_split_eq": [_vp, _vp, _i],

@@ -101,6 +101,7 @@ template <> struct CombTraits<ZOLT_SC_GRUEN_AB> { static constexpr int K = 2, NE
 template <> struct CombTraits<ZOLT_SC_GRUEN_AB_MINUS_C> { static constexpr int K = 3, NE = 2, NW = 2, DEG = 0; static constexpr bool GRUEN = true; };
 template <> struct CombTraits<ZOLT_SC_STAGE4_GRUEN> { static constexpr int K = 4, NE = 2, NW = 2, DEG = 0; static constexpr bool GRUEN = true; };
 template <> struct CombTraits<ZOLT_SC_STAGE4_DENSE> { static constexpr int K = 5, NE = 3, NW = 3, DEG = 0; static constexpr bool GRUEN = false; };
+template <> struct CombTraits<ZOLT_SC_EQ_DOT2> { static constexpr int K = 5, NE = 3, NW = 3, DEG = 0; static constexpr bool GRUEN = false; };
 
 constexpr int kRaw = 4;  // field elements per partial result
 
@@ -356,6 +357,25 @@ __device__ __forceinline__ void accumulate_pair(uint32_t (*wacc)[16], Fr* facc, 
     wide_acc(wacc[0], e0, c0);
     wide_acc(wacc[1], e2, c2);
     wide_acc(wacc[2], fr_add(e2, de), c3);
+  } else if constexpr (COMB == ZOLT_SC_EQ_DOT2) {
+    // w(X) * (a(X) b(X) + c(X) d(X)) at X = 0, 2, 3: one side of InstructionInputProver.computeRoundEvals
+    // (stage3_prover.zig:2029-2105: flag * value + flag * value under the eq weight, sampled where the reference samples).
+    // Each inner sum is two products under one Montgomery reduction.
+    Fr s0, s2, s3;
+    {
+      const Fr a0 = LO(1), b0 = LO(2), c0 = LO(3), d0 = LO(4);
+      s0 = fp_mul2_add<FrParams>(a0, b0, c0, d0);
+      const Fr da = fr_sub(HI(1), a0), db = fr_sub(HI(2), b0), dc = fr_sub(HI(3), c0), dd = fr_sub(HI(4), d0);
+      const Fr a2 = fr_add(HI(1), da), b2 = fr_add(HI(2), db), c2 = fr_add(HI(3), dc), d2 = fr_add(HI(4), dd);
+      s2 = fp_mul2_add<FrParams>(a2, b2, c2, d2);
+      s3 = fp_mul2_add<FrParams>(fr_add(a2, da), fr_add(b2, db), fr_add(c2, dc), fr_add(d2, dd));
+    }
+    const Fr e0 = LO(0), e1 = HI(0);
+    const Fr de = fr_sub(e1, e0);
+    const Fr e2 = fr_add(e1, de);
+    wide_acc(wacc[0], e0, s0);
+    wide_acc(wacc[1], e2, s2);
+    wide_acc(wacc[2], fr_add(e2, de), s3);
   }
 #undef LO
 #undef HI
@@ -990,7 +1010,7 @@ __device__ __noinline__ Fr small_term(const SmallArgs& a, int e, const Fr (*stas
   if (a.deg == 3) pt = e == 0 ? PT_0 : (e == 1 ? (a.p1_direct ? PT_1 : PT_NONE) : (e == 2 ? PT_2 : PT_LEAD));
   else if (a.deg == 2) pt = e == 0 ? PT_0 : (e == 1 ? (a.p1_direct ? PT_1 : PT_NONE) : (e == 2 ? PT_LEAD : PT_NONE));
   else if (gruen) pt = e == 0 ? PT_0 : (e == 1 ? PT_LEAD : PT_NONE);
-  else if (a.comb == ZOLT_SC_STAGE4_DENSE) pt = e == 0 ? PT_0 : (e == 1 ? PT_2 : (e == 2 ? PT_3 : PT_NONE));
+  else if (a.comb == ZOLT_SC_STAGE4_DENSE || a.comb == ZOLT_SC_EQ_DOT2) pt = e == 0 ? PT_0 : (e == 1 ? PT_2 : (e == 2 ? PT_3 : PT_NONE));
   else pt = e == 0 ? PT_0 : (e == 1 ? PT_1 : PT_NONE);
   if (pt == PT_NONE) return Fr::zero();
   Fr v[kSmallTables];
@@ -1018,6 +1038,8 @@ __device__ __noinline__ Fr small_term(const SmallArgs& a, int e, const Fr (*stas
     }
     case ZOLT_SC_STAGE4_DENSE:  // eq * (ra val + wa (val + inc)) at the sample point
       return fr_mul_cold(v[0], fr_add_cold(fr_mul_cold(v[1], v[3]), fr_mul_cold(v[2], fr_add_cold(v[3], v[4]))));
+    case ZOLT_SC_EQ_DOT2:  // w * (a b + c d) at the sample point
+      return fr_mul_cold(v[0], fr_add_cold(fr_mul_cold(v[1], v[2]), fr_mul_cold(v[3], v[4])));
     case ZOLT_SC_STAGE4_GRUEN: {  // weight * (ra val + wa (val + inc))
       const size_t x_out = (g >> sq.in_bits) & sq.out_mask, x_in = g & ((size_t(1) << sq.in_bits) - 1);
       const Fr w = fr_mul_cold(ld_fr(sq.e_out + x_out), ld_fr(sq.e_in + x_in));
@@ -1445,6 +1467,67 @@ __global__ void __launch_bounds__(kScThreads) eq_level_kernel(Fr* res, size_t si
 
 __global__ void set_one_kernel(Fr* p, Fr v) { st_fr(p, v); }
 
+// EqPlusOnePolynomial.mle(r, j) for every j in {0,1}^n (src/poly/mod.zig:387-421, tabulated by stage3_prover.zig:1878-1895 with
+// one O(n^2) mle per entry).  For a boolean point only the term k = (number of trailing zeros of j) survives -- the low k bits
+// of y must be 0 and bit k must be 1 -- so entry j is  prod_{i<k} r_i' * (1 - r_k') * prod_{i>k} (j_i ? r_i' : 1 - r_i'),
+// r_i' = r[n-1-i] (bit 0 of the index pairs with the LAST coordinate); entry 0 is zero.  The vanishing terms are exact zeros
+// in the reference's sum, so the field elements are the same.
+__global__ void __launch_bounds__(kScThreads) eq_plus_one_kernel(Fr* __restrict__ out, const Fr* __restrict__ r, int n) {
+  const size_t size = size_t(1) << n;
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < size; j += (size_t)gridDim.x * blockDim.x) {
+    if (j == 0) {
+      st_fr(out, Fr::zero());
+      continue;
+    }
+    const int k = __ffsll((long long)j) - 1;
+    Fr acc = fr_sub(Fr::one(), r[n - 1 - k]);
+    for (int i = 0; i < k; i++) acc = fr_mul(acc, r[n - 1 - i]);
+    for (int i = k + 1; i < n; i++) {
+      const Fr x = r[n - 1 - i];
+      acc = fr_mul(acc, ((j >> i) & 1) ? x : fr_sub(Fr::one(), x));
+    }
+    st_fr(out + j, acc);
+  }
+}
+
+// out[x_lo] = scale * sum_{x_hi} in[x_lo + x_hi * n_lo] * w[x_hi]: the Q buffers of the prefix-suffix provers
+// (stage3_prover.zig:1053-1112 ShiftPrefixSuffixProver.init, :2262-2300 RegistersPrefixSuffixProver.init), an O(T) weighted
+// fold of a trace column over the HIGH half of the cycle index.  A warp reads 32 consecutive x_lo (1 KB) of one row, the
+// rows are dealt to the warps of the block and to gridDim.y row slices; unreduced 512-bit sums per thread.
+constexpr int kFoldWarps = 8;
+__global__ void __launch_bounds__(32 * kFoldWarps)
+fold_high_kernel(const Fr* __restrict__ in, const Fr* __restrict__ w, size_t n_lo, size_t n_hi, Fr* __restrict__ partial) {
+  __shared__ Fr smem[kFoldWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t x_lo = (size_t)blockIdx.x * 32 + lane;
+  uint32_t acc[16];
+  wide_zero(acc);
+  if (x_lo < n_lo) {
+    for (size_t x_hi = (size_t)blockIdx.y * kFoldWarps + warp; x_hi < n_hi; x_hi += (size_t)gridDim.y * kFoldWarps) {
+      const Fr v = ld_fr(in + x_lo + x_hi * n_lo), s = ld_fr(w + x_hi);
+      wide_acc(acc, v, s);
+    }
+  }
+  smem[warp][lane] = wide_collapse(acc);
+  __syncthreads();
+  if (warp == 0 && x_lo < n_lo) {
+    Fr t = smem[0][lane];
+#pragma unroll 1
+    for (int k = 1; k < kFoldWarps; k++) t = fr_add_cold(t, smem[k][lane]);
+    st_fr(partial + (size_t)blockIdx.y * n_lo + x_lo, t);
+  }
+}
+__global__ void __launch_bounds__(kScThreads)
+fold_finish_kernel(const Fr* __restrict__ partial, int slices, size_t n_lo, Fr* __restrict__ out, const Fr* __restrict__ scale) {
+  const size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (x >= n_lo) return;
+  Fr t = ld_fr(partial + x);
+#pragma unroll 1
+  for (int k = 1; k < slices; k++) t = fr_add_cold(t, ld_fr(partial + (size_t)k * n_lo + x));
+  if (scale) t = fr_mul_cold(t, ld_fr(scale));
+  st_fr(out + x, t);
+}
+
 // Element-wise construction of device-resident tables, one pass over HBM each.
 template <int OP>
 __global__ void __launch_bounds__(kScThreads)
@@ -1584,15 +1667,17 @@ int combiner_k(int comb) {
     case ZOLT_SC_GRUEN_AB_MINUS_C: return 3;
     case ZOLT_SC_STAGE4_GRUEN: return 4;
     case ZOLT_SC_STAGE4_DENSE: return 5;
+    case ZOLT_SC_EQ_DOT2: return 5;
     default: return -1;
   }
 }
 int combiner_ne(int comb) {
-  if (comb == ZOLT_SC_STAGE4_DENSE) return 3;
+  if (comb == ZOLT_SC_STAGE4_DENSE || comb == ZOLT_SC_EQ_DOT2) return 3;
   return (comb == ZOLT_SC_SUM || comb == ZOLT_SC_GRUEN_AB || comb == ZOLT_SC_GRUEN_AB_MINUS_C || comb == ZOLT_SC_STAGE4_GRUEN) ? 2 : 4;
 }
 bool combiner_gruen(int comb) { return comb == ZOLT_SC_GRUEN_AB || comb == ZOLT_SC_GRUEN_AB_MINUS_C || comb == ZOLT_SC_STAGE4_GRUEN; }
-bool combiner_stage4(int comb) { return comb == ZOLT_SC_STAGE4_GRUEN || comb == ZOLT_SC_STAGE4_DENSE; }
+// the combiners written for the Stage 3 / Stage 4 provers: adjacent pairs only, never sharded
+bool combiner_stage4(int comb) { return comb == ZOLT_SC_STAGE4_GRUEN || comb == ZOLT_SC_STAGE4_DENSE || comb == ZOLT_SC_EQ_DOT2; }
 
 SplitEqDev split_eq_for(const zolt_sc* sc, size_t n_cur) {
   // getWindowEqTables with window_size 1 (src/poly/split_eq.zig:311-343); u = unbound variables.
@@ -1849,7 +1934,8 @@ int launch_round_any(zolt_sc* sc, bool fused, const Fr& r) {
     case ZOLT_SC_GRUEN_AB_MINUS_C: return launch_round_p<ZOLT_SC_GRUEN_AB_MINUS_C>(sc, fused, r);
     // the Stage-4 combiners exist for adjacent pairs only (sc_alloc refuses the other pairing)
     case ZOLT_SC_STAGE4_GRUEN: return launch_round<ZOLT_SC_STAGE4_GRUEN, ZOLT_PAIR_ADJACENT>(sc, fused, r);
-    default: return launch_round<ZOLT_SC_STAGE4_DENSE, ZOLT_PAIR_ADJACENT>(sc, fused, r);
+    case ZOLT_SC_STAGE4_DENSE: return launch_round<ZOLT_SC_STAGE4_DENSE, ZOLT_PAIR_ADJACENT>(sc, fused, r);
+    default: return launch_round<ZOLT_SC_EQ_DOT2, ZOLT_PAIR_ADJACENT>(sc, fused, r);
   }
 }
 
@@ -2438,6 +2524,50 @@ extern "C" int zolt_eq_evals(zolt_ctx* ctx, const uint64_t* r, int n_vars, const
     size *= 2;
   }
   ZOLT_CUDA_TRY(cudaGetLastError());
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_eq_plus_one_evals(zolt_ctx* ctx, const uint64_t* r, int n_vars, void* d_out) {
+  if (!ctx || !d_out || n_vars < 1 || n_vars > 40 || !r) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Fr* d_r = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, 40 * sizeof(Fr), (void**)&d_r));
+  OnFail give_back([&] { pool_release(ctx, d_r, 40 * sizeof(Fr)); });
+  ZOLT_CUDA_TRY(cudaMemcpyAsync(d_r, r, (size_t)n_vars * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  eq_plus_one_kernel<<<grid_for(ctx, size_t(1) << n_vars, 8), kScThreads, 0, ctx->stream>>>((Fr*)d_out, d_r, n_vars);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // r is a borrowed host buffer
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_fr_fold_high_dev(zolt_ctx* ctx, void* d_out, const void* d_in, const void* d_w, size_t n_lo, size_t n_hi,
+                                     const uint64_t* scale) {
+  if (!ctx || !d_out || !d_in || !d_w || n_lo == 0 || n_hi == 0) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t tiles = (n_lo + 31) / 32;
+  // enough row slices to fill the device twice over, never more slices than groups of rows
+  size_t slices = (2 * (size_t)ctx->num_sms + tiles - 1) / tiles;
+  const size_t row_groups = (n_hi + kFoldWarps - 1) / kFoldWarps;
+  if (slices > row_groups) slices = row_groups;
+  if (slices > 1024) slices = 1024;
+  if (slices < 1) slices = 1;
+  const size_t bytes = (slices * n_lo + 1) * sizeof(Fr);
+  Fr* d_part = nullptr;
+  ZOLT_CUDA_TRY(pool_alloc(ctx, bytes, (void**)&d_part));
+  OnFail give_back([&] { pool_release(ctx, d_part, bytes); });  // runs on every exit
+  Fr* d_scale = nullptr;
+  if (scale) {
+    d_scale = d_part + slices * n_lo;
+    ZOLT_CUDA_TRY(cudaMemcpyAsync(d_scale, scale, sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  fold_high_kernel<<<dim3((unsigned)tiles, (unsigned)slices), 32 * kFoldWarps, 0, ctx->stream>>>((const Fr*)d_in, (const Fr*)d_w, n_lo,
+                                                                                             n_hi, d_part);
+  fold_finish_kernel<<<(unsigned)((n_lo + kScThreads - 1) / kScThreads), kScThreads, 0, ctx->stream>>>(d_part, (int)slices, n_lo,
+                                                                                                    (Fr*)d_out, d_scale);
+  ctx->launches += 2;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // scale is a borrowed host buffer; the partials go back to the cache
   return ZOLT_OK;
 }
 

@@ -56,6 +56,7 @@ def load_host() -> C.CDLL:
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]
         _host.zolt_host_stage4_run.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _host.zolt_host_stage3_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)] + [C.c_void_p] * 8
         _host.zolt_host_eq_mle.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         _host.zolt_host_horner_eval.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _host.zolt_host_dense_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -178,6 +179,27 @@ def stage4_run(ctx: Context, log_T: int, d_val, d_rd_wa, d_rs1_ra, d_rs2_ra, d_i
                                           _ptr(evals), _ptr(chal), _ptr(finals), _ptr(claims))
     _lib.check(st, "zolt_host_stage4_run")
     return evals, chal, finals, claims
+
+
+STAGE3_COLUMNS = ("shift.unexpanded_pc", "shift.pc", "shift.is_virtual", "shift.is_first_in_sequence", "shift.is_noop",
+                  "instr.left_is_rs1", "instr.rs1_value", "instr.left_is_pc", "instr.unexpanded_pc", "instr.right_is_rs2", "instr.rs2_value",
+                  "instr.right_is_imm", "instr.imm", "reg.rd_write_value", "reg.rs1_value", "reg.rs2_value")
+
+
+def stage3_run(ctx: Context, log_T: int, d_cols, r_outer, r_product, gammas, batching, challenges):
+    """The Stage 3 provers (src/zkvm/spartan/stage3_prover.zig) over 16 device-resident trace columns (STAGE3_COLUMNS order),
+    driven by the caller's challenges.  gammas: shift gamma_powers[0..4], instr gamma, reg gamma.  Returns
+    (evals (rounds, 14, 4): shift 3 | instr 4 | reg 3 | combined 4, claims (6, 4): 3 input + 3 final, finals (16, 4))."""
+    assert len(d_cols) == 16
+    arr = (C.c_void_p * 16)(*d_cols)
+    ro, rp, g, b, ch = (_as_u64(x, 4) for x in (r_outer, r_product, gammas, batching, challenges))
+    evals = np.zeros((log_T, 14, 4), dtype=np.uint64)
+    claims = np.zeros((6, 4), dtype=np.uint64)
+    finals = np.zeros((16, 4), dtype=np.uint64)
+    st = load_host().zolt_host_stage3_run(ctx.handle, log_T, arr, _ptr(ro), _ptr(rp), _ptr(g), _ptr(b), _ptr(ch), _ptr(evals), _ptr(claims),
+                                          _ptr(finals))
+    _lib.check(st, "zolt_host_stage3_run")
+    return evals, claims, finals
 
 
 def eq_mle(r, x) -> np.ndarray:

@@ -202,6 +202,50 @@ int zolt_host_stage4_run(zolt_ctx* ctx, int log_T, const void* d_val, const void
   return ZOLT_OK;
 }
 
+// Stage 3 (stage3_prover.zig): the three provers over device-resident trace columns, driven by the caller's challenges like
+// generateStage3Proof's loop (:393-560).  cols: 16 device pointers -- shift (unexpanded_pc, pc, is_virtual,
+// is_first_in_sequence, is_noop), instr (left_is_rs1, rs1_value, left_is_pc, unexpanded_pc, right_is_rs2, rs2_value,
+// right_is_imm, imm), reg (rd_write_value, rs1_value, rs2_value).  gammas: shift gamma_powers[0..4], instr gamma, reg gamma.
+// evals_out: rounds x 14 field elements (shift 3, instr 4, reg 3, combined 4); claims_out: the 3 input claims then the 3
+// claims after the last round; finals_out: the 16 final claims in the order of cols.
+int zolt_host_stage3_run(zolt_ctx* ctx, int log_T, const void* const* cols, const uint64_t* r_outer, const uint64_t* r_product,
+                         const uint64_t* gammas, const uint64_t* batching, const uint64_t* challenges, uint64_t* evals_out,
+                         uint64_t* claims_out, uint64_t* finals_out) {
+  using namespace stage3;
+  Context c(ctx);
+  std::vector<Fr> ro(log_T), rp(log_T), gp(5);
+  for (int i = 0; i < log_T; i++) {
+    ro[i] = Fr::fromRaw(r_outer + 4 * i);
+    rp[i] = Fr::fromRaw(r_product + 4 * i);
+  }
+  for (int i = 0; i < 5; i++) gp[i] = Fr::fromRaw(gammas + 4 * i);
+  const Fr ig = Fr::fromRaw(gammas + 20), rg = Fr::fromRaw(gammas + 24);
+  ShiftPrefixSuffixProver shift(c, log_T, {cols[0], cols[1], cols[2], cols[3], cols[4]}, ro, rp, gp);
+  InstructionInputProver instr(c, log_T, {cols[5], cols[6], cols[7], cols[8], cols[9], cols[10], cols[11], cols[12]}, ro, rp, ig, ig.mul(ig));
+  RegistersPrefixSuffixProver reg(c, log_T, {cols[13], cols[14], cols[15]}, ro, rg, rg.mul(rg));
+  Provers all{shift, instr, reg, {shift.inputClaim(), instr.inputClaim(), reg.inputClaim()}};
+  for (int i = 0; i < 3; i++) all.claims[i].store(claims_out + 4 * i);
+  const std::array<Fr, 3> bc = {Fr::fromRaw(batching), Fr::fromRaw(batching + 4), Fr::fromRaw(batching + 8)};
+  for (int round = 0; round < log_T; round++) {
+    const RoundEvals e = all.computeRound(bc);
+    uint64_t* o = evals_out + (size_t)round * 14 * 4;
+    for (int i = 0; i < 3; i++) e.shift[i].store(o + 4 * i);
+    for (int i = 0; i < 4; i++) e.instr[i].store(o + 12 + 4 * i);
+    for (int i = 0; i < 3; i++) e.reg[i].store(o + 28 + 4 * i);
+    for (int i = 0; i < 4; i++) e.combined[i].store(o + 40 + 4 * i);
+    all.bind(e, Fr::fromRaw(challenges + 4 * round));
+  }
+  for (int i = 0; i < 3; i++) all.claims[i].store(claims_out + 12 + 4 * i);
+  const ShiftPrefixSuffixProver::FinalClaims sf = shift.finalClaims();
+  const InstructionInputProver::FinalClaims inf = instr.finalClaims();
+  const RegistersPrefixSuffixProver::FinalClaims rf = reg.finalClaims();
+  const Fr fin[16] = {sf.unexpanded_pc, sf.pc, sf.is_virtual, sf.is_first_in_sequence, sf.is_noop,
+                      inf.left_is_rs1, inf.rs1_value, inf.left_is_pc, inf.unexpanded_pc, inf.right_is_rs2, inf.rs2_value, inf.right_is_imm, inf.imm,
+                      rf.rd_write_value, rf.rs1_value, rf.rs2_value};
+  for (int i = 0; i < 16; i++) fin[i].store(finals_out + 4 * i);
+  return ZOLT_OK;
+}
+
 // SRS container parsers: kind 0 raw binary (srs.zig:256-306), 1 snarkjs PTAU (:733-900), 2 Jolt Dory SRS (dory.zig:740-826).
 // Returns the srs::Error code (0 = ok); *bases_out is a zolt_bases handle the caller frees.
 int zolt_host_srs_load(zolt_ctx* ctx, int kind, const uint8_t* data, size_t len, zolt_bases** bases_out, size_t* count,

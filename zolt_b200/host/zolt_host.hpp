@@ -758,6 +758,414 @@ class Stage4GruenProver {
   std::vector<std::pair<void*, size_t>> owned_;
 };
 
+// ---- Stage 3 (src/zkvm/spartan/stage3_prover.zig): Shift, InstructionInput and RegistersClaimReduction provers ------------
+// The provers are entered with the trace COLUMNS they read out of cycle_witnesses (device tables of 2^log_T elements, only
+// read).  Everything O(T) runs on the device:
+//   * Q buffers: zolt_fr_fold_high_dev (column folded over the high half of the cycle index against the suffix table);
+//   * phase 1 of the prefix-suffix provers: ONE ZOLT_SC_PROD2 instance over the P buffers / the Q buffers laid end to end
+//     (adjacent pairs never straddle two buffers, low-to-high binds keep the blocks apart);
+//   * the witness columns bound in lock-step by a ZOLT_SC_SUM instance with extra tables -- the reference rebuilds them at
+//     the transition as sum_i eq(r_prefix, i) w[j P + i] (:1626-1707), which is the same field element as the chain of binds;
+//   * phase 2: ZOLT_SC_PROD2 instances (eq x batched value) with the columns as bound-only extras for finalClaims;
+//   * InstructionInputProver: two ZOLT_SC_EQ_DOT2 instances (right and left operand) under w = eq_outer + gamma^2 eq_product.
+// Batched values (linear combinations of columns) are built with ZOLT_VEC_LIN2: binding is linear, so the bound batched
+// table is the batched bound tables, exactly.
+namespace stage3 {
+
+class DevPool {
+ public:
+  explicit DevPool(Context& ctx) : ctx_(ctx) {}
+  ~DevPool() {
+    for (auto& b : owned_) zolt_dev_release_cached(ctx_.raw(), b.first, b.second);
+  }
+  DevPool(const DevPool&) = delete;
+  DevPool& operator=(const DevPool&) = delete;
+  Fr* alloc(size_t elems) {
+    void* p = nullptr;
+    const size_t bytes = (elems ? elems : 1) * sizeof(Fr);
+    must(zolt_dev_alloc_cached(ctx_.raw(), bytes, &p), "zolt_dev_alloc_cached");
+    owned_.emplace_back(p, bytes);
+    return static_cast<Fr*>(p);
+  }
+  // out = s0 a + s1 b
+  void lin2(Fr* out, const void* a, const Fr& s0, const void* b, const Fr& s1, size_t n) {
+    const Fr s[2] = {s0, s1};
+    must(zolt_fr_vec_dev(ctx_.raw(), ZOLT_VEC_LIN2, out, a, b, nullptr, nullptr, reinterpret_cast<const uint64_t*>(s), n), "zolt_fr_vec_dev");
+  }
+  void fill(Fr* out, const Fr& v, size_t n) {
+    const Fr s[2] = {v, Fr::zero()};
+    must(zolt_fr_vec_dev(ctx_.raw(), ZOLT_VEC_AFFINE_INDEX, out, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const uint64_t*>(s), n),
+         "zolt_fr_vec_dev");
+  }
+  void eq(Fr* out, const std::vector<Fr>& r) {
+    if (r.empty()) return fill(out, Fr::one(), 1);
+    must(zolt_eq_evals(ctx_.raw(), reinterpret_cast<const uint64_t*>(r.data()), (int)r.size(), nullptr, out), "zolt_eq_evals");
+  }
+  void eqPlusOne(Fr* out, const std::vector<Fr>& r) {
+    if (r.empty()) return fill(out, Fr::zero(), 1);  // the empty sum of EqPlusOnePolynomial.mle
+    must(zolt_eq_plus_one_evals(ctx_.raw(), reinterpret_cast<const uint64_t*>(r.data()), (int)r.size(), out), "zolt_eq_plus_one_evals");
+  }
+  void fold(Fr* out, const void* in, const void* w, size_t n_lo, size_t n_hi, const Fr* scale = nullptr) {
+    must(zolt_fr_fold_high_dev(ctx_.raw(), out, in, w, n_lo, n_hi, scale ? scale->limbs.data() : nullptr), "zolt_fr_fold_high_dev");
+  }
+  void put(Fr* d, const Fr& v) { must(zolt_dev_upload(ctx_.raw(), d, &v, sizeof(Fr)), "zolt_dev_upload"); }
+  Context& ctx() { return ctx_; }
+
+ private:
+  Context& ctx_;
+  std::vector<std::pair<void*, size_t>> owned_;
+};
+
+inline std::array<Fr, 4> scEvals(zolt_sc* sc) {
+  uint64_t buf[16] = {0};
+  must(zolt_sc_round_evals(sc, buf), "zolt_sc_round_evals");
+  return {Fr::fromRaw(buf), Fr::fromRaw(buf + 4), Fr::fromRaw(buf + 8), Fr::fromRaw(buf + 12)};
+}
+inline void scBind(zolt_sc* sc, const Fr& r) { must(zolt_sc_bind(sc, r.limbs.data()), "zolt_sc_bind"); }
+inline Fr scEntry(Context& ctx, zolt_sc* sc, int table, size_t index = 0) {
+  const void* d = nullptr;
+  must(zolt_sc_table_dev(sc, table, &d), "zolt_sc_table_dev");
+  Fr v;
+  must(zolt_dev_download(ctx.raw(), &v, static_cast<const Fr*>(d) + index, sizeof(Fr)), "zolt_dev_download");
+  return v;
+}
+inline const void* scTable(zolt_sc* sc, int table) {
+  const void* d = nullptr;
+  must(zolt_sc_table_dev(sc, table, &d), "zolt_sc_table_dev");
+  return d;
+}
+inline Fr product(const std::vector<Fr>& r) {
+  Fr m = Fr::one();
+  for (const Fr& x : r) m = m.mul(x);
+  return m;
+}
+
+// InstructionInputProver (:1921-2150): degree 3, evaluations [p(0), p(1), p(2), p(3)]
+class InstructionInputProver {
+ public:
+  struct Columns {
+    const void *left_is_rs1, *rs1_value, *left_is_pc, *unexpanded_pc, *right_is_rs2, *rs2_value, *right_is_imm, *imm;
+  };
+  struct FinalClaims {
+    Fr left_is_rs1, rs1_value, left_is_pc, unexpanded_pc, right_is_rs2, rs2_value, right_is_imm, imm;
+  };
+  InstructionInputProver(Context& ctx, int log_T, const Columns& c, const std::vector<Fr>& r_outer, const std::vector<Fr>& r_product,
+                         const Fr& gamma, const Fr& gamma_sqr)
+      : pool_(ctx), gamma_(gamma), cols_(c), T_(size_t(1) << log_T) {
+    if (log_T < 1 || (int)r_outer.size() != log_T || (int)r_product.size() != log_T) panic("InstructionInputProver: bad point", ZOLT_ERR_ARG);
+    const size_t T = T_;
+    Fr* eo = pool_.alloc(T);
+    Fr* ep = pool_.alloc(T);
+    pool_.eq(eo, r_outer);
+    pool_.eq(ep, r_product);
+    w_ = pool_.alloc(T);
+    pool_.lin2(w_, eo, Fr::one(), ep, gamma_sqr, T);
+    const void* right[5] = {w_, c.right_is_rs2, c.rs2_value, c.right_is_imm, c.imm};
+    const void* left[5] = {w_, c.left_is_rs1, c.rs1_value, c.left_is_pc, c.unexpanded_pc};
+    must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_EQ_DOT2, ZOLT_PAIR_ADJACENT, log_T, 5, 0, right, &right_), "zolt_sc_create_dev");
+    must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_EQ_DOT2, ZOLT_PAIR_ADJACENT, log_T, 5, 0, left, &left_), "zolt_sc_create_dev");
+  }
+  ~InstructionInputProver() {
+    if (right_) zolt_sc_free(right_);
+    if (left_) zolt_sc_free(left_);
+  }
+  // sum_i w_i (right_i + gamma left_i): the full_sum of :262-276 (what the opening claims must add up to)
+  // (in the prover it comes from the opening claims, computeInstructionInputClaim :808-825; call before the first bind)
+  Fr inputClaim() {
+    auto mul = [&](Fr* out, const void* a, const void* b) {
+      must(zolt_fr_vec_dev(pool_.ctx().raw(), ZOLT_VEC_MUL, out, a, b, nullptr, nullptr, nullptr, T_), "zolt_fr_vec_dev");
+    };
+    Fr* x = pool_.alloc(T_);
+    Fr* y = pool_.alloc(T_);
+    Fr* right = pool_.alloc(T_);
+    Fr* left = pool_.alloc(T_);
+    mul(x, cols_.right_is_rs2, cols_.rs2_value);
+    mul(y, cols_.right_is_imm, cols_.imm);
+    pool_.lin2(right, x, Fr::one(), y, Fr::one(), T_);
+    mul(x, cols_.left_is_rs1, cols_.rs1_value);
+    mul(y, cols_.left_is_pc, cols_.unexpanded_pc);
+    pool_.lin2(left, x, Fr::one(), y, Fr::one(), T_);
+    pool_.lin2(x, right, Fr::one(), left, gamma_, T_);
+    Fr claim;
+    must(zolt_fr_inner_product_dev(pool_.ctx().raw(), w_, x, T_, claim.limbs.data()), "zolt_fr_inner_product_dev");
+    return claim;
+  }
+  std::array<Fr, 4> computeRoundEvals(const Fr& previous_claim) {
+    const std::array<Fr, 4> r = scEvals(right_), l = scEvals(left_);  // [p(0), p(2), p(3)] of each side
+    const Fr p0 = r[0].add(gamma_.mul(l[0]));
+    return {p0, previous_claim.sub(p0), r[1].add(gamma_.mul(l[1])), r[2].add(gamma_.mul(l[2]))};
+  }
+  void bind(const Fr& r_j) {
+    scBind(right_, r_j);
+    scBind(left_, r_j);
+  }
+  FinalClaims finalClaims() {
+    return {scEntry(pool_.ctx(), left_, 1), scEntry(pool_.ctx(), left_, 2), scEntry(pool_.ctx(), left_, 3), scEntry(pool_.ctx(), left_, 4),
+            scEntry(pool_.ctx(), right_, 1), scEntry(pool_.ctx(), right_, 2), scEntry(pool_.ctx(), right_, 3), scEntry(pool_.ctx(), right_, 4)};
+  }
+
+ private:
+  DevPool pool_;
+  Fr gamma_;
+  Columns cols_;
+  size_t T_;
+  Fr* w_ = nullptr;
+  zolt_sc* right_ = nullptr;
+  zolt_sc* left_ = nullptr;
+};
+
+// ShiftPrefixSuffixProver (:928-1920): degree 2, evaluations [p(0), p(1), p(2)]
+class ShiftPrefixSuffixProver {
+ public:
+  struct Columns {
+    const void *unexpanded_pc, *pc, *is_virtual, *is_first_in_sequence, *is_noop;
+  };
+  struct FinalClaims {
+    Fr unexpanded_pc, pc, is_virtual, is_first_in_sequence, is_noop;
+  };
+  ShiftPrefixSuffixProver(Context& ctx, int log_T, const Columns& c, const std::vector<Fr>& r_outer, const std::vector<Fr>& r_product,
+                          const std::vector<Fr>& gamma_powers)
+      : pool_(ctx), gp_(gamma_powers) {
+    if (log_T < 2 || (int)r_outer.size() != log_T || (int)r_product.size() != log_T || gamma_powers.size() < 5)
+      panic("ShiftPrefixSuffixProver: bad arguments", ZOLT_ERR_ARG);
+    const int split = log_T / 2;
+    prefix_vars_ = log_T - split;
+    suffix_vars_ = split;
+    const size_t ps = size_t(1) << prefix_vars_, ss = size_t(1) << suffix_vars_, T = size_t(1) << log_T;
+    r_hi_[0].assign(r_outer.begin(), r_outer.begin() + split);
+    r_hi_[1].assign(r_product.begin(), r_product.begin() + split);
+    const std::vector<Fr> lo_o(r_outer.begin() + split, r_outer.end()), lo_p(r_product.begin() + split, r_product.end());
+    // P buffers end to end: eq+1(r_lo, .), is_max(r_lo) delta_0, for r_outer then r_product (:1006-1030)
+    Fr* P = pool_.alloc(4 * ps);
+    pool_.eqPlusOne(P, lo_o);
+    pool_.fill(P + ps, Fr::zero(), ps);
+    pool_.put(P + ps, product(lo_o));
+    pool_.eqPlusOne(P + 2 * ps, lo_p);
+    pool_.fill(P + 3 * ps, Fr::zero(), ps);
+    pool_.put(P + 3 * ps, product(lo_p));
+    // suffix tables eq(r_hi, .), eq+1(r_hi, .) (:1046-1047)
+    for (int k = 0; k < 2; k++) {
+      suf_[2 * k] = pool_.alloc(ss);
+      suf_[2 * k + 1] = pool_.alloc(ss);
+      pool_.eq(suf_[2 * k], r_hi_[k]);
+      pool_.eqPlusOne(suf_[2 * k + 1], r_hi_[k]);
+    }
+    // v = upc + gamma pc + gamma^2 virt + gamma^3 first, nn = 1 - noop (:1086-1098)
+    Fr* t1 = pool_.alloc(T);
+    Fr* t2 = pool_.alloc(T);
+    Fr* v = pool_.alloc(T);
+    pool_.lin2(t1, c.unexpanded_pc, Fr::one(), c.pc, gp_[1], T);
+    pool_.lin2(t2, c.is_virtual, gp_[2], c.is_first_in_sequence, gp_[3], T);
+    pool_.lin2(v, t1, Fr::one(), t2, Fr::one(), T);
+    pool_.fill(t1, Fr::one(), T);
+    pool_.lin2(t2, t1, Fr::one(), c.is_noop, Fr::one().neg(), T);  // nn
+    Fr* Q = pool_.alloc(4 * ps);
+    pool_.fold(Q, v, suf_[0], ps, ss);
+    pool_.fold(Q + ps, v, suf_[1], ps, ss);
+    pool_.fold(Q + 2 * ps, t2, suf_[2], ps, ss, &gp_[4]);
+    pool_.fold(Q + 3 * ps, t2, suf_[3], ps, ss, &gp_[4]);
+    const void* pq[2] = {P, Q};
+    must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_PROD2, ZOLT_PAIR_ADJACENT, prefix_vars_ + 2, 2, 0, pq, &pq_), "zolt_sc_create_dev");
+    const void* wit[5] = {c.unexpanded_pc, c.pc, c.is_virtual, c.is_first_in_sequence, c.is_noop};
+    must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_SUM, ZOLT_PAIR_ADJACENT, log_T, 1, 4, wit, &wit_), "zolt_sc_create_dev");
+  }
+  ~ShiftPrefixSuffixProver() {
+    for (zolt_sc* s : {pq_, wit_, a_, b_})
+      if (s) zolt_sc_free(s);
+  }
+  // grand_sum(P * Q) (:1131-1139)
+  Fr inputClaim() {
+    const std::array<Fr, 4> e = scEvals(pq_);
+    return e[0].add(e[1]);
+  }
+  std::array<Fr, 3> computeRoundEvals(const Fr& previous_claim) {
+    if (!in_phase2_) {
+      const std::array<Fr, 4> e = scEvals(pq_);
+      return {e[0], e[1], e[2]};
+    }
+    const std::array<Fr, 4> a = scEvals(a_), b = scEvals(b_);
+    const Fr p0 = a[0].add(b[0]);
+    return {p0, previous_claim.sub(p0), a[2].add(b[2])};
+  }
+  void bind(const Fr& r_j) {
+    if (in_phase2_) {
+      scBind(a_, r_j);
+      scBind(b_, r_j);
+      return;
+    }
+    scEvals(pq_);
+    scBind(pq_, r_j);
+    scEvals(wit_);
+    scBind(wit_, r_j);
+    if (++bound_ == prefix_vars_) transitionToPhase2();
+  }
+  FinalClaims finalClaims() { return {scEntry(pool_.ctx(), a_, 2), scEntry(pool_.ctx(), a_, 3), scEntry(pool_.ctx(), a_, 4), scEntry(pool_.ctx(), a_, 5), scEntry(pool_.ctx(), b_, 2)}; }
+
+ private:
+  void transitionToPhase2() {
+    in_phase2_ = true;
+    const size_t ss = size_t(1) << suffix_vars_;
+    // the bound P buffers ARE evaluateMle(prefix, r_prefix) (:1571-1603)
+    const Fr p0o = scEntry(pool_.ctx(), pq_, 0, 0), p1o = scEntry(pool_.ctx(), pq_, 0, 1), p0p = scEntry(pool_.ctx(), pq_, 0, 2), p1p = scEntry(pool_.ctx(), pq_, 0, 3);
+    Fr* eo = pool_.alloc(ss);
+    Fr* ep = pool_.alloc(ss);
+    pool_.lin2(eo, suf_[0], p0o, suf_[1], p1o, ss);
+    pool_.lin2(ep, suf_[2], p0p, suf_[3], p1p, ss);
+    const void* w[5];
+    for (int k = 0; k < 5; k++) w[k] = scTable(wit_, k);
+    Fr* t1 = pool_.alloc(ss);
+    Fr* t2 = pool_.alloc(ss);
+    Fr* val = pool_.alloc(ss);
+    pool_.lin2(t1, w[0], Fr::one(), w[1], gp_[1], ss);
+    pool_.lin2(t2, w[2], gp_[2], w[3], gp_[3], ss);
+    pool_.lin2(val, t1, Fr::one(), t2, Fr::one(), ss);
+    Fr* nn = pool_.alloc(ss);
+    pool_.fill(t1, Fr::one(), ss);
+    pool_.lin2(nn, t1, gp_[4], w[4], gp_[4].neg(), ss);  // gamma^4 (1 - noop)
+    const void* ta[6] = {eo, val, w[0], w[1], w[2], w[3]};
+    const void* tb[3] = {ep, nn, w[4]};
+    must(zolt_sc_create_dev(pool_.ctx().raw(), ZOLT_SC_PROD2, ZOLT_PAIR_ADJACENT, suffix_vars_, 2, 4, ta, &a_), "zolt_sc_create_dev");
+    must(zolt_sc_create_dev(pool_.ctx().raw(), ZOLT_SC_PROD2, ZOLT_PAIR_ADJACENT, suffix_vars_, 2, 1, tb, &b_), "zolt_sc_create_dev");
+  }
+
+  DevPool pool_;
+  std::vector<Fr> gp_;
+  std::vector<Fr> r_hi_[2];
+  int prefix_vars_ = 0, suffix_vars_ = 0, bound_ = 0;
+  bool in_phase2_ = false;
+  Fr* suf_[4] = {};
+  zolt_sc *pq_ = nullptr, *wit_ = nullptr, *a_ = nullptr, *b_ = nullptr;
+};
+
+// RegistersPrefixSuffixProver (:2156-2496): degree 2, evaluations [p(0), p(1), p(2)]
+class RegistersPrefixSuffixProver {
+ public:
+  struct Columns {
+    const void *rd_write_value, *rs1_value, *rs2_value;
+  };
+  struct FinalClaims {
+    Fr rd_write_value, rs1_value, rs2_value;
+  };
+  RegistersPrefixSuffixProver(Context& ctx, int log_T, const Columns& c, const std::vector<Fr>& r_spartan, const Fr& gamma,
+                              const Fr& gamma_sqr)
+      : pool_(ctx), gamma_(gamma), gamma_sqr_(gamma_sqr) {
+    if (log_T < 2 || (int)r_spartan.size() != log_T) panic("RegistersPrefixSuffixProver: bad arguments", ZOLT_ERR_ARG);
+    const int split = log_T / 2;
+    prefix_vars_ = log_T - split;
+    suffix_vars_ = split;
+    r_hi_.assign(r_spartan.begin(), r_spartan.begin() + split);
+    r_lo_.assign(r_spartan.begin() + split, r_spartan.end());
+    const size_t ps = size_t(1) << prefix_vars_, ss = size_t(1) << suffix_vars_, T = size_t(1) << log_T;
+    Fr* P = pool_.alloc(ps);
+    pool_.eq(P, r_lo_);
+    suffix_ = pool_.alloc(ss);
+    pool_.eq(suffix_, r_hi_);
+    Fr* v = pool_.alloc(T);
+    Fr* t = pool_.alloc(T);
+    pool_.lin2(t, c.rd_write_value, Fr::one(), c.rs1_value, gamma, T);
+    pool_.lin2(v, t, Fr::one(), c.rs2_value, gamma_sqr, T);
+    Fr* Q = pool_.alloc(ps);
+    pool_.fold(Q, v, suffix_, ps, ss);
+    const void* pq[2] = {P, Q};
+    must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_PROD2, ZOLT_PAIR_ADJACENT, prefix_vars_, 2, 0, pq, &pq_), "zolt_sc_create_dev");
+    const void* wit[3] = {c.rd_write_value, c.rs1_value, c.rs2_value};
+    must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_SUM, ZOLT_PAIR_ADJACENT, log_T, 1, 2, wit, &wit_), "zolt_sc_create_dev");
+  }
+  ~RegistersPrefixSuffixProver() {
+    for (zolt_sc* s : {pq_, wit_, eqv_})
+      if (s) zolt_sc_free(s);
+  }
+  Fr inputClaim() {
+    const std::array<Fr, 4> e = scEvals(pq_);
+    return e[0].add(e[1]);
+  }
+  std::array<Fr, 3> computeRoundEvals(const Fr& previous_claim) {
+    const std::array<Fr, 4> e = scEvals(in_phase2_ ? eqv_ : pq_);
+    return {e[0], previous_claim.sub(e[0]), e[2]};
+  }
+  void bind(const Fr& r_j) {
+    if (in_phase2_) return scBind(eqv_, r_j);
+    scEvals(pq_);
+    scBind(pq_, r_j);
+    scEvals(wit_);
+    scBind(wit_, r_j);
+    prefix_challenges_.push_back(r_j);
+    if ((int)prefix_challenges_.size() == prefix_vars_) transitionToPhase2();
+  }
+  FinalClaims finalClaims() { return {scEntry(pool_.ctx(), eqv_, 2), scEntry(pool_.ctx(), eqv_, 3), scEntry(pool_.ctx(), eqv_, 4)}; }
+
+ private:
+  void transitionToPhase2() {
+    in_phase2_ = true;
+    const size_t ss = size_t(1) << suffix_vars_;
+    // phase2_eq[j] = eq(r_hi, j) * eq(r_lo, reversed prefix challenges) (:2427-2465)
+    const std::vector<Fr> reversed(prefix_challenges_.rbegin(), prefix_challenges_.rend());
+    const Fr eq_prefix_eval = EqPolynomial::mle(r_lo_, reversed);
+    Fr* eq = pool_.alloc(ss);
+    pool_.lin2(eq, suffix_, eq_prefix_eval, suffix_, Fr::zero(), ss);
+    const void* w[3];
+    for (int k = 0; k < 3; k++) w[k] = scTable(wit_, k);
+    Fr* t = pool_.alloc(ss);
+    Fr* v = pool_.alloc(ss);
+    pool_.lin2(t, w[0], Fr::one(), w[1], gamma_, ss);
+    pool_.lin2(v, t, Fr::one(), w[2], gamma_sqr_, ss);
+    const void* tabs[5] = {eq, v, w[0], w[1], w[2]};
+    must(zolt_sc_create_dev(pool_.ctx().raw(), ZOLT_SC_PROD2, ZOLT_PAIR_ADJACENT, suffix_vars_, 2, 3, tabs, &eqv_), "zolt_sc_create_dev");
+  }
+
+  DevPool pool_;
+  Fr gamma_, gamma_sqr_;
+  std::vector<Fr> r_hi_, r_lo_, prefix_challenges_;
+  int prefix_vars_ = 0, suffix_vars_ = 0;
+  bool in_phase2_ = false;
+  Fr* suffix_ = nullptr;
+  zolt_sc *pq_ = nullptr, *wit_ = nullptr, *eqv_ = nullptr;
+};
+
+// the quadratic through (0, e0) (1, e1) (2, e2) at r (evalsToCoeffs + evaluatePolyAtPoint, :846-926)
+inline Fr quadAt(const std::array<Fr, 3>& e, const Fr& r) {
+  static const Fr two_inv = Fr::fromU64(2).inverse();
+  const Fr c2 = e[2].sub(e[1]).sub(e[1]).add(e[0]).mul(two_inv);
+  const Fr c1 = e[1].sub(e[0]).sub(c2);
+  return e[0].add(r.mul(c1.add(r.mul(c2))));
+}
+
+// One round of generateStage3Proof's loop (:393-560): the three provers' evaluations and the batched cubic
+struct RoundEvals {
+  std::array<Fr, 3> shift;
+  std::array<Fr, 4> instr;
+  std::array<Fr, 3> reg;
+  std::array<Fr, 4> combined;
+};
+struct Provers {
+  ShiftPrefixSuffixProver& shift;
+  InstructionInputProver& instr;
+  RegistersPrefixSuffixProver& reg;
+  std::array<Fr, 3> claims;  // current_shift_claim, current_instr_claim, current_reg_claim
+  RoundEvals computeRound(const std::array<Fr, 3>& batching_coeffs) {
+    RoundEvals e;
+    e.shift = shift.computeRoundEvals(claims[0]);
+    e.instr = instr.computeRoundEvals(claims[1]);
+    e.reg = reg.computeRoundEvals(claims[2]);
+    const Fr three = Fr::fromU64(3);
+    const Fr s3 = e.shift[2].mul(three).sub(e.shift[1].mul(three)).add(e.shift[0]);
+    const Fr r3 = e.reg[2].mul(three).sub(e.reg[1].mul(three)).add(e.reg[0]);
+    for (int i = 0; i < 4; i++) {
+      const Fr sv = i < 3 ? e.shift[i] : s3, rv = i < 3 ? e.reg[i] : r3;
+      e.combined[i] = sv.mul(batching_coeffs[0]).add(e.instr[i].mul(batching_coeffs[1])).add(rv.mul(batching_coeffs[2]));
+    }
+    return e;
+  }
+  void bind(const RoundEvals& e, const Fr& r_j) {
+    claims = {quadAt(e.shift, r_j), evaluateCubicAtPoint(e.instr, r_j), quadAt(e.reg, r_j)};
+    shift.bind(r_j);
+    instr.bind(r_j);
+    reg.bind(r_j);
+  }
+};
+
+}  // namespace stage3
+
 struct SumcheckProof {
   std::vector<std::array<Fr, 4>> round_polys;  // evaluations at 0..3
   std::vector<Fr> challenges;
