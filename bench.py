@@ -833,6 +833,51 @@ def extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, tim
         g1 = _fr_ints(gamma)[0]
         body = ((g1 * f[1] + g1 * g1 * f[2]) * f[0] + f[3] * (f[0] + f[4])) % B.FR_MOD
         out[f"stage4_gruen_T2^{log_T}_ok"] = bool(ok and cl == f[5] * body % B.FR_MOD and (s_evals == first[0]).all())
+        # the Stage 3 provers (Shift / InstructionInput / RegistersClaimReduction, stage3_prover.zig) run together
+        # like generateStage3Proof's loop over T = 2^(sc_log_n - 2) cycles; the 16 trace columns are the quarters of the four
+        # resident tables.  Whole prover per run: eq / eq+1 tables, Q-buffer folds, batched columns, input claims, log T rounds
+        # with challenges from the host, final claims.
+        log_T3 = lg - 2
+        cols3 = [d_tab_ptrs[t] + q * (32 << log_T3) for t in range(4) for q in range(4)]
+        r_o, r_p = rows_global(STREAM_EQ, (1 << 17) + 256, log_T3), rows_global(STREAM_EQ, (1 << 17) + 320, log_T3)
+        gam3 = rows_global(STREAM_EQ, (1 << 17) + 384, 7)
+        g_int = _fr_ints(gam3[0:1])[0]
+        gam3[0:5] = B.ints_to_mont_array([pow(g_int, i, B.FR_MOD) for i in range(5)], B.FR_MOD)
+        bc3, chal3 = rows_global(STREAM_EQ, (1 << 17) + 448, 3), rows_global(STREAM_EQ, (1 << 17) + 512, log_T3)
+
+        def run_s3():
+            res[0] = H.stage3_run(ctx, log_T3, cols3, r_o, r_p, gam3, bc3, chal3)
+
+        run_s3()
+        ctx.prof_enable(True)
+        wall = time_ms(run_s3, 3, warm=0)
+        ks = [ms for tag, ms in ctx.prof_read() if tag in (16, 17, 18)]
+        ctx.prof_enable(False)
+        out[f"stage3_T2^{log_T3}_ms"] = wall
+        out[f"stage3_T2^{log_T3}_round_kernel_ms"] = sum(ks) / 3
+        # InstructionInputProver streams 2 x 5 tables, the witness binders 5 + 3: 128 B per entry and table over a whole proof
+        out[f"stage3_T2^{log_T3}_rounds_frac_hbm"] = 128 * 18 * (1 << log_T3) / (sum(ks) / 3 * 1e-3) / 1e9 / hbm_peak if ks else None
+        e3, c3, f3 = res[0]
+        bcs, cl3 = _fr_ints(bc3), _fr_ints(c3)
+        comb = sum(a * b for a, b in zip(cl3[:3], bcs)) % B.FR_MOD
+        ok = True
+        for j in range(log_T3):
+            e = _fr_ints(e3[j])[10:14]
+            ok = ok and (e[0] + e[1]) % B.FR_MOD == comb
+            comb = OP.evaluate_cubic_at_point(e, _fr_ints(chal3[j:j + 1])[0])
+        ok = ok and comb == sum(a * b for a, b in zip(cl3[3:], bcs)) % B.FR_MOD
+        # final-claim relations (stage3_prover.zig:620-700)
+        from oracle import stage3 as OS3
+
+        rev = _fr_ints(chal3)[::-1]
+        ro_i, rp_i, gi, fi = _fr_ints(r_o), _fr_ints(r_p), _fr_ints(gam3), _fr_ints(f3)
+        Pm = B.FR_MOD
+        sval = (fi[0] + gi[1] * fi[1] + gi[2] * fi[2] + gi[3] * fi[3]) % Pm
+        ok = ok and cl3[3] == (OS3.eq_plus_one_mle(ro_i, rev) * sval + gi[4] * ((1 - fi[4]) % Pm) % Pm * OS3.eq_plus_one_mle(rp_i, rev)) % Pm
+        left, right = (fi[5] * fi[6] + fi[7] * fi[8]) % Pm, (fi[9] * fi[10] + fi[11] * fi[12]) % Pm
+        ok = ok and cl3[4] == (OP.eq_mle(ro_i, rev) + gi[5] * gi[5] % Pm * OP.eq_mle(rp_i, rev)) % Pm * ((right + gi[5] * left) % Pm) % Pm
+        ok = ok and cl3[5] == OP.eq_mle(ro_i, rev) * ((fi[13] + gi[6] * fi[14] + gi[6] * gi[6] % Pm * fi[15]) % Pm) % Pm
+        out[f"stage3_T2^{log_T3}_ok"] = bool(ok)
     return {k: (round(v, 5) if isinstance(v, float) else v) for k, v in out.items()}
 
 
