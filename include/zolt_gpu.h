@@ -258,6 +258,15 @@ int zolt_fr_vec_dev(zolt_ctx* ctx, int op, void* d_out, const void* d_a, const v
 int zolt_fr_fold_high_dev(zolt_ctx* ctx, void* d_out, const void* d_in, const void* d_w, size_t n_lo, size_t n_hi,
                           const uint64_t* scale /* 4 or NULL */);
 
+/* LassoProver address rounds over device-resident eq_evals (n field elements, updated in place) and the 128-bit lookup indices
+ * (n x 16 bytes, little-endian), src/zkvm/lasso/prover.zig: one pass applies the previous challenge -- eq_evals[j] *= r if bit
+ * bind_bit of index j is set, else (1 - r) (receiveChallenge :380-400; bind_bit < 0: nothing to apply) -- and returns the partition
+ * sums of computeAddressRoundPoly (:265-310) for bit sum_bit: sums_out = [sum_0, sum_1] (sum_bit < 0: [sum of the table, 0]).
+ * sum_0 + sum_1 is the reference's claim after the bind (:402-407).  The cycle rounds (:312-364, :421-452) are the
+ * ZOLT_SC_SUM / ZOLT_PAIR_HALF instance over the same table. */
+int zolt_lasso_addr_round(zolt_ctx* ctx, void* d_eq_evals, const void* d_indices, size_t n, int bind_bit, const uint64_t* r /* 4 */,
+                          int sum_bit, uint64_t sums_out[8]);
+
 /* dst[i] = src[((i / d1) % m1) * s1 + ((i / d2) % m2) * s2] for i < n: re-layouts between the phases of a prover --
  * transpose [k][j] -> [j][k] (d1 = 1, m1 = K, s1 = T, d2 = K, m2 = T, s2 = 1), a vector replicated over rows (d1 = 1,
  * m1 = len, s1 = 1, s2 = 0), every element repeated (d1 = K, m1 = len, s1 = 1, s2 = 0).  m = 0 disables a term. */

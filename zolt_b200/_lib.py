@@ -94,6 +94,7 @@ SIGNATURES = {
     "zolt_poly_sum": [_vp, _vp, _sz, _vp],
     "zolt_eq_plus_one_evals": [_vp, _vp, _i, _vp],
     "zolt_fr_fold_high_dev": [_vp, _vp, _vp, _vp, _sz, _sz, _vp],
+    "zolt_lasso_addr_round": [_vp, _vp, _vp, _sz, _i, _vp, _i, _vp],
     "zolt_sc_create": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)],
     "zolt_sc_create_dev": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)],
     "zolt_sc_set_split_eq": [_vp, _vp, _i],

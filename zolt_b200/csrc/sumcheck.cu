@@ -1443,6 +1443,31 @@ __global__ void __launch_bounds__(kScThreads) inner_product_kernel(const Fr* a, 
   grid_finish<1>(acc, smem, out, Fr::zero());
 }
 
+// LassoProver address rounds (src/zkvm/lasso/prover.zig:265-310 computeAddressRoundPoly, :380-412 receiveChallenge): one pass
+// that applies the PREVIOUS round's challenge -- eq_evals[j] *= bit(idx_j, bind_bit) ? r : 1 - r -- and accumulates this round's
+// partition sums sum_b = sum over { j : bit(idx_j, sum_bit) = b } of eq_evals[j].  The reference's claim after the bind is the
+// sum of the updated table, i.e. sum_0 + sum_1 of this very pass.  idx: 128-bit little-endian lookup indices.
+__global__ void __launch_bounds__(kScThreads)
+lasso_addr_kernel(Fr* __restrict__ eq, const uint4* __restrict__ idx, size_t n, int bind_bit, const __grid_constant__ Fr r, int sum_bit,
+                  ScOut out) {
+  __shared__ Fr smem[64];
+  Fr acc[2] = {Fr::zero(), Fr::zero()};
+  const Fr one_minus_r = fr_sub(Fr::one(), r);
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+    const uint4 w = __ldg(idx + j);
+    const uint32_t limb[4] = {w.x, w.y, w.z, w.w};
+    Fr e = eq[j];
+    if (bind_bit >= 0) {
+      e = fr_mul(e, ((limb[bind_bit >> 5] >> (bind_bit & 31)) & 1u) ? r : one_minus_r);
+      st_fr(eq + j, e);
+    }
+    const unsigned b = sum_bit >= 0 ? ((limb[sum_bit >> 5] >> (sum_bit & 31)) & 1u) : 0u;
+    if (b) acc[1] = fr_add(acc[1], e);
+    else acc[0] = fr_add(acc[0], e);
+  }
+  grid_finish<2>(acc, smem, out, Fr::zero());
+}
+
 // rows x cols matrix of Fr -> column sums (multi-GPU fold of gathered partial evaluations)
 __global__ void sum_rows_kernel(const Fr* rows, size_t n_rows, size_t cols, Fr* d_out, Fr* h_out) {
   const size_t c = threadIdx.x;
@@ -2690,6 +2715,30 @@ extern "C" int zolt_fr_inner_product_dev(zolt_ctx* ctx, const void* d_a, const v
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(out, ctx->h_mailbox, 32);
+  scratch_free(ctx, &s);
+  return ZOLT_OK;
+}
+
+extern "C" int zolt_lasso_addr_round(zolt_ctx* ctx, void* d_eq_evals, const void* d_indices, size_t n, int bind_bit, const uint64_t* r,
+                                     int sum_bit, uint64_t sums_out[8]) {
+  if (!ctx || !d_eq_evals || !d_indices || !sums_out || bind_bit > 127 || sum_bit > 127 || (bind_bit >= 0 && !r)) return ZOLT_ERR_ARG;
+  ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
+  Scratch s;
+  ZOLT_TRY(scratch_alloc(ctx, &s));
+  ScOut so{};
+  so.partials = s.partials;
+  so.ticket = s.ticket;
+  so.d_raw = s.d_out + 8;
+  so.d_evals = s.d_out;
+  so.h_evals = (Fr*)ctx->d_mailbox;
+  so.finalize = 1;
+  const Fr rr = bind_bit >= 0 ? fr_from_host(r) : Fr::zero();
+  lasso_addr_kernel<<<grid_for(ctx, n, 4), kScThreads, 0, ctx->stream>>>((Fr*)d_eq_evals, (const uint4*)d_indices, n, bind_bit < 0 ? -1 : bind_bit,
+                                                                        rr, sum_bit < 0 ? -1 : sum_bit, so);
+  ctx->launches++;
+  ZOLT_CUDA_TRY(cudaGetLastError());
+  ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(sums_out, ctx->h_mailbox, 64);
   scratch_free(ctx, &s);
   return ZOLT_OK;
 }

@@ -57,6 +57,7 @@ def load_host() -> C.CDLL:
         _host.zolt_host_stage4_run.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _host.zolt_host_stage3_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)] + [C.c_void_p] * 8
+        _host.zolt_host_lasso_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 6
         _host.zolt_host_eq_mle.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         _host.zolt_host_horner_eval.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _host.zolt_host_dense_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -200,6 +201,23 @@ def stage3_run(ctx: Context, log_T: int, d_cols, r_outer, r_product, gammas, bat
                                           _ptr(finals))
     _lib.check(st, "zolt_host_stage3_run")
     return evals, claims, finals
+
+
+def lasso_run(ctx: Context, d_indices, num_lookups: int, log_T: int, log_K: int, r_reduction, challenges=None):
+    """LassoProver (src/zkvm/lasso/prover.zig) over device-resident u128 lookup indices.  With `challenges`: the caller's loop;
+    without: runLassoProver with the reference's deriveChallenge.  Returns (coeffs (rounds, 3, 4), claims (rounds + 1, 4),
+    challenges (rounds, 4), final_eval (4,))."""
+    rounds = log_T + log_K
+    rr = _as_u64(r_reduction, 4) if log_T else np.zeros((1, 4), dtype=np.uint64)
+    ch = None if challenges is None else _as_u64(challenges, 4)
+    coeffs = np.zeros((rounds, 3, 4), dtype=np.uint64)
+    claims = np.zeros((rounds + 1, 4), dtype=np.uint64)
+    chal = np.zeros((max(rounds, 1), 4), dtype=np.uint64)
+    final = np.zeros(4, dtype=np.uint64)
+    st = load_host().zolt_host_lasso_run(ctx.handle, C.c_void_p(d_indices), num_lookups, log_T, log_K, _ptr(rr), _ptr(ch) if ch is not None else None,
+                                         _ptr(coeffs), _ptr(claims), _ptr(chal), _ptr(final))
+    _lib.check(st, "zolt_host_lasso_run")
+    return coeffs, claims, chal[:rounds], final
 
 
 def eq_mle(r, x) -> np.ndarray:

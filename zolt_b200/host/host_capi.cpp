@@ -246,6 +246,34 @@ int zolt_host_stage3_run(zolt_ctx* ctx, int log_T, const void* const* cols, cons
   return ZOLT_OK;
 }
 
+// LassoProver over device-resident lookup indices (n x u128).  challenges != NULL: the caller's loop (computeRoundPolynomial /
+// receiveChallenge, "lasso prover claim tracking"); NULL: runLassoProver with the reference's deriveChallenge, challenges_out
+// filled.  coeffs_out: rounds x 3; claims_out: rounds + 1 (the claim before every round, then the last); final_out: final_eval.
+int zolt_host_lasso_run(zolt_ctx* ctx, const void* d_indices, size_t num_lookups, int log_T, int log_K, const uint64_t* r_reduction,
+                        const uint64_t* challenges, uint64_t* coeffs_out, uint64_t* claims_out, uint64_t* challenges_out,
+                        uint64_t* final_out) {
+  Context c(ctx);
+  LassoParams params;
+  params.gamma = Fr::zero();
+  params.log_T = (size_t)log_T;
+  params.log_K = (size_t)log_K;
+  for (int i = 0; i < log_T; i++) params.r_reduction.push_back(Fr::fromRaw(r_reduction + 4 * i));
+  LassoProver prover(c, d_indices, num_lookups, params);
+  size_t round = 0;
+  while (!prover.isComplete()) {
+    prover.current_claim.store(claims_out + 4 * round);
+    const std::array<Fr, 3> p = prover.computeRoundPolynomial();
+    for (int j = 0; j < 3; j++) p[j].store(coeffs_out + 12 * round + 4 * j);
+    const Fr ch = challenges ? Fr::fromRaw(challenges + 4 * round) : lassoDeriveChallenge(p, round);
+    if (challenges_out) ch.store(challenges_out + 4 * round);
+    prover.receiveChallenge(ch);
+    round++;
+  }
+  prover.current_claim.store(claims_out + 4 * round);
+  prover.getFinalEval().store(final_out);
+  return ZOLT_OK;
+}
+
 // SRS container parsers: kind 0 raw binary (srs.zig:256-306), 1 snarkjs PTAU (:733-900), 2 Jolt Dory SRS (dory.zig:740-826).
 // Returns the srs::Error code (0 = ok); *bases_out is a zolt_bases handle the caller frees.
 int zolt_host_srs_load(zolt_ctx* ctx, int kind, const uint8_t* data, size_t len, zolt_bases** bases_out, size_t* count,

@@ -1166,6 +1166,155 @@ struct Provers {
 
 }  // namespace stage3
 
+// ---- LassoProver (src/zkvm/lasso/prover.zig:82-470) -------------------------------------------------------------------------
+// eq_evals lives on the device.  Address rounds: zolt_lasso_addr_round applies the previous challenge and returns this round's
+// partition sums in ONE pass over the table (the claim the reference recomputes after every bind, :402-407, is p(r) of the
+// polynomial just sent -- the same field element -- so it costs nothing here).  Cycle rounds: the ZOLT_SC_SUM half-split
+// instance over the same table (sum of the first / second half, fold (1 - r) lo + r hi = bindFirst).  expanding_v.get(0),
+// the prover's final_eval, is prod (1 - r_i) over the address challenges; the 2^log_K-entry table is not materialised.
+// The prefix-suffix decompositions and the split eq's bindOuter / bindInner never reach the prover's outputs and have no mirror.
+struct LassoParams {
+  Fr gamma;
+  size_t log_T = 0, log_K = 0;
+  std::vector<Fr> r_reduction;
+};
+class LassoProver {
+ public:
+  // d_lookup_indices: num_lookups x 16 bytes (u128, little-endian), device-resident and only read
+  LassoProver(Context& ctx, const void* d_lookup_indices, size_t num_lookups, const LassoParams& params)
+      : pool_(ctx), params_(params), d_idx_(d_lookup_indices), num_lookups_(num_lookups) {
+    const size_t log_T = params.log_T, padded = size_t(1) << log_T;
+    if (params.r_reduction.size() != log_T || num_lookups > padded || params.log_K > 128 || log_T > 40)
+      panic("LassoProver: bad parameters", ZOLT_ERR_ARG);
+    // eq_evals[j] = E_out[j >> inner] * E_in[j & mask] (:166-176), variable i of each half <-> bit i of its index
+    // (split_eq.zig:120-142): as ONE big-endian table, the point is (w_out reversed, w_in reversed)
+    const size_t outer = log_T / 2;
+    std::vector<Fr> be(params.r_reduction.rend() - (long)outer, params.r_reduction.rend());
+    be.insert(be.end(), params.r_reduction.rbegin(), params.r_reduction.rbegin() + (long)(log_T - outer));
+    eq_ = pool_.alloc(padded);
+    pool_.eq(eq_, be);
+    if (num_lookups < padded) pool_.fill(eq_ + num_lookups, Fr::zero(), padded - num_lookups);  // cycles without lookups (:171-174)
+    must(zolt_poly_sum(ctx.raw(), eq_, padded, current_claim.limbs.data()), "zolt_poly_sum");
+  }
+  ~LassoProver() {
+    if (cycle_) zolt_sc_free(cycle_);
+  }
+  LassoProver(const LassoProver&) = delete;
+  LassoProver& operator=(const LassoProver&) = delete;
+
+  Fr computeInitialClaim() const { return current_claim; }
+  bool isAddressPhase() const { return round < params_.log_K; }
+  bool isComplete() const { return round >= params_.log_K + params_.log_T; }
+
+  // coefficients [c0, c1, c2] of the round polynomial (UniPoly, :232-364)
+  std::array<Fr, 3> computeRoundPolynomial() {
+    if (have_poly_) return poly_;
+    Fr s0, s1;
+    if (isAddressPhase()) {
+      uint64_t sums[8];
+      must(zolt_lasso_addr_round(pool_.ctx().raw(), eq_, d_idx_, num_lookups_, pending_bit_, pending_bit_ >= 0 ? pending_r_.limbs.data() : nullptr,
+                                 (int)round, sums),
+           "zolt_lasso_addr_round");
+      pending_bit_ = -1;
+      s0 = Fr::fromRaw(sums);
+      s1 = Fr::fromRaw(sums + 4);
+    } else {
+      enterCyclePhase();
+      if (!cycle_) {  // log_T == 0: a single entry, nothing left to fold (:322-331)
+        poly_ = {current_claim, Fr::zero(), Fr::zero()};
+        have_poly_ = true;
+        return poly_;
+      }
+      const std::array<Fr, 4> e = stage3::scEvals(cycle_);
+      s0 = e[0];
+      s1 = e[1];
+    }
+    poly_ = {s0, s1.sub(s0), Fr::zero()};
+    have_poly_ = true;
+    return poly_;
+  }
+
+  void receiveChallenge(const Fr& challenge) {
+    const std::array<Fr, 3> p = computeRoundPolynomial();
+    challenges.push_back(challenge);
+    if (isAddressPhase()) {
+      pending_bit_ = (int)round;  // applied by the next pass over the table
+      pending_r_ = challenge;
+      expanding_v0_ = expanding_v0_.mul(Fr::one().sub(challenge));
+    } else if (cycle_) {
+      stage3::scBind(cycle_, challenge);
+    }
+    // the sum of the updated table (:402-407, :441-446) = p(challenge)
+    current_claim = p[0].add(p[1].mul(challenge)).add(p[2].mul(challenge).mul(challenge));
+    have_poly_ = false;
+    round++;
+  }
+  Fr getFinalEval() const { return expanding_v0_; }
+
+  Fr current_claim;
+  size_t round = 0;
+  std::vector<Fr> challenges;
+
+ private:
+  void enterCyclePhase() {
+    if (cycle_entered_) return;
+    cycle_entered_ = true;
+    if (pending_bit_ >= 0) {  // the last address challenge is still to be applied
+      uint64_t sums[8];
+      must(zolt_lasso_addr_round(pool_.ctx().raw(), eq_, d_idx_, num_lookups_, pending_bit_, pending_r_.limbs.data(), -1, sums),
+           "zolt_lasso_addr_round");
+      pending_bit_ = -1;
+    }
+    if (params_.log_T == 0) return;
+    const void* t[1] = {eq_};
+    must(zolt_sc_create_dev(pool_.ctx().raw(), ZOLT_SC_SUM, ZOLT_PAIR_HALF, (int)params_.log_T, 1, 0, t, &cycle_), "zolt_sc_create_dev");
+  }
+
+  stage3::DevPool pool_;
+  LassoParams params_;
+  const void* d_idx_;
+  size_t num_lookups_;
+  Fr* eq_ = nullptr;
+  zolt_sc* cycle_ = nullptr;
+  bool cycle_entered_ = false, have_poly_ = false;
+  std::array<Fr, 3> poly_{};
+  int pending_bit_ = -1;
+  Fr pending_r_, expanding_v0_ = Fr::one();
+};
+
+// deriveChallenge (:537-551): the reference's stand-in for Fiat-Shamir inside runLassoProver
+inline Fr lassoDeriveChallenge(const std::array<Fr, 3>& coeffs, size_t round) {
+  uint64_t h = 0x9e3779b97f4a7c15ull;
+  h ^= (uint64_t)round;
+  h *= 0xff51afd7ed558ccdull;
+  for (const Fr& c : coeffs)
+    for (uint64_t limb : c.limbs) {
+      h ^= limb;
+      h *= 0xc4ceb9fe1a85ec53ull;
+    }
+  h ^= h >> 33;
+  return Fr::fromU64(h);
+}
+struct LassoProof {
+  std::vector<std::array<Fr, 3>> round_polys;
+  Fr final_eval;
+  std::vector<Fr> challenges;
+};
+// runLassoProver (:495-535)
+inline LassoProof runLassoProver(Context& ctx, const void* d_lookup_indices, size_t num_lookups, const LassoParams& params) {
+  LassoProver prover(ctx, d_lookup_indices, num_lookups, params);
+  LassoProof proof;
+  size_t round = 0;
+  while (!prover.isComplete()) {
+    proof.round_polys.push_back(prover.computeRoundPolynomial());
+    prover.receiveChallenge(lassoDeriveChallenge(proof.round_polys.back(), round));
+    round++;
+  }
+  proof.final_eval = prover.getFinalEval();
+  proof.challenges = prover.challenges;
+  return proof;
+}
+
 struct SumcheckProof {
   std::vector<std::array<Fr, 4>> round_polys;  // evaluations at 0..3
   std::vector<Fr> challenges;
