@@ -878,6 +878,31 @@ def extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, tim
         ok = ok and cl3[4] == (OP.eq_mle(ro_i, rev) + gi[5] * gi[5] % Pm * OP.eq_mle(rp_i, rev)) % Pm * ((right + gi[5] * left) % Pm) % Pm
         ok = ok and cl3[5] == OP.eq_mle(ro_i, rev) * ((fi[13] + gi[6] * fi[14] + gi[6] * gi[6] % Pm * fi[15]) % Pm) % Pm
         out[f"stage3_T2^{log_T3}_ok"] = bool(ok)
+        # LassoProver (lasso/prover.zig) with the reference's own deriveChallenge: 2^(sc_log_n - 2) lookups with
+        # 64-bit indices -- 64 one-pass address rounds over eq_evals and the index list, then the half-split cycle rounds
+        log_TL, log_KL = lg - 2, 64
+        idx_host = np.zeros((1 << log_TL, 2), dtype=np.uint64)
+        idx_host[:, 0] = np.random.default_rng([0x5A17, 0x1A550]).integers(0, 1 << 64, size=1 << log_TL, dtype=np.uint64)
+        d_idx = Z.DeviceBuffer.from_host(ctx, idx_host)
+        r_red = rows_global(STREAM_EQ, (1 << 17) + 640, log_TL)
+
+        def run_lasso():
+            res[0] = H.lasso_run(ctx, d_idx.ptr, 1 << log_TL, log_TL, log_KL, r_red)
+
+        run_lasso()
+        wall = time_ms(run_lasso, 3, warm=0)
+        d_idx.free()
+        out[f"lasso_T2^{log_TL}_K2^{log_KL}_ms"] = wall
+        lc, lcl, lch, lfin = res[0]
+        cl_i, ch_i = _fr_ints(lcl), _fr_ints(lch)
+        ok = cl_i[0] == 1  # every cycle has a lookup: eq(r, .) sums to one
+        fe = 1
+        for j in range(log_TL + log_KL):
+            c = _fr_ints(lc[j])
+            ok = ok and (2 * c[0] + c[1] + c[2]) % B.FR_MOD == cl_i[j] and (c[0] + c[1] * ch_i[j] + c[2] * ch_i[j] * ch_i[j]) % B.FR_MOD == cl_i[j + 1]
+            if j < log_KL:
+                fe = fe * (1 - ch_i[j]) % B.FR_MOD
+        out[f"lasso_T2^{log_TL}_K2^{log_KL}_ok"] = bool(ok and _fr_ints(lfin.reshape(1, 4))[0] == fe)
     return {k: (round(v, 5) if isinstance(v, float) else v) for k, v in out.items()}
 
 

@@ -970,7 +970,7 @@ class ShiftPrefixSuffixProver {
     must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_SUM, ZOLT_PAIR_ADJACENT, log_T, 1, 4, wit, &wit_), "zolt_sc_create_dev");
   }
   ~ShiftPrefixSuffixProver() {
-    for (zolt_sc* s : {pq_, wit_, a_, b_})
+    for (zolt_sc* s : {a_, b_, pq_, wit_})  // the phase-2 instances borrow wit_'s tables: they go first
       if (s) zolt_sc_free(s);
   }
   // grand_sum(P * Q) (:1131-1139)
@@ -1072,7 +1072,7 @@ class RegistersPrefixSuffixProver {
     must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_SUM, ZOLT_PAIR_ADJACENT, log_T, 1, 2, wit, &wit_), "zolt_sc_create_dev");
   }
   ~RegistersPrefixSuffixProver() {
-    for (zolt_sc* s : {pq_, wit_, eqv_})
+    for (zolt_sc* s : {eqv_, pq_, wit_})  // eqv_ borrows wit_'s tables: it goes first
       if (s) zolt_sc_free(s);
   }
   Fr inputClaim() {
