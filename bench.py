@@ -674,7 +674,10 @@ def run_b200(args):
         if not all(v for k, v in checks.items() if isinstance(v, bool)):
             line["error"] = "a result check failed: see `checks`"
     if world == 1 and not args.no_extras:
-        line["extras"].update(extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, time_ms, args))
+        try:
+            line["extras"].update(extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, time_ms, args))
+        except Exception as e:  # noqa: BLE001 - an extra leg must never cost the headline line; the failure is reported in it
+            line["extras"]["error"] = f"{type(e).__name__}: {e}"
     if rank == 0:
         if world == 1 and not args.no_cpu:
             threads = min(8, cores)

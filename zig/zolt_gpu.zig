@@ -192,3 +192,24 @@ pub fn initMulti(device_ids: []const c_int) *c.zolt_multi {
     must(c.zolt_gpu_init_multi(device_ids.ptr, @intCast(device_ids.len), &m), "gpu_init_multi");
     return m.?;
 }
+
+/// Stage 3 building blocks over device tables (src/zkvm/spartan/stage3_prover.zig).  `d_*` are device pointers obtained
+/// from zolt_dev_alloc / zolt_dev_upload; the sequence of calls for the three provers is zolt_host.hpp `stage3::*`.
+/// eq+1(r, .) as a table (computeEqPlusOneEvals, :1878-1895); r big-endian like EqPolynomial.evals.
+pub fn eqPlusOneEvals(r: []const F, d_out: *anyopaque) void {
+    must(c.zolt_eq_plus_one_evals(ctx(), @ptrCast(r.ptr), @intCast(r.len), d_out), "eq_plus_one_evals");
+}
+/// Q[x_lo] = scale * sum_{x_hi} v[x_lo + x_hi * n_lo] * suffix[x_hi]  (ShiftPrefixSuffixProver.init :1053-1112,
+/// RegistersPrefixSuffixProver.init :2262-2300)
+pub fn foldHigh(d_q: *anyopaque, d_v: *const anyopaque, d_suffix: *const anyopaque, n_lo: usize, n_hi: usize, scale: ?*const F) void {
+    must(c.zolt_fr_fold_high_dev(ctx(), d_q, d_v, d_suffix, n_lo, n_hi, if (scale) |s| &s.limbs else null), "fr_fold_high_dev");
+}
+
+/// LassoProver address round (src/zkvm/lasso/prover.zig:265-310, :380-407): applies the previous challenge (bind_bit < 0:
+/// none) and returns [sum_0, sum_1] for bit `sum_bit` of the lookup indices in one pass over eq_evals.
+/// lookup_indices is the prover's `[]const u128` uploaded as is (16 bytes each, little-endian).
+pub fn lassoAddrRound(d_eq_evals: *anyopaque, d_indices: *const anyopaque, n: usize, bind_bit: c_int, r: ?*const F, sum_bit: c_int) [2]F {
+    var sums: [8]u64 = undefined;
+    must(c.zolt_lasso_addr_round(ctx(), d_eq_evals, d_indices, n, bind_bit, if (r) |x| &x.limbs else null, sum_bit, &sums), "lasso_addr_round");
+    return .{ .{ .limbs = sums[0..4].* }, .{ .limbs = sums[4..8].* } };
+}
