@@ -117,8 +117,8 @@ def test_wide_accumulator(host_shim, field, mod):
 
 @pytest.mark.parametrize("field,mod", [(0, B.FR_MOD), (1, B.FQ_MOD)])
 def test_fixed_multiplier_bind(host_shim, field, mod):
-    """fp_bind_fixed (the streaming sumcheck kernels' bind: table of r * 2^(32 i) mod p, plain 8 x 8 product, one Barrett
-    step) returns the canonical lo + r (hi - lo), i.e. exactly what the Montgomery-product form returns, for random and
+    """fp_bind_fixed (the streaming sumcheck kernels' bind: table of r * 2^(32 i) * 2^64 mod p, plain 8 x 8 product, the
+    addend shifted up two limbs, two Montgomery reduction rows -- the Barrett form of r2 v7 behind -DZOLT_BIND_BARRETT) returns the canonical lo + r (hi - lo), i.e. exactly what the Montgomery-product form returns, for random and
     extreme operands (0, p-1, all-ones limbs in the difference, r = 0, 1, p-1)."""
     rng = np.random.default_rng(11)
     rinv = pow(1 << 256, -1, mod)

@@ -765,7 +765,7 @@ struct FixedMulTable {
 
 // c[i] = mont_mul(r, 2^(32 i) as a raw integer) = r_std * 2^(32 i) mod p
 template <class P>
-ZOLT_HD FixedMulTable fixed_mul_table(const Fp<P>& r) {
+ZOLT_HD FixedMulTable fixed_mul_table_barrett(const Fp<P>& r) {
   FixedMulTable t;
   for (int i = 0; i < 8; i++) {
     Fp<P> e = Fp<P>::zero();
@@ -851,7 +851,7 @@ ZOLT_HD Fp<P> fp_barrett_289(const uint32_t* x) {
 
 // canonical (addend + r * d) for the table of r;  addend < p canonical, d any 256-bit representative.
 template <class P>
-ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) {
+ZOLT_HD Fp<P> fp_fixed_mul_add_barrett(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) {
   // x = addend + sum_i d_i * c[i] = E + (O << 32): E takes the even limbs of c[i], O the odd ones
   uint32_t e[9], o[9];
 #pragma unroll
@@ -873,6 +873,83 @@ ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const Fix
   x[9] = ptx::addc(o[8], 0u);
   return fp_barrett_289<P>(x);
 }
+
+// ---------------------------------------------------------------------------------------------
+// The same product with the table scaled by 2^64 and a two-limb Montgomery reduction instead of the Barrett step (r2 v23).
+//   c64[i] = (r_std * 2^(32 i) * 2^64) mod p
+//   x = (addend << 64) + sum_i d_i * c64[i]          < 2^64 p + 8 * 2^32 p
+//   two reduction rows (m0 = x_0 * INV, m1 = x_1 * INV) clear the two low limbs:  (x + m0 p + m1 p 2^32) / 2^64
+//   is congruent to addend + r_std * d and below 2p + p / 2^29: two conditional subtractions give the canonical value --
+//   the field element montgomeryMul / the Barrett form return.  The addend enters shifted by two limbs, so it costs no
+//   multiplication.  64 + 16 wide multiplies and 2 narrow ones, against 64 + 15 (q p) + ~8 (the quotient estimate: a 64 x 64
+//   high product and its corrections) of the Barrett form, and no 64-bit quotient arithmetic on the ALU.
+// ---------------------------------------------------------------------------------------------
+template <class P>
+ZOLT_HD FixedMulTable fixed_mul_table_mont2(const Fp<P>& r) {
+  FixedMulTable t;
+  Fp<P> e = Fp<P>::zero();
+  e.v[2] = 1u;
+  const Fp<P> base_std = fp_mul<P>(r, e);                 // r_std * 2^64 mod p, as a plain integer
+  const Fp<P> base = fp_mul<P>(base_std, Fp<P>::r2());     // its Montgomery form
+  for (int i = 0; i < 8; i++) {
+    Fp<P> s = Fp<P>::zero();
+    s.v[i] = 1u;
+    const Fp<P> ci = fp_mul<P>(base, s);                   // r_std * 2^64 * 2^(32 i) mod p
+    for (int j = 0; j < 8; j++) t.c[i][j] = ci.v[j];
+  }
+  return t;
+}
+
+template <class P>
+ZOLT_HD Fp<P> fp_fixed_mul_add_mont2(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) {
+  // sum_i d_i * c64[i] = E + (O << 32): E takes the even limbs of the rows, O the odd ones
+  uint32_t e[11], o[9];
+#pragma unroll
+  for (int j = 0; j < 11; j++) e[j] = 0;
+#pragma unroll
+  for (int j = 0; j < 9; j++) o[j] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    fixed_chain(e, t.c[i][0], t.c[i][2], t.c[i][4], t.c[i][6], d[i]);
+    fixed_chain(o, t.c[i][1], t.c[i][3], t.c[i][5], t.c[i][7], d[i]);
+  }
+  // row m0: limb 0 of x is e[0] (the addend starts at limb 2, O at limb 1)
+  const uint32_t m0 = ptx::mul_lo(e[0], P::INV);
+  fixed_chain(e, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m0);
+  fixed_chain(o, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m0);
+  // row m1 (shifted by one limb): limb 1 of x is e[1] + o[0]; the even limbs of p land on the O alignment, the odd ones on
+  // E two limbs up
+  const uint32_t m1 = ptx::mul_lo(e[1] + o[0], P::INV);
+  fixed_chain(o, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m1);
+  fixed_chain(e + 2, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m1);
+  // (E + (O << 32) + (addend << 64)) >> 64: limb 0 is zero, limb 1 sums to zero and leaves its carry
+  uint32_t x[8];
+  (void)ptx::add_cc(e[1], o[0]);
+#pragma unroll
+  for (int j = 0; j < 7; j++) x[j] = ptx::addc_cc(e[j + 2], o[j + 1]);
+  x[7] = ptx::addc(e[9], o[8]);
+  Fp<P> r;
+  r.v[0] = ptx::add_cc(x[0], addend.v[0]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) r.v[j] = ptx::addc_cc(x[j], addend.v[j]);
+  r.v[7] = ptx::addc(x[7], addend.v[7]);
+  fp_reduce_once<P>(r.v);  // [0, 2p + p / 2^29) -> [0, p + p / 2^29)
+  fp_reduce_once<P>(r.v);  // -> [0, p)
+  return r;
+}
+
+// The form in use.  ZOLT_BIND_BARRETT selects the r2 v7 Barrett reduction (kept for A/B timing; same values).
+#if defined(ZOLT_BIND_BARRETT)
+template <class P>
+ZOLT_HD FixedMulTable fixed_mul_table(const Fp<P>& r) { return fixed_mul_table_barrett<P>(r); }
+template <class P>
+ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) { return fp_fixed_mul_add_barrett<P>(addend, d, t); }
+#else
+template <class P>
+ZOLT_HD FixedMulTable fixed_mul_table(const Fp<P>& r) { return fixed_mul_table_mont2<P>(r); }
+template <class P>
+ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) { return fp_fixed_mul_add_mont2<P>(addend, d, t); }
+#endif
 
 // lo + r * (hi - lo)  (DensePolynomial.bindLow, src/poly/mod.zig:171) through the table of r.  The difference
 // is taken as hi + (p - lo), a non-canonical representative below 2p: the table product accepts any limbs.

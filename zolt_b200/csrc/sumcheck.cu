@@ -1744,13 +1744,8 @@ FixedMulTable fixed_mul_table_host(const Fr& r) {
   const Fr r_std = fp_mul<FrParams>(r, one_raw);
   uint64_t c[4];
   for (int j = 0; j < 4; j++) c[j] = (uint64_t)r_std.v[2 * j] | ((uint64_t)r_std.v[2 * j + 1] << 32);
-  FixedMulTable t;
-  for (int i = 0; i < 8; i++) {
-    for (int j = 0; j < 4; j++) {
-      t.c[i][2 * j] = (uint32_t)c[j];
-      t.c[i][2 * j + 1] = (uint32_t)(c[j] >> 32);
-    }
-    for (int d = 0; d < 32; d++) {
+  auto doublings = [&](int count) {
+    for (int d = 0; d < count; d++) {
       // c = 2c mod p  (c < p < 2^254: no overflow)
       c[3] = (c[3] << 1) | (c[2] >> 63);
       c[2] = (c[2] << 1) | (c[1] >> 63);
@@ -1766,6 +1761,17 @@ FixedMulTable fixed_mul_table_host(const Fr& r) {
       if (!bw)
         for (int j = 0; j < 4; j++) c[j] = s[j];
     }
+  };
+#if !defined(ZOLT_BIND_BARRETT)
+  doublings(64);  // the two-limb Montgomery form of the bind takes the rows scaled by 2^64 (field.cuh fp_fixed_mul_add_mont2)
+#endif
+  FixedMulTable t;
+  for (int i = 0; i < 8; i++) {
+    for (int j = 0; j < 4; j++) {
+      t.c[i][2 * j] = (uint32_t)c[j];
+      t.c[i][2 * j + 1] = (uint32_t)(c[j] >> 32);
+    }
+    doublings(32);
   }
   return t;
 }
