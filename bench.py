@@ -906,6 +906,63 @@ def extra_legs(ctx, Z, H, R, bases, h_logs, h_scalars, d_tab_ptrs, int_peak, tim
             if j < log_KL:
                 fe = fe * (1 - ch_i[j]) % B.FR_MOD
         out[f"lasso_T2^{log_TL}_K2^{log_KL}_ok"] = bool(ok and _fr_ints(lfin.reshape(1, 4))[0] == fe)
+    # K4: Dory row commitments (dory.zig:989-1042) of a 2^log_n-entry polynomial: 2^nu row MSMs over the first 2^sigma bases,
+    # device-resident evaluations (the MSM scalars); rows 0 and last checked against the closed form (sum_j e[r, j] k_j) G
+    d_ev = Z.DeviceBuffer.from_host(ctx, h_scalars)
+    try:
+        def run_dory():
+            res[0] = Z.Dory.row_commitments(bases, d_ev.ptr, device_len=n)
+
+        run_dory()
+        out["dory_rows_ms"] = time_ms(run_dory, 3, warm=0)
+        xy, inf, rows_d, cols_d = res[0]
+        out["dory_rows_shape"] = f"{rows_d}x{cols_d}"
+        ok = True
+        for r_ in (0, rows_d - 1):
+            ok = ok and check_msm_closed_form((xy[r_], inf[r_]), [R.fr_dot(h_logs[:cols_d], h_scalars[r_ * cols_d:(r_ + 1) * cols_d])])
+        out["dory_rows_ok"] = bool(ok)
+        # the same rows over the G1 vector as a long-lived SRS handle of its own (DorySRS.g1_vec, 2^sigma points) with its
+        # window-level table (c = 12, built untimed like the headline MSM's table)
+        g1 = Z.Bases.fixed_base_mul(ctx, h_logs[:cols_d])
+        try:
+            g1.precompute(12)
+
+            def run_dory_t():
+                res[0] = Z.Dory.row_commitments(g1, d_ev.ptr, device_len=n)
+
+            run_dory_t()
+            out["dory_rows_table_ms"] = time_ms(run_dory_t, 3, warm=0)
+            xy_t, inf_t, _, _ = res[0]
+            out["dory_rows_table_ok"] = bool((xy_t == xy).all() and (inf_t == inf).all())
+        finally:
+            g1.free()
+        # f1: HyperKZG.open (commitment/mod.zig:261-324) of the same polynomial at a random point: log n quotient commitments
+        # (MSMs of 2^(log n - 1) ... 1 points over the resident bases) and the folds between them, nothing leaves the device
+        # but the commitments; the final evaluation is checked against a chain of zolt_poly_bind_first over the same point
+        log_n_open = n.bit_length() - 1
+        pt = rows_global(STREAM_EQ, (1 << 17) + 768, log_n_open)
+
+        def run_open():
+            res[0] = Z.HyperKZG.open_dev(bases, d_ev.ptr, n, pt)
+
+        run_open()
+        out[f"hyperkzg_open_2^{log_n_open}_ms"] = time_ms(run_open, 3, warm=0)
+        q_xy, q_inf, fin = res[0]
+        d_tmp = Z.DeviceBuffer(ctx, 32 * (n // 2 + 1))
+        try:
+            cur, cur_n = d_ev.ptr, n
+            for j in range(log_n_open):  # open's own fold, (1 - r_i) lo + r_i hi over the two halves (mod.zig:298-305) = bindFirst
+                rj = np.ascontiguousarray(pt[j])
+                Z._lib.check(ctx.lib.zolt_poly_bind_first(ctx.handle, C.c_void_p(d_tmp.ptr), C.c_void_p(cur), cur_n,
+                                                          rj.ctypes.data_as(C.c_void_p)), "zolt_poly_bind_first")
+                cur, cur_n = d_tmp.ptr, cur_n // 2
+            ev0 = d_tmp.download((1, 4))
+        finally:
+            d_tmp.free()
+        out[f"hyperkzg_open_2^{log_n_open}_quotients"] = int(len(q_xy))
+        out[f"hyperkzg_open_2^{log_n_open}_final_matches_bind_chain"] = bool((np.asarray(fin).reshape(-1)[:4] == ev0.reshape(-1)).all())
+    finally:
+        d_ev.free()
     return {k: (round(v, 5) if isinstance(v, float) else v) for k, v in out.items()}
 
 
