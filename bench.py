@@ -270,6 +270,7 @@ def run_reference(args):
     threads = min(8, cores)  # detectOptimalThreads caps at 8 (src/msm/mod.zig:673-678)
     log_n = args.log_n
     s, _ = pick_cpu_sample(threads, budget_s=max(4.0, 40.0 / max(1, args.steps + args.warmup)))
+    s = min(s, log_n)  # a workload smaller than the sample is timed whole
     for _ in range(args.warmup):
         cpu_msm_sample(s, threads)
     t0 = time.perf_counter()
@@ -682,6 +683,9 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             threads = min(8, cores)
             s, ms = pick_cpu_sample(threads, budget_s=10.0)
+            if s > log_n:  # a workload smaller than the sample is timed whole
+                s = log_n
+                ms = cpu_msm_sample(s, threads)
             scale = float(1 << (log_n - s))
             sc_s = min(sc_log_n, 20)
             sc_cpu = cpu_sumcheck_sample(sc_s)
