@@ -938,12 +938,91 @@ ZOLT_HD Fp<P> fp_fixed_mul_add_mont2(const Fp<P>& addend, const uint32_t* d, con
   return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One reduction row (r2 v24).  Table scaled by 2^32: x = (addend << 32) + sum_i d_i * c32[i] < 9 * 2^32 p; one row
+// (m0 = x_0 * INV) clears the low limb and y = (x + m0 p) / 2^32 < 10 p is brought to [0, p) by a subtraction ladder
+// (8p, 4p, 2p, p: compare-and-select on the ALU pipe, which has the headroom the multiplier lacks).  64 + 8 wide multiplies
+// and 1 narrow one.
+// ---------------------------------------------------------------------------------------------
+// limb i (0..8) of (p << sh), sh < 32
+template <class P>
+ZOLT_HD constexpr uint32_t mod_shl(int sh, int i) {
+  const uint32_t lo = i < 8 ? P::mod(i) : 0u;
+  const uint32_t below = i > 0 ? P::mod(i - 1) : 0u;
+  return sh == 0 ? lo : ((lo << sh) | (below >> (32 - sh)));
+}
+// y (9 limbs) -= (p << SH) if that leaves it non-negative
+template <class P, int SH>
+ZOLT_HD void fp_ladder_step(uint32_t* y) {
+  uint32_t t[9];
+  t[0] = ptx::sub_cc(y[0], mod_shl<P>(SH, 0));
+#pragma unroll
+  for (int i = 1; i < 9; i++) t[i] = ptx::subc_cc(y[i], mod_shl<P>(SH, i));
+  const uint32_t borrow = ptx::subc(0u, 0u);  // 0xffffffff if y < (p << SH)
+#pragma unroll
+  for (int i = 0; i < 9; i++) y[i] = borrow ? y[i] : t[i];
+}
+
+template <class P>
+ZOLT_HD FixedMulTable fixed_mul_table_mont1(const Fp<P>& r) {
+  FixedMulTable t;
+  Fp<P> e = Fp<P>::zero();
+  e.v[1] = 1u;
+  const Fp<P> base_std = fp_mul<P>(r, e);                 // r_std * 2^32 mod p, as a plain integer
+  const Fp<P> base = fp_mul<P>(base_std, Fp<P>::r2());     // its Montgomery form
+  for (int i = 0; i < 8; i++) {
+    Fp<P> s = Fp<P>::zero();
+    s.v[i] = 1u;
+    const Fp<P> ci = fp_mul<P>(base, s);                   // r_std * 2^32 * 2^(32 i) mod p
+    for (int j = 0; j < 8; j++) t.c[i][j] = ci.v[j];
+  }
+  return t;
+}
+
+template <class P>
+ZOLT_HD Fp<P> fp_fixed_mul_add_mont1(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) {
+  uint32_t e[9], o[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) e[j] = o[j] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    fixed_chain(e, t.c[i][0], t.c[i][2], t.c[i][4], t.c[i][6], d[i]);
+    fixed_chain(o, t.c[i][1], t.c[i][3], t.c[i][5], t.c[i][7], d[i]);
+  }
+  const uint32_t m0 = ptx::mul_lo(e[0], P::INV);  // limb 0 of x is e[0]: O and the addend start one limb up
+  fixed_chain(e, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m0);
+  fixed_chain(o, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m0);
+  // y = (E + ((O + addend) << 32)) >> 32; e[0] is zero now
+  uint32_t y[9];
+  y[0] = ptx::add_cc(e[1], o[0]);
+#pragma unroll
+  for (int j = 1; j < 8; j++) y[j] = ptx::addc_cc(e[j + 1], o[j]);
+  y[8] = ptx::addc(o[8], 0u);
+  y[0] = ptx::add_cc(y[0], addend.v[0]);
+#pragma unroll
+  for (int j = 1; j < 8; j++) y[j] = ptx::addc_cc(y[j], addend.v[j]);
+  y[8] = ptx::addc(y[8], 0u);
+  fp_ladder_step<P, 3>(y);  // [0, 10p) -> [0, 8p)
+  fp_ladder_step<P, 2>(y);  // -> [0, 4p)
+  fp_ladder_step<P, 1>(y);  // -> [0, 2p)
+  fp_ladder_step<P, 0>(y);  // -> [0, p)
+  Fp<P> r;
+#pragma unroll
+  for (int j = 0; j < 8; j++) r.v[j] = y[j];
+  return r;
+}
+
 // The form in use.  ZOLT_BIND_BARRETT selects the r2 v7 Barrett reduction (kept for A/B timing; same values).
 #if defined(ZOLT_BIND_BARRETT)
 template <class P>
 ZOLT_HD FixedMulTable fixed_mul_table(const Fp<P>& r) { return fixed_mul_table_barrett<P>(r); }
 template <class P>
 ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) { return fp_fixed_mul_add_barrett<P>(addend, d, t); }
+#elif defined(ZOLT_BIND_MONT1)
+template <class P>
+ZOLT_HD FixedMulTable fixed_mul_table(const Fp<P>& r) { return fixed_mul_table_mont1<P>(r); }
+template <class P>
+ZOLT_HD Fp<P> fp_fixed_mul_add(const Fp<P>& addend, const uint32_t* d, const FixedMulTable& t) { return fp_fixed_mul_add_mont1<P>(addend, d, t); }
 #else
 template <class P>
 ZOLT_HD FixedMulTable fixed_mul_table(const Fp<P>& r) { return fixed_mul_table_mont2<P>(r); }

@@ -1762,7 +1762,9 @@ FixedMulTable fixed_mul_table_host(const Fr& r) {
         for (int j = 0; j < 4; j++) c[j] = s[j];
     }
   };
-#if !defined(ZOLT_BIND_BARRETT)
+#if defined(ZOLT_BIND_MONT1)
+  doublings(32);  // one reduction row: rows scaled by 2^32 (field.cuh fp_fixed_mul_add_mont1)
+#elif !defined(ZOLT_BIND_BARRETT)
   doublings(64);  // the two-limb Montgomery form of the bind takes the rows scaled by 2^64 (field.cuh fp_fixed_mul_add_mont2)
 #endif
   FixedMulTable t;
