@@ -2,7 +2,6 @@
 table, the Q-buffer fold, the w * (a b + c d) combiner, and the three provers (Shift / InstructionInput / Registers) run
 together like generateStage3Proof's loop -- every prover's evaluations in every round, the batched cubic, the running claims
 and the 16 final claims; sizes force the streaming rounds, the small-round kernel and the resident tail into use."""
-import ctypes as C
 import random
 
 import pytest
@@ -13,7 +12,6 @@ from oracle.bn254 import FR_MOD as P
 from tests.test_oracle_stage3 import _columns
 from tests.util import fr_arr, fr_ints, rand_fr
 from zolt_b200 import host as H
-from zolt_b200._lib import check
 
 pytestmark = pytest.mark.gpu
 
@@ -25,17 +23,12 @@ def ctx(built_lib):
     c.close()
 
 
-def _ptr(a):
-    return a.ctypes.data_as(C.c_void_p)
-
-
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 9, 13])
 def test_eq_plus_one_evals(ctx, n):
     r = rand_fr(300 + n, n)
     out = Z.DeviceBuffer(ctx, 32 << n)
     try:
-        rr = fr_arr(r)
-        check(ctx.lib.zolt_eq_plus_one_evals(ctx.handle, _ptr(rr), n, C.c_void_p(out.ptr)), "zolt_eq_plus_one_evals")
+        ctx.eq_plus_one_evals_dev(fr_arr(r), out.ptr)
         got = fr_ints(out.download((1 << n, 4)))
     finally:
         out.free()
@@ -50,7 +43,7 @@ def test_eq_plus_one_evals(ctx, n):
     xb = fr_arr(S3._bits_be(x, n))
     out = Z.DeviceBuffer(ctx, 32 << n)
     try:
-        check(ctx.lib.zolt_eq_plus_one_evals(ctx.handle, _ptr(xb), n, C.c_void_p(out.ptr)), "zolt_eq_plus_one_evals")
+        ctx.eq_plus_one_evals_dev(xb, out.ptr)
         got = fr_ints(out.download((1 << n, 4)))
     finally:
         out.free()
@@ -75,9 +68,7 @@ def test_fold_high(ctx, n_lo, n_hi, scaled):
     bufs = [Z.DeviceBuffer.from_host(ctx, fr_arr(t)) for t in (tab, w)]
     out = Z.DeviceBuffer(ctx, 32 * n_lo)
     try:
-        sc = fr_arr([scale]) if scaled else None
-        check(ctx.lib.zolt_fr_fold_high_dev(ctx.handle, C.c_void_p(out.ptr), C.c_void_p(bufs[0].ptr), C.c_void_p(bufs[1].ptr), n_lo, n_hi,
-                                            _ptr(sc) if scaled else None), "zolt_fr_fold_high_dev")
+        ctx.fr_fold_high_dev(out.ptr, bufs[0].ptr, bufs[1].ptr, n_lo, n_hi, fr_arr([scale]) if scaled else None)
         got = fr_ints(out.download((n_lo, 4)))
     finally:
         for b in bufs + [out]:

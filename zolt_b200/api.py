@@ -115,6 +115,25 @@ class Context:
         check(self.lib.zolt_fr_vec_dev(self.handle, op, C.c_void_p(d_out), C.c_void_p(d_a or None), C.c_void_p(d_b or None), C.c_void_p(d_c or None),
                                        C.c_void_p(d_e or None), _ptr(sv), n), "zolt_fr_vec_dev")
 
+    def eq_plus_one_evals_dev(self, r, d_out: int):
+        """EqPlusOnePolynomial as a table (zolt_eq_plus_one_evals): 2^len(r) elements at d_out, r big-endian."""
+        rr = _as_u64(r, 4)
+        check(self.lib.zolt_eq_plus_one_evals(self.handle, _ptr(rr), rr.shape[0], C.c_void_p(d_out)), "zolt_eq_plus_one_evals")
+
+    def fr_fold_high_dev(self, d_out: int, d_in: int, d_w: int, n_lo: int, n_hi: int, scale=None):
+        """out[x_lo] = scale * sum_{x_hi} in[x_lo + x_hi n_lo] w[x_hi]: the Q buffers of the prefix-suffix provers."""
+        sv = _as_u64(scale, 4) if scale is not None else None
+        check(self.lib.zolt_fr_fold_high_dev(self.handle, C.c_void_p(d_out), C.c_void_p(d_in), C.c_void_p(d_w), n_lo, n_hi, _ptr(sv)),
+              "zolt_fr_fold_high_dev")
+
+    def lasso_addr_round(self, d_eq_evals: int, d_indices: int, n: int, bind_bit: int, r, sum_bit: int) -> np.ndarray:
+        """One LassoProver address round over device tables (zolt_lasso_addr_round) -> [sum_0, sum_1] as (2, 4) limbs."""
+        rr = _as_u64(r, 4) if r is not None else None
+        sums = np.zeros((2, 4), dtype=np.uint64)
+        check(self.lib.zolt_lasso_addr_round(self.handle, C.c_void_p(d_eq_evals), C.c_void_p(d_indices), n, bind_bit, _ptr(rr), sum_bit,
+                                             _ptr(sums)), "zolt_lasso_addr_round")
+        return sums
+
     def poly_sum(self, d_src: int, n: int) -> np.ndarray:
         out = np.zeros(4, dtype=np.uint64)
         check(self.lib.zolt_poly_sum(self.handle, C.c_void_p(d_src), n, _ptr(out)), "zolt_poly_sum")
