@@ -1443,28 +1443,61 @@ __global__ void __launch_bounds__(kScThreads) inner_product_kernel(const Fr* a, 
   grid_finish<1>(acc, smem, out, Fr::zero());
 }
 
+// x (10 limbs, below 2^288) -> canonical x mod r; once per thread
+struct Limbs10 { uint32_t v[10]; };
+__device__ __noinline__ Fr lasso_reduce_288_cold(Limbs10 x) { return fp_barrett_289<FrParams>(x.v); }
+__device__ __forceinline__ Fr lasso_reduce_288(const uint32_t* x) {
+  Limbs10 t;
+#pragma unroll
+  for (int k = 0; k < 10; k++) t.v[k] = x[k];
+  return lasso_reduce_288_cold(t);
+}
+
 // LassoProver address rounds (src/zkvm/lasso/prover.zig:265-310 computeAddressRoundPoly, :380-412 receiveChallenge): one pass
 // that applies the PREVIOUS round's challenge -- eq_evals[j] *= bit(idx_j, bind_bit) ? r : 1 - r -- and accumulates this round's
 // partition sums sum_b = sum over { j : bit(idx_j, sum_bit) = b } of eq_evals[j].  The reference's claim after the bind is the
 // sum of the updated table, i.e. sum_0 + sum_1 of this very pass.  idx: 128-bit little-endian lookup indices.
 __global__ void __launch_bounds__(kScThreads)
-lasso_addr_kernel(Fr* __restrict__ eq, const uint4* __restrict__ idx, size_t n, int bind_bit, const __grid_constant__ Fr r, int sum_bit,
-                  ScOut out) {
+lasso_addr_kernel(Fr* __restrict__ eq, const uint4* __restrict__ idx, size_t n, int bind_bit, const __grid_constant__ FixedMulTable rt,
+                  int sum_bit, ScOut out) {
   __shared__ Fr smem[64];
-  Fr acc[2] = {Fr::zero(), Fr::zero()};
-  const Fr one_minus_r = fr_sub(Fr::one(), r);
-  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
-    const uint4 w = __ldg(idx + j);
+  // per-thread sums as plain 288-bit integers (canonical entries, at most 2^23 of them per thread: no overflow), reduced
+  // once at the end: 9 carry-chain adds per entry and sum instead of an add and a conditional subtraction.
+  // tot = all entries, one = the entries whose index has bit sum_bit set; sum_0 = tot - one.
+  uint32_t tot[10], one[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) tot[k] = one[k] = 0;
+  // two entries per iteration, both loaded before either is used: the pass is bound by memory latency, not by arithmetic
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  auto step = [&](size_t j, const uint4& w, Fr e) {
     const uint32_t limb[4] = {w.x, w.y, w.z, w.w};
-    Fr e = eq[j];
     if (bind_bit >= 0) {
-      e = fr_mul(e, ((limb[bind_bit >> 5] >> (bind_bit & 31)) & 1u) ? r : one_minus_r);
+      // the multiplier is the same for every entry of a launch: one product through the table of r (field.cuh
+      // fp_fixed_mul_add, 80 wide multiplies instead of 136), and e (1 - r) = e - e r costs a subtraction
+      const Fr er = fp_fixed_mul_add<FrParams>(Fr::zero(), e.v, rt);
+      e = ((limb[bind_bit >> 5] >> (bind_bit & 31)) & 1u) ? er : fr_sub(e, er);
       st_fr(eq + j, e);
     }
-    const unsigned b = sum_bit >= 0 ? ((limb[sum_bit >> 5] >> (sum_bit & 31)) & 1u) : 0u;
-    if (b) acc[1] = fr_add(acc[1], e);
-    else acc[0] = fr_add(acc[0], e);
+    const uint32_t mask = sum_bit >= 0 ? 0u - ((limb[sum_bit >> 5] >> (sum_bit & 31)) & 1u) : 0u;
+    tot[0] = ptx::add_cc(tot[0], e.v[0]);
+#pragma unroll
+    for (int k = 1; k < 8; k++) tot[k] = ptx::addc_cc(tot[k], e.v[k]);
+    tot[8] = ptx::addc(tot[8], 0u);
+    one[0] = ptx::add_cc(one[0], e.v[0] & mask);
+#pragma unroll
+    for (int k = 1; k < 8; k++) one[k] = ptx::addc_cc(one[k], e.v[k] & mask);
+    one[8] = ptx::addc(one[8], 0u);
+  };
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; j + stride < n; j += 2 * stride) {
+    const uint4 w0 = __ldg(idx + j), w1 = __ldg(idx + j + stride);
+    const Fr e0 = eq[j], e1 = eq[j + stride];
+    step(j, w0, e0);
+    step(j + stride, w1, e1);
   }
+  if (j < n) step(j, __ldg(idx + j), eq[j]);
+  const Fr s_one = lasso_reduce_288(one), s_tot = lasso_reduce_288(tot);
+  Fr acc[2] = {fr_sub_cold(s_tot, s_one), s_one};
   grid_finish<2>(acc, smem, out, Fr::zero());
 }
 
@@ -2740,9 +2773,9 @@ extern "C" int zolt_lasso_addr_round(zolt_ctx* ctx, void* d_eq_evals, const void
   so.d_evals = s.d_out;
   so.h_evals = (Fr*)ctx->d_mailbox;
   so.finalize = 1;
-  const Fr rr = bind_bit >= 0 ? fr_from_host(r) : Fr::zero();
+  const FixedMulTable rt = bind_bit >= 0 ? fixed_mul_table_host(fr_from_host(r)) : FixedMulTable{};
   lasso_addr_kernel<<<grid_for(ctx, n, 4), kScThreads, 0, ctx->stream>>>((Fr*)d_eq_evals, (const uint4*)d_indices, n, bind_bit < 0 ? -1 : bind_bit,
-                                                                        rr, sum_bit < 0 ? -1 : sum_bit, so);
+                                                                        rt, sum_bit < 0 ? -1 : sum_bit, so);
   ctx->launches++;
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
