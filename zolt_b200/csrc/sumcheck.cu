@@ -2766,6 +2766,7 @@ extern "C" int zolt_lasso_addr_round(zolt_ctx* ctx, void* d_eq_evals, const void
   ZOLT_CUDA_TRY(cudaSetDevice(ctx->device));
   Scratch s;
   ZOLT_TRY(scratch_alloc(ctx, &s));
+  OnFail give_back([&] { scratch_free(ctx, &s); });  // runs on every exit
   ScOut so{};
   so.partials = s.partials;
   so.ticket = s.ticket;
@@ -2780,7 +2781,6 @@ extern "C" int zolt_lasso_addr_round(zolt_ctx* ctx, void* d_eq_evals, const void
   ZOLT_CUDA_TRY(cudaGetLastError());
   ZOLT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(sums_out, ctx->h_mailbox, 64);
-  scratch_free(ctx, &s);
   return ZOLT_OK;
 }
 

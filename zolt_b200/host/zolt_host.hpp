@@ -787,6 +787,15 @@ class DevPool {
     owned_.emplace_back(p, bytes);
     return static_cast<Fr*>(p);
   }
+  // hand a temporary back to the context's cache before the prover ends (work queued on it is ordered on the same stream)
+  void release(void* p) {
+    for (size_t i = 0; i < owned_.size(); i++)
+      if (owned_[i].first == p) {
+        zolt_dev_release_cached(ctx_.raw(), p, owned_[i].second);
+        owned_.erase(owned_.begin() + (long)i);
+        return;
+      }
+  }
   // out = s0 a + s1 b
   void lin2(Fr* out, const void* a, const Fr& s0, const void* b, const Fr& s1, size_t n) {
     const Fr s[2] = {s0, s1};
@@ -860,6 +869,8 @@ class InstructionInputProver {
     pool_.eq(ep, r_product);
     w_ = pool_.alloc(T);
     pool_.lin2(w_, eo, Fr::one(), ep, gamma_sqr, T);
+    pool_.release(eo);
+    pool_.release(ep);
     const void* right[5] = {w_, c.right_is_rs2, c.rs2_value, c.right_is_imm, c.imm};
     const void* left[5] = {w_, c.left_is_rs1, c.rs1_value, c.left_is_pc, c.unexpanded_pc};
     must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_EQ_DOT2, ZOLT_PAIR_ADJACENT, log_T, 5, 0, right, &right_), "zolt_sc_create_dev");
@@ -888,6 +899,7 @@ class InstructionInputProver {
     pool_.lin2(x, right, Fr::one(), left, gamma_, T_);
     Fr claim;
     must(zolt_fr_inner_product_dev(pool_.ctx().raw(), w_, x, T_, claim.limbs.data()), "zolt_fr_inner_product_dev");
+    for (Fr* t : {x, y, right, left}) pool_.release(t);
     return claim;
   }
   std::array<Fr, 4> computeRoundEvals(const Fr& previous_claim) {
@@ -964,6 +976,7 @@ class ShiftPrefixSuffixProver {
     pool_.fold(Q + ps, v, suf_[1], ps, ss);
     pool_.fold(Q + 2 * ps, t2, suf_[2], ps, ss, &gp_[4]);
     pool_.fold(Q + 3 * ps, t2, suf_[3], ps, ss, &gp_[4]);
+    for (Fr* t : {t1, t2, v}) pool_.release(t);  // T-sized temporaries: only the sqrt(T)-sized buffers live on
     const void* pq[2] = {P, Q};
     must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_PROD2, ZOLT_PAIR_ADJACENT, prefix_vars_ + 2, 2, 0, pq, &pq_), "zolt_sc_create_dev");
     const void* wit[5] = {c.unexpanded_pc, c.pc, c.is_virtual, c.is_first_in_sequence, c.is_noop};
@@ -1066,6 +1079,8 @@ class RegistersPrefixSuffixProver {
     pool_.lin2(v, t, Fr::one(), c.rs2_value, gamma_sqr, T);
     Fr* Q = pool_.alloc(ps);
     pool_.fold(Q, v, suffix_, ps, ss);
+    pool_.release(v);
+    pool_.release(t);
     const void* pq[2] = {P, Q};
     must(zolt_sc_create_dev(ctx.raw(), ZOLT_SC_PROD2, ZOLT_PAIR_ADJACENT, prefix_vars_, 2, 0, pq, &pq_), "zolt_sc_create_dev");
     const void* wit[3] = {c.rd_write_value, c.rs1_value, c.rs2_value};
