@@ -653,8 +653,8 @@ def run_b200(args):
                 "achieved": sc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sc_gbs / hbm_peak, "peak_source": peak_src,
                 "frac_of_8000_spec": sc_gbs / 8000.0, "bytes_per_sumcheck": sc_bytes, "kernel_ms": sc_kernel_ms,
                 "traffic": ncu_traffic("sc_round_kernel") if world == 1 else None,
-                "binding_unit": "integer multiplier (ncu sm__pipe_fmaheavy_cycles_active 83 % on the fused round, DRAM 49 %, traffic = "
-                                "algorithmic bytes: profiles/r2_v15_sc_round_full.txt); at 100 % of that pipe the kernels would reach 0.51 of "
+                "binding_unit": "integer multiplier (ncu sm__pipe_fmaheavy_cycles_active 79-83 % on the fused round, DRAM 50 %, traffic = "
+                                "algorithmic bytes: profiles/r2_v23_sc_round_full.txt); at 100 % of that pipe the kernels would reach 0.55 of "
                                 "the HBM peak",
             },
             "sumcheck": {
