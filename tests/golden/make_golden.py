@@ -13,7 +13,8 @@ from pathlib import Path
 REF = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
 OUT = Path(__file__).resolve().parent
 
-pat = re.compile(r"\[ZOLT\] (STAGE\d+)_ROUND_(\d+): (current_claim|c0|c2|c3|challenge|next_claim) = \{+ ([0-9, ]+?),? \}+")
+# generateBatchedProof prints `= { 1, 2, ... }`, generateStage3Proof (src/zkvm/spartan/stage3_prover.zig:430-560) `= { { 1, 2, ... } }`
+pat = re.compile(r"\[ZOLT\] (STAGE\d+)_ROUND_(\d+): (current_claim|c0|c2|c3|challenge|next_claim|p0|p1|shift_p0|shift_p1) = (?:\{ )+([0-9, ]+?),? (?:\} ?)+$")
 rounds = {}
 for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines():
     m = pat.match(line)
@@ -23,11 +24,21 @@ for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines()
     vals = [int(x) for x in body.replace(" ", "").split(",") if x]
     if len(vals) != 32:
         continue
-    rounds.setdefault((stage, int(rnd)), {})[key] = vals
+    rounds.setdefault((stage, int(rnd)), {}).setdefault(key, vals)  # the first print of a key in a round
 
 kats = []
 for (stage, rnd), d in sorted(rounds.items()):
     if all(k in d for k in ("current_claim", "c0", "c2", "c3", "challenge", "next_claim")):
         kats.append({"stage": stage, "round": rnd, **d})
-(OUT / "zolt_log_kats.json").write_text(json.dumps({"source": "logs/zolt.log", "format": "canonical LE bytes (toBytes)", "kats": kats}))
+# Stage 3 preamble (stage3_prover.zig:150-215): the three input claims and the Shift gamma powers the run printed
+pre_pat = re.compile(r"\[ZOLT\] (?:STAGE3_PRE: input_claim\[(\d)\] \(\w+\)|STAGE3_SHIFT: gamma_powers\[(\d)\]) = (?:\{ )+([0-9, ]+?),? (?:\} ?)+$")
+stage3_pre = {}
+for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines():
+    m = pre_pat.match(line)
+    if m:
+        vals = [int(x) for x in m.group(3).replace(" ", "").split(",") if x]
+        if len(vals) == 32:
+            stage3_pre.setdefault(f"input_claim_{m.group(1)}" if m.group(1) else f"gamma_power_{m.group(2)}", vals)
+(OUT / "zolt_log_kats.json").write_text(json.dumps({"source": "logs/zolt.log", "format": "canonical LE bytes (toBytes)", "kats": kats,
+                                                   "stage3_pre": stage3_pre}))
 print(f"{len(kats)} claim-update KATs")

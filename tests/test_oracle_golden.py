@@ -26,6 +26,38 @@ def test_log_claim_update_kats():
         assert B.fr_to_bytes(got) == bytes(k["next_claim"])  # toBytes = canonical LE (field/mod.zig:685-695)
 
 
+def test_log_stage3_round_kats():
+    """The eight STAGE3_ROUND_k tuples generateStage3Proof printed in the captured run (stage3_prover.zig:430-560): the batched
+    cubic's p(0) is c0, p(0) + p(1) is the running claim, and the claim after the challenge is what the evaluation-form path
+    of the Stage 3 mirror (evaluate_cubic_at_point over [p(0..3)]) and the compressed-coefficient path both return."""
+    from oracle import stage3 as S3
+
+    kats = [k for k in json.loads((GOLD / "zolt_log_kats.json").read_text())["kats"] if k["stage"] == "STAGE3"]
+    assert len(kats) == 8  # trace_len 256 -> 8 rounds
+    le = lambda b: int.from_bytes(bytes(b), "little")  # noqa: E731
+    prev_next = None
+    for k in sorted(kats, key=lambda x: x["round"]):
+        claim, c0, c2, c3, r = (le(k[x]) for x in ("current_claim", "c0", "c2", "c3", "challenge"))
+        if "p0" in k:  # printed for the first rounds only
+            assert le(k["p0"]) == c0 and (le(k["p0"]) + le(k["p1"])) % P == claim
+        if prev_next is not None:
+            assert claim == prev_next  # the rounds chain
+        c1 = (claim - 2 * c0 - c2 - c3) % P
+        evals = [(c0 + c1 * x + c2 * x * x + c3 * x ** 3) % P for x in range(4)]
+        if "p1" in k:
+            assert evals[1] == le(k["p1"])
+        assert S3._cubic_at(evals, r) == le(k["next_claim"])
+        # the Shift instance's own p(0), p(1) of the same round are field elements below r
+        assert all(le(k[x]) < P for x in ("shift_p0", "shift_p1") if x in k)
+        prev_next = le(k["next_claim"])
+    # the preamble of the same run: Shift's first round sums to its input claim (the identity oracle/stage3.py's phase 1
+    # relies on), and the Shift gamma powers are powers of one gamma (what the Stage 3 tests feed the provers)
+    pre = json.loads((GOLD / "zolt_log_kats.json").read_text())["stage3_pre"]
+    r0 = min(kats, key=lambda x: x["round"])
+    assert (le(r0["shift_p0"]) + le(r0["shift_p1"])) % P == le(pre["input_claim_0"])
+    assert le(pre["gamma_power_0"]) == 1 and le(pre["gamma_power_4"]) == pow(le(pre["gamma_power_1"]), 4, P)
+
+
 def test_montgomery_constants_match_reference_source():
     # src/field/mod.zig:24-41 (Fr) and :59-75 (Fq)
     assert B.int_to_limbs(B.FR_R) == [0xAC96341C4FFFFFFB, 0x36FC76959F60CD29, 0x666EA36F7879462E, 0x0E0A77C19A07DF2F]
