@@ -11,7 +11,8 @@ The prefix-suffix decompositions and the split eq's bindOuter / bindInner the pr
 its outputs (round polynomials, claims, final_eval, challenges) and are not restated.
 Pinned by the reference's unit tests (prover.zig "lasso prover claim tracking" :620-690, integration_test.zig "lasso
 end-to-end simple case" :68-120 and "lasso multiple rounds consistent" :282-338), whose inputs and assertions
-tests/test_oracle_lasso.py replays.
+tests/test_oracle_lasso.py replays, and by the 24 round tuples of the reference's own captured run (logs/zolt.log ->
+tests/golden/zolt_log_kats.json): claim = p(0) + p(1), the re-summed claim after a challenge = p(challenge), c2 = 0.
 """
 from __future__ import annotations
 

@@ -39,6 +39,26 @@ for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines()
         vals = [int(x) for x in m.group(3).replace(" ", "").split(",") if x]
         if len(vals) == 32:
             stage3_pre.setdefault(f"input_claim_{m.group(1)}" if m.group(1) else f"gamma_power_{m.group(2)}", vals)
+# LassoProver's own run in the same log (src/zkvm/lasso/prover.zig:232-456 prints): per round the claim, the coefficients, the
+# challenge and the claim after receiveChallenge, as hex of limbs[3..0] -- MONTGOMERY limbs, kept as printed
+lasso, cur = [], None
+for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines():
+    if not line.startswith("[LASSO PROVER]"):
+        continue
+    m = re.match(r"\[LASSO PROVER\] computeRoundPolynomial round=(\d+) phase=(\w+)", line)
+    if m:
+        cur = {"round": int(m.group(1)), "phase": m.group(2)}
+        lasso.append(cur)
+        continue
+    if cur is None:
+        continue
+    m = re.match(r"\[LASSO PROVER\]\s+(current_claim|c\[0\]|c\[1\]|c\[2\]|challenge|current_claim \(after\)) = ([0-9a-f]{64})$", line)
+    if m:
+        key = {"current_claim": "claim", "c[0]": "c0", "c[1]": "c1", "c[2]": "c2", "challenge": "challenge", "current_claim (after)": "claim_after"}[m.group(1)]
+        cur.setdefault(key, m.group(2))
+lasso = [r for r in lasso if all(k in r for k in ("claim", "c0", "c1", "c2", "challenge", "claim_after"))]
 (OUT / "zolt_log_kats.json").write_text(json.dumps({"source": "logs/zolt.log", "format": "canonical LE bytes (toBytes)", "kats": kats,
-                                                   "stage3_pre": stage3_pre}))
+                                                   "stage3_pre": stage3_pre,
+                                                   "lasso_rounds": lasso, "lasso_format": "hex of Montgomery limbs[3..0]; log_K = 16, log_T = 8"}))
+print(f"{len(lasso)} Lasso round tuples")
 print(f"{len(kats)} claim-update KATs")

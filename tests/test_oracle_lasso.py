@@ -2,7 +2,9 @@
 (:620-690: p(0) + p(1) = current_claim every round, the claim after receiveChallenge = p(challenge)), integration_test.zig
 "lasso end-to-end simple case" (:68-120: the first round's g(0) + g(1) equals expanding_v.sum() = 1) and "lasso multiple rounds
 consistent" (:282-338)."""
+import json
 import random
+from pathlib import Path
 
 import pytest
 
@@ -67,3 +69,24 @@ def test_table_convention_and_final_eval(log_T, log_K, fill):
 def test_derive_challenge_is_a_u64_mix():
     a = L.derive_challenge([[1, 2, 3, 4], [0, 0, 0, 0], [5, 6, 7, 8]], 3)
     assert 0 <= a < 1 << 64 and a != L.derive_challenge([[1, 2, 3, 4], [0, 0, 0, 0], [5, 6, 7, 8]], 4)
+
+
+def test_reference_run_round_tuples():
+    """The 24 rounds LassoProver printed in the reference's captured run (logs/zolt.log, log_K = 16, log_T = 8; committed in
+    tests/golden/zolt_log_kats.json): p(0) + p(1) is the claim, the claim the reference RE-SUMS from the updated table after
+    receiveChallenge (prover.zig:402-407, :441-446) is p(challenge) -- which is how the device mirror obtains it without a
+    pass over the table -- and the rounds chain.  Address rounds send degree-1 polynomials (c2 = 0).  The run's lookup indices
+    are not in the log, so the tuples pin these identities, not the table values."""
+    d = json.loads((Path(__file__).resolve().parent / "golden" / "zolt_log_kats.json").read_text())
+    rounds = d["lasso_rounds"]
+    assert len(rounds) == 24 and [r["round"] for r in rounds] == list(range(24))
+    assert [r["phase"] for r in rounds] == ["address"] * 16 + ["cycle"] * 8
+    rinv = pow(1 << 256, -1, P)
+    std = lambda h: int(h, 16) * rinv % P  # noqa: E731  (printed limbs are Montgomery form)
+    for i, r in enumerate(rounds):
+        c0, c1, c2, ch = (std(r[k]) for k in ("c0", "c1", "c2", "challenge"))
+        assert c2 == 0
+        assert (2 * c0 + c1 + c2) % P == std(r["claim"])
+        assert (c0 + c1 * ch + c2 * ch * ch) % P == std(r["claim_after"])
+        if i + 1 < len(rounds):
+            assert rounds[i + 1]["claim"] == r["claim_after"]
