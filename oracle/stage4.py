@@ -12,6 +12,10 @@ Reference anchors (relative to /root/reference):
 The witness generation from an ExecutionTrace (initWithPhaseConfig :139-366) is not restated: the prover is entered with its
 dense K x T tables (val, rd_wa, rs1_ra, rs2_ra), inc (T) and the phase configuration, which is the state that function leaves.
 Tables are indexed [k * T + j] with the ORIGINAL stride T throughout, like the reference.
+Pinned value by value where the reference's captured run allows it: logs/zolt.log prints E_out[0..3], E_in[0..3] and two
+E_out * E_in weights of the Stage 4 split eq over r_cycle = that run's Stage 3 challenges (tests/golden/zolt_log_kats.json,
+tests/test_oracle_stage4.py); the witness tables of the run are not in the log, the rest is pinned through the protocol's
+identities and the reference's unit expectations.
 """
 from __future__ import annotations
 

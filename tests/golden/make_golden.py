@@ -57,8 +57,24 @@ for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines()
         key = {"current_claim": "claim", "c[0]": "c0", "c[1]": "c1", "c[2]": "c2", "challenge": "challenge", "current_claim (after)": "claim_after"}[m.group(1)]
         cur.setdefault(key, m.group(2))
 lasso = [r for r in lasso if all(k in r for k in ("claim", "c0", "c1", "c2", "challenge", "claim_after"))]
+# Stage4GruenProver's split-eq tables in the same run (src/zkvm/spartan/gruen_eq.zig:19-112 through the STAGE4_GRUEN_INIT prints):
+# the first four entries of E_out / E_in (LE bytes); the r_cycle_be lines print the 128-bit challenge encodings, not the field
+# elements -- those are the STAGE3_ROUND_k challenges above, reversed
+stage4 = {"r_cycle_be": {}, "E_out": {}, "E_in": {}}
+for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines():
+    m = re.match(r"\[STAGE4_GRUEN_INIT\]\s+r_cycle_be\[(\d+)\] = \{ ([0-9a-f ]+) \}", line)
+    if m:
+        stage4["r_cycle_be"].setdefault(int(m.group(1)), int(m.group(2).replace(" ", ""), 16))
+    m = re.match(r"\[STAGE4_GRUEN_INIT\]\s+(E_out|E_in)\[(\d+)\] = \{ ([0-9, ]+) \}", line)
+    if m:
+        vals = [int(x) for x in m.group(3).replace(" ", "").split(",") if x]
+        if len(vals) == 32:
+            stage4[m.group(1)].setdefault(int(m.group(2)), vals)
+stage4 = {"r_cycle_be": [str(stage4["r_cycle_be"][i]) for i in sorted(stage4["r_cycle_be"])],
+          "E_out": [stage4["E_out"][i] for i in sorted(stage4["E_out"])], "E_in": [stage4["E_in"][i] for i in sorted(stage4["E_in"])]}
 (OUT / "zolt_log_kats.json").write_text(json.dumps({"source": "logs/zolt.log", "format": "canonical LE bytes (toBytes)", "kats": kats,
                                                    "stage3_pre": stage3_pre,
+                                                   "stage4_gruen_init": stage4,
                                                    "lasso_rounds": lasso, "lasso_format": "hex of Montgomery limbs[3..0]; log_K = 16, log_T = 8"}))
 print(f"{len(lasso)} Lasso round tuples")
 print(f"{len(kats)} claim-update KATs")

@@ -50,3 +50,26 @@ def test_gruen_eq_reference_unit_expectations():
     # "gruen poly deg 3" (:387-414): p(0) + p(1) = claim
     c = S.GruenEq([1, 2]).gruen_poly_deg3(10, 5, 100)
     assert (c[0] + sum(c)) % P == 100
+
+
+def test_gruen_eq_tables_match_the_reference_run():
+    """Value-level vectors from the reference's own captured run (logs/zolt.log -> tests/golden/zolt_log_kats.json): Stage 4's
+    r_cycle is the Stage 3 challenge vector (round order; the split eq takes it big-endian, stage4_gruen_prover.zig:259-281),
+    and STAGE4_GRUEN_INIT printed E_out.len = 16, E_in.len = 8 and the first four entries of each table
+    (gruen_eq.zig evalsCached :296-334).  The first two STAGE4_CONTRIB lines give E_out[x_out] * E_in[x_in] (low 8 bytes)."""
+    import json
+    from pathlib import Path
+
+    d = json.loads((Path(__file__).resolve().parent / "golden" / "zolt_log_kats.json").read_text())
+    le = lambda b: int.from_bytes(bytes(b), "little")  # noqa: E731
+    ch = [le(k["challenge"]) for k in sorted((k for k in d["kats"] if k["stage"] == "STAGE3"), key=lambda x: x["round"])]
+    assert len(ch) == 8
+    g = S.GruenEq(ch[::-1])
+    e_out, e_in = g.E_out_current(), g.E_in_current()
+    assert len(e_out) == 16 and len(e_in) == 8
+    init = d["stage4_gruen_init"]
+    assert e_out[:4] == [le(v) for v in init["E_out"]]
+    assert e_in[:4] == [le(v) for v in init["E_in"]]
+    # [STAGE4_CONTRIB #1] x_out=0, x_in=0 and [#2] x_out=0, x_in=1: E_combined, first 8 bytes
+    assert (e_out[0] * e_in[0] % P).to_bytes(32, "little")[:8] == bytes([35, 129, 211, 100, 28, 19, 13, 225])
+    assert (e_out[0] * e_in[1] % P).to_bytes(32, "little")[:8] == bytes([102, 202, 125, 226, 26, 250, 145, 82])
