@@ -14,7 +14,8 @@ scope): lists of length trace_len = 2^n.  Parity is pinned by the refe
 sumcheck identities the reference's own debug lines assert (p(0) + p(1) = claim every round, grand_sum(P*Q) = direct_sum,
 the final-claim relations of :620-700) and by what the reference's own captured run printed for this stage (logs/zolt.log,
 committed as tests/golden/zolt_log_kats.json: the eight STAGE3_ROUND_k tuples chain through the cubic evaluation used here,
-shift_p0 + shift_p1 of round 0 equals input_claim[0], gamma_powers[4] = gamma_powers[1]^4; trace_len 256 -> prefix_size 16,
+shift_p0 + shift_p1 of round 0 equals input_claim[0], gamma_powers[4] = gamma_powers[1]^4, and eq+1(r_outer, k) for
+k = 0..4, 255 plus eq(r_outer, 255) equal the printed values for r_outer = that run's Stage 1 challenges; trace_len 256 -> prefix_size 16,
 suffix_size 16).  The run's witness columns are not in the log, so the provers' per-round values are pinned through these
 identities, not value by value.
 """

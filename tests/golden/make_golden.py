@@ -30,6 +30,8 @@ kats = []
 for (stage, rnd), d in sorted(rounds.items()):
     if all(k in d for k in ("current_claim", "c0", "c2", "c3", "challenge", "next_claim")):
         kats.append({"stage": stage, "round": rnd, **d})
+# the Stage 1 challenges (9 rounds): r_outer of Stage 3 is rounds 8..1 of them (SHIFT_INIT prints r_outer[0] and r_outer[last])
+stage1_challenges = [rounds[("STAGE1", i)]["challenge"] for i in range(9) if ("STAGE1", i) in rounds and "challenge" in rounds[("STAGE1", i)]]
 # Stage 3 preamble (stage3_prover.zig:150-215): the three input claims and the Shift gamma powers the run printed
 pre_pat = re.compile(r"\[ZOLT\] (?:STAGE3_PRE: input_claim\[(\d)\] \(\w+\)|STAGE3_SHIFT: gamma_powers\[(\d)\]) = (?:\{ )+([0-9, ]+?),? (?:\} ?)+$")
 stage3_pre = {}
@@ -73,7 +75,7 @@ for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines()
 stage4 = {"r_cycle_be": [str(stage4["r_cycle_be"][i]) for i in sorted(stage4["r_cycle_be"])],
           "E_out": [stage4["E_out"][i] for i in sorted(stage4["E_out"])], "E_in": [stage4["E_in"][i] for i in sorted(stage4["E_in"])]}
 (OUT / "zolt_log_kats.json").write_text(json.dumps({"source": "logs/zolt.log", "format": "canonical LE bytes (toBytes)", "kats": kats,
-                                                   "stage3_pre": stage3_pre,
+                                                   "stage3_pre": stage3_pre, "stage1_challenges": stage1_challenges,
                                                    "stage4_gruen_init": stage4,
                                                    "lasso_rounds": lasso, "lasso_format": "hex of Montgomery limbs[3..0]; log_K = 16, log_T = 8"}))
 print(f"{len(lasso)} Lasso round tuples")

@@ -110,3 +110,28 @@ def test_stage3_oracle_invariants(n, trace_like):
     rr = dict(zip(S.RegistersPrefixSuffixProver.COLS, reg.final_claims()))
     assert eq_mle(r_outer, rev) * ((rr["rd_write_value"] + rg * rr["rs1_value"] + rg * rg % P * rr["rs2_value"]) % P) % P == final[2]
     assert combined_claim == sum(c * b for c, b in zip(final, bc)) % P
+
+
+def test_eq_plus_one_matches_the_reference_run():
+    """Value-level vectors from the reference's captured run (logs/zolt.log -> tests/golden/zolt_log_kats.json): Stage 3's r_outer
+    is the Stage 1 challenge vector, rounds 8..1 (SHIFT_INIT prints r_outer[0] and r_outer[last]), and SHIFT_INIT printed the
+    first 8 bytes of eq+1(r_outer, k) for k = 0..4 and 255 and of eq(r_outer, 255) (stage3_prover.zig:1250-1290)."""
+    import json
+    from pathlib import Path
+
+    d = json.loads((Path(__file__).resolve().parent / "golden" / "zolt_log_kats.json").read_text())
+    ch = [int.from_bytes(bytes(c), "little") for c in d["stage1_challenges"]]
+    assert len(ch) == 9
+    r = [ch[i] for i in range(8, 0, -1)]
+    assert list(r[0].to_bytes(32, "little")[:8]) == [70, 3, 78, 128, 115, 33, 214, 219]      # SHIFT_INIT: r_outer[0]
+    assert list(r[-1].to_bytes(32, "little")[:8]) == [41, 25, 57, 228, 184, 23, 13, 80]     # SHIFT_INIT: r_outer[last]
+    logged = {0: [0] * 8, 1: [166, 164, 37, 130, 206, 91, 156, 95], 2: [118, 194, 206, 228, 136, 232, 207, 27],
+              3: [255, 73, 251, 187, 24, 103, 109, 214], 4: [9, 98, 82, 241, 126, 140, 187, 237], 255: [101, 82, 14, 229, 68, 52, 48, 82]}
+    table = S.eq_plus_one_evals(r)
+    for k, want in logged.items():
+        assert list(S.eq_plus_one_mle(r, S._bits_be(k, 8)).to_bytes(32, "little")[:8]) == want
+        assert list(table[k].to_bytes(32, "little")[:8]) == want
+    assert list(eq_mle(r, S._bits_be(255, 8)).to_bytes(32, "little")[:8]) == [147, 167, 237, 58, 11, 177, 233, 250]
+    # "eq(r, k-1) = eq+1(r, k)" as the run verified it for k = 1..4
+    for k in range(1, 5):
+        assert eq_mle(r, S._bits_be(k - 1, 8)) == table[k]
