@@ -183,3 +183,24 @@ def test_stage3_streaming_kernels_only(ctx):
     finally:
         ctx.set_tuning(Z.TUNE_SC_SMALL_PAIRS, 1 << 14)
         ctx.set_tuning(Z.TUNE_SC_TAIL_PAIRS, 1 << 12)
+
+
+def test_device_eq_plus_one_table_matches_the_reference_run(ctx):
+    """The device table for r_outer of the reference's captured run (its Stage 1 challenges, rounds 8..1) against the values
+    that run printed: eq+1(r_outer, k), first 8 bytes, k = 0..4 and 255 (logs/zolt.log SHIFT_INIT -> tests/golden)."""
+    import json
+    from pathlib import Path
+
+    d = json.loads((Path(__file__).resolve().parent / "golden" / "zolt_log_kats.json").read_text())
+    ch = [int.from_bytes(bytes(c), "little") for c in d["stage1_challenges"]]
+    r = [ch[i] for i in range(8, 0, -1)]
+    out = Z.DeviceBuffer(ctx, 32 << 8)
+    try:
+        ctx.eq_plus_one_evals_dev(fr_arr(r), out.ptr)
+        got = fr_ints(out.download((256, 4)))
+    finally:
+        out.free()
+    logged = {0: [0] * 8, 1: [166, 164, 37, 130, 206, 91, 156, 95], 2: [118, 194, 206, 228, 136, 232, 207, 27],
+              3: [255, 73, 251, 187, 24, 103, 109, 214], 4: [9, 98, 82, 241, 126, 140, 187, 237], 255: [101, 82, 14, 229, 68, 52, 48, 82]}
+    for k, want in logged.items():
+        assert list(got[k].to_bytes(32, "little")[:8]) == want
