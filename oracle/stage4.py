@@ -13,7 +13,8 @@ The witness generation from an ExecutionTrace (initWithPhaseConfig :139-366) is 
 dense K x T tables (val, rd_wa, rs1_ra, rs2_ra), inc (T) and the phase configuration, which is the state that function leaves.
 Tables are indexed [k * T + j] with the ORIGINAL stride T throughout, like the reference.
 Pinned value by value where the reference's captured run allows it: logs/zolt.log prints E_out[0..3], E_in[0..3] and two
-E_out * E_in weights of the Stage 4 split eq over r_cycle = that run's Stage 3 challenges (tests/golden/zolt_log_kats.json,
+E_out * E_in weights of the Stage 4 split eq over r_cycle = that run's Stage 3 challenges, and the cubic gruenPolyDeg3 returned
+in its first two rounds from the logged q(0), q_X2 and claim (the second after bind) (tests/golden/zolt_log_kats.json,
 tests/test_oracle_stage4.py); the witness tables of the run are not in the log, the rest is pinned through the protocol's
 identities and the reference's unit expectations.
 """

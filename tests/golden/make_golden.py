@@ -72,7 +72,27 @@ for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines()
         vals = [int(x) for x in m.group(3).replace(" ", "").split(",") if x]
         if len(vals) == 32:
             stage4[m.group(1)].setdefault(int(m.group(2)), vals)
-stage4 = {"r_cycle_be": [str(stage4["r_cycle_be"][i]) for i in sorted(stage4["r_cycle_be"])],
+# ... and its phase-1 rounds: the two weighted sums, the claim, the cubic gruenPolyDeg3 returned and the challenge bound next
+# (stage4_gruen_prover.zig:561-757, gruen_eq.zig:120-160, :214-262)
+p1_rounds, blk = [], None
+for line in (REF / "logs" / "zolt.log").read_text(errors="replace").splitlines():
+    m = re.match(r"\[STAGE4\] Round (\d+) -> Phase (\d)", line)
+    if m:
+        blk = {"round": int(m.group(1))} if m.group(2) == "1" else None
+        if blk is not None:
+            p1_rounds.append(blk)
+        continue
+    if blk is None:
+        continue
+    m = re.match(r"\[ZOLT PHASE1 (q_0|q_X2|previous_claim)\] = \{ ([0-9, ]+) \}", line) or re.match(r"\[ZOLT PHASE1 COEFFS\] (c[0-3])=\{ ([0-9, ]+) \}", line)
+    if not m:
+        m = re.match(r"\[ZOLT STAGE4\] Round \d+: (challenge) \(LE\) = \{ ([0-9, ]+) \}", line)
+    if m:
+        vals = [int(x) for x in m.group(2).replace(" ", "").split(",") if x]
+        if len(vals) == 32:
+            blk.setdefault(m.group(1), vals)
+p1_rounds = [b for b in p1_rounds if all(k in b for k in ("q_0", "q_X2", "previous_claim", "c0", "c1", "c2", "c3"))]
+stage4 = {"r_cycle_be": [str(stage4["r_cycle_be"][i]) for i in sorted(stage4["r_cycle_be"])], "phase1_rounds": p1_rounds,
           "E_out": [stage4["E_out"][i] for i in sorted(stage4["E_out"])], "E_in": [stage4["E_in"][i] for i in sorted(stage4["E_in"])]}
 (OUT / "zolt_log_kats.json").write_text(json.dumps({"source": "logs/zolt.log", "format": "canonical LE bytes (toBytes)", "kats": kats,
                                                    "stage3_pre": stage3_pre, "stage1_challenges": stage1_challenges,

@@ -73,3 +73,23 @@ def test_gruen_eq_tables_match_the_reference_run():
     # [STAGE4_CONTRIB #1] x_out=0, x_in=0 and [#2] x_out=0, x_in=1: E_combined, first 8 bytes
     assert (e_out[0] * e_in[0] % P).to_bytes(32, "little")[:8] == bytes([35, 129, 211, 100, 28, 19, 13, 225])
     assert (e_out[0] * e_in[1] % P).to_bytes(32, "little")[:8] == bytes([102, 202, 125, 226, 26, 250, 145, 82])
+
+
+def test_gruen_poly_deg3_and_bind_match_the_reference_run():
+    """The first phase-1 rounds of the reference's captured Stage 4 run: from the logged weighted sums q(0), q_X2 and the claim,
+    gruenPolyDeg3 (gruen_eq.zig:214-262) must return the logged cubic c0..c3; the second round only does after bind
+    (:120-160) has taken the first round's challenge, so the running scalar and the bound-variable bookkeeping are pinned too."""
+    import json
+    from pathlib import Path
+
+    d = json.loads((Path(__file__).resolve().parent / "golden" / "zolt_log_kats.json").read_text())
+    le = lambda b: int.from_bytes(bytes(b), "little")  # noqa: E731
+    ch = [le(k["challenge"]) for k in sorted((k for k in d["kats"] if k["stage"] == "STAGE3"), key=lambda x: x["round"])]
+    g = S.GruenEq(ch[::-1])
+    rounds = d["stage4_gruen_init"]["phase1_rounds"]
+    assert [r["round"] for r in rounds] == [0, 1]
+    for r in rounds:
+        got = g.gruen_poly_deg3(le(r["q_0"]), le(r["q_X2"]), le(r["previous_claim"]))
+        assert list(got) == [le(r[f"c{i}"]) for i in range(4)], r["round"]
+        assert (2 * got[0] + got[1] + got[2] + got[3]) % P == le(r["previous_claim"])
+        g.bind(le(r["challenge"]))
